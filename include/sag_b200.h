@@ -1,0 +1,129 @@
+/*
+ * sag_b200.h -- C ABI of the B200-native batched safe-adaptation-gym hot path.
+ *
+ * Drop-in boundary.  In the reference the only door from the environment / world / task code to the
+ * simulator is the Python class MujocoBridge (safe_adaptation_gym/mujoco_bridge.py:15-280) and the env
+ * methods built on it (safe_adaptation_gym/safe_adaptation_gym.py:56-107).  This library replaces that
+ * whole per-step path (dynamics -> reward / goal logic -> cost -> pseudo-lidar observation, plus layout
+ * rejection sampling at reset) for N environments at once.  Each entry point below names the reference
+ * interface it stands in for.  INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions: extern "C", plain pointers and sizes, no C++ / torch types.  Every call returns an int
+ * status (0 = ok); sag_last_error() gives the message of the last failure on the calling thread.
+ * Launches are asynchronous on the caller's cudaStream_t (passed as void*).  The caller owns all I/O
+ * buffers; the library owns the handle's internal SoA state.  One handle per device; not thread-safe.
+ */
+#ifndef SAG_B200_H
+#define SAG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAG_ABI_VERSION 1
+#define SAG_LIDAR_BINS 16   /* safe_adaptation_gym.py:22 */
+#define SAG_OBS_POINT 60    /* 3*16 lidar + 12 sensor floats, safe_adaptation_gym.py:120-139,225-237 */
+#define SAG_MAX_SLOTS 32
+
+enum { SAG_ROBOT_POINT = 0, SAG_ROBOT_CAR = 1 };
+/* task ids: alphabetical registry order of the reference, benchmark/__init__.py:16-20 */
+enum {
+  SAG_T_CATCH_GOAL = 0, SAG_T_COLLECT, SAG_T_DRIBBLE_BALL, SAG_T_GO_TO_GOAL, SAG_T_GO_TO_GOAL_DAMPING,
+  SAG_T_GO_TO_GOAL_MOTOR, SAG_T_GO_TO_GOAL_SCARCE, SAG_T_HAUL_BOX, SAG_T_PRESS_BUTTONS,
+  SAG_T_PRESS_BUTTONS_SCARCE, SAG_T_PUSH_BOX, SAG_T_PUSH_BOX_SCARCE, SAG_T_ROLL_ROD, SAG_T_UNSUPERVISED,
+  SAG_NUM_TASKS
+};
+/* per-env flag bits (sag_read_field(SAG_F_FLAGS)) */
+enum { SAG_FLAG_PHYSICS_ERROR = 1, SAG_FLAG_RESAMPLE_FAILED = 2, SAG_FLAG_NEEDS_RESET = 4 };
+
+/* World.DEFAULT (world.py:17-34) + batching parameters.  POD, copied at sag_create. */
+typedef struct SagConfig {
+  int32_t n_envs;             /* environments on this device */
+  int32_t robot;              /* SAG_ROBOT_* */
+  uint64_t seed;              /* Philox key */
+  uint32_t env_id_base;       /* global id of env 0 (multi-GPU sharding: results do not depend on the GPU count) */
+  int32_t max_episode_steps;  /* 0 = never flag NEEDS_RESET on step count (reference behaviour) */
+  int32_t max_layout_draws;   /* draw budget of one layout rejection sampling; 0 = 1<<22 */
+  int32_t reserved;
+  double placements_margin, robot_keepout;
+  double hazards_size, vases_size, pillars_size, gremlins_size;
+  double hazards_keepout, gremlins_keepout, vases_keepout, pillars_keepout;
+  double gremlins_travel, robot_ctrl_range_scale, action_noise, max_bound;
+} SagConfig;
+
+/* state fields for injection / extraction (parity tests, checkpointing).  All arrays are SoA,
+ * environment-minor with element stride sag_stride(h):  field[k][env]. */
+enum {
+  SAG_F_ROBOT = 0,    /* double [6][stride]: x, y, yaw, vx, vy, w */
+  SAG_F_OBJECTS = 1,  /* double [6][SAG_MAX_SLOTS][stride]: x, y, yaw, vx, vy, w per object slot */
+  SAG_F_TASK_F64 = 2, /* double [12][stride]: last0,last1,cg_cur,cg_next,cg_ox,cg_oy,time,clearance,ep_return,ep_cost,ctrl0,ctrl1 */
+  SAG_F_TASK_I32 = 3, /* int32 [9][stride]: task, goal_button, btn_state, btn_timer, active_mask, cg_timer, n_step, step_ctr, episode */
+  SAG_F_FLAGS = 4,    /* uint8 [stride] */
+  SAG_NUM_FIELDS
+};
+
+const char* sag_last_error(void);
+int sag_abi_version(void);
+void sag_default_config(SagConfig* cfg); /* world.py:17-34 defaults */
+
+/* lifetime.  replaces SafeAdaptationGym.__init__ + MujocoBridge.__init__ (safe_adaptation_gym.py:30-54) */
+int sag_create(const SagConfig* cfg, int device, void** handle);
+int sag_destroy(void* handle);
+int sag_stride(void* handle);
+int sag_obs_dim(void* handle);
+size_t sag_field_bytes(void* handle, int field);
+
+/* env.set_task (safe_adaptation_gym.py:165-168): task_ids is a DEVICE int32[n_envs] array */
+int sag_set_tasks(void* handle, const int32_t* task_ids_dev, void* stream);
+
+/* env.seed (safe_adaptation_gym.py:113-118): new Philox key; per-env episode counters restart */
+int sag_seed(void* handle, uint64_t seed);
+
+/* env.reset / _build_world (safe_adaptation_gym.py:85-107,170-172): layout rejection sampling
+ * (world.py:172-217), yaw draws (world.py:108-137), fresh physics (mujoco_bridge.py:170-175), task.reset.
+ * mask_dev: DEVICE uint8[n_envs] or NULL (= all).  only_flagged != 0 resets only envs whose NEEDS_RESET
+ * flag is set (auto-reset).  new_task != 0 re-initialises task-instance state (a new Task object).
+ * episode numbers are incremented per env (safe_adaptation_gym.py:97-100 `self._seed += 1`). */
+int sag_reset(void* handle, const uint8_t* mask_dev, int only_flagged, int new_task, void* stream);
+
+/* env.step (safe_adaptation_gym.py:56-83).  DEVICE buffers: act float[n][2]; obs float[n][obs_dim];
+ * reward double[n]; reward2 double[n][2] or NULL (Unsupervised's 2-vector, unsupervised.py:66);
+ * cost uint8[n] (world.py:155 binary); done uint8[n]. */
+int sag_step(void* handle, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done,
+             void* stream);
+/* env.observation (safe_adaptation_gym.py:120-131) at the current state; also refreshes internal caches
+ * after sag_write_field. */
+int sag_observe(void* handle, float* obs, void* stream);
+/* same as sag_step with HOST buffers (pinned for full speed: sag_host_alloc): H2D, kernel, D2H, sync. */
+int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward_h, uint8_t* cost_h, uint8_t* done_h);
+int sag_observe_host(void* handle, float* obs_h);
+void* sag_host_alloc(size_t bytes);
+void sag_host_free(void* p);
+
+/* K steps per launch with on-device Philox U(-1,1) actions (stream 2); benchmark helper.  Writes the last
+ * step's obs/reward/cost/done (any may be NULL). */
+int sag_rollout(void* handle, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* stream);
+
+/* state injection / extraction; buffers are DEVICE pointers of sag_field_bytes(field) bytes */
+int sag_read_field(void* handle, int field, void* dst_dev, void* stream);
+int sag_write_field(void* handle, int field, const void* src_dev, void* stream);
+/* per-task episode statistics accumulated by the steps since the last call with reset != 0:
+ * DEVICE double out[SAG_NUM_TASKS][3] = {sum reward, sum cost, env-steps} (the buffer NCCL all-reduces) */
+int sag_task_stats(void* handle, double* out_dev, int reset, void* stream);
+
+/* stand-alone streaming kernels on caller-provided SoA buffers (roofline evidence)
+ * lidar: SafeAdaptationGym._lidar x3 (safe_adaptation_gym.py:133-139,174-223)
+ *   robot double[3][n] (x,y,yaw); obj_xy double[2][nslots][n]; group uint8[nslots][n] (0 skip,1,2,3);
+ *   out float[n][48] = obstacles, objects, goal */
+int sag_lidar(const double* robot, const double* obj_xy, const uint8_t* group, int n, int nslots, float* out, void* stream);
+/* cost: World.compute_cost (world.py:144-155)
+ *   robot_xy double[2][n]; hazard_xy float[2][nh][n]; contact uint8[n] (robot-obstacle contact flag); out uint8[n] */
+int sag_cost(const double* robot_xy, const float* hazard_xy, const uint8_t* contact, int n, int nh, double hazard_size,
+             uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1152 @@
+// sag_core.cuh -- per-environment step / reset / observe logic of the B200 path.
+//
+// One CUDA thread owns one environment.  All state is SoA, environment-minor (field[slot][env]),
+// so every load/store in here is coalesced across the 32 environments of a warp.  The functions are
+// __host__ __device__ so that tests/hostemu can compile the very same body with g++ and compare it
+// with the oracle on the GPU-less build container; the product only ever launches them from
+// sag_kernels.cu on the device.
+//
+// Reference lines cited as file:line are relative to lasgroup/safe-adaptation-gym.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SAG_HD __host__ __device__ __forceinline__
+#define SAG_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define SAG_HD inline
+#define SAG_HD_NOINLINE
+#endif
+
+namespace sag {
+
+// ------------------------------------------------------------------------------------------------
+// constants (assets/xmls/point.xml, primitive_objects.py, tasks/*.py)
+// ------------------------------------------------------------------------------------------------
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 2.0 * kPi;
+constexpr double kGrav = 9.81;
+constexpr double kPtH = 0.004;          // point.xml:3
+constexpr int kPtNsub = 5;              // safe_adaptation_gym.py:17
+constexpr double kPtR = 0.1;            // point.xml:18
+constexpr double kPtArrowOff = 0.1;     // point.xml:19
+constexpr double kPtArrowH = 0.05;      // point.xml:19
+constexpr double kPtForceLim = 0.05;    // point.xml:7-8
+constexpr double kPtGearX = 0.3;        // point.xml:36
+constexpr double kPtGearZ = 0.3;        // point.xml:37
+constexpr double kPtDampXY = 0.01;      // point.xml:15-16
+constexpr double kPtDampZ = 0.005;      // point.xml:17
+constexpr double kPtZ = 0.1;            // point.xml:13
+constexpr double kGoalZ = 0.16;         // primitive_objects.py:140
+constexpr double kGoalSize = 0.3;       // go_to_goal.py:12
+constexpr double kGoalKeepout = 0.4;    // go_to_goal.py:13
+constexpr double kButtonSize = 0.1;     // press_buttons.py:15
+constexpr double kButtonsKeepout = 0.2; // press_buttons.py:14
+constexpr int kButtonDelay = 5;         // press_buttons.py:17
+constexpr double kBoxSize = 0.2;        // push_box.py:12
+constexpr double kBoxDensity = 0.001;   // push_box.py:15
+constexpr double kVaseDensity = 0.001;  // consts.py:21
+constexpr double kLidarMax = 5.0;       // safe_adaptation_gym.py:23
+constexpr int kLidarBins = 16;          // safe_adaptation_gym.py:22
+constexpr double kTendonMax = kBoxSize * 3.75;  // haul_box.py:25
+// MuJoCo default soft-constraint parameters [EXT]
+constexpr double kSolTc = 0.02, kImpD0 = 0.9, kImpDmax = 0.95, kImpWidth = 0.001;
+constexpr double kMu = 1.0;
+constexpr int kSweeps = 10;
+constexpr double kSleepV = 1e-8;
+constexpr int kMaxObj = 32;
+constexpr int kMaxCon = 24;
+constexpr double kRobotReach = 0.16;    // >= |hinge -> far arrow corner| = hypot(0.15, 0.05)
+
+// point robot mass properties (MuJoCo uniform-density rule, density 1, point.xml:5,18-19)
+constexpr double kPtMs = 4.0 / 3.0 * kPi * kPtR * kPtR * kPtR;
+constexpr double kPtMa = 8.0 * kPtArrowH * kPtArrowH * kPtArrowH;
+constexpr double kPtM = kPtMs + kPtMa;
+constexpr double kPtMc = kPtMa * kPtArrowOff;
+constexpr double kPtIo = 0.4 * kPtMs * kPtR * kPtR + kPtMa * (8.0 * kPtArrowH * kPtArrowH) / 12.0 + kPtMa * kPtArrowOff * kPtArrowOff;
+
+enum ObjKind : int { K_NONE = 0, K_HAZARD, K_VASE, K_GREMLIN, K_PILLAR, K_GOAL, K_BUTTON, K_BOX, K_ROD, K_BALL };
+enum Task : int {
+  T_CATCH_GOAL = 0, T_COLLECT, T_DRIBBLE_BALL, T_GO_TO_GOAL, T_GO_TO_GOAL_DAMPING, T_GO_TO_GOAL_MOTOR, T_GO_TO_GOAL_SCARCE,
+  T_HAUL_BOX, T_PRESS_BUTTONS, T_PRESS_BUTTONS_SCARCE, T_PUSH_BOX, T_PUSH_BOX_SCARCE, T_ROLL_ROD, T_UNSUPERVISED, T_COUNT
+};
+enum Flags : unsigned char { F_PHYS_ERROR = 1, F_RESAMPLE_FAILED = 2, F_NEEDS_RESET = 4 };
+
+// per-task descriptor (tasks/*.py; SURVEY Appendix C, corrected: Collect inherits PressButtons.obstacles)
+struct TaskSpec {
+  int nh, nv, ng, np;   // hazards, vases, gremlins, pillars
+  int kind;             // 0 goal, 1 buttons, 2 goal + box
+  int nbuttons;
+  int box_kind;
+  double extent, button_rect, box_keepout, box_rect;
+  double damp_xy, gear_x;
+};
+
+SAG_HD TaskSpec task_spec(int t) {
+  TaskSpec s = {9, 10, 0, 1, 0, 0, 0, 2.0, 0.0, 0.0, 0.0, kPtDampXY, kPtGearX};
+  switch (t) {
+    case T_COLLECT: s = {6, 8, 0, 0, 1, 6, 0, 2.25, 1.5, 0.0, 0.0, kPtDampXY, kPtGearX}; break;
+    case T_PRESS_BUTTONS: s = {6, 8, 0, 0, 1, 4, 0, 2.0, 1.35, 0.0, 0.0, kPtDampXY, kPtGearX}; break;
+    case T_PRESS_BUTTONS_SCARCE: s = {6, 8, 0, 0, 1, 4, 0, 2.0, 1.75, 0.0, 0.0, kPtDampXY, kPtGearX}; break;
+    case T_HAUL_BOX: case T_PUSH_BOX: s = {2, 3, 0, 1, 2, 0, K_BOX, 1.75, 0.0, 0.5, 0.0, kPtDampXY, kPtGearX}; break;
+    case T_PUSH_BOX_SCARCE: s = {2, 3, 0, 1, 2, 0, K_BOX, 1.75, 0.0, 0.55, 2.25, kPtDampXY, kPtGearX}; break;
+    case T_ROLL_ROD: s = {2, 3, 0, 1, 2, 0, K_ROD, 1.75, 0.0, 0.7, 0.0, kPtDampXY, kPtGearX}; break;
+    case T_DRIBBLE_BALL: s = {2, 3, 0, 1, 2, 0, K_BALL, 1.75, 0.0, 0.2, 0.0, kPtDampXY, kPtGearX}; break;
+    case T_UNSUPERVISED: s = {5, 6, 0, 1, 0, 0, 0, 2.0, 0.0, 0.0, 0.0, kPtDampXY, kPtGearX}; break;
+    case T_GO_TO_GOAL_DAMPING: s.damp_xy = kPtDampXY * 0.1; break;   // go_to_goal_damping.py:12-17
+    case T_GO_TO_GOAL_MOTOR: s.gear_x = kPtGearX * 10.0; break;      // go_to_goal_motor.py:12-16
+    default: break;
+  }
+  return s;
+}
+
+// slot layout = placement order without the robot (world.py:83-90): hazards, vases, gremlins, pillars, task objects
+struct Slots {
+  int h0, v0, g0, p0, t0, n;  // first slot of each kind, total
+  int goal, box, btn0, nbtn;
+};
+SAG_HD Slots make_slots(const TaskSpec& s) {
+  Slots L;
+  L.h0 = 0; L.v0 = s.nh; L.g0 = L.v0 + s.nv; L.p0 = L.g0 + s.ng; L.t0 = L.p0 + s.np;
+  L.goal = L.box = L.btn0 = -1; L.nbtn = 0;
+  if (s.kind == 0) { L.goal = L.t0; L.n = L.t0 + 1; }
+  else if (s.kind == 1) { L.btn0 = L.t0; L.nbtn = s.nbuttons; L.n = L.t0 + s.nbuttons; }
+  else { L.goal = L.t0; L.box = L.t0 + 1; L.n = L.t0 + 2; }
+  return L;
+}
+SAG_HD int slot_kind(const TaskSpec& s, const Slots& L, int k) {
+  if (k < L.v0) return K_HAZARD;
+  if (k < L.g0) return K_VASE;
+  if (k < L.p0) return K_GREMLIN;
+  if (k < L.t0) return K_PILLAR;
+  if (k == L.goal) return K_GOAL;
+  if (k == L.box) return s.box_kind;
+  return K_BUTTON;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident state (SoA, env-minor) + config.  Passed by value to every kernel.
+// ------------------------------------------------------------------------------------------------
+struct Dev {
+  int n, stride, nslots, robot;
+  // World.DEFAULT (world.py:17-34), keepouts already max'ed with sizes (world.py:60-66)
+  double action_noise, placements_margin, robot_keepout;
+  double hazards_size, vases_size, pillars_size, gremlins_size;
+  double k_hazard, k_vase, k_gremlin, k_pillar;
+  double max_bound;
+  unsigned long long seed;
+  unsigned gid_base;
+  int max_layout_draws, max_episode_steps;
+  // robot
+  double *rx, *ry, *ryaw, *rvx, *rvy, *rw;
+  double *ctrl0, *ctrl1;
+  // objects [slot][env]
+  double *ox, *oy, *oyaw, *ovx, *ovy, *ow;
+  // task / bookkeeping
+  int* task;
+  double *last0, *last1;
+  int *gbtn, *bstate, *btimer, *amask;
+  double *cgcur, *cgnext, *cgox, *cgoy;
+  int* cgtimer;
+  double *time, *clear;
+  unsigned *ctr, *episode;
+  int* nstep;
+  double *epret, *epcost;
+  unsigned char* flags;
+};
+
+SAG_HD size_t oidx(const Dev& D, int slot, int e) { return (size_t)slot * D.stride + e; }
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10, counter = (ctr, episode, global env id, stream), key = seed
+// ------------------------------------------------------------------------------------------------
+SAG_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+struct Rng {
+  uint64_t seed;
+  uint32_t gid, episode;
+  SAG_HD void pair(uint32_t stream, uint32_t ctr, double& u1, double& u2) const {
+    uint32_t r[4];
+    philox4x32_10(ctr, episode, gid, stream, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    u1 = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6)) * (1.0 / 9007199254740992.0);
+    u2 = ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6)) * (1.0 / 9007199254740992.0);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// planar collision primitives (MuJoCo contact convention [EXT]: signed dist, normal geom1->geom2,
+// point at the midpoint; listed when dist <= 0)
+// ------------------------------------------------------------------------------------------------
+struct Geom { int is_box; double cx, cy, c, s, hx, hy, r; };
+struct Hit { double nx, ny, px, py, dist; };
+
+SAG_HD int hit_circle_circle(const Geom& A, const Geom& B, Hit* o) {
+  double dx = B.cx - A.cx, dy = B.cy - A.cy;
+  double len = sqrt(dx * dx + dy * dy);
+  double dist = len - A.r - B.r;
+  if (dist > 0.0) return 0;
+  double nx = 1.0, ny = 0.0;
+  if (len > 1e-14) { nx = dx / len; ny = dy / len; }
+  o->nx = nx; o->ny = ny;
+  o->px = A.cx + nx * (A.r + 0.5 * dist);
+  o->py = A.cy + ny * (A.r + 0.5 * dist);
+  o->dist = dist;
+  return 1;
+}
+
+SAG_HD int hit_circle_box(const Geom& Cc, const Geom& B, bool circle_is_a, Hit* o) {
+  double rx = Cc.cx - B.cx, ry = Cc.cy - B.cy;
+  double lx = rx * B.c + ry * B.s, ly = -rx * B.s + ry * B.c;
+  double qx = lx < -B.hx ? -B.hx : (lx > B.hx ? B.hx : lx);
+  double qy = ly < -B.hy ? -B.hy : (ly > B.hy ? B.hy : ly);
+  double nlx, nly, dist;
+  if (qx == lx && qy == ly) {
+    double penx = B.hx - fabs(lx), peny = B.hy - fabs(ly);
+    if (penx <= peny) { nlx = lx >= 0.0 ? 1.0 : -1.0; nly = 0.0; qx = nlx * B.hx; dist = -penx - Cc.r; }
+    else { nlx = 0.0; nly = ly >= 0.0 ? 1.0 : -1.0; qy = nly * B.hy; dist = -peny - Cc.r; }
+  } else {
+    double ex = lx - qx, ey = ly - qy;
+    double len = sqrt(ex * ex + ey * ey);
+    dist = len - Cc.r;
+    if (dist > 0.0) return 0;
+    nlx = ex / len; nly = ey / len;
+  }
+  double nwx = nlx * B.c - nly * B.s, nwy = nlx * B.s + nly * B.c;
+  double pbx = B.cx + qx * B.c - qy * B.s, pby = B.cy + qx * B.s + qy * B.c;
+  double pcx = Cc.cx - nwx * Cc.r, pcy = Cc.cy - nwy * Cc.r;
+  o->px = 0.5 * (pbx + pcx); o->py = 0.5 * (pby + pcy); o->dist = dist;
+  if (circle_is_a) { o->nx = -nwx; o->ny = -nwy; } else { o->nx = nwx; o->ny = nwy; }
+  return 1;
+}
+
+SAG_HD_NOINLINE int hit_box_box(const Geom& A, const Geom& B, Hit* o) {
+  double dx = B.cx - A.cx, dy = B.cy - A.cy;
+  double best = -1e300, bsign = 1.0, bux = 0.0, buy = 0.0;
+  int bi = -1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double ux = k == 0 ? A.c : (k == 1 ? -A.s : (k == 2 ? B.c : -B.s));
+    double uy = k == 0 ? A.s : (k == 1 ? A.c : (k == 2 ? B.s : B.c));
+    double dp = dx * ux + dy * uy;
+    double ra = A.hx * fabs(A.c * ux + A.s * uy) + A.hy * fabs(-A.s * ux + A.c * uy);
+    double rb = B.hx * fabs(B.c * ux + B.s * uy) + B.hy * fabs(-B.s * ux + B.c * uy);
+    double sep = fabs(dp) - (ra + rb);
+    if (sep > 0.0) return 0;
+    if (sep > best) { best = sep; bi = k; bsign = dp >= 0.0 ? 1.0 : -1.0; bux = ux; buy = uy; }
+  }
+  bool ref_is_a = bi < 2;
+  const Geom& R = ref_is_a ? A : B;
+  const Geom& I = ref_is_a ? B : A;
+  double Nx = ref_is_a ? bsign * bux : -bsign * bux, Ny = ref_is_a ? bsign * buy : -bsign * buy;
+  int ref_axis = bi & 1;
+  double hn = ref_axis == 0 ? R.hx : R.hy, ht = ref_axis == 0 ? R.hy : R.hx;
+  double Tx = -Ny, Ty = Nx;
+  double nlx = Nx * I.c + Ny * I.s, nly = -Nx * I.s + Ny * I.c;
+  double v1x, v1y, v2x, v2y;
+  if (fabs(nlx) >= fabs(nly)) { double sx = nlx > 0.0 ? -1.0 : 1.0; v1x = sx * I.hx; v1y = -I.hy; v2x = sx * I.hx; v2y = I.hy; }
+  else { double sy = nly > 0.0 ? -1.0 : 1.0; v1x = -I.hx; v1y = sy * I.hy; v2x = I.hx; v2y = sy * I.hy; }
+  double w1x = I.cx + v1x * I.c - v1y * I.s - R.cx, w1y = I.cy + v1x * I.s + v1y * I.c - R.cy;
+  double w2x = I.cx + v2x * I.c - v2y * I.s - R.cx, w2y = I.cy + v2x * I.s + v2y * I.c - R.cy;
+  double n1 = w1x * Nx + w1y * Ny, t1 = w1x * Tx + w1y * Ty;
+  double n2 = w2x * Nx + w2y * Ny, t2 = w2x * Tx + w2y * Ty;
+  double lo = 0.0, hi = 1.0, dt = t2 - t1;
+  if (t1 > ht && t2 > ht) return 0;
+  if (t1 < -ht && t2 < -ht) return 0;
+  if (dt != 0.0) {
+    if (t1 > ht) { double s = (ht - t1) / dt; if (s > lo) lo = s; }
+    if (t2 > ht) { double s = (ht - t1) / dt; if (s < hi) hi = s; }
+    if (t1 < -ht) { double s = (-ht - t1) / dt; if (s > lo) lo = s; }
+    if (t2 < -ht) { double s = (-ht - t1) / dt; if (s < hi) hi = s; }
+  }
+  if (lo > hi) return 0;
+  int n = 0;
+  int npts = (hi - lo) > 1e-12 ? 2 : 1;
+  for (int k = 0; k < npts; ++k) {
+    double s = k == 0 ? lo : hi;
+    double pn = n1 + s * (n2 - n1), pt = t1 + s * dt;
+    double sep = pn - hn;
+    if (sep > 0.0) continue;
+    Hit& c = o[n];
+    c.px = R.cx + pn * Nx + pt * Tx - 0.5 * sep * Nx;
+    c.py = R.cy + pn * Ny + pt * Ty - 0.5 * sep * Ny;
+    if (ref_is_a) { c.nx = Nx; c.ny = Ny; } else { c.nx = -Nx; c.ny = -Ny; }
+    c.dist = sep;
+    ++n;
+  }
+  return n;
+}
+
+SAG_HD int collide(const Geom& A, const Geom& B, Hit* o) {
+  if (!A.is_box && !B.is_box) return hit_circle_circle(A, B, o);
+  if (!A.is_box) return hit_circle_box(A, B, true, o);
+  if (!B.is_box) return hit_circle_box(B, A, false, o);
+  return hit_box_box(A, B, o);
+}
+
+SAG_HD bool kind_collidable(int k) { return k == K_VASE || k == K_GREMLIN || k == K_PILLAR || k == K_BUTTON || k == K_BOX; }
+SAG_HD bool kind_movable(int k) { return k == K_VASE || k == K_GREMLIN || k == K_BOX; }
+SAG_HD int kind_nparts(int k) { return k == K_BOX ? 5 : (kind_collidable(k) ? 1 : 0); }
+// bounding radius about the body centre (for the broad phase)
+SAG_HD double kind_bound(const Dev& D, int k) {
+  switch (k) {
+    case K_VASE: return D.vases_size * 1.4142135623730951 + 1e-9;
+    case K_GREMLIN: return D.gremlins_size * 1.4142135623730951 + 1e-9;
+    case K_PILLAR: return D.pillars_size;
+    case K_BUTTON: return kButtonSize;
+    case K_BOX: return kBoxSize * 1.5 * 1.4142135623730951 + 1e-9;
+    default: return 0.0;
+  }
+}
+SAG_HD void kind_mass(const Dev& D, int k, double& m, double& iz, double& reff) {
+  if (k == K_BOX) {
+    const double d = kBoxSize, wd = kBoxSize / 2;
+    const double m0 = 8.0 * d * d * d * kBoxDensity, mc = 8.0 * wd * wd * d * kBoxDensity;
+    m = m0 + 4.0 * mc;
+    iz = m0 * (2.0 / 3.0) * d * d + 4.0 * (mc * (2.0 / 3.0) * wd * wd + mc * (2.0 * d * d));
+    reff = 1.5 * d;
+  } else {
+    double s = k == K_VASE ? D.vases_size : D.gremlins_size;
+    m = 8.0 * s * s * s * kVaseDensity;
+    iz = m * (2.0 / 3.0) * s * s;
+    reff = s * sqrt(2.0);
+  }
+}
+
+SAG_HD void obj_geom(const Dev& D, int kind, int part, double x, double y, double c, double s, Geom& g) {
+  g.c = c; g.s = s; g.cx = x; g.cy = y; g.r = 0.0; g.hx = g.hy = 0.0; g.is_box = 0;
+  switch (kind) {
+    case K_VASE: g.is_box = 1; g.hx = g.hy = D.vases_size; break;
+    case K_GREMLIN: g.is_box = 1; g.hx = g.hy = D.gremlins_size; break;
+    case K_PILLAR: g.r = D.pillars_size; break;
+    case K_BUTTON: g.r = kButtonSize; break;
+    case K_BOX:
+      g.is_box = 1;
+      if (part == 0) { g.hx = g.hy = kBoxSize; }
+      else {
+        double sx = (part == 1 || part == 3) ? 1.0 : -1.0, sy = (part <= 2) ? 1.0 : -1.0;
+        double ox = sx * kBoxSize, oy = sy * kBoxSize;
+        g.hx = g.hy = kBoxSize / 2;
+        g.cx = x + ox * c - oy * s; g.cy = y + ox * s + oy * c;
+      }
+      break;
+    default: break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// point robot (point.xml): generalised coordinates (x, y, yaw) in the world frame
+// ------------------------------------------------------------------------------------------------
+struct PtMat { double a, b, p, q, s; };  // [[a,0,p],[0,b,q],[p,q,I]], s = Schur complement
+
+SAG_HD PtMat pt_matrix(double sn, double cs, double hd, double damp_xy) {
+  PtMat M;
+  M.a = kPtM + hd * damp_xy; M.b = kPtM + hd * damp_xy;
+  M.p = -kPtMc * sn; M.q = kPtMc * cs;
+  double I = kPtIo + hd * kPtDampZ;
+  M.s = I - M.p * M.p / M.a - M.q * M.q / M.b;
+  return M;
+}
+SAG_HD void pt_solve(const PtMat& M, const double* f, double* out) {
+  double al = (f[2] - M.p * f[0] / M.a - M.q * f[1] / M.b) / M.s;
+  out[0] = (f[0] - M.p * al) / M.a;
+  out[1] = (f[1] - M.q * al) / M.b;
+  out[2] = al;
+}
+SAG_HD double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+struct Robot { double q[3], v[3]; double ctrl[2]; double damp_xy, gear_x; };
+
+// qfrc_smooth = actuation + passive - bias  (SURVEY Appendix A.1 / B.2-3 [EXT])
+SAG_HD void pt_smooth(const Robot& R, double sn, double cs, double* f) {
+  double w = R.v[2];
+  double fx = clampd(R.ctrl[0], -kPtForceLim, kPtForceLim);
+  double fz = clampd(R.ctrl[1] - kPtGearZ * w, -kPtForceLim, kPtForceLim);
+  f[0] = R.gear_x * fx * cs - R.damp_xy * R.v[0] + kPtMc * w * w * cs;
+  f[1] = R.gear_x * fx * sn - R.damp_xy * R.v[1] + kPtMc * w * w * sn;
+  f[2] = kPtGearZ * fz - kPtDampZ * w;
+}
+
+SAG_HD bool bad_val(double x) { return !(fabs(x) <= 1e10); }
+
+// one contact-free substep: forward dynamics + semi-implicit Euler with implicit joint damping
+SAG_HD void pt_substep_free(Robot& R, double h, int& err) {
+  double sn = sin(R.q[2]), cs = cos(R.q[2]);
+  double f[3], a[3];
+  pt_smooth(R, sn, cs, f);
+  PtMat Mh = pt_matrix(sn, cs, h, R.damp_xy);
+  pt_solve(Mh, f, a);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) R.v[k] += h * a[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) R.q[k] += h * R.v[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) if (bad_val(R.q[k]) || bad_val(R.v[k]) || bad_val(a[k])) err = 1;
+}
+
+SAG_HD double impedance(double r) {
+  double x = fabs(r) / kImpWidth;
+  if (x > 1.0) x = 1.0;
+  double y = x < 0.5 ? 2.0 * x * x : 1.0 - 2.0 * (1.0 - x) * (1.0 - x);
+  return kImpD0 + y * (kImpDmax - kImpD0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// full forward dynamics with contacts (slow path; only taken near objects)
+// ------------------------------------------------------------------------------------------------
+struct Con { int ba, bb; double nx, ny, px, py, dist; };
+struct Row { int ba, bb; double ja[2][3], jb[2][3]; double aref[2], diag[2], R[2], f[2]; };
+
+struct FwdOut {
+  double qacc[3], fsmooth[3], fcon[3];
+  unsigned touch;        // bit s: robot geom in contact (dist <= 0) with object slot s
+  unsigned touched_mov;  // bit s: movable body s had an active constraint row
+  int err;
+};
+
+struct Ctx {  // per-thread view of one environment
+  const Dev& D;
+  int e;
+  TaskSpec sp;
+  Slots L;
+  int task;
+};
+
+SAG_HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+SAG_HD_NOINLINE void forward_full(const Ctx& C, const Robot& R, FwdOut& out, double (*oacc)[3]) {
+  const Dev& D = C.D;
+  const int e = C.e;
+  Con con[kMaxCon];
+  int ncon = 0;
+  unsigned active = 0, touch = 0;
+  out.err = 0;
+  const double sn = sin(R.q[2]), cs = cos(R.q[2]);
+  Geom gr[2];
+  gr[0].is_box = 0; gr[0].cx = R.q[0]; gr[0].cy = R.q[1]; gr[0].c = cs; gr[0].s = sn; gr[0].r = kPtR; gr[0].hx = gr[0].hy = 0.0;
+  gr[1].is_box = 1; gr[1].cx = R.q[0] + kPtArrowOff * cs; gr[1].cy = R.q[1] + kPtArrowOff * sn; gr[1].c = cs; gr[1].s = sn;
+  gr[1].hx = gr[1].hy = kPtArrowH; gr[1].r = 0.0;
+  Hit hits[2];
+  // ---- phase 1: robot geoms vs objects, slot order
+  for (int s = C.L.v0; s < C.L.n; ++s) {
+    int kind = slot_kind(C.sp, C.L, s);
+    if (!kind_collidable(kind)) continue;
+    size_t i = oidx(D, s, e);
+    double x = D.ox[i], y = D.oy[i];
+    bool mov = kind_movable(kind);
+    if (mov && (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0)) active |= 1u << s;
+    double dx = x - R.q[0], dy = y - R.q[1], reach = kRobotReach + kind_bound(D, kind);
+    if (dx * dx + dy * dy > reach * reach) continue;
+    double oc = 1.0, os = 0.0;
+    if (mov) { double yaw = D.oyaw[i]; oc = cos(yaw); os = sin(yaw); }
+    for (int rg = 0; rg < 2; ++rg)
+      for (int p = 0; p < kind_nparts(kind); ++p) {
+        Geom go;
+        obj_geom(D, kind, p, x, y, oc, os, go);
+        int n = collide(gr[rg], go, hits);
+        for (int k = 0; k < n; ++k) {
+          if (ncon >= kMaxCon) { out.err = 1; break; }
+          Con& c = con[ncon++];
+          c.ba = 0; c.bb = mov ? 1 + s : -1;
+          c.nx = hits[k].nx; c.ny = hits[k].ny; c.px = hits[k].px; c.py = hits[k].py; c.dist = hits[k].dist;
+        }
+        if (n) { touch |= 1u << s; if (mov) active |= 1u << s; }
+      }
+  }
+  // ---- phase 2: object pairs with at least one awake / robot-touched movable body
+  if (active) {
+    for (int j = C.L.v0; j < C.L.n; ++j) {
+      int kj = slot_kind(C.sp, C.L, j);
+      if (!kind_collidable(kj)) continue;
+      size_t ij = oidx(D, j, e);
+      double xj = D.ox[ij], yj = D.oy[ij], bj = kind_bound(D, kj);
+      for (int i = C.L.v0; i < j; ++i) {
+        if (!((active >> i) & 1u) && !((active >> j) & 1u)) continue;
+        int ki = slot_kind(C.sp, C.L, i);
+        if (!kind_collidable(ki)) continue;
+        size_t ii = oidx(D, i, e);
+        double xi = D.ox[ii], yi = D.oy[ii];
+        double dx = xj - xi, dy = yj - yi, reach = bj + kind_bound(D, ki);
+        if (dx * dx + dy * dy > reach * reach) continue;
+        bool mi = kind_movable(ki), mj = kind_movable(kj);
+        double ci = 1.0, si = 0.0, cj = 1.0, sj = 0.0;
+        if (mi) { double yaw = D.oyaw[ii]; ci = cos(yaw); si = sin(yaw); }
+        if (mj) { double yaw = D.oyaw[ij]; cj = cos(yaw); sj = sin(yaw); }
+        for (int pi = 0; pi < kind_nparts(ki); ++pi) {
+          Geom gi;
+          obj_geom(D, ki, pi, xi, yi, ci, si, gi);
+          for (int pj = 0; pj < kind_nparts(kj); ++pj) {
+            Geom gj;
+            obj_geom(D, kj, pj, xj, yj, cj, sj, gj);
+            int n = collide(gi, gj, hits);
+            for (int k = 0; k < n; ++k) {
+              if (ncon >= kMaxCon) { out.err = 1; break; }
+              Con& c = con[ncon++];
+              c.ba = mi ? 1 + i : -1; c.bb = mj ? 1 + j : -1;
+              c.nx = hits[k].nx; c.ny = hits[k].ny; c.px = hits[k].px; c.py = hits[k].py; c.dist = hits[k].dist;
+            }
+          }
+        }
+      }
+    }
+  }
+  out.touch = touch;
+  // ---- smooth dynamics
+  PtMat M = pt_matrix(sn, cs, 0.0, R.damp_xy);
+  pt_smooth(R, sn, cs, out.fsmooth);
+  double racc[3];
+  pt_solve(M, out.fsmooth, racc);
+  for (int s = 0; s < C.L.n; ++s) { oacc[s][0] = oacc[s][1] = oacc[s][2] = 0.0; }
+  // ---- constraint rows
+  Row rows[kMaxCon + 1];
+  int nrow = 0, tendon_row = -1;
+  unsigned touched = 0;
+  const double bdamp = 2.0 / (kImpDmax * kSolTc);
+  const double kbase = 1.0 / (kImpDmax * kImpDmax * kSolTc * kSolTc);
+  auto minv = [&](int body, const double* j, double* o) {
+    if (body == 0) { pt_solve(M, j, o); return; }
+    double m, iz, rf;
+    kind_mass(D, slot_kind(C.sp, C.L, body - 1), m, iz, rf);
+    o[0] = j[0] * (1.0 / m); o[1] = j[1] * (1.0 / m); o[2] = j[2] * (1.0 / iz);
+  };
+  auto bvel = [&](int body, double* v) {
+    if (body == 0) { v[0] = R.v[0]; v[1] = R.v[1]; v[2] = R.v[2]; }
+    else { size_t i = oidx(D, body - 1, e); v[0] = D.ovx[i]; v[1] = D.ovy[i]; v[2] = D.ow[i]; }
+  };
+  auto bpos = [&](int body, double* p) {
+    if (body == 0) { p[0] = R.q[0]; p[1] = R.q[1]; }
+    else { size_t i = oidx(D, body - 1, e); p[0] = D.ox[i]; p[1] = D.oy[i]; }
+  };
+  for (int i = 0; i < ncon; ++i) {
+    const Con& c = con[i];
+    if (!(c.dist < 0.0)) continue;
+    if (c.ba < 0 && c.bb < 0) continue;
+    Row& r = rows[nrow++];
+    r.ba = c.ba; r.bb = c.bb;
+    double tx = -c.ny, ty = c.nx;
+    double pa[2] = {0, 0}, pb[2] = {0, 0}, va[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
+    if (c.ba >= 0) { bpos(c.ba, pa); bvel(c.ba, va); if (c.ba > 0) touched |= 1u << (c.ba - 1); }
+    if (c.bb >= 0) { bpos(c.bb, pb); bvel(c.bb, vb); if (c.bb > 0) touched |= 1u << (c.bb - 1); }
+    double rax = c.px - pa[0], ray = c.py - pa[1], rbx = c.px - pb[0], rby = c.py - pb[1];
+    r.ja[0][0] = -c.nx; r.ja[0][1] = -c.ny; r.ja[0][2] = -(rax * c.ny - ray * c.nx);
+    r.jb[0][0] = c.nx; r.jb[0][1] = c.ny; r.jb[0][2] = rbx * c.ny - rby * c.nx;
+    r.ja[1][0] = -tx; r.ja[1][1] = -ty; r.ja[1][2] = -(rax * ty - ray * tx);
+    r.jb[1][0] = tx; r.jb[1][1] = ty; r.jb[1][2] = rbx * ty - rby * tx;
+    double d = impedance(c.dist);
+    for (int k = 0; k < 2; ++k) {
+      double t[3], diag = 0.0, vel = 0.0;
+      if (c.ba >= 0) { minv(c.ba, r.ja[k], t); diag += dot3(r.ja[k], t); vel += dot3(r.ja[k], va); }
+      if (c.bb >= 0) { minv(c.bb, r.jb[k], t); diag += dot3(r.jb[k], t); vel += dot3(r.jb[k], vb); }
+      r.diag[k] = diag;
+      r.R[k] = (1.0 - d) / d * diag;
+      r.aref[k] = -bdamp * vel - (k == 0 ? d * kbase * c.dist : 0.0);
+      r.f[k] = 0.0;
+    }
+  }
+  if (C.task == T_HAUL_BOX) {  // tendon length limit, haul_box.py:21-30
+    size_t ib = oidx(D, C.L.box, e);
+    double dx = D.ox[ib] - R.q[0], dy = D.oy[ib] - R.q[1], dz = kBoxSize - kPtZ;
+    double len = sqrt(dx * dx + dy * dy + dz * dz);
+    double dist = kTendonMax - len;
+    if (dist < 0.0) {
+      Row& r = rows[nrow]; tendon_row = nrow++;
+      r.ba = 0; r.bb = 1 + C.L.box;
+      r.ja[0][0] = dx / len; r.ja[0][1] = dy / len; r.ja[0][2] = 0.0;
+      r.jb[0][0] = -dx / len; r.jb[0][1] = -dy / len; r.jb[0][2] = 0.0;
+      double va[3], vb[3], t[3], diag = 0.0;
+      bvel(0, va); bvel(r.bb, vb);
+      minv(0, r.ja[0], t); diag += dot3(r.ja[0], t);
+      minv(r.bb, r.jb[0], t); diag += dot3(r.jb[0], t);
+      double d = impedance(dist);
+      r.diag[0] = diag; r.R[0] = (1.0 - d) / d * diag;
+      r.aref[0] = -bdamp * (dot3(r.ja[0], va) + dot3(r.jb[0], vb)) - d * kbase * dist;
+      r.f[0] = 0.0;
+      touched |= 1u << C.L.box;
+    }
+  }
+  out.touched_mov = touched;
+  // floor friction bodies: awake or touched movable bodies
+  unsigned fl = (touched | active);
+  double ffl[kMaxObj][3];
+  for (int s = 0; s < C.L.n; ++s) { ffl[s][0] = ffl[s][1] = ffl[s][2] = 0.0; }
+  auto acc_of = [&](int body) -> double* { return body == 0 ? racc : oacc[body - 1]; };
+  auto apply = [&](int body, const double* j, double df) {
+    if (body < 0) return;
+    double t[3];
+    minv(body, j, t);
+    double* a = acc_of(body);
+    a[0] += t[0] * df; a[1] += t[1] * df; a[2] += t[2] * df;
+  };
+  const double rr = (1.0 - kImpD0) / kImpD0;
+  if (nrow > 0 || fl) {
+    for (int it = 0; it < kSweeps; ++it) {
+      for (int i = 0; i < nrow; ++i) {
+        Row& r = rows[i];
+        int nk = (i == tendon_row) ? 1 : 2;
+        for (int k = 0; k < nk; ++k) {
+          double a = 0.0;
+          if (r.ba >= 0) a += dot3(r.ja[k], acc_of(r.ba));
+          if (r.bb >= 0) a += dot3(r.jb[k], acc_of(r.bb));
+          double fn = r.f[k] - (a - r.aref[k] + r.R[k] * r.f[k]) / (r.diag[k] + r.R[k]);
+          if (k == 0) { if (fn < 0.0) fn = 0.0; }
+          else { double lim = kMu * r.f[0]; fn = clampd(fn, -lim, lim); }
+          double df = fn - r.f[k];
+          r.f[k] = fn;
+          if (df != 0.0) { apply(r.ba, r.ja[k], df); apply(r.bb, r.jb[k], df); }
+        }
+      }
+      for (int s = C.L.v0; s < C.L.n; ++s) {
+        if (!((fl >> s) & 1u)) continue;
+        int kind = slot_kind(C.sp, C.L, s);
+        if (!kind_movable(kind)) continue;
+        double m, iz, rf;
+        kind_mass(D, kind, m, iz, rf);
+        size_t i = oidx(D, s, e);
+        double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
+        double lim = kMu * m * kGrav;
+        double* ac = oacc[s];
+        double Al = 1.0 / m, At = 1.0 / iz;
+        double f0 = ffl[s][0] - (ac[0] + bdamp * vx + rr * Al * ffl[s][0]) / (Al + rr * Al);
+        double f1 = ffl[s][1] - (ac[1] + bdamp * vy + rr * Al * ffl[s][1]) / (Al + rr * Al);
+        double nf = sqrt(f0 * f0 + f1 * f1);
+        if (nf > lim) { f0 *= lim / nf; f1 *= lim / nf; }
+        ac[0] += (f0 - ffl[s][0]) * Al; ac[1] += (f1 - ffl[s][1]) * Al;
+        ffl[s][0] = f0; ffl[s][1] = f1;
+        double f2 = ffl[s][2] - (ac[2] + bdamp * w + rr * At * ffl[s][2]) / (At + rr * At);
+        f2 = clampd(f2, -lim * rf, lim * rf);
+        ac[2] += (f2 - ffl[s][2]) * At;
+        ffl[s][2] = f2;
+      }
+    }
+  }
+  out.qacc[0] = racc[0]; out.qacc[1] = racc[1]; out.qacc[2] = racc[2];
+  out.fcon[0] = out.fcon[1] = out.fcon[2] = 0.0;
+  for (int i = 0; i < nrow; ++i) {
+    const Row& r = rows[i];
+    int nk = (i == tendon_row) ? 1 : 2;
+    for (int k = 0; k < nk; ++k) {
+      if (r.ba == 0) for (int d = 0; d < 3; ++d) out.fcon[d] += r.ja[k][d] * r.f[k];
+      if (r.bb == 0) for (int d = 0; d < 3; ++d) out.fcon[d] += r.jb[k][d] * r.f[k];
+    }
+  }
+}
+
+// one full substep (contacts possible): forward + integrate robot and awake/touched movable bodies
+SAG_HD_NOINLINE void substep_full(const Ctx& C, Robot& R, double h, int& err) {
+  const Dev& D = C.D;
+  FwdOut F;
+  double oacc[kMaxObj][3];
+  forward_full(C, R, F, oacc);
+  if (F.err) err = 1;
+  double sn = sin(R.q[2]), cs = cos(R.q[2]);
+  PtMat Mh = pt_matrix(sn, cs, h, R.damp_xy);
+  double rhs[3], a[3];
+  for (int k = 0; k < 3; ++k) rhs[k] = F.fsmooth[k] + F.fcon[k];
+  pt_solve(Mh, rhs, a);
+  for (int k = 0; k < 3; ++k) R.v[k] += h * a[k];
+  for (int k = 0; k < 3; ++k) R.q[k] += h * R.v[k];
+  for (int k = 0; k < 3; ++k) if (bad_val(R.q[k]) || bad_val(R.v[k]) || bad_val(a[k])) err = 1;
+  for (int s = C.L.v0; s < C.L.n; ++s) {
+    int kind = slot_kind(C.sp, C.L, s);
+    if (!kind_movable(kind)) continue;
+    size_t i = oidx(D, s, C.e);
+    double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
+    bool touched = (F.touched_mov >> s) & 1u;
+    if (!(touched || vx != 0.0 || vy != 0.0 || w != 0.0)) continue;
+    vx += h * oacc[s][0]; vy += h * oacc[s][1]; w += h * oacc[s][2];
+    if (!touched && vx * vx + vy * vy < kSleepV * kSleepV && fabs(w) < kSleepV) { vx = vy = w = 0.0; }
+    double x = D.ox[i] + h * vx, y = D.oy[i] + h * vy, yaw = D.oyaw[i] + h * w;
+    D.ovx[i] = vx; D.ovy[i] = vy; D.ow[i] = w; D.ox[i] = x; D.oy[i] = y; D.oyaw[i] = yaw;
+    if (bad_val(x) || bad_val(y) || bad_val(vx) || bad_val(vy) || bad_val(w)) err = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lidar (safe_adaptation_gym.py:174-223) -- accumulate one object into a 16-bin group
+// bins are stored strided (bins[bin * bstride]) so that the caller can keep them in shared memory
+// ------------------------------------------------------------------------------------------------
+SAG_HD void lidar_accum(double rx, double ry, double cs, double sn, double px, double py, float* bins, int bstride) {
+  double wx = px - rx, wy = py - ry;
+  double ex = wx * cs + wy * sn, ey = -wx * sn + wy * cs;   // :197-202
+  double dist = sqrt(ex * ex + ey * ey);                    // :209
+  double angle = atan2(ey, ex);                             // :210
+  if (angle < 0.0) angle += kTwoPi;
+  const double bin_size = kTwoPi / kLidarBins;              // :211
+  int bin = (int)(angle / bin_size);                        // :212
+  double bin_angle = bin_size * bin;                        // :213
+  double sensor = kLidarMax - dist;                         // :214
+  if (sensor < 0.0) sensor = 0.0;
+  sensor /= kLidarMax;
+  double alias = (angle - bin_angle) / bin_size;            // :216
+  int b0 = bin & (kLidarBins - 1), bp = (bin + 1) & (kLidarBins - 1), bm = (bin + kLidarBins - 1) & (kLidarBins - 1);
+  float s0 = (float)sensor, sp = (float)(alias * sensor), sm = (float)((1.0 - alias) * sensor);
+  if (s0 > bins[b0 * bstride]) bins[b0 * bstride] = s0;     // :215
+  if (sp > bins[bp * bstride]) bins[bp * bstride] = sp;     // :221
+  if (sm > bins[bm * bstride]) bins[bm * bstride] = sm;     // :222
+}
+
+// lidar group of a slot (consts.py:13-16; press_buttons.py:78-91; collect.py:34,44-45)
+SAG_HD int slot_group(const Ctx& C, int s, int kind, int gbtn, int bstate, int amask) {
+  if (kind == K_GOAL) return 2;
+  if (kind == K_BUTTON) {
+    int i = s - C.L.btn0;
+    if (C.task == T_COLLECT) return ((amask >> i) & 1) ? 2 : 0;
+    if (bstate == 0) return 0;
+    return i == gbtn ? 2 : 3;
+  }
+  if (kind == K_BOX || kind == K_ROD || kind == K_BALL) return 3;
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// goal resampling (go_to_goal.py:59-80): the rectangle grows x1.01 after every failed draw
+// ------------------------------------------------------------------------------------------------
+SAG_HD int resample_goal(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& ctr, double rx, double ry, double& gx, double& gy) {
+  const Dev& D = C.D;
+  double rect[4] = {-1.5, -1.5, 1.5, 1.5};
+  for (int j = 0; j < 500000; ++j) {
+    double u1, u2;
+    rng.pair(stream, ctr++, u1, u2);
+    double xmin = rect[0] + kGoalKeepout, ymin = rect[1] + kGoalKeepout, xmax = rect[2] - kGoalKeepout, ymax = rect[3] - kGoalKeepout;
+    double x = xmin + (xmax - xmin) * u1, y = ymin + (ymax - ymin) * u2;
+    bool valid = true;
+    { double dx = x - rx, dy = y - ry; if (sqrt(dx * dx + dy * dy) < D.robot_keepout + kGoalKeepout) valid = false; }
+    for (int s = 0; valid && s < C.L.n; ++s) {
+      if (s == C.L.goal) continue;
+      int kind = slot_kind(C.sp, C.L, s);
+      double ko = kind == K_HAZARD ? D.k_hazard : kind == K_VASE ? D.k_vase : kind == K_GREMLIN ? D.k_gremlin
+                : kind == K_PILLAR ? D.k_pillar : kind == K_BUTTON ? kButtonsKeepout : C.sp.box_keepout;
+      size_t i = oidx(D, s, C.e);
+      double dx = x - D.ox[i], dy = y - D.oy[i];
+      if (sqrt(dx * dx + dy * dy) < ko + kGoalKeepout) valid = false;
+    }
+    if (valid) { gx = x; gy = y; return 0; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rect[k] = rect[k] * 1.01;
+  }
+  return 1;
+}
+
+SAG_HD double dist2d(double ax, double ay, double bx, double by) { double dx = ax - bx, dy = ay - by; return sqrt(dx * dx + dy * dy); }
+
+// per-env task scalars kept in registers during a step
+struct TaskState {
+  double last0, last1;
+  int gbtn, bstate, btimer, amask;
+  double cgcur, cgnext, cgox, cgoy;
+  int cgtimer;
+  uint32_t ctr;
+};
+
+SAG_HD void load_task_state(const Dev& D, int e, TaskState& T) {
+  T.last0 = D.last0[e]; T.last1 = D.last1[e];
+  T.gbtn = D.gbtn[e]; T.bstate = D.bstate[e]; T.btimer = D.btimer[e]; T.amask = D.amask[e];
+  T.cgcur = D.cgcur[e]; T.cgnext = D.cgnext[e]; T.cgox = D.cgox[e]; T.cgoy = D.cgoy[e]; T.cgtimer = D.cgtimer[e];
+  T.ctr = D.ctr[e];
+}
+SAG_HD void store_task_state(const Dev& D, int e, const TaskState& T) {
+  D.last0[e] = T.last0; D.last1[e] = T.last1;
+  D.gbtn[e] = T.gbtn; D.bstate[e] = T.bstate; D.btimer[e] = T.btimer; D.amask[e] = T.amask;
+  D.cgcur[e] = T.cgcur; D.cgnext[e] = T.cgnext; D.cgox[e] = T.cgox; D.cgoy[e] = T.cgoy; D.cgtimer[e] = T.cgtimer;
+  D.ctr[e] = T.ctr;
+}
+
+SAG_HD void sample_goal_button(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& ctr, const Robot& R, TaskState& T) {
+  double u1, u2;  // press_buttons.py:70-76
+  rng.pair(stream, ctr++, u1, u2);
+  int k = (int)(u1 * C.L.nbtn);
+  if (k >= C.L.nbtn) k = C.L.nbtn - 1;
+  T.gbtn = k;
+  T.btimer = kButtonDelay;
+  size_t i = oidx(C.D, C.L.btn0 + k, C.e);
+  T.last0 = dist2d(R.q[0], R.q[1], C.D.ox[i], C.D.oy[i]);
+}
+
+// task.reset(): go_to_goal.py:50-57, push_box.py:94-100, press_buttons.py:65-68, collect.py:41-47, catch_goal.py:36-40
+SAG_HD int task_reset(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& ctr, const Robot& R, TaskState& T) {
+  const Dev& D = C.D;
+  if (C.sp.kind == 1) {
+    if (C.task == T_COLLECT) T.amask = (1 << C.L.nbtn) - 1;
+    else sample_goal_button(C, rng, stream, ctr, R, T);
+    return 0;
+  }
+  double gx, gy;
+  if (resample_goal(C, rng, stream, ctr, R.q[0], R.q[1], gx, gy)) return 1;
+  size_t ig = oidx(D, C.L.goal, C.e);
+  D.ox[ig] = gx; D.oy[ig] = gy;
+  T.last0 = dist2d(R.q[0], R.q[1], gx, gy);
+  if (C.task == T_CATCH_GOAL) { T.cgox = gx; T.cgoy = gy; }
+  if (C.sp.kind == 2) {
+    size_t ib = oidx(D, C.L.box, C.e);
+    double bx = D.ox[ib], by = D.oy[ib];
+    T.last1 = dist2d(gx, gy, bx, by);
+    T.last0 = dist2d(R.q[0], R.q[1], bx, by);
+  }
+  return 0;
+}
+
+// task.compute_reward family; touch = robot contact bitmask from the forward pass
+SAG_HD int compute_reward(const Ctx& C, const Rng& rng, const Robot& R, TaskState& T, unsigned touch, double* reward) {
+  const Dev& D = C.D;
+  reward[0] = reward[1] = 0.0;
+  if (C.sp.kind == 0) {  // go_to_goal.py:31-45
+    size_t ig = oidx(D, C.L.goal, C.e);
+    double dx = R.q[0] - D.ox[ig], dy = R.q[1] - D.oy[ig], dz = kPtZ - kGoalZ;
+    double distance = sqrt(dx * dx + dy * dy + dz * dz);
+    double r = T.last0 - distance;
+    if (C.task == T_GO_TO_GOAL_SCARCE) r = ((distance >= 0.0 && distance <= kGoalSize * 1.5) ? 1.0 : 0.0) * r;
+    T.last0 = distance;
+    if (distance <= kGoalSize) {
+      if (task_reset(C, rng, 1u, T.ctr, R, T)) return 1;
+      r += 1.0;
+    }
+    if (C.task == T_UNSUPERVISED) {  // unsupervised.py:48-67
+      const double c = kPtMc / kPtM;
+      double cs = cos(R.q[2]), sn = sin(R.q[2]);
+      double x = R.q[0] + c * cs, y = R.q[1] + c * sn;
+      double u = R.v[0] - c * R.v[2] * sn, v = R.v[1] + c * R.v[2] * cs;
+      double radius = sqrt(x * x + y * y);
+      reward[0] = (((-u * y + v * x) / radius) / (1.0 + fabs(radius - 1.5))) * 1e-1;
+      reward[1] = r;
+    } else reward[0] = r;
+    return 0;
+  }
+  if (C.sp.kind == 1 && C.task == T_COLLECT) {  // collect.py:24-39
+    if (!T.amask) T.amask = (1 << C.L.nbtn) - 1;
+    for (int i = 0; i < C.L.nbtn; ++i) {
+      if (!((T.amask >> i) & 1)) continue;
+      if ((touch >> (C.L.btn0 + i)) & 1u) { reward[0] += 1.0; T.amask &= ~(1 << i); break; }
+    }
+    return 0;
+  }
+  if (C.sp.kind == 1) {  // press_buttons.py:42-63, press_buttons_scarce.py:22-55
+    size_t ib = oidx(D, C.L.btn0 + T.gbtn, C.e);
+    double d = dist2d(R.q[0], R.q[1], D.ox[ib], D.oy[ib]);
+    double r = C.task == T_PRESS_BUTTONS_SCARCE ? 0.0 : T.last0 - d;
+    T.last0 = d;
+    if ((touch >> (C.L.btn0 + T.gbtn)) & 1u) {
+      r += 1.0;
+      sample_goal_button(C, rng, 1u, T.ctr, R, T);
+      T.bstate = 0;
+    }
+    if (T.bstate == 0) {
+      if (T.btimer != 0) T.btimer = T.btimer - 1 > 0 ? T.btimer - 1 : 0;
+      else { T.bstate = 1; T.btimer = kButtonDelay; }
+    }
+    reward[0] = r;
+    return 0;
+  }
+  // push_box.py:74-92, push_box_scarce.py:22-50, haul_box.py:34-48
+  size_t ig = oidx(D, C.L.goal, C.e), ib = oidx(D, C.L.box, C.e);
+  double bx = D.ox[ib], by = D.oy[ib];
+  double r = 0.0;
+  if (C.task != T_HAUL_BOX) {
+    double bd = dist2d(R.q[0], R.q[1], bx, by);
+    double sh = T.last0 - bd;
+    if (C.task == T_PUSH_BOX_SCARCE) sh = ((bd >= 0.0 && bd <= kGoalSize * 1.70) ? 1.0 : 0.0) * sh;
+    r += sh;
+    T.last0 = bd;
+  }
+  double bg = dist2d(bx, by, D.ox[ig], D.oy[ig]);
+  r += T.last1 - bg;
+  T.last1 = bg;
+  if (bg <= kGoalSize) {
+    if (task_reset(C, rng, 1u, T.ctr, R, T)) return 1;
+    r += 1.0;
+  }
+  reward[0] = r;
+  return 0;
+}
+
+// CatchGoal.set_mocaps, catch_goal.py:20-31
+SAG_HD void set_mocaps(const Ctx& C, const Rng& rng, TaskState& T, double time) {
+  if (C.task != T_CATCH_GOAL) return;
+  T.cgtimer = T.cgtimer - 1 > 0 ? T.cgtimer - 1 : 0;
+  if (T.cgtimer == 0) {
+    T.cgcur = T.cgnext;
+    double u1, u2;
+    rng.pair(1u, T.ctr++, u1, u2);
+    T.cgnext = 0.2 + (1.0 - 0.2) * u1;
+    T.cgtimer = 10;
+  }
+  double progress = (10 - T.cgtimer) / 10.0;
+  double radius = progress * (T.cgnext - T.cgcur) + T.cgcur;
+  size_t ig = oidx(C.D, C.L.goal, C.e);
+  C.D.ox[ig] = T.cgox + sin(time) * radius;
+  C.D.oy[ig] = T.cgoy + cos(time) * radius;
+}
+
+// ------------------------------------------------------------------------------------------------
+// end-of-step pass: forward() (contacts, qacc) + cost + observation + clearance for the next step.
+// obs_s: 60 floats for this env, strided by ostride (shared-memory tile in the kernels).
+// ------------------------------------------------------------------------------------------------
+struct PostOut { unsigned touch; double qacc[3]; double clear; int err; };
+
+// contacts + accelerations at the current state; chooses the free path when nothing is near
+SAG_HD void forward_any(const Ctx& C, const Robot& R, PostOut& P) {
+  const Dev& D = C.D;
+  // broad phase over collidable objects: min clearance and "any moving body" check
+  double clear = 1e30;
+  bool moving = false;
+  for (int s = C.L.v0; s < C.L.n; ++s) {
+    int kind = slot_kind(C.sp, C.L, s);
+    if (!kind_collidable(kind)) continue;
+    size_t i = oidx(D, s, C.e);
+    double dx = D.ox[i] - R.q[0], dy = D.oy[i] - R.q[1];
+    double c = sqrt(dx * dx + dy * dy) - (kRobotReach + kind_bound(D, kind));
+    if (c < clear) clear = c;
+    if (kind_movable(kind) && (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0)) moving = true;
+  }
+  bool tendon = false;
+  if (C.task == T_HAUL_BOX) tendon = true;
+  P.err = 0;
+  if (clear > 0.0 && !moving && !tendon) {
+    double sn = sin(R.q[2]), cs = cos(R.q[2]), f[3];
+    pt_smooth(R, sn, cs, f);
+    PtMat M = pt_matrix(sn, cs, 0.0, R.damp_xy);
+    pt_solve(M, f, P.qacc);
+    P.touch = 0;
+    P.clear = clear;
+  } else {
+    FwdOut F;
+    double oacc[kMaxObj][3];
+    forward_full(C, R, F, oacc);
+    P.qacc[0] = F.qacc[0]; P.qacc[1] = F.qacc[1]; P.qacc[2] = F.qacc[2];
+    P.touch = F.touch;
+    P.err = F.err;
+    P.clear = (moving || tendon) ? -1.0 : clear;
+  }
+}
+
+// World.compute_cost, world.py:144-155
+SAG_HD double compute_cost(const Ctx& C, const Robot& R, unsigned touch) {
+  const Dev& D = C.D;
+  unsigned obstacle_mask = C.L.t0 >= 32 ? 0xffffffffu : ((1u << C.L.t0) - 1u);  // hazards..pillars slots
+  bool hit = (touch & obstacle_mask) != 0;
+  for (int s = C.L.h0; s < C.L.v0; ++s) {
+    size_t i = oidx(D, s, C.e);
+    double dx = R.q[0] - D.ox[i], dy = R.q[1] - D.oy[i];
+    if (sqrt(dx * dx + dy * dy) <= D.hazards_size) hit = true;
+  }
+  return hit ? 1.0 : 0.0;
+}
+
+// observation, safe_adaptation_gym.py:120-139,225-237: [obstacles(16), objects(16), goal(16), sensors(12)]
+SAG_HD void write_obs(const Ctx& C, const Robot& R, const TaskState& T, const double* qacc, float* obs_s, int ostride) {
+  const Dev& D = C.D;
+  for (int k = 0; k < 48; ++k) obs_s[k * ostride] = 0.0f;
+  double sn = sin(R.q[2]), cs = cos(R.q[2]);
+  for (int s = 0; s < C.L.n; ++s) {
+    int kind = slot_kind(C.sp, C.L, s);
+    int g = slot_group(C, s, kind, T.gbtn, T.bstate, T.amask);
+    if (g == 0) continue;
+    size_t i = oidx(D, s, C.e);
+    int off = g == 1 ? 0 : (g == 3 ? 16 : 32);
+    lidar_accum(R.q[0], R.q[1], cs, sn, D.ox[i], D.oy[i], obs_s + off * ostride, ostride);
+  }
+  float* o = obs_s + 48 * ostride;
+  o[0 * ostride] = (float)(qacc[0] * cs + qacc[1] * sn);    // accelerometer (SURVEY App. B.6 [EXT])
+  o[1 * ostride] = (float)(-qacc[0] * sn + qacc[1] * cs);
+  o[2 * ostride] = (float)kGrav;
+  o[3 * ostride] = (float)(R.v[0] * cs + R.v[1] * sn);      // velocimeter
+  o[4 * ostride] = (float)(-R.v[0] * sn + R.v[1] * cs);
+  o[5 * ostride] = 0.0f;
+  o[6 * ostride] = 0.0f; o[7 * ostride] = 0.0f; o[8 * ostride] = (float)R.v[2];  // gyro
+  o[9 * ostride] = (float)(-0.5 * sn); o[10 * ostride] = (float)(-0.5 * cs); o[11 * ostride] = 0.0f;  // magnetometer
+}
+
+SAG_HD void load_robot(const Dev& D, int e, const TaskSpec& sp, Robot& R) {
+  R.q[0] = D.rx[e]; R.q[1] = D.ry[e]; R.q[2] = D.ryaw[e];
+  R.v[0] = D.rvx[e]; R.v[1] = D.rvy[e]; R.v[2] = D.rw[e];
+  R.ctrl[0] = D.ctrl0[e]; R.ctrl[1] = D.ctrl1[e];
+  R.damp_xy = sp.damp_xy; R.gear_x = sp.gear_x;
+}
+SAG_HD void store_robot(const Dev& D, int e, const Robot& R) {
+  D.rx[e] = R.q[0]; D.ry[e] = R.q[1]; D.ryaw[e] = R.q[2];
+  D.rvx[e] = R.v[0]; D.rvy[e] = R.v[1]; D.rw[e] = R.v[2];
+  D.ctrl0[e] = R.ctrl[0]; D.ctrl1[e] = R.ctrl[1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// SafeAdaptationGym.step for one environment (safe_adaptation_gym.py:56-83)
+// ------------------------------------------------------------------------------------------------
+SAG_HD void env_step(const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2, unsigned char* cost,
+                     unsigned char* done) {
+  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
+  C.L = make_slots(C.sp);
+  Robot R;
+  load_robot(D, e, C.sp, R);
+  TaskState T;
+  load_task_state(D, e, T);
+  Rng rng = {D.seed, D.gid_base + (uint32_t)e, D.episode[e]};
+  double time = D.time[e];
+  // action noise + clip (:58-67)
+  double act0 = (double)a0, act1 = (double)a1;
+  if (D.action_noise != 0.0) {
+    double u1, u2;
+    rng.pair(1u, T.ctr++, u1, u2);
+    double rad = sqrt(-2.0 * log(1.0 - u1));
+    act0 += D.action_noise * (rad * cos(kTwoPi * u2));
+    act1 += D.action_noise * (rad * sin(kTwoPi * u2));
+  }
+  R.ctrl[0] = clampd(act0, -1.0, 1.0);
+  R.ctrl[1] = clampd(act1, -1.0, 1.0);
+  set_mocaps(C, rng, T, time);  // :71
+  // physics.step(nstep) (:72).  Quiet envs (nothing within reach for the whole step) take the closed-form path.
+  const double h = kPtH;
+  unsigned char fl = D.flags[e];
+  int err = (fl & F_PHYS_ERROR) ? 1 : 0;  // a physics error is sticky until the env is reset
+  // conservative bound on how far the hinge point can move during this step (see DESIGN.md "quiet path")
+  const double tstep = kPtNsub * kPtH;
+  double speed = sqrt(R.v[0] * R.v[0] + R.v[1] * R.v[1]), wabs = fabs(R.v[2]);
+  double alpha_max = 750.0 + 200.0 * wabs, wmax = wabs + alpha_max * tstep;
+  double a_bound = 2.0 * (R.gear_x * kPtForceLim + R.damp_xy * speed) / kPtM + (kPtMc / kPtM) * (alpha_max + wmax * wmax);
+  double travel = tstep * speed + tstep * tstep * a_bound + 1e-3;
+  if (D.clear[e] > travel) {
+#pragma unroll
+    for (int k = 0; k < kPtNsub; ++k) pt_substep_free(R, h, err);
+  } else {
+    for (int k = 0; k < kPtNsub; ++k) substep_full(C, R, h, err);
+  }
+#pragma unroll
+  for (int k = 0; k < kPtNsub; ++k) time += h;
+  double rew[2] = {0.0, 0.0};
+  double cst = 0.0;
+  unsigned char dn = 0;
+  PostOut P;
+  forward_any(C, R, P);  // :76
+  if (err || P.err) {    // :73-75 PhysicsError
+    rew[0] = -10.0; cst = 0.0; dn = 1; fl |= F_PHYS_ERROR;
+  } else {
+    if (compute_reward(C, rng, R, T, P.touch, rew)) fl |= F_RESAMPLE_FAILED;  // :77
+    cst = compute_cost(C, R, P.touch);                                        // :78
+  }
+  write_obs(C, R, T, P.qacc, obs_s, ostride);  // :80
+  // bookkeeping
+  int ns = D.nstep[e] + 1;
+  if (D.max_episode_steps > 0 && ns >= D.max_episode_steps) fl |= F_NEEDS_RESET;
+  if (dn) fl |= F_NEEDS_RESET;
+  D.nstep[e] = ns;
+  D.epret[e] += rew[0];
+  D.epcost[e] += cst;
+  D.flags[e] = fl;
+  D.time[e] = time;
+  D.clear[e] = P.clear;
+  store_robot(D, e, R);
+  store_task_state(D, e, T);
+  reward2[0] = rew[0]; reward2[1] = rew[1];
+  *cost = (unsigned char)(cst > 0.0);
+  *done = dn;
+}
+
+// observation at the current state (reset return value / state injection refresh)
+SAG_HD void env_observe(const Dev& D, int e, float* obs_s, int ostride) {
+  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
+  C.L = make_slots(C.sp);
+  Robot R;
+  load_robot(D, e, C.sp, R);
+  TaskState T;
+  load_task_state(D, e, T);
+  PostOut P;
+  forward_any(C, R, P);
+  write_obs(C, R, T, P.qacc, obs_s, ostride);
+  D.clear[e] = P.clear;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset: layout rejection sampling (world.py:172-217, utils.py:22-70), yaw draws (world.py:108-137),
+// fresh physics (mujoco_bridge.py:170-175), task.reset (world.py:167-170)
+// ------------------------------------------------------------------------------------------------
+SAG_HD double slot_keepout(const Dev& D, const TaskSpec& sp, int kind) {
+  return kind == K_HAZARD ? D.k_hazard : kind == K_VASE ? D.k_vase : kind == K_GREMLIN ? D.k_gremlin
+       : kind == K_PILLAR ? D.k_pillar : kind == K_GOAL ? kGoalKeepout : kind == K_BUTTON ? kButtonsKeepout : sp.box_keepout;
+}
+
+SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_task) {
+  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
+  C.L = make_slots(C.sp);
+  Rng rng = {D.seed, D.gid_base + (uint32_t)e, episode};
+  uint32_t ctr = 0;
+  long draws_left = D.max_layout_draws > 0 ? D.max_layout_draws : (1L << 22);
+  unsigned char fl = 0;
+  double rxy[2] = {0.0, 0.0};
+  bool ok = false;
+  const double ext = C.sp.extent;
+  for (int attempt = 0; attempt < 10000 && !ok && draws_left >= 0; ++attempt) {
+    bool failed = false;
+    for (int idx = -1; idx < C.L.n && !failed; ++idx) {
+      int kind = idx < 0 ? K_NONE : slot_kind(C.sp, C.L, idx);
+      double keepout = idx < 0 ? D.robot_keepout : slot_keepout(D, C.sp, kind);
+      double half = ext;  // free placement in the task extents
+      if (kind == K_GOAL) half = 1.5;
+      else if (kind == K_BUTTON) half = C.sp.button_rect;
+      else if ((kind == K_BOX || kind == K_ROD || kind == K_BALL) && C.sp.box_rect > 0.0) half = C.sp.box_rect;
+      double xmin = -half + keepout, xmax = half - keepout;
+      bool placed = false;
+      double x = 0.0, y = 0.0;
+      for (int k = 0; k < 1000; ++k) {
+        if (--draws_left < 0) { failed = true; break; }
+        double u1, u2;
+        rng.pair(0u, ctr++, u1, u2);
+        x = xmin + (xmax - xmin) * u1; y = xmin + (xmax - xmin) * u2;
+        bool valid = true;
+        if (idx >= 0) {
+          double dx = x - rxy[0], dy = y - rxy[1];
+          if (sqrt(dx * dx + dy * dy) < D.robot_keepout + D.placements_margin + keepout) valid = false;
+          for (int j = 0; valid && j < idx; ++j) {
+            size_t i = oidx(D, j, e);
+            double ex = x - D.ox[i], ey = y - D.oy[i];
+            double ko = slot_keepout(D, C.sp, slot_kind(C.sp, C.L, j));
+            if (sqrt(ex * ex + ey * ey) < ko + D.placements_margin + keepout) valid = false;
+          }
+        }
+        if (valid) { placed = true; break; }
+      }
+      if (!placed) { failed = true; break; }
+      if (idx < 0) { rxy[0] = x; rxy[1] = y; }
+      else { size_t i = oidx(D, idx, e); D.ox[i] = x; D.oy[i] = y; }
+    }
+    if (!failed) ok = true;
+  }
+  if (!ok) fl |= F_RESAMPLE_FAILED;
+  // yaw draws in the reference's order
+  double u1, u2;
+  rng.pair(0u, ctr++, u1, u2);
+  double robot_rot = kTwoPi * u1;
+  for (int s = 0; s < C.L.t0; ++s) {
+    rng.pair(0u, ctr++, u1, u2);
+    size_t i = oidx(D, s, e);
+    D.oyaw[i] = kTwoPi * u1; D.ovx[i] = 0.0; D.ovy[i] = 0.0; D.ow[i] = 0.0;
+  }
+  for (int s = C.L.t0; s < C.L.n; ++s) { size_t i = oidx(D, s, e); D.oyaw[i] = 0.0; D.ovx[i] = 0.0; D.ovy[i] = 0.0; D.ow[i] = 0.0; }
+  if (C.task == T_HAUL_BOX) { size_t ib = oidx(D, C.L.box, e); D.ox[ib] = rxy[0] + kBoxSize * 3.0; D.oy[ib] = rxy[1]; }
+  if (C.sp.kind == 0 || C.sp.kind == 2) { rng.pair(0u, ctr++, u1, u2); D.oyaw[oidx(D, C.L.goal, e)] = kTwoPi * u1; }
+  if (C.sp.kind == 2 && C.sp.box_kind == K_BOX) { rng.pair(0u, ctr++, u1, u2); D.oyaw[oidx(D, C.L.box, e)] = kTwoPi * u1; }
+  if (C.sp.kind == 1) for (int i = 0; i < C.L.nbtn; ++i) { rng.pair(0u, ctr++, u1, u2); D.oyaw[oidx(D, C.L.btn0 + i, e)] = kTwoPi * u1; }
+  Robot R;
+  R.q[0] = rxy[0]; R.q[1] = rxy[1]; R.q[2] = robot_rot; R.v[0] = R.v[1] = R.v[2] = 0.0; R.ctrl[0] = R.ctrl[1] = 0.0;
+  R.damp_xy = C.sp.damp_xy; R.gear_x = C.sp.gear_x;
+  TaskState T;
+  load_task_state(D, e, T);
+  if (new_task) {  // fresh Task instance (catch_goal.py:12-18, press_buttons.py:20-24, collect.py:15-16)
+    T.cgcur = 1.0; T.cgnext = 0.2; T.cgtimer = 0; T.bstate = 1; T.btimer = kButtonDelay; T.gbtn = 0;
+    T.amask = C.task == T_COLLECT ? (1 << C.L.nbtn) - 1 : 0; T.cgox = T.cgoy = 0.0; T.last0 = T.last1 = 0.0;
+  }
+  if (ok && task_reset(C, rng, 0u, ctr, R, T)) fl |= F_RESAMPLE_FAILED;
+  T.ctr = 0;
+  store_robot(D, e, R);
+  store_task_state(D, e, T);
+  D.episode[e] = episode; D.nstep[e] = 0; D.time[e] = 0.0; D.epret[e] = 0.0; D.epcost[e] = 0.0; D.flags[e] = fl;
+  D.clear[e] = -1.0;
+}
+
+}  // namespace sag

@@ -1,0 +1,388 @@
+// sag_kernels.cu -- CUDA kernels (sm_100a) + the C ABI declared in include/sag_b200.h.
+//
+// Mapping: one thread per environment, 128 environments per CTA.  State is SoA / environment-minor so
+// that every global access of a warp is one contiguous 256-byte (fp64) segment.  Each CTA stages its
+// 128 x obs_dim observation tile in shared memory (lidar bins are accumulated there) and writes it out
+// as one contiguous, fully coalesced block.  No tensor cores: nothing here is a dense contraction.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/sag_b200.h"
+#include "sag_core.cuh"
+#include "sag_layout.h"
+
+using namespace sag;
+
+namespace {
+
+constexpr int kBS = 128;          // environments (threads) per CTA
+constexpr int kObs = SAG_OBS_POINT;
+constexpr int kTileStride = kBS + 1;
+
+thread_local char g_err[512] = "";
+
+int fail(const char* what, cudaError_t ce = cudaSuccess) {
+  if (ce != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(ce));
+  else snprintf(g_err, sizeof(g_err), "%s", what);
+  return 1;
+}
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t ce_ = (call);                      \
+    if (ce_ != cudaSuccess) return fail(#call, ce_); \
+  } while (0)
+
+struct Handle {
+  Dev D;
+  int device;
+  void* slab;
+  size_t slab_bytes;
+  void* field_ptr[SAG_NUM_FIELDS];
+  size_t field_bytes[SAG_NUM_FIELDS];
+  double *sret, *scost, *sn;  // per-env finished-episode statistics
+  // device staging for the host-buffer API
+  float* act_d;
+  float* obs_d;
+  double* rew_d;
+  uint8_t *cost_d, *done_d;
+  cudaStream_t own_stream;
+};
+
+// coalesced write-out of the CTA's observation tile: tile[k][t] -> out[(e0 + t) * kObs + k]
+__device__ __forceinline__ void write_tile(const float* tile, float* out, int e0, int n) {
+  int cnt = min(kBS, n - e0) * kObs;
+  float* dst = out + (size_t)e0 * kObs;
+  for (int i = threadIdx.x; i < cnt; i += kBS) {
+    int t = i / kObs, k = i - t * kObs;
+    dst[i] = tile[k * kTileStride + t];
+  }
+}
+
+__global__ void __launch_bounds__(kBS) k_step(Dev D, const float* __restrict__ act, float* __restrict__ obs,
+                                               double* __restrict__ reward, double* __restrict__ reward2,
+                                               uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
+  __shared__ float tile[kObs * kTileStride];
+  const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
+  if (e < D.n) {
+    float2 a = reinterpret_cast<const float2*>(act)[e];
+    double rew[2];
+    unsigned char c, d;
+    env_step(D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d);
+    reward[e] = rew[0];
+    if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
+    cost[e] = c;
+    done[e] = d;
+  }
+  __syncthreads();
+  write_tile(tile, obs, e0, D.n);
+}
+
+__global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs) {
+  __shared__ float tile[kObs * kTileStride];
+  const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
+  if (e < D.n) env_observe(D, e, tile + threadIdx.x, kTileStride);
+  __syncthreads();
+  write_tile(tile, obs, e0, D.n);
+}
+
+__global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __restrict__ obs, double* __restrict__ reward,
+                                                  uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
+  __shared__ float tile[kObs * kTileStride];
+  const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
+  if (e < D.n) {
+    double rew[2] = {0.0, 0.0};
+    unsigned char c = 0, d = 0;
+    Rng rng = {D.seed, D.gid_base + (uint32_t)e, D.episode[e]};
+    uint32_t base = (uint32_t)D.nstep[e];
+    for (int k = 0; k < k_steps; ++k) {
+      double u1, u2;
+      rng.pair(2u, base + (uint32_t)k, u1, u2);
+      env_step(D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + threadIdx.x, kTileStride, rew, &c, &d);
+    }
+    if (reward) reward[e] = rew[0];
+    if (cost) cost[e] = c;
+    if (done) done[e] = d;
+  }
+  __syncthreads();
+  if (obs) write_tile(tile, obs, e0, D.n);
+}
+
+__global__ void __launch_bounds__(kBS) k_reset(Dev D, const uint8_t* __restrict__ mask, int only_flagged, int new_task,
+                                                double* sret, double* scost, double* sn) {
+  const int e = blockIdx.x * kBS + threadIdx.x;
+  if (e >= D.n) return;
+  if (mask && !mask[e]) return;
+  if (only_flagged && !(D.flags[e] & F_NEEDS_RESET)) return;
+  if (D.nstep[e] > 0) { sret[e] += D.epret[e]; scost[e] += D.epcost[e]; sn[e] += 1.0; }
+  env_reset(D, e, D.episode[e] + 1u, new_task != 0);
+}
+
+__global__ void k_set_tasks(Dev D, const int32_t* __restrict__ ids) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < D.n) D.task[e] = ids[e];
+}
+
+// per-task statistic reduction: out[task][3] += (sum return, sum cost, episodes) of finished episodes
+__global__ void k_task_stats(Dev D, const double* sret, const double* scost, const double* sn, double* out) {
+  __shared__ double acc[SAG_NUM_TASKS][3];
+  for (int i = threadIdx.x; i < SAG_NUM_TASKS * 3; i += blockDim.x) (&acc[0][0])[i] = 0.0;
+  __syncthreads();
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < D.n; e += gridDim.x * blockDim.x) {
+    int t = D.task[e];
+    if (sn[e] != 0.0) { atomicAdd(&acc[t][0], sret[e]); atomicAdd(&acc[t][1], scost[e]); atomicAdd(&acc[t][2], sn[e]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SAG_NUM_TASKS * 3; i += blockDim.x)
+    if ((&acc[0][0])[i] != 0.0) atomicAdd(out + i, (&acc[0][0])[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone streaming kernels (SoA env-minor inputs, one thread per environment)
+// ------------------------------------------------------------------------------------------------
+constexpr int kLidarTileStride = kBS + 1;
+
+__global__ void __launch_bounds__(kBS) k_lidar(const double* __restrict__ robot, const double* __restrict__ obj_xy,
+                                               const uint8_t* __restrict__ group, int n, int nslots, float* __restrict__ out) {
+  __shared__ float tile[48 * kLidarTileStride];
+  const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
+  if (e < n) {
+    float* bins = tile + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 48; ++k) bins[k * kLidarTileStride] = 0.0f;
+    double rx = robot[e], ry = robot[(size_t)n + e], yaw = robot[2 * (size_t)n + e];
+    double sn, cs;
+    sincos(yaw, &sn, &cs);
+    const double* oxp = obj_xy;
+    const double* oyp = obj_xy + (size_t)nslots * n;
+    for (int s = 0; s < nslots; ++s) {
+      int g = group[(size_t)s * n + e];
+      if (g == 0) continue;
+      int off = g == 1 ? 0 : (g == 3 ? 16 : 32);
+      lidar_accum(rx, ry, cs, sn, oxp[(size_t)s * n + e], oyp[(size_t)s * n + e], bins + off * kLidarTileStride, kLidarTileStride);
+    }
+  }
+  __syncthreads();
+  int cnt = min(kBS, n - e0) * 48;
+  float* dst = out + (size_t)e0 * 48;
+  for (int i = threadIdx.x; i < cnt; i += kBS) {
+    int t = i / 48, k = i - t * 48;
+    dst[i] = tile[k * kLidarTileStride + t];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cost(const double* __restrict__ robot_xy, const float* __restrict__ hazard_xy,
+                                              const uint8_t* __restrict__ contact, int n, int nh, double hazard_size,
+                                              uint8_t* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double rx = robot_xy[e], ry = robot_xy[(size_t)n + e];
+  bool hit = contact[e] != 0;                                        // world.py:146
+  const float* hx = hazard_xy;
+  const float* hy = hazard_xy + (size_t)nh * n;
+  for (int s = 0; s < nh; ++s) {                                     // world.py:148-153
+    double dx = rx - (double)hx[(size_t)s * n + e], dy = ry - (double)hy[(size_t)s * n + e];
+    if (sqrt(dx * dx + dy * dy) <= hazard_size) hit = true;
+  }
+  out[e] = hit ? 1 : 0;                                              // world.py:155
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* sag_last_error(void) { return g_err; }
+int sag_abi_version(void) { return SAG_ABI_VERSION; }
+
+void sag_default_config(SagConfig* c) {
+  memset(c, 0, sizeof(*c));
+  c->n_envs = 1; c->robot = SAG_ROBOT_POINT; c->seed = 666;
+  c->placements_margin = 0.0; c->robot_keepout = 0.4;
+  c->hazards_size = 0.2; c->vases_size = 0.1; c->pillars_size = 0.2; c->gremlins_size = 0.1;
+  c->hazards_keepout = 0.18; c->gremlins_keepout = 0.4; c->vases_keepout = 0.15; c->pillars_keepout = 0.3;
+  c->gremlins_travel = 0.35; c->robot_ctrl_range_scale = 0.0; c->action_noise = 0.01; c->max_bound = 25.0;
+}
+
+int sag_create(const SagConfig* cfg, int device, void** handle) {
+  if (!cfg || !handle) return fail("sag_create: null argument");
+  if (cfg->n_envs <= 0) return fail("sag_create: n_envs must be positive");
+  if (cfg->robot != SAG_ROBOT_POINT) return fail("sag_create: only the point robot is implemented on the device path");
+  if (cfg->robot_ctrl_range_scale != 0.0) return fail("sag_create: robot_ctrl_range_scale != 0 is not implemented");
+  CK(cudaSetDevice(device));
+  Handle* H = new (std::nothrow) Handle();
+  if (!H) return fail("sag_create: out of host memory");
+  memset(H, 0, sizeof(*H));
+  H->device = device;
+  Dev& D = H->D;
+  dev_from_config(D, *cfg);
+  SlabLayout LY = slab_layout(D.n, D.stride, kObs);
+  cudaError_t ce = cudaMalloc(&H->slab, LY.total);
+  if (ce != cudaSuccess) { delete H; return fail("sag_create: cudaMalloc", ce); }
+  H->slab_bytes = LY.total;
+  ce = cudaMemset(H->slab, 0, LY.total);
+  if (ce != cudaSuccess) { cudaFree(H->slab); delete H; return fail("sag_create: cudaMemset", ce); }
+  char* base = (char*)H->slab;
+  const size_t st = (size_t)D.stride;
+  slab_bind(D, LY, base);
+  for (int f = 0; f < SAG_NUM_FIELDS; ++f) { H->field_ptr[f] = base + LY.off[f]; H->field_bytes[f] = LY.bytes[f]; }
+  H->sret = (double*)(base + LY.stats_off); H->scost = H->sret + st; H->sn = H->sret + 2 * st;
+  H->act_d = (float*)(base + LY.act_off); H->obs_d = (float*)(base + LY.obs_off); H->rew_d = (double*)(base + LY.rew_off);
+  H->cost_d = (uint8_t*)(base + LY.cost_off); H->done_d = (uint8_t*)(base + LY.done_off);
+  // default task: go_to_goal; episode counters start at 0xFFFFFFFF so that the first reset is episode 0
+  ce = cudaMemset(D.episode, 0xFF, st * sizeof(unsigned));
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&H->own_stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { cudaFree(H->slab); delete H; return fail("sag_create: init", ce); }
+  *handle = H;
+  return 0;
+}
+
+int sag_destroy(void* handle) {
+  Handle* H = (Handle*)handle;
+  if (!H) return 0;
+  cudaSetDevice(H->device);
+  cudaDeviceSynchronize();
+  if (H->own_stream) cudaStreamDestroy(H->own_stream);
+  cudaFree(H->slab);
+  delete H;
+  return 0;
+}
+
+int sag_stride(void* handle) { return ((Handle*)handle)->D.stride; }
+int sag_obs_dim(void* handle) { (void)handle; return kObs; }
+size_t sag_field_bytes(void* handle, int field) {
+  if (field < 0 || field >= SAG_NUM_FIELDS) return 0;
+  return ((Handle*)handle)->field_bytes[field];
+}
+
+static inline int grid_for(int n) { return (n + kBS - 1) / kBS; }
+
+int sag_set_tasks(void* handle, const int32_t* ids, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H || !ids) return fail("sag_set_tasks: null argument");
+  k_set_tasks<<<(H->D.n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(H->D, ids);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int sag_seed(void* handle, uint64_t seed) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail("sag_seed: null handle");
+  CK(cudaSetDevice(H->device));
+  CK(cudaDeviceSynchronize());
+  H->D.seed = seed;
+  CK(cudaMemset(H->D.episode, 0xFF, (size_t)H->D.stride * sizeof(unsigned)));
+  return 0;
+}
+
+int sag_reset(void* handle, const uint8_t* mask, int only_flagged, int new_task, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail("sag_reset: null handle");
+  k_reset<<<grid_for(H->D.n), kBS, 0, (cudaStream_t)stream>>>(H->D, mask, only_flagged, new_task, H->sret, H->scost, H->sn);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int sag_step(void* handle, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done,
+             void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H || !act || !obs || !reward || !cost || !done) return fail("sag_step: null argument");
+  k_step<<<grid_for(H->D.n), kBS, 0, (cudaStream_t)stream>>>(H->D, act, obs, reward, reward2, cost, done);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int sag_observe(void* handle, float* obs, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H || !obs) return fail("sag_observe: null argument");
+  k_observe<<<grid_for(H->D.n), kBS, 0, (cudaStream_t)stream>>>(H->D, obs);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int sag_rollout(void* handle, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H || k_steps <= 0) return fail("sag_rollout: bad argument");
+  k_rollout<<<grid_for(H->D.n), kBS, 0, (cudaStream_t)stream>>>(H->D, k_steps, obs, reward, cost, done);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward_h, uint8_t* cost_h, uint8_t* done_h) {
+  Handle* H = (Handle*)handle;
+  if (!H || !act_h || !obs_h || !reward_h || !cost_h || !done_h) return fail("sag_step_host: null argument");
+  cudaStream_t s = H->own_stream;
+  const size_t n = (size_t)H->D.n;
+  CK(cudaMemcpyAsync(H->act_d, act_h, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+  k_step<<<grid_for(H->D.n), kBS, 0, s>>>(H->D, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(obs_h, H->obs_d, n * kObs * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(reward_h, H->rew_d, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(cost_h, H->cost_d, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(done_h, H->done_d, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sag_observe_host(void* handle, float* obs_h) {
+  Handle* H = (Handle*)handle;
+  if (!H || !obs_h) return fail("sag_observe_host: null argument");
+  cudaStream_t s = H->own_stream;
+  k_observe<<<grid_for(H->D.n), kBS, 0, s>>>(H->D, H->obs_d);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(obs_h, H->obs_d, (size_t)H->D.n * kObs * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+void* sag_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { fail("sag_host_alloc: cudaHostAlloc failed"); return nullptr; }
+  return p;
+}
+void sag_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int sag_read_field(void* handle, int field, void* dst, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H || !dst || field < 0 || field >= SAG_NUM_FIELDS) return fail("sag_read_field: bad argument");
+  CK(cudaMemcpyAsync(dst, H->field_ptr[field], H->field_bytes[field], cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int sag_write_field(void* handle, int field, const void* src, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H || !src || field < 0 || field >= SAG_NUM_FIELDS) return fail("sag_write_field: bad argument");
+  CK(cudaMemcpyAsync(H->field_ptr[field], src, H->field_bytes[field], cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int sag_task_stats(void* handle, double* out, int reset, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H || !out) return fail("sag_task_stats: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(out, 0, SAG_NUM_TASKS * 3 * sizeof(double), s));
+  k_task_stats<<<148, 256, 0, s>>>(H->D, H->sret, H->scost, H->sn, out);
+  CK(cudaGetLastError());
+  if (reset) CK(cudaMemsetAsync(H->sret, 0, 3 * (size_t)H->D.stride * sizeof(double), s));
+  return 0;
+}
+
+int sag_lidar(const double* robot, const double* obj_xy, const uint8_t* group, int n, int nslots, float* out, void* stream) {
+  if (!robot || !obj_xy || !group || !out || n <= 0 || nslots < 0) return fail("sag_lidar: bad argument");
+  k_lidar<<<grid_for(n), kBS, 0, (cudaStream_t)stream>>>(robot, obj_xy, group, n, nslots, out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int sag_cost(const double* robot_xy, const float* hazard_xy, const uint8_t* contact, int n, int nh, double hazard_size,
+             uint8_t* out, void* stream) {
+  if (!robot_xy || !hazard_xy || !contact || !out || n <= 0 || nh < 0) return fail("sag_cost: bad argument");
+  k_cost<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(robot_xy, hazard_xy, contact, n, nh, hazard_size, out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+"""Batched drop-in variant of ``SafeAdaptationGym`` (reference: safe_adaptation_gym/safe_adaptation_gym.py:21-257).
+
+Same method names and argument meaning as the reference env, with a leading batch dimension:
+
+    obs[N, D], reward[N], done[N], info{'cost'[N], 'bound'[N]} = env.step(actions[N, nu])
+    obs[N, D] = env.reset(options={'task': task_or_list_of_tasks})
+
+All per-step arithmetic (dynamics, reward / goal logic, cost, pseudo-lidar) runs in the CUDA library behind
+the C ABI of ``include/sag_b200.h``; this class only owns torch tensors and passes raw pointers.  There is
+no CPU fallback: without the built library and a CUDA device construction raises.
+"""
+import ctypes as C
+from typing import Dict, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from safe_adaptation_gym_b200 import _abi
+from safe_adaptation_gym_b200 import tasks as _tasks
+from safe_adaptation_gym_b200.spaces import Box
+from safe_adaptation_gym_b200.utils import ResamplingError
+
+# World.DEFAULT, world.py:17-34
+WORLD_DEFAULT = {
+    'placements_margin': 0.0, 'robot_keepout': 0.4, 'hazards_size': 0.2, 'vases_size': 0.1, 'pillars_size': 0.2,
+    'gremlins_size': 0.1, 'hazards_keepout': 0.18, 'gremlins_keepout': 0.4, 'vases_keepout': 0.15,
+    'pillars_keepout': 0.3, 'gremlins_travel': 0.35, 'obstacles_size_noise_scale': 0.0,
+    'robot_ctrl_range_scale': 0.0, 'action_noise': 0.01, 'max_bound': 25, 'random_bound': False,
+}
+_EXTRA_KEYS = {'max_layout_draws'}
+_ROBOT_TO_CONTROL_FREQUENCY = {'doggo': 12, 'point': 5, 'car': 10}  # safe_adaptation_gym.py:15-19
+
+
+def _robot_name(path: str) -> str:
+    base = path.replace('\\', '/').split('/')[-1]
+    return base[:-4] if base.endswith('.xml') else base
+
+
+class BatchedSafeAdaptationGym:
+    NUM_LIDAR_BINS = 16
+    LIDAR_MAX_DIST = 5.
+    BASE_SENSORS = ['accelerometer', 'velocimeter', 'gyro', 'magnetometer']
+
+    def __init__(self,
+                 robot_base: str,
+                 rgb_observation: bool = False,
+                 config: Optional[Dict] = None,
+                 render_lidars_and_collision: bool = False,
+                 render_options: Optional[Dict] = None,
+                 num_envs: int = 1,
+                 device: Union[str, torch.device, None] = None,
+                 env_id_base: int = 0,
+                 max_episode_steps: int = 0,
+                 _test_lib=None):
+        if rgb_observation:
+            raise NotImplementedError('rgb_observation needs a rasteriser and is outside the B200 hot path '
+                                      '(reference: safe_adaptation_gym.py:122-126)')
+        self.robot_name = _robot_name(robot_base)
+        if self.robot_name not in _ROBOT_TO_CONTROL_FREQUENCY:
+            raise KeyError(self.robot_name)
+        if self.robot_name != 'point':
+            raise NotImplementedError(f"robot '{self.robot_name}' is not implemented on the device path yet")
+        cfg = dict(WORLD_DEFAULT)
+        for k, v in (config or {}).items():
+            if k not in WORLD_DEFAULT and k not in _EXTRA_KEYS:
+                raise KeyError(f'unknown config key {k!r}')
+            cfg[k] = v
+        if cfg['random_bound'] or cfg['robot_ctrl_range_scale'] != 0.0:
+            raise NotImplementedError('random_bound / robot_ctrl_range_scale are not implemented on the device path yet')
+        self.base_config = cfg
+        self.num_envs = int(num_envs)
+        if _test_lib is None:
+            self._lib = _abi.load()
+            if not torch.cuda.is_available():
+                raise _abi.SagError('no CUDA device: the B200 path has no CPU fallback')
+            self.device = torch.device(device if device is not None else 'cuda:0')
+            if self.device.type != 'cuda':
+                raise _abi.SagError('the B200 path runs on CUDA devices only')
+            dev_index = self.device.index or 0
+        else:  # tests/hostemu: same ABI compiled for the host, CPU tensors
+            self._lib = _test_lib
+            self.device = torch.device('cpu')
+            dev_index = 0
+        L = self._lib
+        c = L.default_config()
+        c.n_envs = self.num_envs
+        c.robot = 0
+        c.env_id_base = int(env_id_base)
+        c.max_episode_steps = int(max_episode_steps)
+        c.max_layout_draws = int(cfg.get('max_layout_draws', 0))
+        for k in ('placements_margin', 'robot_keepout', 'hazards_size', 'vases_size', 'pillars_size', 'gremlins_size',
+                  'hazards_keepout', 'gremlins_keepout', 'vases_keepout', 'pillars_keepout', 'gremlins_travel',
+                  'robot_ctrl_range_scale', 'action_noise', 'max_bound'):
+            setattr(c, k, float(cfg[k]))
+        self._seed = int(np.random.randint(2**32))  # safe_adaptation_gym.py:47
+        c.seed = self._seed
+        self._h = C.c_void_p()
+        L.check(L.L.sag_create(C.byref(c), dev_index, C.byref(self._h)))
+        self.stride = L.L.sag_stride(self._h)
+        self.obs_dim = L.L.sag_obs_dim(self._h)
+        self.max_episode_steps = int(max_episode_steps)
+        self._steps_to_expiry = None
+        n, dev = self.num_envs, self.device
+        self._obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=dev)
+        self._reward = torch.empty((n,), dtype=torch.float64, device=dev)
+        self._reward2 = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        self._cost = torch.empty((n,), dtype=torch.uint8, device=dev)
+        self._done = torch.empty((n,), dtype=torch.uint8, device=dev)
+        self._bound = torch.full((n,), float(cfg['max_bound']), dtype=torch.float64, device=dev)
+        self._task_ids = None
+        self._tasks = None
+        self._any_unsupervised = False
+        self._action_space = Box(-1, 1, (2,), dtype=np.float32)  # safe_adaptation_gym.py:49-50 (nu = 2)
+        self._observation_space = None
+
+    # ------------------------------------------------------------------------------------------
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                self._lib.L.sag_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def close(self):
+        self.__del__()
+
+    def _stream(self):
+        if self.device.type == 'cuda':
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(0)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    # ------------------------------------------------------------------------------------------
+    # reference API
+    # ------------------------------------------------------------------------------------------
+    def step(self, action):
+        """safe_adaptation_gym.py:56-83.  `action`: [N, 2] tensor / array in [-1, 1]."""
+        act = self._as_action(action)
+        L = self._lib
+        r2 = self._reward2 if self._any_unsupervised else None
+        L.check(L.L.sag_step(self._h, self._p(act), self._p(self._obs), self._p(self._reward), self._p(r2),
+                             self._p(self._cost), self._p(self._done), self._stream()))
+        refreshed = False
+        if self.max_episode_steps > 0:
+            L.check(L.L.sag_reset(self._h, None, 1, 0, self._stream()))
+            if self._steps_to_expiry is not None:
+                self._steps_to_expiry -= 1
+                if self._steps_to_expiry <= 0:
+                    refreshed = True
+            else:
+                refreshed = True
+        reward = self._reward2 if self._any_unsupervised else self._reward
+        info = {'cost': self._cost.to(torch.float32), 'bound': self._bound}
+        done = self._done.to(torch.bool)
+        if refreshed:  # envs that were auto-reset return the first observation of their new episode
+            L.check(L.L.sag_observe(self._h, self._p(self._obs), self._stream()))
+            self._steps_to_expiry = self.max_episode_steps
+        return self._obs, reward, done, info
+
+    def reset(self, *, seed: Optional[int] = None, return_info: bool = False, options: Optional[dict] = None):
+        """safe_adaptation_gym.py:85-107"""
+        assert self._task_ids is not None or (options is not None and 'task' in options), (
+            'A task should be first set before reset.')
+        if seed is not None:
+            self.seed(seed)
+        if options is not None and 'task' in options:
+            self.set_task(options['task'])
+            return self.observation
+        self._reset_all(new_task=False)
+        return self.observation
+
+    def seed(self, seed=None):
+        """safe_adaptation_gym.py:113-118: new stream key; episode counters restart"""
+        self._seed = int(np.random.randint(2**32)) if seed is None else int(seed)
+        self._lib.check(self._lib.L.sag_seed(self._h, C.c_uint64(self._seed)))
+
+    def set_task(self, task):
+        """safe_adaptation_gym.py:165-168.  `task`: a Task, or a sequence of N Tasks (one per environment)."""
+        if isinstance(task, _tasks.Task):
+            task_list = [task] * self.num_envs
+        else:
+            task_list = list(task)
+            if len(task_list) != self.num_envs:
+                raise ValueError(f'need {self.num_envs} tasks, got {len(task_list)}')
+        for t in task_list:
+            if t.name in _tasks.DEVICE_UNSUPPORTED:
+                raise NotImplementedError(f"task '{t.name}' is not implemented on the device path yet")
+        ids = torch.tensor([t.task_id for t in task_list], dtype=torch.int32)
+        self._tasks = task_list
+        self._task_ids = ids.to(self.device)
+        self._any_unsupervised = bool((ids == _tasks.Unsupervised.task_id).any())
+        self._lib.check(self._lib.L.sag_set_tasks(self._h, self._p(self._task_ids), self._stream()))
+        self._observation_space = None
+        self._reset_all(new_task=True)
+
+    def render(self, mode='human'):
+        raise NotImplementedError('rendering is outside the B200 hot path (reference: safe_adaptation_gym.py:109-111)')
+
+    @property
+    def observation(self) -> torch.Tensor:
+        """safe_adaptation_gym.py:120-131: [obstacles lidar, objects lidar, goal lidar, sensors]"""
+        L = self._lib
+        L.check(L.L.sag_observe(self._h, self._p(self._obs), self._stream()))
+        return self._obs
+
+    @property
+    def lidar_observations(self) -> torch.Tensor:
+        return self.observation[:, :3 * self.NUM_LIDAR_BINS]
+
+    @property
+    def action_space(self) -> Box:
+        return self._action_space
+
+    @property
+    def observation_space(self) -> Box:
+        if self._observation_space is None:  # safe_adaptation_gym.py:145-163
+            lidar_size = 3 * self.NUM_LIDAR_BINS
+            rest = self.obs_dim - lidar_size
+            low = np.array([0.] * lidar_size + [-np.inf] * rest)
+            high = np.array([1.] * lidar_size + [np.inf] * rest)
+            self._observation_space = Box(low, high, shape=(self.obs_dim,), dtype=np.float32)
+        return self._observation_space
+
+    # ------------------------------------------------------------------------------------------
+    # batched extras
+    # ------------------------------------------------------------------------------------------
+    def _as_action(self, action):
+        if not torch.is_tensor(action):
+            action = torch.as_tensor(np.asarray(action, dtype=np.float32))
+        act = action.to(device=self.device, dtype=torch.float32).reshape(self.num_envs, 2).contiguous()
+        return act
+
+    def _reset_all(self, new_task: bool, mask: Optional[torch.Tensor] = None):
+        L = self._lib
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        L.check(L.L.sag_reset(self._h, self._p(m), 0, 1 if new_task else 0, self._stream()))
+        self._steps_to_expiry = self.max_episode_steps if (mask is None and self.max_episode_steps > 0) else None
+        flags = self.get_field('flags')[:self.num_envs]
+        bad = (flags & _abi.FLAG_RESAMPLE_FAILED) != 0
+        if bool(bad.any()):
+            raise ResamplingError('Failed to generate layout')  # world.py:189
+
+    def reset_envs(self, mask):
+        """Reset only the environments where `mask` is true (vectorised-wrapper helper)."""
+        self._reset_all(new_task=False, mask=torch.as_tensor(mask))
+        return self.observation
+
+    def check_errors(self):
+        """Raise the reference's exceptions for conditions recorded on the device since the last check."""
+        flags = self.get_field('flags')[:self.num_envs]
+        if bool(((flags & _abi.FLAG_RESAMPLE_FAILED) != 0).any()):
+            raise ResamplingError('Failed to generate goal')  # go_to_goal.py:80
+
+    _FIELDS = {'robot': (_abi.F_ROBOT, torch.float64, (6,)), 'objects': (_abi.F_OBJECTS, torch.float64, (6, _abi.MAX_SLOTS)),
+               'task_f64': (_abi.F_TASK_F64, torch.float64, (12,)), 'task_i32': (_abi.F_TASK_I32, torch.int32, (9,)),
+               'flags': (_abi.F_FLAGS, torch.uint8, ())}
+
+    def get_field(self, name: str) -> torch.Tensor:
+        """Copy of an internal SoA state field, shape (*lead, stride) (see include/sag_b200.h SAG_F_*)."""
+        fid, dt, lead = self._FIELDS[name]
+        t = torch.empty(tuple(lead) + (self.stride,), dtype=dt, device=self.device)
+        assert t.numel() * t.element_size() == self._lib.L.sag_field_bytes(self._h, fid)
+        self._lib.check(self._lib.L.sag_read_field(self._h, fid, self._p(t), self._stream()))
+        return t
+
+    def set_field(self, name: str, value: torch.Tensor):
+        fid, dt, lead = self._FIELDS[name]
+        t = torch.as_tensor(value).to(device=self.device, dtype=dt).contiguous()
+        assert tuple(t.shape) == tuple(lead) + (self.stride,), (t.shape, lead, self.stride)
+        self._lib.check(self._lib.L.sag_write_field(self._h, fid, self._p(t), self._stream()))
+        if self.device.type == 'cuda':
+            torch.cuda.current_stream(self.device).synchronize()  # `t` may be a temporary
+
+    def rollout(self, k_steps: int):
+        """K steps per launch with on-device Philox U(-1,1) actions; returns the last step's outputs."""
+        L = self._lib
+        L.check(L.L.sag_rollout(self._h, int(k_steps), self._p(self._obs), self._p(self._reward), self._p(self._cost),
+                                self._p(self._done), self._stream()))
+        return self._obs, self._reward, self._done.to(torch.bool), {'cost': self._cost.to(torch.float32), 'bound': self._bound}
+
+    def task_stats(self, reset: bool = False) -> torch.Tensor:
+        """[14, 3] float64: per-task (sum of finished-episode returns, sum of costs, #episodes) on this device."""
+        out = torch.zeros((_abi.NUM_TASKS, 3), dtype=torch.float64, device=self.device)
+        self._lib.check(self._lib.L.sag_task_stats(self._h, self._p(out), 1 if reset else 0, self._stream()))
+        return out

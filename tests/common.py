@@ -1,0 +1,143 @@
+"""Shared helpers for the parity tests: build the test-only host emulation, drive the batched env and the
+oracle side by side."""
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+import oracle as O
+from safe_adaptation_gym_b200 import _abi, tasks
+from safe_adaptation_gym_b200.benchmark import TASKS
+from safe_adaptation_gym_b200.env import BatchedSafeAdaptationGym
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOSTEMU_SRC = os.path.join(ROOT, "tests", "hostemu", "sag_hostemu.cpp")
+HOSTEMU_LIB = os.path.join(ROOT, "tests", "hostemu", "libsag_hostemu.so")
+_hostemu = None
+
+
+def hostemu_lib():
+    """g++ build of the kernel body (tests/hostemu) -- test infrastructure, see the file header."""
+    global _hostemu
+    if _hostemu is None:
+        deps = [HOSTEMU_SRC, os.path.join(ROOT, "safe_adaptation_gym_b200", "csrc", "sag_core.cuh"),
+                os.path.join(ROOT, "safe_adaptation_gym_b200", "csrc", "sag_layout.h"), os.path.join(ROOT, "include", "sag_b200.h")]
+        if not os.path.exists(HOSTEMU_LIB) or os.path.getmtime(HOSTEMU_LIB) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", HOSTEMU_LIB, HOSTEMU_SRC])
+        _hostemu = _abi.SagLib(HOSTEMU_LIB, host_api=False)
+    return _hostemu
+
+
+def make_env(backend, n, task_names, seed, config=None, **kw):
+    """backend: 'hostemu' (CPU, kernel body compiled by g++) or 'cuda' (the product library)."""
+    lib = hostemu_lib() if backend == "hostemu" else None
+    env = BatchedSafeAdaptationGym("xmls/point.xml", config=config, num_envs=n, _test_lib=lib, **kw)
+    env.seed(seed)
+    if isinstance(task_names, str):
+        task_names = [task_names] * n
+    env.set_task([TASKS[t]() for t in task_names])
+    return env
+
+
+def make_oracles(n, task_names, seed, config=None, gid_base=0):
+    if isinstance(task_names, str):
+        task_names = [task_names] * n
+    cfg = {k: v for k, v in (config or {}).items()}
+    envs = [O.OracleEnv("point", task_names[e], config=cfg, seed=seed, env_gid=gid_base + e) for e in range(n)]
+    for e in envs:
+        assert e.reset(0) == 0
+    return envs
+
+
+def env_state(env):
+    """(robot [n,6], objects [n,32,6]) as numpy"""
+    n = env.num_envs
+    robot = env.get_field("robot").cpu().numpy()[:, :n].T.copy()
+    objs = env.get_field("objects").cpu().numpy()[:, :, :n].transpose(2, 1, 0).copy()
+    return robot, objs
+
+
+def oracle_state(envs):
+    robot = np.stack([e.robot_state for e in envs])
+    objs = np.zeros((len(envs), 32, 6))
+    for i, e in enumerate(envs):
+        o = e.objects()
+        objs[i, :len(o)] = o[:, 2:8]
+    return robot, objs
+
+
+def drive_action(oenv, rng, p_random=0.15):
+    """scripted drive-to-target policy from the oracle state, so that goals / hazards / vases are visited"""
+    s = oenv.robot_state
+    objs = oenv.objects()
+    ts = oenv.task_state
+    kinds = objs[:, 0].astype(int)
+    target = None
+    if (kinds == O.BUTTON).any():
+        btn = np.where(kinds == O.BUTTON)[0]
+        groups = objs[btn, 1].astype(int)
+        goal = btn[groups == 2]
+        target = objs[goal[0], 2:4] if len(goal) else objs[btn[int(ts[2]) % len(btn)], 2:4]
+    elif (kinds == O.BOX).any() and oenv.task != O.TASK_ID["haul_box"]:
+        box = objs[kinds == O.BOX][0, 2:4]
+        goal = objs[kinds == O.GOAL][0, 2:4]
+        d = goal - box
+        target = box - 0.35 * d / (np.linalg.norm(d) + 1e-9)
+        if np.linalg.norm(target - s[:2]) < 0.15:
+            target = goal
+    elif (kinds == O.GOAL).any():
+        target = objs[kinds == O.GOAL][0, 2:4]
+    if target is None or rng.uniform() < p_random:
+        return rng.uniform(-1, 1, 2)
+    d = target - s[:2]
+    err = (np.arctan2(d[1], d[0]) - s[2] + np.pi) % (2 * np.pi) - np.pi
+    a = np.array([np.clip(1.0 - abs(err), 0.02, 1.0), np.clip(2.0 * err, -1, 1)])
+    return np.clip(a + 0.2 * rng.normal(size=2), -1, 1)
+
+
+def run_parity(backend, task_names, n, steps, seed, config=None, policy="drive", pos_tol=1e-9, check_every=1):
+    """Step the batched env and n oracle envs on identical actions; assert parity every step.
+    Returns summary statistics (so tests can assert that interesting events actually happened)."""
+    cfg = dict(config or {})
+    cfg.setdefault("action_noise", 0.0)
+    env = make_env(backend, n, task_names, seed, cfg)
+    orc = make_oracles(n, task_names, seed, cfg)
+    r0, o0 = env_state(env)
+    ro, oo = oracle_state(orc)
+    np.testing.assert_array_equal(r0, ro)  # layout sampling is integer Philox + exact IEEE ops: bit-exact
+    np.testing.assert_array_equal(o0[:, :, :3], oo[:, :, :3])
+    obs = env.observation.cpu().numpy()
+    for e in range(n):
+        np.testing.assert_allclose(obs[e], orc[e].observation(), rtol=1e-5, atol=1e-6)
+    rng = np.random.RandomState(seed + 17)
+    stats = {"cost": 0.0, "reward": 0.0, "goals": 0, "max_pos_err": 0.0, "contacts": 0}
+    for t in range(steps):
+        acts = np.zeros((n, 2), dtype=np.float32)
+        for e in range(n):
+            a = drive_action(orc[e], rng) if policy == "drive" else rng.uniform(-1, 1, 2)
+            acts[e] = a.astype(np.float32)
+        obs, rew, done, info = env.step(torch.from_numpy(acts))
+        obs = obs.cpu().numpy(); rew = rew.cpu().numpy(); cost = info["cost"].cpu().numpy(); done = done.cpu().numpy()
+        for e in range(n):
+            oobs, orew, ocost, odone, rc = orc[e].step(acts[e].astype(np.float64))
+            assert rc == 0
+            msg = f"env {e} step {t} task {orc[e].task}"
+            assert cost[e] == ocost, msg                      # bit-exact
+            assert bool(done[e]) == odone, msg                # bit-exact
+            r = rew[e] if rew.ndim == 1 else rew[e]
+            np.testing.assert_allclose(np.atleast_1d(r), orew[:np.atleast_1d(r).size], rtol=1e-5, atol=1e-9, err_msg=msg)
+            np.testing.assert_allclose(obs[e], oobs, rtol=1e-5, atol=2e-6, err_msg=msg)
+            stats["cost"] += ocost
+            stats["reward"] += orew[-1] if np.atleast_1d(r).size == 2 else orew[0]
+            stats["goals"] += int((orew[-1] if np.atleast_1d(r).size == 2 else orew[0]) > 0.5)
+            stats["contacts"] += len(orc[e].contacts())
+        if t % check_every == 0 or t == steps - 1:
+            r1, o1 = env_state(env)
+            ro, oo = oracle_state(orc)
+            err = np.abs(r1 - ro).max()
+            stats["max_pos_err"] = max(stats["max_pos_err"], float(err))
+            np.testing.assert_allclose(r1, ro, rtol=0, atol=pos_tol, err_msg=f"robot state step {t}")
+            np.testing.assert_allclose(o1, oo, rtol=0, atol=pos_tol * 10, err_msg=f"object state step {t}")
+    env.close()
+    return stats

@@ -1,0 +1,163 @@
+// sag_hostemu.cpp -- TEST INFRASTRUCTURE ONLY (never loaded by the product package).
+//
+// Compiles the per-environment kernel body (safe_adaptation_gym_b200/csrc/sag_core.cuh) with g++ and
+// drives it with the same CTA/tile structure as sag_kernels.cu, behind the same C ABI symbols, with
+// "device" pointers being host pointers.  It lets the GPU-less build container check the kernel body
+// against the oracle (tests/test_hostemu_parity.py); on the B200 box the same tests run on the real
+// library (tests/test_gpu_parity.py).  The product (safe_adaptation_gym_b200/_abi.py) loads only
+// csrc/libsag_b200.so and raises if it is missing.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/sag_b200.h"
+#include "../../safe_adaptation_gym_b200/csrc/sag_core.cuh"
+#include "../../safe_adaptation_gym_b200/csrc/sag_layout.h"
+
+using namespace sag;
+
+namespace {
+constexpr int kBS = 128, kObs = SAG_OBS_POINT, kTileStride = kBS + 1;
+char g_err[512] = "";
+int fail(const char* w) { snprintf(g_err, sizeof(g_err), "%s", w); return 1; }
+struct Handle {
+  Dev D;
+  char* slab;
+  SlabLayout LY;
+  double *sret, *scost, *sn;
+};
+void write_tile(const float* tile, float* out, int e0, int n) {
+  int cnt = (n - e0 < kBS ? n - e0 : kBS) * kObs;
+  float* dst = out + (size_t)e0 * kObs;
+  for (int i = 0; i < cnt; ++i) { int t = i / kObs, k = i - t * kObs; dst[i] = tile[k * kTileStride + t]; }
+}
+}  // namespace
+
+extern "C" {
+const char* sag_last_error(void) { return g_err; }
+int sag_abi_version(void) { return SAG_ABI_VERSION; }
+void sag_default_config(SagConfig* c) {
+  memset(c, 0, sizeof(*c));
+  c->n_envs = 1; c->robot = SAG_ROBOT_POINT; c->seed = 666;
+  c->placements_margin = 0.0; c->robot_keepout = 0.4;
+  c->hazards_size = 0.2; c->vases_size = 0.1; c->pillars_size = 0.2; c->gremlins_size = 0.1;
+  c->hazards_keepout = 0.18; c->gremlins_keepout = 0.4; c->vases_keepout = 0.15; c->pillars_keepout = 0.3;
+  c->gremlins_travel = 0.35; c->robot_ctrl_range_scale = 0.0; c->action_noise = 0.01; c->max_bound = 25.0;
+}
+int sag_create(const SagConfig* cfg, int device, void** handle) {
+  (void)device;
+  if (!cfg || !handle || cfg->n_envs <= 0) return fail("sag_create: bad argument");
+  Handle* H = new Handle();
+  memset(H, 0, sizeof(*H));
+  dev_from_config(H->D, *cfg);
+  H->LY = slab_layout(H->D.n, H->D.stride, kObs);
+  H->slab = (char*)calloc(1, H->LY.total);
+  slab_bind(H->D, H->LY, H->slab);
+  size_t st = H->D.stride;
+  H->sret = (double*)(H->slab + H->LY.stats_off); H->scost = H->sret + st; H->sn = H->sret + 2 * st;
+  memset(H->D.episode, 0xFF, st * sizeof(unsigned));
+  *handle = H;
+  return 0;
+}
+int sag_destroy(void* h) { Handle* H = (Handle*)h; if (H) { free(H->slab); delete H; } return 0; }
+int sag_stride(void* h) { return ((Handle*)h)->D.stride; }
+int sag_obs_dim(void* h) { (void)h; return kObs; }
+size_t sag_field_bytes(void* h, int f) { return (f < 0 || f >= SAG_NUM_FIELDS) ? 0 : ((Handle*)h)->LY.bytes[f]; }
+int sag_set_tasks(void* h, const int32_t* ids, void* s) {
+  (void)s; Handle* H = (Handle*)h;
+  for (int e = 0; e < H->D.n; ++e) H->D.task[e] = ids[e];
+  return 0;
+}
+int sag_seed(void* h, uint64_t seed) { Handle* H = (Handle*)h; H->D.seed = seed; memset(H->D.episode, 0xFF, (size_t)H->D.stride * sizeof(unsigned)); return 0; }
+int sag_reset(void* h, const uint8_t* mask, int only_flagged, int new_task, void* s) {
+  (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
+  for (int e = 0; e < D.n; ++e) {
+    if (mask && !mask[e]) continue;
+    if (only_flagged && !(D.flags[e] & F_NEEDS_RESET)) continue;
+    if (D.nstep[e] > 0) { H->sret[e] += D.epret[e]; H->scost[e] += D.epcost[e]; H->sn[e] += 1.0; }
+    env_reset(D, e, D.episode[e] + 1u, new_task != 0);
+  }
+  return 0;
+}
+int sag_step(void* h, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done, void* s) {
+  (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
+  static float tile[kObs * kTileStride];
+  for (int e0 = 0; e0 < D.n; e0 += kBS) {
+    for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
+      int e = e0 + t; double rew[2]; unsigned char c, d;
+      env_step(D, e, act[2 * e], act[2 * e + 1], tile + t, kTileStride, rew, &c, &d);
+      reward[e] = rew[0];
+      if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
+      cost[e] = c; done[e] = d;
+    }
+    write_tile(tile, obs, e0, D.n);
+  }
+  return 0;
+}
+int sag_observe(void* h, float* obs, void* s) {
+  (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
+  static float tile[kObs * kTileStride];
+  for (int e0 = 0; e0 < D.n; e0 += kBS) {
+    for (int t = 0; t < kBS && e0 + t < D.n; ++t) env_observe(D, e0 + t, tile + t, kTileStride);
+    write_tile(tile, obs, e0, D.n);
+  }
+  return 0;
+}
+int sag_rollout(void* h, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* s) {
+  (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
+  static float tile[kObs * kTileStride];
+  for (int e0 = 0; e0 < D.n; e0 += kBS) {
+    for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
+      int e = e0 + t; double rew[2] = {0, 0}; unsigned char c = 0, d = 0;
+      Rng rng = {D.seed, D.gid_base + (uint32_t)e, D.episode[e]};
+      uint32_t base = (uint32_t)D.nstep[e];
+      for (int k = 0; k < k_steps; ++k) {
+        double u1, u2; rng.pair(2u, base + (uint32_t)k, u1, u2);
+        env_step(D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + t, kTileStride, rew, &c, &d);
+      }
+      if (reward) reward[e] = rew[0];
+      if (cost) cost[e] = c;
+      if (done) done[e] = d;
+    }
+    if (obs) write_tile(tile, obs, e0, D.n);
+  }
+  return 0;
+}
+int sag_read_field(void* h, int f, void* dst, void* s) { (void)s; Handle* H = (Handle*)h; memcpy(dst, H->slab + H->LY.off[f], H->LY.bytes[f]); return 0; }
+int sag_write_field(void* h, int f, const void* src, void* s) { (void)s; Handle* H = (Handle*)h; memcpy(H->slab + H->LY.off[f], src, H->LY.bytes[f]); return 0; }
+int sag_task_stats(void* h, double* out, int reset, void* s) {
+  (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
+  memset(out, 0, SAG_NUM_TASKS * 3 * sizeof(double));
+  for (int e = 0; e < D.n; ++e) { int t = D.task[e]; out[3 * t] += H->sret[e]; out[3 * t + 1] += H->scost[e]; out[3 * t + 2] += H->sn[e]; }
+  if (reset) memset(H->sret, 0, 3 * (size_t)D.stride * sizeof(double));
+  return 0;
+}
+int sag_lidar(const double* robot, const double* obj_xy, const uint8_t* group, int n, int nslots, float* out, void* s) {
+  (void)s;
+  for (int e = 0; e < n; ++e) {
+    float bins[48]; for (int k = 0; k < 48; ++k) bins[k] = 0.f;
+    double sn = sin(robot[2 * (size_t)n + e]), cs = cos(robot[2 * (size_t)n + e]);
+    for (int sl = 0; sl < nslots; ++sl) {
+      int g = group[(size_t)sl * n + e]; if (!g) continue;
+      int off = g == 1 ? 0 : (g == 3 ? 16 : 32);
+      lidar_accum(robot[e], robot[(size_t)n + e], cs, sn, obj_xy[(size_t)sl * n + e], obj_xy[((size_t)nslots + sl) * n + e], bins + off, 1);
+    }
+    memcpy(out + (size_t)e * 48, bins, sizeof(bins));
+  }
+  return 0;
+}
+int sag_cost(const double* robot_xy, const float* hazard_xy, const uint8_t* contact, int n, int nh, double hazard_size, uint8_t* out, void* s) {
+  (void)s;
+  for (int e = 0; e < n; ++e) {
+    bool hit = contact[e] != 0;
+    for (int k = 0; k < nh; ++k) {
+      double dx = robot_xy[e] - (double)hazard_xy[(size_t)k * n + e], dy = robot_xy[(size_t)n + e] - (double)hazard_xy[((size_t)nh + k) * n + e];
+      if (sqrt(dx * dx + dy * dy) <= hazard_size) hit = true;
+    }
+    out[e] = hit;
+  }
+  return 0;
+}
+}

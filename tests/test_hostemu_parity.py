@@ -1,0 +1,27 @@
+"""Kernel body (sag_core.cuh compiled by g++, tests/hostemu) vs the oracle -- runs on the GPU-less
+container.  The same checks run against the CUDA library in tests/test_gpu_parity.py."""
+import pytest
+
+from common import run_parity
+
+
+def test_go_to_goal_random_actions():
+    s = run_parity("hostemu", "go_to_goal", n=6, steps=150, seed=11, policy="random")
+    assert s["max_pos_err"] < 1e-9
+
+
+def test_go_to_goal_drive_hits_goals_hazards_and_vases():
+    s = run_parity("hostemu", "go_to_goal", n=6, steps=400, seed=5)
+    assert s["goals"] >= 3 and s["cost"] >= 10 and s["contacts"] >= 10, s
+
+
+@pytest.mark.parametrize("task", ["go_to_goal_scarce", "go_to_goal_damping", "go_to_goal_motor", "catch_goal", "unsupervised",
+                                  "press_buttons", "press_buttons_scarce", "collect", "push_box", "push_box_scarce", "haul_box"])
+def test_other_tasks(task):
+    s = run_parity("hostemu", task, n=3, steps=250, seed=23)
+    assert s["max_pos_err"] < 1e-8
+
+
+def test_mixed_task_batch_with_noise():
+    names = ["go_to_goal", "press_buttons", "push_box", "collect", "catch_goal", "haul_box", "unsupervised", "go_to_goal_scarce"]
+    run_parity("hostemu", names, n=8, steps=120, seed=3, config={"action_noise": 0.01}, pos_tol=1e-8)
