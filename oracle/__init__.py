@@ -46,8 +46,9 @@ def build(force=False):
     """Compile the oracle with gcc (recipe: oracle/Makefile)."""
     src = os.path.join(_HERE, "sag_oracle.c")
     hdr = os.path.join(_HERE, "sag_oracle.h")
+    dm = os.path.join(_HERE, "..", "include", "sag_detmath.h")
     if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(dm))):
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -107,6 +108,7 @@ def lib():
     L.orc_task_slot_types.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.orc_batch_rollout.restype = C.c_long
     L.orc_batch_rollout.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, dp, dp]
+    L.orc_detmath.argtypes = [C.c_int, dp, dp, C.c_int, dp, dp]
     _lib = L
     return L
 
@@ -297,3 +299,12 @@ def batch_rollout(envs, steps, nthreads):
     sc = C.c_double()
     n = lib().orc_batch_rollout(arr, len(envs), steps, nthreads, C.byref(sr), C.byref(sc))
     return n, sr.value, sc.value
+
+
+def detmath(fn, a, b=None):
+    """fn: 'sincos' | 'atan2' | 'log' evaluated by include/sag_detmath.h"""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b if b is not None else a, dtype=np.float64)
+    o1, o2 = np.zeros_like(a), np.zeros_like(a)
+    lib().orc_detmath({"sincos": 0, "atan2": 1, "log": 2}[fn], _dp(a), _dp(b), len(a), _dp(o1), _dp(o2))
+    return (o1, o2) if fn == "sincos" else o1

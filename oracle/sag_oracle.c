@@ -6,6 +6,7 @@
  * -ffp-contract=off so that the arithmetic is plain IEEE double.
  */
 #include "sag_oracle.h"
+#include "../include/sag_detmath.h" /* deterministic sin/cos/atan2/log (bit-identical on the GPU) */
 
 #include <math.h>
 #include <pthread.h>
@@ -193,7 +194,7 @@ static int circle_box(double cx, double cy, double r, const obox* B, int circle_
 
 int orc_collide_circle_box(double cx, double cy, double r, double bx, double by, double byaw, double hx, double hy,
                            int circle_is_a, double* out5) {
-  obox B = {bx, by, cos(byaw), sin(byaw), hx, hy};
+  obox B = {bx, by, sag_cos(byaw), sag_sin(byaw), hx, hy};
   return circle_box(cx, cy, r, &B, circle_is_a, out5);
 }
 
@@ -260,7 +261,7 @@ static int box_box(const obox* A, const obox* B, double* o /* [2][5] */) {
 
 int orc_collide_box_box(double ax, double ay, double ayaw, double ahx, double ahy, double bx, double by, double byaw,
                         double bhx, double bhy, double* out10) {
-  obox A = {ax, ay, cos(ayaw), sin(ayaw), ahx, ahy}, B = {bx, by, cos(byaw), sin(byaw), bhx, bhy};
+  obox A = {ax, ay, sag_cos(ayaw), sag_sin(ayaw), ahx, ahy}, B = {bx, by, sag_cos(byaw), sag_sin(byaw), bhx, bhy};
   return box_box(&A, &B, out10);
 }
 
@@ -277,7 +278,7 @@ static int obj_nparts(int type) { return type == ORC_BOX ? 5 : (obj_collidable(t
 
 static void obj_geom(const orc_env* e, int slot, int part, geom2* g) {
   const orc_obj* o = &e->obj[slot];
-  double c = cos(o->yaw), s = sin(o->yaw);
+  double c = sag_cos(o->yaw), s = sag_sin(o->yaw);
   g->c = c; g->s = s; g->cx = o->x; g->cy = o->y; g->r = 0.0; g->hx = g->hy = 0.0;
   switch (o->type) {
     case ORC_VASE: g->is_box = 1; g->hx = g->hy = e->cfg.vases_size; break;        /* primitive_objects.py:46-47 */
@@ -298,7 +299,7 @@ static void obj_geom(const orc_env* e, int slot, int part, geom2* g) {
   }
 }
 static void robot_geom(const orc_env* e, int part, geom2* g) {
-  double c = cos(e->q[2]), s = sin(e->q[2]);
+  double c = sag_cos(e->q[2]), s = sag_sin(e->q[2]);
   g->c = c; g->s = s;
   if (part == 0) { g->is_box = 0; g->cx = e->q[0]; g->cy = e->q[1]; g->r = PT_R; g->hx = g->hy = 0; }
   else { g->is_box = 1; g->cx = e->q[0] + PT_ARROW_OFF * c; g->cy = e->q[1] + PT_ARROW_OFF * s; g->hx = g->hy = PT_ARROW_H; g->r = 0; }
@@ -387,7 +388,7 @@ typedef struct { double a, b, p, q, s; } pt_mat; /* [[a,0,p],[0,b,q],[p,q,I]] wi
 static void pt_matrix(const orc_env* e, double hd, pt_mat* M) {
   double m = pt_mass(), mc = pt_mc();
   M->a = m + hd * e->damp_x; M->b = m + hd * e->damp_y;
-  M->p = -mc * sin(e->q[2]); M->q = mc * cos(e->q[2]);
+  M->p = -mc * sag_sin(e->q[2]); M->q = mc * sag_cos(e->q[2]);
   double I = pt_inertia_o() + hd * e->damp_z;
   M->s = I - M->p * M->p / M->a - M->q * M->q / M->b;
 }
@@ -400,7 +401,7 @@ static void pt_solve(const pt_mat* M, const double* f, double* out) {
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 static void pt_smooth(const orc_env* e, double* f) {
-  double mc = pt_mc(), c = cos(e->q[2]), s = sin(e->q[2]), w = e->v[2];
+  double mc = pt_mc(), c = sag_cos(e->q[2]), s = sag_sin(e->q[2]), w = e->v[2];
   /* actuators: motor 'x' (site transmission, gear 0.3 along body x) and velocity servo 'z' */
   double u0 = clampd(e->ctrl[0], e->ctrl_lo[0], e->ctrl_hi[0]);
   double u1 = clampd(e->ctrl[1], e->ctrl_lo[1], e->ctrl_hi[1]);
@@ -627,7 +628,7 @@ double orc_phys_time(const orc_env* e) { return e->time; }
 
 /* _sensors(), safe_adaptation_gym.py:225-237; sensor semantics SURVEY Appendix B.6 [EXT] */
 void orc_phys_sensors(const orc_env* e, double* out) {
-  double c = cos(e->q[2]), s = sin(e->q[2]);
+  double c = sag_cos(e->q[2]), s = sag_sin(e->q[2]);
   out[0] = e->qacc[0] * c + e->qacc[1] * s;      /* accelerometer */
   out[1] = -e->qacc[0] * s + e->qacc[1] * c;
   out[2] = GRAV;
@@ -646,7 +647,7 @@ static void lidar_accum(double rx, double ry, double c, double s, double px, dou
   double wx = px - rx, wy = py - ry;
   double ex = wx * c + wy * s, ey = -wx * s + wy * c;
   double dist = sqrt(ex * ex + ey * ey);                      /* :209 np.abs(z) */
-  double angle = atan2(ey, ex);                               /* :210 np.angle(z) % 2pi */
+  double angle = sag_atan2(ey, ex);                               /* :210 np.angle(z) % 2pi */
   if (angle < 0.0) angle += TWO_PI;
   double bin_size = TWO_PI / ORC_NUM_LIDAR_BINS;              /* :211 */
   int bin = (int)(angle / bin_size);                          /* :212 */
@@ -663,14 +664,14 @@ static void lidar_accum(double rx, double ry, double c, double s, double px, dou
 }
 
 void orc_lidar(double rx, double ry, double ryaw, int n, const double* xs, const double* ys, double* out16) {
-  double c = cos(ryaw), s = sin(ryaw);
+  double c = sag_cos(ryaw), s = sag_sin(ryaw);
   for (int i = 0; i < ORC_NUM_LIDAR_BINS; ++i) out16[i] = 0.0;
   for (int i = 0; i < n; ++i) lidar_accum(rx, ry, c, s, xs[i], ys[i], out16);
 }
 
 /* observation: safe_adaptation_gym.py:120-139 -- [obstacles(16), objects(16), goal(16), sensors] */
 void orc_env_observation(orc_env* e, double* obs) {
-  double c = cos(e->q[2]), s = sin(e->q[2]);
+  double c = sag_cos(e->q[2]), s = sag_sin(e->q[2]);
   for (int i = 0; i < 48; ++i) obs[i] = 0.0;
   for (int k = 0; k < e->nobj; ++k) {
     const orc_obj* o = &e->obj[k];
@@ -987,7 +988,7 @@ static int compute_reward(orc_env* e, double* reward) {
     }
     if (e->task == ORC_T_UNSUPERVISED) {                   /* unsupervised.py:48-67 */
       double c = pt_mc() / pt_mass();
-      double cs = cos(e->q[2]), sn = sin(e->q[2]);
+      double cs = sag_cos(e->q[2]), sn = sag_sin(e->q[2]);
       double x = e->q[0] + c * cs, y = e->q[1] + c * sn;   /* subtree_com */
       double u = e->v[0] - c * e->v[2] * sn, v = e->v[1] + c * e->v[2] * cs; /* subtree_linvel */
       double radius = sqrt(x * x + y * y);
@@ -1062,8 +1063,8 @@ static void set_mocaps(orc_env* e) {
   double phase = e->time;
   double progress = (10 - e->cg_timer) / 10.0;
   double radius = progress * (e->cg_next - e->cg_cur) + e->cg_cur;
-  e->obj[e->goal_slot].x = e->cg_ox + sin(phase) * radius;
-  e->obj[e->goal_slot].y = e->cg_oy + cos(phase) * radius;
+  e->obj[e->goal_slot].x = e->cg_ox + sag_sin(phase) * radius;
+  e->obj[e->goal_slot].y = e->cg_oy + sag_cos(phase) * radius;
 }
 
 /* SafeAdaptationGym.step, safe_adaptation_gym.py:56-83 */
@@ -1075,9 +1076,9 @@ int orc_env_step(orc_env* e, const double* action, double* obs, double* reward, 
   } else if (e->cfg.action_noise != 0.0) {
     double u1, u2;
     rng_pair(e, 1, &u1, &u2);
-    double rad = sqrt(-2.0 * log(1.0 - u1));               /* Box-Muller */
-    a[0] += e->cfg.action_noise * (rad * cos(TWO_PI * u2));
-    a[1] += e->cfg.action_noise * (rad * sin(TWO_PI * u2));
+    double rad = sqrt(-2.0 * sag_log(1.0 - u1));               /* Box-Muller */
+    a[0] += e->cfg.action_noise * (rad * sag_cos(TWO_PI * u2));
+    a[1] += e->cfg.action_noise * (rad * sag_sin(TWO_PI * u2));
   }
   double u[2] = {clampd(a[0], e->ctrl_lo[0], e->ctrl_hi[0]), clampd(a[1], e->ctrl_lo[1], e->ctrl_hi[1])}; /* :66-67 */
   orc_phys_set_control(e, u);
@@ -1170,4 +1171,13 @@ long orc_batch_rollout(orc_env** envs, int n, int steps, int nthreads, double* s
   for (int t = 0; t < nthreads; ++t) { pthread_join(th[t], 0); sr += jobs[t].sr; sc += jobs[t].sc; count += jobs[t].count; }
   *sum_reward = sr; *sum_cost = sc;
   return count;
+}
+
+/* deterministic math exports (tests/test_detmath.py): fn 0 sincos, 1 atan2(a,b), 2 log */
+void orc_detmath(int fn, const double* a, const double* b, int n, double* out, double* out2) {
+  for (int i = 0; i < n; ++i) {
+    if (fn == 0) sag_sincos(a[i], out + i, out2 + i);
+    else if (fn == 1) out[i] = sag_atan2(a[i], b[i]);
+    else out[i] = sag_log(a[i]);
+  }
 }

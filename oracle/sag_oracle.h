@@ -138,6 +138,8 @@ int orc_collide_circle_box(double cx, double cy, double r, double bx, double by,
 int orc_collide_box_box(double ax, double ay, double ayaw, double ahx, double ahy, double bx, double by, double byaw,
                         double bhx, double bhy, double* out10);
 
+void orc_detmath(int fn, const double* a, const double* b, int n, double* out, double* out2);
+
 /* task table (shared facts: obstacle counts etc.) */
 int orc_task_nobj(int task);
 void orc_task_slot_types(int task, int* types32);

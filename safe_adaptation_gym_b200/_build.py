@@ -7,8 +7,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(CSRC, "libsag_b200.so")
 SOURCES = ["sag_kernels.cu"]
-DEPS = ["sag_core.cuh", "sag_layout.h", os.path.join("..", "..", "include", "sag_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+DEPS = ["sag_core.cuh", "sag_layout.h", os.path.join("..", "..", "include", "sag_b200.h"),
+        os.path.join("..", "..", "include", "sag_detmath.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
 

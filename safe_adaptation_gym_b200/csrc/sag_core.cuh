@@ -11,6 +11,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "../../include/sag_detmath.h"
+
 #if defined(__CUDACC__)
 #define SAG_HD __host__ __device__ __forceinline__
 #define SAG_HD_NOINLINE __host__ __device__ __noinline__
@@ -380,7 +382,7 @@ SAG_HD bool bad_val(double x) { return !(fabs(x) <= 1e10); }
 
 // one contact-free substep: forward dynamics + semi-implicit Euler with implicit joint damping
 SAG_HD void pt_substep_free(Robot& R, double h, int& err) {
-  double sn = sin(R.q[2]), cs = cos(R.q[2]);
+  double sn = sag_sin(R.q[2]), cs = sag_cos(R.q[2]);
   double f[3], a[3];
   pt_smooth(R, sn, cs, f);
   PtMat Mh = pt_matrix(sn, cs, h, R.damp_xy);
@@ -430,7 +432,7 @@ SAG_HD_NOINLINE void forward_full(const Ctx& C, const Robot& R, FwdOut& out, dou
   int ncon = 0;
   unsigned active = 0, touch = 0;
   out.err = 0;
-  const double sn = sin(R.q[2]), cs = cos(R.q[2]);
+  const double sn = sag_sin(R.q[2]), cs = sag_cos(R.q[2]);
   Geom gr[2];
   gr[0].is_box = 0; gr[0].cx = R.q[0]; gr[0].cy = R.q[1]; gr[0].c = cs; gr[0].s = sn; gr[0].r = kPtR; gr[0].hx = gr[0].hy = 0.0;
   gr[1].is_box = 1; gr[1].cx = R.q[0] + kPtArrowOff * cs; gr[1].cy = R.q[1] + kPtArrowOff * sn; gr[1].c = cs; gr[1].s = sn;
@@ -447,7 +449,7 @@ SAG_HD_NOINLINE void forward_full(const Ctx& C, const Robot& R, FwdOut& out, dou
     double dx = x - R.q[0], dy = y - R.q[1], reach = kRobotReach + kind_bound(D, kind);
     if (dx * dx + dy * dy > reach * reach) continue;
     double oc = 1.0, os = 0.0;
-    if (mov) { double yaw = D.oyaw[i]; oc = cos(yaw); os = sin(yaw); }
+    if (mov) { double yaw = D.oyaw[i]; oc = sag_cos(yaw); os = sag_sin(yaw); }
     for (int rg = 0; rg < 2; ++rg)
       for (int p = 0; p < kind_nparts(kind); ++p) {
         Geom go;
@@ -479,8 +481,8 @@ SAG_HD_NOINLINE void forward_full(const Ctx& C, const Robot& R, FwdOut& out, dou
         if (dx * dx + dy * dy > reach * reach) continue;
         bool mi = kind_movable(ki), mj = kind_movable(kj);
         double ci = 1.0, si = 0.0, cj = 1.0, sj = 0.0;
-        if (mi) { double yaw = D.oyaw[ii]; ci = cos(yaw); si = sin(yaw); }
-        if (mj) { double yaw = D.oyaw[ij]; cj = cos(yaw); sj = sin(yaw); }
+        if (mi) { double yaw = D.oyaw[ii]; ci = sag_cos(yaw); si = sag_sin(yaw); }
+        if (mj) { double yaw = D.oyaw[ij]; cj = sag_cos(yaw); sj = sag_sin(yaw); }
         for (int pi = 0; pi < kind_nparts(ki); ++pi) {
           Geom gi;
           obj_geom(D, ki, pi, xi, yi, ci, si, gi);
@@ -647,7 +649,7 @@ SAG_HD_NOINLINE void substep_full(const Ctx& C, Robot& R, double h, int& err) {
   double oacc[kMaxObj][3];
   forward_full(C, R, F, oacc);
   if (F.err) err = 1;
-  double sn = sin(R.q[2]), cs = cos(R.q[2]);
+  double sn = sag_sin(R.q[2]), cs = sag_cos(R.q[2]);
   PtMat Mh = pt_matrix(sn, cs, h, R.damp_xy);
   double rhs[3], a[3];
   for (int k = 0; k < 3; ++k) rhs[k] = F.fsmooth[k] + F.fcon[k];
@@ -678,7 +680,7 @@ SAG_HD void lidar_accum(double rx, double ry, double cs, double sn, double px, d
   double wx = px - rx, wy = py - ry;
   double ex = wx * cs + wy * sn, ey = -wx * sn + wy * cs;   // :197-202
   double dist = sqrt(ex * ex + ey * ey);                    // :209
-  double angle = atan2(ey, ex);                             // :210
+  double angle = sag_atan2(ey, ex);                             // :210
   if (angle < 0.0) angle += kTwoPi;
   const double bin_size = kTwoPi / kLidarBins;              // :211
   int bin = (int)(angle / bin_size);                        // :212
@@ -811,7 +813,7 @@ SAG_HD int compute_reward(const Ctx& C, const Rng& rng, const Robot& R, TaskStat
     }
     if (C.task == T_UNSUPERVISED) {  // unsupervised.py:48-67
       const double c = kPtMc / kPtM;
-      double cs = cos(R.q[2]), sn = sin(R.q[2]);
+      double cs = sag_cos(R.q[2]), sn = sag_sin(R.q[2]);
       double x = R.q[0] + c * cs, y = R.q[1] + c * sn;
       double u = R.v[0] - c * R.v[2] * sn, v = R.v[1] + c * R.v[2] * cs;
       double radius = sqrt(x * x + y * y);
@@ -881,8 +883,8 @@ SAG_HD void set_mocaps(const Ctx& C, const Rng& rng, TaskState& T, double time) 
   double progress = (10 - T.cgtimer) / 10.0;
   double radius = progress * (T.cgnext - T.cgcur) + T.cgcur;
   size_t ig = oidx(C.D, C.L.goal, C.e);
-  C.D.ox[ig] = T.cgox + sin(time) * radius;
-  C.D.oy[ig] = T.cgoy + cos(time) * radius;
+  C.D.ox[ig] = T.cgox + sag_sin(time) * radius;
+  C.D.oy[ig] = T.cgoy + sag_cos(time) * radius;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -910,7 +912,7 @@ SAG_HD void forward_any(const Ctx& C, const Robot& R, PostOut& P) {
   if (C.task == T_HAUL_BOX) tendon = true;
   P.err = 0;
   if (clear > 0.0 && !moving && !tendon) {
-    double sn = sin(R.q[2]), cs = cos(R.q[2]), f[3];
+    double sn = sag_sin(R.q[2]), cs = sag_cos(R.q[2]), f[3];
     pt_smooth(R, sn, cs, f);
     PtMat M = pt_matrix(sn, cs, 0.0, R.damp_xy);
     pt_solve(M, f, P.qacc);
@@ -944,7 +946,7 @@ SAG_HD double compute_cost(const Ctx& C, const Robot& R, unsigned touch) {
 SAG_HD void write_obs(const Ctx& C, const Robot& R, const TaskState& T, const double* qacc, float* obs_s, int ostride) {
   const Dev& D = C.D;
   for (int k = 0; k < 48; ++k) obs_s[k * ostride] = 0.0f;
-  double sn = sin(R.q[2]), cs = cos(R.q[2]);
+  double sn = sag_sin(R.q[2]), cs = sag_cos(R.q[2]);
   for (int s = 0; s < C.L.n; ++s) {
     int kind = slot_kind(C.sp, C.L, s);
     int g = slot_group(C, s, kind, T.gbtn, T.bstate, T.amask);
@@ -994,9 +996,9 @@ SAG_HD void env_step(const Dev& D, int e, float a0, float a1, float* obs_s, int 
   if (D.action_noise != 0.0) {
     double u1, u2;
     rng.pair(1u, T.ctr++, u1, u2);
-    double rad = sqrt(-2.0 * log(1.0 - u1));
-    act0 += D.action_noise * (rad * cos(kTwoPi * u2));
-    act1 += D.action_noise * (rad * sin(kTwoPi * u2));
+    double rad = sqrt(-2.0 * sag_log(1.0 - u1));
+    act0 += D.action_noise * (rad * sag_cos(kTwoPi * u2));
+    act1 += D.action_noise * (rad * sag_sin(kTwoPi * u2));
   }
   R.ctrl[0] = clampd(act0, -1.0, 1.0);
   R.ctrl[1] = clampd(act1, -1.0, 1.0);

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kBS) k_lidar(const double* __restrict__ robot,
     for (int k = 0; k < 48; ++k) bins[k * kLidarTileStride] = 0.0f;
     double rx = robot[e], ry = robot[(size_t)n + e], yaw = robot[2 * (size_t)n + e];
     double sn, cs;
-    sincos(yaw, &sn, &cs);
+    sag_sincos(yaw, &sn, &cs);
     const double* oxp = obj_xy;
     const double* oyp = obj_xy + (size_t)nslots * n;
     for (int s = 0; s < nslots; ++s) {

@@ -138,7 +138,7 @@ int sag_lidar(const double* robot, const double* obj_xy, const uint8_t* group, i
   (void)s;
   for (int e = 0; e < n; ++e) {
     float bins[48]; for (int k = 0; k < 48; ++k) bins[k] = 0.f;
-    double sn = sin(robot[2 * (size_t)n + e]), cs = cos(robot[2 * (size_t)n + e]);
+    double sn, cs; sag_sincos(robot[2 * (size_t)n + e], &sn, &cs);
     for (int sl = 0; sl < nslots; ++sl) {
       int g = group[(size_t)sl * n + e]; if (!g) continue;
       int off = g == 1 ? 0 : (g == 3 ? 16 : 32);
