@@ -262,6 +262,7 @@ def main():
             "config": {"workload": WORKLOAD, "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-shard x{world}",
                        "l2": "flushed between steps (256 MiB memset outside the event pair)", "action_noise": 0.01},
             "value_l2_warm": value_warm,
+            "ms_per_step_first10": float(sum(ms[:10]) / max(1, len(ms[:10]))), "ms_per_step_last10": float(sum(ms[-10:]) / max(1, len(ms[-10:]))),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "api": "sag_step_host (C ABI, pinned host buffers)"},
             "gpu_launches": launches,

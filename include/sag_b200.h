@@ -59,7 +59,8 @@ enum {
   SAG_F_ROBOT = 0,    /* double [6][stride]: x, y, yaw, vx, vy, w */
   SAG_F_OBJECTS = 1,  /* double [6][SAG_MAX_SLOTS][stride]: x, y, yaw, vx, vy, w per object slot */
   SAG_F_TASK_F64 = 2, /* double [12][stride]: last0,last1,cg_cur,cg_next,cg_ox,cg_oy,time,clearance,ep_return,ep_cost,ctrl0,ctrl1 */
-  SAG_F_TASK_I32 = 3, /* int32 [9][stride]: task, goal_button, btn_state, btn_timer, active_mask, cg_timer, n_step, step_ctr, episode */
+  SAG_F_TASK_I32 = 3, /* int32 [10][stride]: task, goal_button, btn_state, btn_timer, active_mask, cg_timer, n_step, step_ctr, episode,
+                         moving_mask (derived; rebuilt by sag_observe after an injection) */
   SAG_F_FLAGS = 4,    /* uint8 [stride] */
   SAG_NUM_FIELDS
 };

@@ -52,6 +52,7 @@
 #define IMP_WIDTH 0.001
 #define FRICTION_MU 1.0        /* max(geom frictions) = 1 for every pair on this path */
 #define PGS_SWEEPS 10
+#define PGS_TOL 1e-8
 #define SLEEP_V 1e-8
 
 static double pt_mass(void) { return 4.0 / 3.0 * PI * PT_R * PT_R * PT_R + 8.0 * PT_ARROW_H * PT_ARROW_H * PT_ARROW_H; }
@@ -383,19 +384,21 @@ static void detect(orc_env* e) {
  * Generalised coordinates are the world-frame (x, y, yaw): the two slide joints are isotropic, so
  * the joint frame rotated by robot_rot (mujoco_bridge.py:60-63) is equivalent.
  * ---------------------------------------------------------------------------------------- */
-typedef struct { double a, b, p, q, s; } pt_mat; /* [[a,0,p],[0,b,q],[p,q,I]] with Schur s */
+typedef struct { double p, q, ia, is; } pt_mat; /* M = [[a,0,p],[0,a,q],[p,q,I]]: ia = 1/a, is = 1/(I - (p^2+q^2)/a) */
 
+/* the two slide joints always share one damping value, so a == b and p^2 + q^2 == (m c)^2: the Schur
+ * complement is a constant of the model and the solve needs no division per substep */
 static void pt_matrix(const orc_env* e, double hd, pt_mat* M) {
   double m = pt_mass(), mc = pt_mc();
-  M->a = m + hd * e->damp_x; M->b = m + hd * e->damp_y;
+  M->ia = 1.0 / (m + hd * e->damp_x);
   M->p = -mc * sag_sin(e->q[2]); M->q = mc * sag_cos(e->q[2]);
   double I = pt_inertia_o() + hd * e->damp_z;
-  M->s = I - M->p * M->p / M->a - M->q * M->q / M->b;
+  M->is = 1.0 / (I - mc * mc * M->ia);
 }
 static void pt_solve(const pt_mat* M, const double* f, double* out) {
-  double al = (f[2] - M->p * f[0] / M->a - M->q * f[1] / M->b) / M->s;
-  out[0] = (f[0] - M->p * al) / M->a;
-  out[1] = (f[1] - M->q * al) / M->b;
+  double al = (f[2] - (M->p * f[0] + M->q * f[1]) * M->ia) * M->is;
+  out[0] = (f[0] - M->p * al) * M->ia;
+  out[1] = (f[1] - M->q * al) * M->ia;
   out[2] = al;
 }
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
@@ -446,7 +449,7 @@ static void body_pos(const orc_env* e, int body, double* p) {
 typedef struct {
   int ba, bb;
   double ja[2][3], jb[2][3]; /* row 0 normal, row 1 tangent */
-  double aref[2], diag[2], R[2], f[2];
+  double aref[2], diag[2], R[2], f[2], inv[2];
 } crow;
 
 static double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -535,7 +538,15 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
     if (touched[s] || o->vx != 0.0 || o->vy != 0.0 || o->w != 0.0) flslot[nfl++] = s;
   }
   const double rr = (1.0 - IMP_D0) / IMP_D0;
+  /* Projected Gauss-Seidel.  Row update: f <- proj(f - (J a - aref + R f) / (A_ii + R)); the reciprocal of the
+   * denominator is taken once per row.  Terminates after PGS_SWEEPS sweeps or when one sweep changes the forces by
+   * less than PGS_TOL relative (L1) -- MuJoCo's own solvers stop at `tolerance` = 1e-8 [EXT]. */
+  for (int i = 0; i < nrow; ++i) {
+    int nk = (i == tendon_row) ? 1 : 2;
+    for (int k = 0; k < nk; ++k) rows[i].inv[k] = 1.0 / (rows[i].diag[k] + rows[i].R[k]);
+  }
   for (int it = 0; it < PGS_SWEEPS; ++it) {
+    double sdf = 0.0, sf = 0.0;
     for (int i = 0; i < nrow; ++i) {
       crow* r = &rows[i];
       int nk = (i == tendon_row) ? 1 : 2;
@@ -543,11 +554,12 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
         double a = 0.0;
         if (r->ba >= 0) a += dot3(r->ja[k], S.acc[r->ba]);
         if (r->bb >= 0) a += dot3(r->jb[k], S.acc[r->bb]);
-        double fn = r->f[k] - (a - r->aref[k] + r->R[k] * r->f[k]) / (r->diag[k] + r->R[k]);
+        double fn = r->f[k] - (a - r->aref[k] + r->R[k] * r->f[k]) * r->inv[k];
         if (k == 0) { if (fn < 0.0) fn = 0.0; }
         else { double lim = FRICTION_MU * r->f[0]; fn = clampd(fn, -lim, lim); }
         double df = fn - r->f[k];
         r->f[k] = fn;
+        sdf += fabs(df); sf += fabs(fn);
         if (df != 0.0) { apply(&S, r->ba, r->ja[k], df); apply(&S, r->bb, r->jb[k], df); }
       }
     }
@@ -558,17 +570,22 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
       double lim = FRICTION_MU * m * GRAV;
       double* ac = S.acc[1 + s];
       double Al = S.im[s], At = S.ii[s];
-      double f0 = ffl[s][0] - (ac[0] + bdamp * o->vx + rr * Al * ffl[s][0]) / (Al + rr * Al);
-      double f1 = ffl[s][1] - (ac[1] + bdamp * o->vy + rr * Al * ffl[s][1]) / (Al + rr * Al);
+      double inv_lin = 1.0 / (Al + rr * Al), inv_tor = 1.0 / (At + rr * At);
+      double f0 = ffl[s][0] - (ac[0] + bdamp * o->vx + rr * Al * ffl[s][0]) * inv_lin;
+      double f1 = ffl[s][1] - (ac[1] + bdamp * o->vy + rr * Al * ffl[s][1]) * inv_lin;
       double nf = sqrt(f0 * f0 + f1 * f1);
-      if (nf > lim) { f0 *= lim / nf; f1 *= lim / nf; }
-      ac[0] += (f0 - ffl[s][0]) * Al; ac[1] += (f1 - ffl[s][1]) * Al;
+      if (nf > lim) { double sc = lim / nf; f0 *= sc; f1 *= sc; }
+      double d0 = f0 - ffl[s][0], d1 = f1 - ffl[s][1];
+      ac[0] += d0 * Al; ac[1] += d1 * Al;
       ffl[s][0] = f0; ffl[s][1] = f1;
-      double f2 = ffl[s][2] - (ac[2] + bdamp * o->w + rr * At * ffl[s][2]) / (At + rr * At);
+      double f2 = ffl[s][2] - (ac[2] + bdamp * o->w + rr * At * ffl[s][2]) * inv_tor;
       f2 = clampd(f2, -lim * rf, lim * rf);
-      ac[2] += (f2 - ffl[s][2]) * At;
+      double d2 = f2 - ffl[s][2];
+      ac[2] += d2 * At;
       ffl[s][2] = f2;
+      sdf += fabs(d0) + fabs(d1) + fabs(d2); sf += fabs(f0) + fabs(f1) + fabs(f2);
     }
+    if (sdf <= PGS_TOL * sf) break;
   }
   /* results */
   for (int k = 0; k < 3; ++k) e->qacc[k] = S.acc[0][k];
@@ -649,13 +666,13 @@ static void lidar_accum(double rx, double ry, double c, double s, double px, dou
   double dist = sqrt(ex * ex + ey * ey);                      /* :209 np.abs(z) */
   double angle = sag_atan2(ey, ex);                               /* :210 np.angle(z) % 2pi */
   if (angle < 0.0) angle += TWO_PI;
-  double bin_size = TWO_PI / ORC_NUM_LIDAR_BINS;              /* :211 */
-  int bin = (int)(angle / bin_size);                          /* :212 */
-  double bin_angle = bin_size * bin;                          /* :213 */
+  const double inv_bin_size = ORC_NUM_LIDAR_BINS / TWO_PI;    /* :211 (1 / bin_size) */
+  double t = angle * inv_bin_size;
+  int bin = (int)t;                                           /* :212 */
   double sensor = LIDAR_MAX_DIST - dist;                      /* :214 */
   if (sensor < 0.0) sensor = 0.0;
-  sensor /= LIDAR_MAX_DIST;
-  double alias = (angle - bin_angle) / bin_size;              /* :216 */
+  sensor *= 1.0 / LIDAR_MAX_DIST;
+  double alias = t - (double)bin;                             /* :213,216: (angle - bin*bin_size)/bin_size */
   int b0 = bin % ORC_NUM_LIDAR_BINS;                          /* quirk D7: wrap instead of IndexError */
   int bp = (bin + 1) % ORC_NUM_LIDAR_BINS, bm = (bin + ORC_NUM_LIDAR_BINS - 1) % ORC_NUM_LIDAR_BINS;
   if (sensor > obs[b0]) obs[b0] = sensor;                     /* :215 */

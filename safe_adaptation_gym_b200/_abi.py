@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsag_b200.so")
+# SAG_B200_LIB: build-variant override for tuning experiments (must still be a CUDA build of csrc/sag_kernels.cu)
+LIB_PATH = os.environ.get("SAG_B200_LIB") or os.path.join(_HERE, "csrc", "libsag_b200.so")
 
 NUM_TASKS = 14
 MAX_SLOTS = 32

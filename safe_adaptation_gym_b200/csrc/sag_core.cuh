@@ -56,6 +56,7 @@ constexpr double kTendonMax = kBoxSize * 3.75;  // haul_box.py:25
 constexpr double kSolTc = 0.02, kImpD0 = 0.9, kImpDmax = 0.95, kImpWidth = 0.001;
 constexpr double kMu = 1.0;
 constexpr int kSweeps = 10;
+constexpr double kPgsTol = 1e-8;
 constexpr double kSleepV = 1e-8;
 constexpr int kMaxObj = 32;
 constexpr int kMaxCon = 24;
@@ -151,6 +152,7 @@ struct Dev {
   int *gbtn, *bstate, *btimer, *amask;
   double *cgcur, *cgnext, *cgox, *cgoy;
   int* cgtimer;
+  int* movmask;  // bit s: movable object s has a non-zero velocity (derived state, rebuilt by env_observe)
   double *time, *clear;
   unsigned *ctr, *episode;
   int* nstep;
@@ -298,16 +300,13 @@ SAG_HD int collide(const Geom& A, const Geom& B, Hit* o) {
 SAG_HD bool kind_collidable(int k) { return k == K_VASE || k == K_GREMLIN || k == K_PILLAR || k == K_BUTTON || k == K_BOX; }
 SAG_HD bool kind_movable(int k) { return k == K_VASE || k == K_GREMLIN || k == K_BOX; }
 SAG_HD int kind_nparts(int k) { return k == K_BOX ? 5 : (kind_collidable(k) ? 1 : 0); }
-// bounding radius about the body centre (for the broad phase)
+// bounding radius about the body centre (for the broad phase); select chain, no jump table
 SAG_HD double kind_bound(const Dev& D, int k) {
-  switch (k) {
-    case K_VASE: return D.vases_size * 1.4142135623730951 + 1e-9;
-    case K_GREMLIN: return D.gremlins_size * 1.4142135623730951 + 1e-9;
-    case K_PILLAR: return D.pillars_size;
-    case K_BUTTON: return kButtonSize;
-    case K_BOX: return kBoxSize * 1.5 * 1.4142135623730951 + 1e-9;
-    default: return 0.0;
-  }
+  return k == K_VASE ? D.vases_size * 1.4142135623730951 + 1e-9
+       : k == K_PILLAR ? D.pillars_size
+       : k == K_BUTTON ? kButtonSize
+       : k == K_BOX ? kBoxSize * 1.5 * 1.4142135623730951 + 1e-9
+       : k == K_GREMLIN ? D.gremlins_size * 1.4142135623730951 + 1e-9 : 0.0;
 }
 SAG_HD void kind_mass(const Dev& D, int k, double& m, double& iz, double& reff) {
   if (k == K_BOX) {
@@ -326,42 +325,42 @@ SAG_HD void kind_mass(const Dev& D, int k, double& m, double& iz, double& reff) 
 
 SAG_HD void obj_geom(const Dev& D, int kind, int part, double x, double y, double c, double s, Geom& g) {
   g.c = c; g.s = s; g.cx = x; g.cy = y; g.r = 0.0; g.hx = g.hy = 0.0; g.is_box = 0;
-  switch (kind) {
-    case K_VASE: g.is_box = 1; g.hx = g.hy = D.vases_size; break;
-    case K_GREMLIN: g.is_box = 1; g.hx = g.hy = D.gremlins_size; break;
-    case K_PILLAR: g.r = D.pillars_size; break;
-    case K_BUTTON: g.r = kButtonSize; break;
-    case K_BOX:
-      g.is_box = 1;
-      if (part == 0) { g.hx = g.hy = kBoxSize; }
-      else {
-        double sx = (part == 1 || part == 3) ? 1.0 : -1.0, sy = (part <= 2) ? 1.0 : -1.0;
-        double ox = sx * kBoxSize, oy = sy * kBoxSize;
-        g.hx = g.hy = kBoxSize / 2;
-        g.cx = x + ox * c - oy * s; g.cy = y + ox * s + oy * c;
-      }
-      break;
-    default: break;
+  if (kind == K_VASE) { g.is_box = 1; g.hx = g.hy = D.vases_size; }
+  else if (kind == K_PILLAR) { g.r = D.pillars_size; }
+  else if (kind == K_BUTTON) { g.r = kButtonSize; }
+  else if (kind == K_GREMLIN) { g.is_box = 1; g.hx = g.hy = D.gremlins_size; }
+  else if (kind == K_BOX) {
+    g.is_box = 1;
+    if (part == 0) { g.hx = g.hy = kBoxSize; }
+    else {
+      double sx = (part == 1 || part == 3) ? 1.0 : -1.0, sy = (part <= 2) ? 1.0 : -1.0;
+      double ox = sx * kBoxSize, oy = sy * kBoxSize;
+      g.hx = g.hy = kBoxSize / 2;
+      g.cx = x + ox * c - oy * s; g.cy = y + ox * s + oy * c;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// point robot (point.xml): generalised coordinates (x, y, yaw) in the world frame
+// point robot (point.xml): generalised coordinates (x, y, yaw) in the world frame.
+// M = [[a,0,p],[0,a,q],[p,q,I]] with p = -mc sin(yaw), q = mc cos(yaw).  Both slide joints share one
+// damping value, so p^2 + q^2 = (mc)^2 and the Schur complement I - (mc)^2 / a is a constant of the
+// model: the 3x3 solve needs no division per substep.
 // ------------------------------------------------------------------------------------------------
-struct PtMat { double a, b, p, q, s; };  // [[a,0,p],[0,b,q],[p,q,I]], s = Schur complement
+struct PtConst { double ia0, is0, iah, ish; };  // 1/a and 1/schur for M (forward dynamics) and M + hD (Euler)
 
-SAG_HD PtMat pt_matrix(double sn, double cs, double hd, double damp_xy) {
-  PtMat M;
-  M.a = kPtM + hd * damp_xy; M.b = kPtM + hd * damp_xy;
-  M.p = -kPtMc * sn; M.q = kPtMc * cs;
-  double I = kPtIo + hd * kPtDampZ;
-  M.s = I - M.p * M.p / M.a - M.q * M.q / M.b;
-  return M;
+SAG_HD PtConst pt_const(double damp_xy, double h) {
+  PtConst K;
+  K.ia0 = 1.0 / (kPtM + 0.0 * damp_xy);
+  K.is0 = 1.0 / ((kPtIo + 0.0 * kPtDampZ) - kPtMc * kPtMc * K.ia0);
+  K.iah = 1.0 / (kPtM + h * damp_xy);
+  K.ish = 1.0 / ((kPtIo + h * kPtDampZ) - kPtMc * kPtMc * K.iah);
+  return K;
 }
-SAG_HD void pt_solve(const PtMat& M, const double* f, double* out) {
-  double al = (f[2] - M.p * f[0] / M.a - M.q * f[1] / M.b) / M.s;
-  out[0] = (f[0] - M.p * al) / M.a;
-  out[1] = (f[1] - M.q * al) / M.b;
+SAG_HD void pt_solve(double p, double q, double ia, double is, const double* f, double* out) {
+  double al = (f[2] - (p * f[0] + q * f[1]) * ia) * is;
+  out[0] = (f[0] - p * al) * ia;
+  out[1] = (f[1] - q * al) * ia;
   out[2] = al;
 }
 SAG_HD double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
@@ -380,21 +379,6 @@ SAG_HD void pt_smooth(const Robot& R, double sn, double cs, double* f) {
 
 SAG_HD bool bad_val(double x) { return !(fabs(x) <= 1e10); }
 
-// one contact-free substep: forward dynamics + semi-implicit Euler with implicit joint damping
-SAG_HD void pt_substep_free(Robot& R, double h, int& err) {
-  double sn = sag_sin(R.q[2]), cs = sag_cos(R.q[2]);
-  double f[3], a[3];
-  pt_smooth(R, sn, cs, f);
-  PtMat Mh = pt_matrix(sn, cs, h, R.damp_xy);
-  pt_solve(Mh, f, a);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) R.v[k] += h * a[k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) R.q[k] += h * R.v[k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) if (bad_val(R.q[k]) || bad_val(R.v[k]) || bad_val(a[k])) err = 1;
-}
-
 SAG_HD double impedance(double r) {
   double x = fabs(r) / kImpWidth;
   if (x > 1.0) x = 1.0;
@@ -403,16 +387,16 @@ SAG_HD double impedance(double r) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// full forward dynamics with contacts (slow path; only taken near objects)
+// contact pass (slow path; only taken by environments with something within reach or in motion):
+// collision detection in the oracle's canonical order, soft-constraint rows, projected Gauss-Seidel,
+// optional integration of the movable bodies.  Work is proportional to the objects actually involved.
 // ------------------------------------------------------------------------------------------------
 struct Con { int ba, bb; double nx, ny, px, py, dist; };
-struct Row { int ba, bb; double ja[2][3], jb[2][3]; double aref[2], diag[2], R[2], f[2]; };
-
-struct FwdOut {
-  double qacc[3], fsmooth[3], fcon[3];
-  unsigned touch;        // bit s: robot geom in contact (dist <= 0) with object slot s
-  unsigned touched_mov;  // bit s: movable body s had an active constraint row
-  int err;
+struct Row {  // one contact (normal k=0, tangent k=1) or the tendon limit (k=0 only)
+  int ba, bb;
+  double ja[2][3], jb[2][3];  // Jacobian rows w.r.t. body a / b
+  double wa[2][3], wb[2][3];  // M^-1 J^T, precomputed
+  double aref[2], R[2], inv[2], f[2];
 };
 
 struct Ctx {  // per-thread view of one environment
@@ -423,16 +407,25 @@ struct Ctx {  // per-thread view of one environment
   int task;
 };
 
+struct Phys {
+  double fc[3];    // generalised constraint force on the robot
+  double qacc[3];  // robot acceleration M^-1 (fsmooth + fc)
+  unsigned touch;  // bit s: a robot geom is in contact (dist <= 0) with object slot s
+  unsigned mov;    // bit s: movable body s has a non-zero velocity (after integration, if any)
+  int err;
+};
+
 SAG_HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
-SAG_HD_NOINLINE void forward_full(const Ctx& C, const Robot& R, FwdOut& out, double (*oacc)[3]) {
+SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, double cs, const PtConst& K, const double* fs,
+                                  unsigned mov, bool integrate, double h, Phys& P) {
   const Dev& D = C.D;
   const int e = C.e;
+  const double p = -kPtMc * sn, q = kPtMc * cs;
   Con con[kMaxCon];
   int ncon = 0;
-  unsigned active = 0, touch = 0;
-  out.err = 0;
-  const double sn = sag_sin(R.q[2]), cs = sag_cos(R.q[2]);
+  unsigned active = mov, touch = 0;
+  P.err = 0;
   Geom gr[2];
   gr[0].is_box = 0; gr[0].cx = R.q[0]; gr[0].cy = R.q[1]; gr[0].c = cs; gr[0].s = sn; gr[0].r = kPtR; gr[0].hx = gr[0].hy = 0.0;
   gr[1].is_box = 1; gr[1].cx = R.q[0] + kPtArrowOff * cs; gr[1].cy = R.q[1] + kPtArrowOff * sn; gr[1].c = cs; gr[1].s = sn;
@@ -444,45 +437,51 @@ SAG_HD_NOINLINE void forward_full(const Ctx& C, const Robot& R, FwdOut& out, dou
     if (!kind_collidable(kind)) continue;
     size_t i = oidx(D, s, e);
     double x = D.ox[i], y = D.oy[i];
-    bool mov = kind_movable(kind);
-    if (mov && (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0)) active |= 1u << s;
     double dx = x - R.q[0], dy = y - R.q[1], reach = kRobotReach + kind_bound(D, kind);
     if (dx * dx + dy * dy > reach * reach) continue;
+    bool mvb = kind_movable(kind);
     double oc = 1.0, os = 0.0;
-    if (mov) { double yaw = D.oyaw[i]; oc = sag_cos(yaw); os = sag_sin(yaw); }
+    if (mvb) sag_sincos(D.oyaw[i], &os, &oc);
     for (int rg = 0; rg < 2; ++rg)
-      for (int p = 0; p < kind_nparts(kind); ++p) {
+      for (int pt = 0; pt < kind_nparts(kind); ++pt) {
         Geom go;
-        obj_geom(D, kind, p, x, y, oc, os, go);
+        obj_geom(D, kind, pt, x, y, oc, os, go);
         int n = collide(gr[rg], go, hits);
         for (int k = 0; k < n; ++k) {
-          if (ncon >= kMaxCon) { out.err = 1; break; }
+          if (ncon >= kMaxCon) { P.err = 1; break; }
           Con& c = con[ncon++];
-          c.ba = 0; c.bb = mov ? 1 + s : -1;
+          c.ba = 0; c.bb = mvb ? 1 + s : -1;
           c.nx = hits[k].nx; c.ny = hits[k].ny; c.px = hits[k].px; c.py = hits[k].py; c.dist = hits[k].dist;
         }
-        if (n) { touch |= 1u << s; if (mov) active |= 1u << s; }
+        if (n) { touch |= 1u << s; if (mvb) active |= 1u << s; }
       }
   }
-  // ---- phase 2: object pairs with at least one awake / robot-touched movable body
+  // ---- phase 2: object pairs (j ascending, i < j ascending) with at least one awake / robot-touched movable body
   if (active) {
     for (int j = C.L.v0; j < C.L.n; ++j) {
       int kj = slot_kind(C.sp, C.L, j);
       if (!kind_collidable(kj)) continue;
+      bool aj = (active >> j) & 1u;
+      unsigned cand = aj ? ((1u << j) - 1u) : (active & ((1u << j) - 1u));
+      cand &= ~((1u << C.L.v0) - 1u);
+      if (!cand) continue;
       size_t ij = oidx(D, j, e);
       double xj = D.ox[ij], yj = D.oy[ij], bj = kind_bound(D, kj);
+      bool mj = kind_movable(kj);
+      double cj = 1.0, sj = 0.0;
+      bool have_j = false;
       for (int i = C.L.v0; i < j; ++i) {
-        if (!((active >> i) & 1u) && !((active >> j) & 1u)) continue;
+        if (!((cand >> i) & 1u)) continue;
         int ki = slot_kind(C.sp, C.L, i);
         if (!kind_collidable(ki)) continue;
         size_t ii = oidx(D, i, e);
         double xi = D.ox[ii], yi = D.oy[ii];
         double dx = xj - xi, dy = yj - yi, reach = bj + kind_bound(D, ki);
         if (dx * dx + dy * dy > reach * reach) continue;
-        bool mi = kind_movable(ki), mj = kind_movable(kj);
-        double ci = 1.0, si = 0.0, cj = 1.0, sj = 0.0;
-        if (mi) { double yaw = D.oyaw[ii]; ci = sag_cos(yaw); si = sag_sin(yaw); }
-        if (mj) { double yaw = D.oyaw[ij]; cj = sag_cos(yaw); sj = sag_sin(yaw); }
+        bool mi = kind_movable(ki);
+        double ci = 1.0, si = 0.0;
+        if (mi) sag_sincos(D.oyaw[ii], &si, &ci);
+        if (mj && !have_j) { sag_sincos(D.oyaw[ij], &sj, &cj); have_j = true; }
         for (int pi = 0; pi < kind_nparts(ki); ++pi) {
           Geom gi;
           obj_geom(D, ki, pi, xi, yi, ci, si, gi);
@@ -491,7 +490,7 @@ SAG_HD_NOINLINE void forward_full(const Ctx& C, const Robot& R, FwdOut& out, dou
             obj_geom(D, kj, pj, xj, yj, cj, sj, gj);
             int n = collide(gi, gj, hits);
             for (int k = 0; k < n; ++k) {
-              if (ncon >= kMaxCon) { out.err = 1; break; }
+              if (ncon >= kMaxCon) { P.err = 1; break; }
               Con& c = con[ncon++];
               c.ba = mi ? 1 + i : -1; c.bb = mj ? 1 + j : -1;
               c.nx = hits[k].nx; c.ny = hits[k].ny; c.px = hits[k].px; c.py = hits[k].py; c.dist = hits[k].dist;
@@ -501,33 +500,51 @@ SAG_HD_NOINLINE void forward_full(const Ctx& C, const Robot& R, FwdOut& out, dou
       }
     }
   }
-  out.touch = touch;
-  // ---- smooth dynamics
-  PtMat M = pt_matrix(sn, cs, 0.0, R.damp_xy);
-  pt_smooth(R, sn, cs, out.fsmooth);
+  P.touch = touch;
+  P.mov = mov;
+  P.fc[0] = P.fc[1] = P.fc[2] = 0.0;
+  // ---- which constraint rows exist?
+  int nact = 0;
+  for (int i = 0; i < ncon; ++i) if (con[i].dist < 0.0 && !(con[i].ba < 0 && con[i].bb < 0)) ++nact;
+  double tdx = 0.0, tdy = 0.0, tlen = 0.0, tdist = 0.0;
+  bool tendon = false;
+  if (C.task == T_HAUL_BOX) {  // tendon length limit, haul_box.py:21-30
+    size_t ib = oidx(D, C.L.box, e);
+    tdx = D.ox[ib] - R.q[0]; tdy = D.oy[ib] - R.q[1];
+    double dz = kBoxSize - kPtZ;
+    tlen = sqrt(tdx * tdx + tdy * tdy + dz * dz);
+    tdist = kTendonMax - tlen;
+    tendon = tdist < 0.0;
+  }
   double racc[3];
-  pt_solve(M, out.fsmooth, racc);
-  for (int s = 0; s < C.L.n; ++s) { oacc[s][0] = oacc[s][1] = oacc[s][2] = 0.0; }
-  // ---- constraint rows
-  Row rows[kMaxCon + 1];
-  int nrow = 0, tendon_row = -1;
-  unsigned touched = 0;
-  const double bdamp = 2.0 / (kImpDmax * kSolTc);
-  const double kbase = 1.0 / (kImpDmax * kImpDmax * kSolTc * kSolTc);
+  pt_solve(p, q, K.ia0, K.is0, fs, racc);
+  if (nact == 0 && !tendon && mov == 0) {  // nothing to solve, nothing to move
+    P.qacc[0] = racc[0]; P.qacc[1] = racc[1]; P.qacc[2] = racc[2];
+    return;
+  }
+  // ---- body tables (only involved bodies are ever touched)
+  double vim, vii, vrf, bim, bii, brf;
+  { double m, iz; kind_mass(D, K_VASE, m, iz, vrf); vim = 1.0 / m; vii = 1.0 / iz; }
+  { double m, iz; kind_mass(D, K_BOX, m, iz, brf); bim = 1.0 / m; bii = 1.0 / iz; }
+  auto is_box_body = [&](int body) { return body - 1 == C.L.box; };
   auto minv = [&](int body, const double* j, double* o) {
-    if (body == 0) { pt_solve(M, j, o); return; }
-    double m, iz, rf;
-    kind_mass(D, slot_kind(C.sp, C.L, body - 1), m, iz, rf);
-    o[0] = j[0] * (1.0 / m); o[1] = j[1] * (1.0 / m); o[2] = j[2] * (1.0 / iz);
+    if (body == 0) { pt_solve(p, q, K.ia0, K.is0, j, o); return; }
+    double im = is_box_body(body) ? bim : vim, ii = is_box_body(body) ? bii : vii;
+    o[0] = j[0] * im; o[1] = j[1] * im; o[2] = j[2] * ii;
   };
   auto bvel = [&](int body, double* v) {
     if (body == 0) { v[0] = R.v[0]; v[1] = R.v[1]; v[2] = R.v[2]; }
     else { size_t i = oidx(D, body - 1, e); v[0] = D.ovx[i]; v[1] = D.ovy[i]; v[2] = D.ow[i]; }
   };
-  auto bpos = [&](int body, double* p) {
-    if (body == 0) { p[0] = R.q[0]; p[1] = R.q[1]; }
-    else { size_t i = oidx(D, body - 1, e); p[0] = D.ox[i]; p[1] = D.oy[i]; }
+  auto bpos = [&](int body, double* o) {
+    if (body == 0) { o[0] = R.q[0]; o[1] = R.q[1]; }
+    else { size_t i = oidx(D, body - 1, e); o[0] = D.ox[i]; o[1] = D.oy[i]; }
   };
+  Row rows[kMaxCon + 1];
+  int nrow = 0, tendon_row = -1;
+  unsigned touched = 0;
+  const double bdamp = 2.0 / (kImpDmax * kSolTc);
+  const double kbase = 1.0 / (kImpDmax * kImpDmax * kSolTc * kSolTc);
   for (int i = 0; i < ncon; ++i) {
     const Con& c = con[i];
     if (!(c.dist < 0.0)) continue;
@@ -545,155 +562,148 @@ SAG_HD_NOINLINE void forward_full(const Ctx& C, const Robot& R, FwdOut& out, dou
     r.jb[1][0] = tx; r.jb[1][1] = ty; r.jb[1][2] = rbx * ty - rby * tx;
     double d = impedance(c.dist);
     for (int k = 0; k < 2; ++k) {
-      double t[3], diag = 0.0, vel = 0.0;
-      if (c.ba >= 0) { minv(c.ba, r.ja[k], t); diag += dot3(r.ja[k], t); vel += dot3(r.ja[k], va); }
-      if (c.bb >= 0) { minv(c.bb, r.jb[k], t); diag += dot3(r.jb[k], t); vel += dot3(r.jb[k], vb); }
-      r.diag[k] = diag;
+      double diag = 0.0, vel = 0.0;
+      if (c.ba >= 0) { minv(c.ba, r.ja[k], r.wa[k]); diag += dot3(r.ja[k], r.wa[k]); vel += dot3(r.ja[k], va); }
+      if (c.bb >= 0) { minv(c.bb, r.jb[k], r.wb[k]); diag += dot3(r.jb[k], r.wb[k]); vel += dot3(r.jb[k], vb); }
       r.R[k] = (1.0 - d) / d * diag;
+      r.inv[k] = 1.0 / (diag + r.R[k]);
       r.aref[k] = -bdamp * vel - (k == 0 ? d * kbase * c.dist : 0.0);
       r.f[k] = 0.0;
     }
   }
-  if (C.task == T_HAUL_BOX) {  // tendon length limit, haul_box.py:21-30
-    size_t ib = oidx(D, C.L.box, e);
-    double dx = D.ox[ib] - R.q[0], dy = D.oy[ib] - R.q[1], dz = kBoxSize - kPtZ;
-    double len = sqrt(dx * dx + dy * dy + dz * dz);
-    double dist = kTendonMax - len;
-    if (dist < 0.0) {
-      Row& r = rows[nrow]; tendon_row = nrow++;
-      r.ba = 0; r.bb = 1 + C.L.box;
-      r.ja[0][0] = dx / len; r.ja[0][1] = dy / len; r.ja[0][2] = 0.0;
-      r.jb[0][0] = -dx / len; r.jb[0][1] = -dy / len; r.jb[0][2] = 0.0;
-      double va[3], vb[3], t[3], diag = 0.0;
-      bvel(0, va); bvel(r.bb, vb);
-      minv(0, r.ja[0], t); diag += dot3(r.ja[0], t);
-      minv(r.bb, r.jb[0], t); diag += dot3(r.jb[0], t);
-      double d = impedance(dist);
-      r.diag[0] = diag; r.R[0] = (1.0 - d) / d * diag;
-      r.aref[0] = -bdamp * (dot3(r.ja[0], va) + dot3(r.jb[0], vb)) - d * kbase * dist;
-      r.f[0] = 0.0;
-      touched |= 1u << C.L.box;
-    }
+  if (tendon) {
+    Row& r = rows[nrow]; tendon_row = nrow++;
+    r.ba = 0; r.bb = 1 + C.L.box;
+    r.ja[0][0] = tdx / tlen; r.ja[0][1] = tdy / tlen; r.ja[0][2] = 0.0;
+    r.jb[0][0] = -tdx / tlen; r.jb[0][1] = -tdy / tlen; r.jb[0][2] = 0.0;
+    double va[3], vb[3], diag = 0.0;
+    bvel(0, va); bvel(r.bb, vb);
+    minv(0, r.ja[0], r.wa[0]); diag += dot3(r.ja[0], r.wa[0]);
+    minv(r.bb, r.jb[0], r.wb[0]); diag += dot3(r.jb[0], r.wb[0]);
+    double d = impedance(tdist);
+    r.R[0] = (1.0 - d) / d * diag;
+    r.inv[0] = 1.0 / (diag + r.R[0]);
+    r.aref[0] = -bdamp * (dot3(r.ja[0], va) + dot3(r.jb[0], vb)) - d * kbase * tdist;
+    r.f[0] = 0.0;
+    touched |= 1u << C.L.box;
   }
-  out.touched_mov = touched;
-  // floor friction bodies: awake or touched movable bodies
-  unsigned fl = (touched | active);
-  double ffl[kMaxObj][3];
-  for (int s = 0; s < C.L.n; ++s) { ffl[s][0] = ffl[s][1] = ffl[s][2] = 0.0; }
-  auto acc_of = [&](int body) -> double* { return body == 0 ? racc : oacc[body - 1]; };
-  auto apply = [&](int body, const double* j, double df) {
-    if (body < 0) return;
-    double t[3];
-    minv(body, j, t);
-    double* a = acc_of(body);
-    a[0] += t[0] * df; a[1] += t[1] * df; a[2] += t[2] * df;
-  };
+  // body accelerations: acc[0] = robot, acc[1 + slot] = movable object; only involved bodies are initialised
+  const unsigned fl = touched | mov;  // floor-friction bodies: awake or touched, slot order
+  double acc[kMaxObj + 1][3], ffl[kMaxObj][3];
+  acc[0][0] = racc[0]; acc[0][1] = racc[1]; acc[0][2] = racc[2];
+  for (unsigned m = fl; m; m &= m - 1) {
+    int s = 0; for (unsigned t = m; !(t & 1u); t >>= 1) ++s;
+    acc[1 + s][0] = acc[1 + s][1] = acc[1 + s][2] = 0.0; ffl[s][0] = ffl[s][1] = ffl[s][2] = 0.0;
+  }
   const double rr = (1.0 - kImpD0) / kImpD0;
-  if (nrow > 0 || fl) {
-    for (int it = 0; it < kSweeps; ++it) {
-      for (int i = 0; i < nrow; ++i) {
-        Row& r = rows[i];
-        int nk = (i == tendon_row) ? 1 : 2;
-        for (int k = 0; k < nk; ++k) {
-          double a = 0.0;
-          if (r.ba >= 0) a += dot3(r.ja[k], acc_of(r.ba));
-          if (r.bb >= 0) a += dot3(r.jb[k], acc_of(r.bb));
-          double fn = r.f[k] - (a - r.aref[k] + r.R[k] * r.f[k]) / (r.diag[k] + r.R[k]);
-          if (k == 0) { if (fn < 0.0) fn = 0.0; }
-          else { double lim = kMu * r.f[0]; fn = clampd(fn, -lim, lim); }
-          double df = fn - r.f[k];
-          r.f[k] = fn;
-          if (df != 0.0) { apply(r.ba, r.ja[k], df); apply(r.bb, r.jb[k], df); }
+  const double v_inv_lin = 1.0 / (vim + rr * vim), v_inv_tor = 1.0 / (vii + rr * vii);
+  const double b_inv_lin = 1.0 / (bim + rr * bim), b_inv_tor = 1.0 / (bii + rr * bii);
+  double vmass, bmass;
+  { double iz, rf; kind_mass(D, K_VASE, vmass, iz, rf); kind_mass(D, K_BOX, bmass, iz, rf); }
+  // projected Gauss-Seidel; stops after kSweeps sweeps or when a sweep changes the forces by < kPgsTol (relative, L1)
+  for (int it = 0; it < kSweeps; ++it) {
+    double sdf = 0.0, sf = 0.0;
+    for (int i = 0; i < nrow; ++i) {
+      Row& r = rows[i];
+      const int nk = (i == tendon_row) ? 1 : 2;
+      for (int k = 0; k < nk; ++k) {
+        double a = 0.0;
+        if (r.ba >= 0) a += dot3(r.ja[k], acc[r.ba]);
+        if (r.bb >= 0) a += dot3(r.jb[k], acc[r.bb]);
+        double fn = r.f[k] - (a - r.aref[k] + r.R[k] * r.f[k]) * r.inv[k];
+        if (k == 0) { if (fn < 0.0) fn = 0.0; }
+        else { double lim = kMu * r.f[0]; fn = clampd(fn, -lim, lim); }
+        double df = fn - r.f[k];
+        r.f[k] = fn;
+        sdf += fabs(df); sf += fabs(fn);
+        if (df != 0.0) {
+          if (r.ba >= 0) { double* ac = acc[r.ba]; ac[0] += r.wa[k][0] * df; ac[1] += r.wa[k][1] * df; ac[2] += r.wa[k][2] * df; }
+          if (r.bb >= 0) { double* ac = acc[r.bb]; ac[0] += r.wb[k][0] * df; ac[1] += r.wb[k][1] * df; ac[2] += r.wb[k][2] * df; }
         }
       }
-      for (int s = C.L.v0; s < C.L.n; ++s) {
-        if (!((fl >> s) & 1u)) continue;
-        int kind = slot_kind(C.sp, C.L, s);
-        if (!kind_movable(kind)) continue;
-        double m, iz, rf;
-        kind_mass(D, kind, m, iz, rf);
-        size_t i = oidx(D, s, e);
-        double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
-        double lim = kMu * m * kGrav;
-        double* ac = oacc[s];
-        double Al = 1.0 / m, At = 1.0 / iz;
-        double f0 = ffl[s][0] - (ac[0] + bdamp * vx + rr * Al * ffl[s][0]) / (Al + rr * Al);
-        double f1 = ffl[s][1] - (ac[1] + bdamp * vy + rr * Al * ffl[s][1]) / (Al + rr * Al);
-        double nf = sqrt(f0 * f0 + f1 * f1);
-        if (nf > lim) { f0 *= lim / nf; f1 *= lim / nf; }
-        ac[0] += (f0 - ffl[s][0]) * Al; ac[1] += (f1 - ffl[s][1]) * Al;
-        ffl[s][0] = f0; ffl[s][1] = f1;
-        double f2 = ffl[s][2] - (ac[2] + bdamp * w + rr * At * ffl[s][2]) / (At + rr * At);
-        f2 = clampd(f2, -lim * rf, lim * rf);
-        ac[2] += (f2 - ffl[s][2]) * At;
-        ffl[s][2] = f2;
-      }
     }
+    for (unsigned m = fl; m; m &= m - 1) {
+      int s = 0; for (unsigned t = m; !(t & 1u); t >>= 1) ++s;
+      const bool isb = s == C.L.box;
+      const double Al = isb ? bim : vim, At = isb ? bii : vii, rf = isb ? brf : vrf;
+      const double inv_lin = isb ? b_inv_lin : v_inv_lin, inv_tor = isb ? b_inv_tor : v_inv_tor;
+      const double lim = kMu * (isb ? bmass : vmass) * kGrav;
+      size_t i = oidx(D, s, e);
+      double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
+      double* ac = acc[1 + s];
+      double f0 = ffl[s][0] - (ac[0] + bdamp * vx + rr * Al * ffl[s][0]) * inv_lin;
+      double f1 = ffl[s][1] - (ac[1] + bdamp * vy + rr * Al * ffl[s][1]) * inv_lin;
+      double nf = sqrt(f0 * f0 + f1 * f1);
+      if (nf > lim) { double sc = lim / nf; f0 *= sc; f1 *= sc; }
+      double d0 = f0 - ffl[s][0], d1 = f1 - ffl[s][1];
+      ac[0] += d0 * Al; ac[1] += d1 * Al;
+      ffl[s][0] = f0; ffl[s][1] = f1;
+      double f2 = ffl[s][2] - (ac[2] + bdamp * w + rr * At * ffl[s][2]) * inv_tor;
+      f2 = clampd(f2, -lim * rf, lim * rf);
+      double d2 = f2 - ffl[s][2];
+      ac[2] += d2 * At;
+      ffl[s][2] = f2;
+      sdf += fabs(d0) + fabs(d1) + fabs(d2); sf += fabs(f0) + fabs(f1) + fabs(f2);
+    }
+    if (sdf <= kPgsTol * sf) break;
   }
-  out.qacc[0] = racc[0]; out.qacc[1] = racc[1]; out.qacc[2] = racc[2];
-  out.fcon[0] = out.fcon[1] = out.fcon[2] = 0.0;
+  P.qacc[0] = acc[0][0]; P.qacc[1] = acc[0][1]; P.qacc[2] = acc[0][2];
   for (int i = 0; i < nrow; ++i) {
     const Row& r = rows[i];
     int nk = (i == tendon_row) ? 1 : 2;
     for (int k = 0; k < nk; ++k) {
-      if (r.ba == 0) for (int d = 0; d < 3; ++d) out.fcon[d] += r.ja[k][d] * r.f[k];
-      if (r.bb == 0) for (int d = 0; d < 3; ++d) out.fcon[d] += r.jb[k][d] * r.f[k];
+      if (r.ba == 0) for (int d = 0; d < 3; ++d) P.fc[d] += r.ja[k][d] * r.f[k];
+      if (r.bb == 0) for (int d = 0; d < 3; ++d) P.fc[d] += r.jb[k][d] * r.f[k];
     }
   }
-}
-
-// one full substep (contacts possible): forward + integrate robot and awake/touched movable bodies
-SAG_HD_NOINLINE void substep_full(const Ctx& C, Robot& R, double h, int& err) {
-  const Dev& D = C.D;
-  FwdOut F;
-  double oacc[kMaxObj][3];
-  forward_full(C, R, F, oacc);
-  if (F.err) err = 1;
-  double sn = sag_sin(R.q[2]), cs = sag_cos(R.q[2]);
-  PtMat Mh = pt_matrix(sn, cs, h, R.damp_xy);
-  double rhs[3], a[3];
-  for (int k = 0; k < 3; ++k) rhs[k] = F.fsmooth[k] + F.fcon[k];
-  pt_solve(Mh, rhs, a);
-  for (int k = 0; k < 3; ++k) R.v[k] += h * a[k];
-  for (int k = 0; k < 3; ++k) R.q[k] += h * R.v[k];
-  for (int k = 0; k < 3; ++k) if (bad_val(R.q[k]) || bad_val(R.v[k]) || bad_val(a[k])) err = 1;
-  for (int s = C.L.v0; s < C.L.n; ++s) {
-    int kind = slot_kind(C.sp, C.L, s);
-    if (!kind_movable(kind)) continue;
-    size_t i = oidx(D, s, C.e);
+  if (!integrate) return;
+  // ---- semi-implicit Euler for the awake / touched movable bodies (free joints: no damping)
+  for (unsigned m = fl; m; m &= m - 1) {
+    int s = 0; for (unsigned t = m; !(t & 1u); t >>= 1) ++s;
+    size_t i = oidx(D, s, e);
     double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
-    bool touched = (F.touched_mov >> s) & 1u;
-    if (!(touched || vx != 0.0 || vy != 0.0 || w != 0.0)) continue;
-    vx += h * oacc[s][0]; vy += h * oacc[s][1]; w += h * oacc[s][2];
-    if (!touched && vx * vx + vy * vy < kSleepV * kSleepV && fabs(w) < kSleepV) { vx = vy = w = 0.0; }
+    bool tch = (touched >> s) & 1u;
+    vx += h * acc[1 + s][0]; vy += h * acc[1 + s][1]; w += h * acc[1 + s][2];
+    if (!tch && vx * vx + vy * vy < kSleepV * kSleepV && fabs(w) < kSleepV) { vx = vy = w = 0.0; }
     double x = D.ox[i] + h * vx, y = D.oy[i] + h * vy, yaw = D.oyaw[i] + h * w;
     D.ovx[i] = vx; D.ovy[i] = vy; D.ow[i] = w; D.ox[i] = x; D.oy[i] = y; D.oyaw[i] = yaw;
-    if (bad_val(x) || bad_val(y) || bad_val(vx) || bad_val(vy) || bad_val(w)) err = 1;
+    if (vx != 0.0 || vy != 0.0 || w != 0.0) P.mov |= 1u << s; else P.mov &= ~(1u << s);
+    if (bad_val(x) || bad_val(y) || bad_val(vx) || bad_val(vy) || bad_val(w)) P.err = 1;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// lidar (safe_adaptation_gym.py:174-223) -- accumulate one object into a 16-bin group
-// bins are stored strided (bins[bin * bstride]) so that the caller can keep them in shared memory
+// lidar (safe_adaptation_gym.py:174-223): one object -> (bin, centre, next, previous) contributions.
+// Bins live in the CTA's shared-memory observation tile (stride = tile row length).
 // ------------------------------------------------------------------------------------------------
-SAG_HD void lidar_accum(double rx, double ry, double cs, double sn, double px, double py, float* bins, int bstride) {
-  double wx = px - rx, wy = py - ry;
-  double ex = wx * cs + wy * sn, ey = -wx * sn + wy * cs;   // :197-202
+struct LidarHit { int bin; float s0, sp, sm; };
+
+SAG_HD LidarHit lidar_eval(double wx, double wy, double cs, double sn) {
+  double ex = wx * cs + wy * sn, ey = -wx * sn + wy * cs;   // :197-202 ego frame
   double dist = sqrt(ex * ex + ey * ey);                    // :209
-  double angle = sag_atan2(ey, ex);                             // :210
+  double angle = sag_atan2(ey, ex);                         // :210
   if (angle < 0.0) angle += kTwoPi;
-  const double bin_size = kTwoPi / kLidarBins;              // :211
-  int bin = (int)(angle / bin_size);                        // :212
-  double bin_angle = bin_size * bin;                        // :213
+  const double inv_bin_size = kLidarBins / kTwoPi;          // :211
+  double t = angle * inv_bin_size;
+  int bin = (int)t;                                         // :212
   double sensor = kLidarMax - dist;                         // :214
   if (sensor < 0.0) sensor = 0.0;
-  sensor /= kLidarMax;
-  double alias = (angle - bin_angle) / bin_size;            // :216
-  int b0 = bin & (kLidarBins - 1), bp = (bin + 1) & (kLidarBins - 1), bm = (bin + kLidarBins - 1) & (kLidarBins - 1);
-  float s0 = (float)sensor, sp = (float)(alias * sensor), sm = (float)((1.0 - alias) * sensor);
-  if (s0 > bins[b0 * bstride]) bins[b0 * bstride] = s0;     // :215
-  if (sp > bins[bp * bstride]) bins[bp * bstride] = sp;     // :221
-  if (sm > bins[bm * bstride]) bins[bm * bstride] = sm;     // :222
+  sensor *= 1.0 / kLidarMax;
+  double alias = t - (double)bin;                           // :213,216
+  LidarHit H;
+  H.bin = bin;
+  H.s0 = (float)sensor; H.sp = (float)(alias * sensor); H.sm = (float)((1.0 - alias) * sensor);
+  return H;
+}
+SAG_HD void lidar_apply(const LidarHit& H, float* bins, int bstride) {
+  int b0 = H.bin & (kLidarBins - 1), bp = (H.bin + 1) & (kLidarBins - 1), bm = (H.bin + kLidarBins - 1) & (kLidarBins - 1);
+  if (H.s0 > bins[b0 * bstride]) bins[b0 * bstride] = H.s0;   // :215
+  if (H.sp > bins[bp * bstride]) bins[bp * bstride] = H.sp;   // :221
+  if (H.sm > bins[bm * bstride]) bins[bm * bstride] = H.sm;   // :222
+}
+SAG_HD void lidar_accum(double rx, double ry, double cs, double sn, double px, double py, float* bins, int bstride) {
+  LidarHit H = lidar_eval(px - rx, py - ry, cs, sn);
+  lidar_apply(H, bins, bstride);
 }
 
 // lidar group of a slot (consts.py:13-16; press_buttons.py:78-91; collect.py:34,44-45)
@@ -888,75 +898,102 @@ SAG_HD void set_mocaps(const Ctx& C, const Rng& rng, TaskState& T, double time) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// end-of-step pass: forward() (contacts, qacc) + cost + observation + clearance for the next step.
-// obs_s: 60 floats for this env, strided by ostride (shared-memory tile in the kernels).
+// end-of-step: forward() (contacts, qacc) -> reward -> cost -> observation, fused into two passes over the
+// objects (obstacle kinds before the reward, task objects after it because the reward may move the goal or
+// change button groups).  obs_s: this env's column of the CTA's shared-memory tile (stride ostride).
 // ------------------------------------------------------------------------------------------------
-struct PostOut { unsigned touch; double qacc[3]; double clear; int err; };
+struct EndOut { double rew[2]; double cost; double clear; unsigned mov; int err; int resample_failed; };
 
-// contacts + accelerations at the current state; chooses the free path when nothing is near
-SAG_HD void forward_any(const Ctx& C, const Robot& R, PostOut& P) {
+SAG_HD bool hazard_hit(double d2, double size) {  // world.py:151-152: ||robot_xy - hazard_xy|| <= size, exactly
+  double lo = size * 0.999, hi = size * 1.001;
+  if (d2 > hi * hi) return false;
+  if (d2 < lo * lo) return true;
+  return sqrt(d2) <= size;
+}
+
+SAG_HD void end_of_step(const Ctx& C, const Robot& R, TaskState& T, const Rng& rng, const PtConst& K, unsigned mov, bool phys_err,
+                        bool with_reward, float* obs_s, int ostride, EndOut& O) {
   const Dev& D = C.D;
-  // broad phase over collidable objects: min clearance and "any moving body" check
-  double clear = 1e30;
-  bool moving = false;
-  for (int s = C.L.v0; s < C.L.n; ++s) {
+  const int e = C.e;
+  double sn, cs;
+  sag_sincos(R.q[2], &sn, &cs);
+  for (int k = 0; k < 48; ++k) obs_s[k * ostride] = 0.0f;
+  // ---- pass A: hazards / vases / gremlins / pillars -> obstacle lidar, hazard cost, clearance
+  bool hz = false;
+  double d2v = 1e300, d2p = 1e300, d2b = 1e300, d2x = 1e300;  // min squared centre distance per collidable kind
+  for (int s = C.L.h0; s < C.L.v0; ++s) {
+    size_t i = oidx(D, s, e);
+    double wx = D.ox[i] - R.q[0], wy = D.oy[i] - R.q[1];
+    hz = hz || hazard_hit(wx * wx + wy * wy, D.hazards_size);
+    lidar_apply(lidar_eval(wx, wy, cs, sn), obs_s, ostride);
+  }
+  for (int s = C.L.v0; s < C.L.p0; ++s) {  // vases (and gremlins: none in any shipped task)
+    size_t i = oidx(D, s, e);
+    double wx = D.ox[i] - R.q[0], wy = D.oy[i] - R.q[1];
+    double d2 = wx * wx + wy * wy;
+    if (d2 < d2v) d2v = d2;
+    lidar_apply(lidar_eval(wx, wy, cs, sn), obs_s, ostride);
+  }
+  for (int s = C.L.p0; s < C.L.t0; ++s) {
+    size_t i = oidx(D, s, e);
+    double wx = D.ox[i] - R.q[0], wy = D.oy[i] - R.q[1];
+    double d2 = wx * wx + wy * wy;
+    if (d2 < d2p) d2p = d2;
+    lidar_apply(lidar_eval(wx, wy, cs, sn), obs_s, ostride);
+  }
+  for (int s = C.L.t0; s < C.L.n; ++s) {  // collidable task objects: buttons, push box
     int kind = slot_kind(C.sp, C.L, s);
     if (!kind_collidable(kind)) continue;
-    size_t i = oidx(D, s, C.e);
-    double dx = D.ox[i] - R.q[0], dy = D.oy[i] - R.q[1];
-    double c = sqrt(dx * dx + dy * dy) - (kRobotReach + kind_bound(D, kind));
-    if (c < clear) clear = c;
-    if (kind_movable(kind) && (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0)) moving = true;
+    size_t i = oidx(D, s, e);
+    double wx = D.ox[i] - R.q[0], wy = D.oy[i] - R.q[1];
+    double d2 = wx * wx + wy * wy;
+    if (kind == K_BUTTON) { if (d2 < d2b) d2b = d2; } else { if (d2 < d2x) d2x = d2; }
   }
-  bool tendon = false;
-  if (C.task == T_HAUL_BOX) tendon = true;
-  P.err = 0;
-  if (clear > 0.0 && !moving && !tendon) {
-    double sn = sag_sin(R.q[2]), cs = sag_cos(R.q[2]), f[3];
-    pt_smooth(R, sn, cs, f);
-    PtMat M = pt_matrix(sn, cs, 0.0, R.damp_xy);
-    pt_solve(M, f, P.qacc);
-    P.touch = 0;
-    P.clear = clear;
+  double clear = 1e30;
+  if (d2v < 1e299) clear = fmin(clear, sqrt(d2v) - (kRobotReach + kind_bound(D, K_VASE)));
+  if (d2p < 1e299) clear = fmin(clear, sqrt(d2p) - (kRobotReach + kind_bound(D, K_PILLAR)));
+  if (d2b < 1e299) clear = fmin(clear, sqrt(d2b) - (kRobotReach + kind_bound(D, K_BUTTON)));
+  if (d2x < 1e299) clear = fmin(clear, sqrt(d2x) - (kRobotReach + kind_bound(D, K_BOX)));
+  // ---- forward(): contacts + acceleration at the final state (safe_adaptation_gym.py:76)
+  double fs[3], qacc[3];
+  pt_smooth(R, sn, cs, fs);
+  unsigned touch = 0;
+  O.err = 0;
+  const bool tendon = C.task == T_HAUL_BOX;
+  if (clear > 0.0 && mov == 0 && !tendon) {
+    pt_solve(-kPtMc * sn, kPtMc * cs, K.ia0, K.is0, fs, qacc);
   } else {
-    FwdOut F;
-    double oacc[kMaxObj][3];
-    forward_full(C, R, F, oacc);
-    P.qacc[0] = F.qacc[0]; P.qacc[1] = F.qacc[1]; P.qacc[2] = F.qacc[2];
-    P.touch = F.touch;
-    P.err = F.err;
-    P.clear = (moving || tendon) ? -1.0 : clear;
+    Phys P;
+    contact_pass(C, R, sn, cs, K, fs, mov, false, 0.0, P);
+    qacc[0] = P.qacc[0]; qacc[1] = P.qacc[1]; qacc[2] = P.qacc[2];
+    touch = P.touch;
+    O.err = P.err;
+    if (mov != 0 || tendon) clear = -1.0;
   }
-}
-
-// World.compute_cost, world.py:144-155
-SAG_HD double compute_cost(const Ctx& C, const Robot& R, unsigned touch) {
-  const Dev& D = C.D;
-  unsigned obstacle_mask = C.L.t0 >= 32 ? 0xffffffffu : ((1u << C.L.t0) - 1u);  // hazards..pillars slots
-  bool hit = (touch & obstacle_mask) != 0;
-  for (int s = C.L.h0; s < C.L.v0; ++s) {
-    size_t i = oidx(D, s, C.e);
-    double dx = R.q[0] - D.ox[i], dy = R.q[1] - D.oy[i];
-    if (sqrt(dx * dx + dy * dy) <= D.hazards_size) hit = true;
+  O.clear = clear;
+  O.mov = mov;
+  // ---- reward (may resample the goal / change button groups) and cost
+  O.rew[0] = O.rew[1] = 0.0; O.cost = 0.0; O.resample_failed = 0;
+  if (with_reward) {
+    if (phys_err || O.err) { O.rew[0] = -10.0; }                            // :73-75
+    else {
+      if (compute_reward(C, rng, R, T, touch, O.rew)) O.resample_failed = 1;  // :77
+      unsigned obstacle_mask = C.L.t0 >= 32 ? 0xffffffffu : ((1u << C.L.t0) - 1u);
+      O.cost = (hz || (touch & obstacle_mask)) ? 1.0 : 0.0;                  // :78, world.py:144-155
+    }
   }
-  return hit ? 1.0 : 0.0;
-}
-
-// observation, safe_adaptation_gym.py:120-139,225-237: [obstacles(16), objects(16), goal(16), sensors(12)]
-SAG_HD void write_obs(const Ctx& C, const Robot& R, const TaskState& T, const double* qacc, float* obs_s, int ostride) {
-  const Dev& D = C.D;
-  for (int k = 0; k < 48; ++k) obs_s[k * ostride] = 0.0f;
-  double sn = sag_sin(R.q[2]), cs = sag_cos(R.q[2]);
-  for (int s = 0; s < C.L.n; ++s) {
+  // ---- pass B: task objects -> objects / goal lidar (safe_adaptation_gym.py:133-139, world.py:219-231)
+  for (int s = C.L.t0; s < C.L.n; ++s) {
     int kind = slot_kind(C.sp, C.L, s);
     int g = slot_group(C, s, kind, T.gbtn, T.bstate, T.amask);
     if (g == 0) continue;
-    size_t i = oidx(D, s, C.e);
+    size_t i = oidx(D, s, e);
     int off = g == 1 ? 0 : (g == 3 ? 16 : 32);
-    lidar_accum(R.q[0], R.q[1], cs, sn, D.ox[i], D.oy[i], obs_s + off * ostride, ostride);
+    lidar_apply(lidar_eval(D.ox[i] - R.q[0], D.oy[i] - R.q[1], cs, sn), obs_s + off * ostride, ostride);
   }
+  // ---- sensors (safe_adaptation_gym.py:225-237; semantics SURVEY App. B.6 [EXT])
   float* o = obs_s + 48 * ostride;
-  o[0 * ostride] = (float)(qacc[0] * cs + qacc[1] * sn);    // accelerometer (SURVEY App. B.6 [EXT])
+  o[0 * ostride] = (float)(qacc[0] * cs + qacc[1] * sn);    // accelerometer
   o[1 * ostride] = (float)(-qacc[0] * sn + qacc[1] * cs);
   o[2 * ostride] = (float)kGrav;
   o[3 * ostride] = (float)(R.v[0] * cs + R.v[1] * sn);      // velocimeter
@@ -991,66 +1028,79 @@ SAG_HD void env_step(const Dev& D, int e, float a0, float a1, float* obs_s, int 
   load_task_state(D, e, T);
   Rng rng = {D.seed, D.gid_base + (uint32_t)e, D.episode[e]};
   double time = D.time[e];
+  unsigned mov = (unsigned)D.movmask[e];
+  const double h = kPtH;
+  const PtConst K = pt_const(R.damp_xy, h);
   // action noise + clip (:58-67)
   double act0 = (double)a0, act1 = (double)a1;
   if (D.action_noise != 0.0) {
     double u1, u2;
     rng.pair(1u, T.ctr++, u1, u2);
     double rad = sqrt(-2.0 * sag_log(1.0 - u1));
-    act0 += D.action_noise * (rad * sag_cos(kTwoPi * u2));
-    act1 += D.action_noise * (rad * sag_sin(kTwoPi * u2));
+    double ns, nc;
+    sag_sincos(kTwoPi * u2, &ns, &nc);
+    act0 += D.action_noise * (rad * nc);
+    act1 += D.action_noise * (rad * ns);
   }
   R.ctrl[0] = clampd(act0, -1.0, 1.0);
   R.ctrl[1] = clampd(act1, -1.0, 1.0);
   set_mocaps(C, rng, T, time);  // :71
-  // physics.step(nstep) (:72).  Quiet envs (nothing within reach for the whole step) take the closed-form path.
-  const double h = kPtH;
+  // physics.step(nstep) (:72).  "Quiet" envs (nothing within reach for the whole step, nothing moving) skip
+  // contact detection; the bound on the hinge point's travel is conservative.
   unsigned char fl = D.flags[e];
   int err = (fl & F_PHYS_ERROR) ? 1 : 0;  // a physics error is sticky until the env is reset
-  // conservative bound on how far the hinge point can move during this step (see DESIGN.md "quiet path")
   const double tstep = kPtNsub * kPtH;
   double speed = sqrt(R.v[0] * R.v[0] + R.v[1] * R.v[1]), wabs = fabs(R.v[2]);
   double alpha_max = 750.0 + 200.0 * wabs, wmax = wabs + alpha_max * tstep;
   double a_bound = 2.0 * (R.gear_x * kPtForceLim + R.damp_xy * speed) / kPtM + (kPtMc / kPtM) * (alpha_max + wmax * wmax);
   double travel = tstep * speed + tstep * tstep * a_bound + 1e-3;
-  if (D.clear[e] > travel) {
+  const bool quiet = D.clear[e] > travel;
+#pragma unroll 1
+  for (int k = 0; k < kPtNsub; ++k) {
+    double sn, cs, fs[3], fc[3] = {0.0, 0.0, 0.0}, rhs[3], a[3];
+    sag_sincos(R.q[2], &sn, &cs);
+    pt_smooth(R, sn, cs, fs);
+    if (!quiet) {
+      Phys P;
+      contact_pass(C, R, sn, cs, K, fs, mov, true, h, P);
+      fc[0] = P.fc[0]; fc[1] = P.fc[1]; fc[2] = P.fc[2];
+      mov = P.mov;
+      if (P.err) err = 1;
+    }
+    rhs[0] = fs[0] + fc[0]; rhs[1] = fs[1] + fc[1]; rhs[2] = fs[2] + fc[2];
+    pt_solve(-kPtMc * sn, kPtMc * cs, K.iah, K.ish, rhs, a);   // (M + hD) a = f: implicit joint damping
 #pragma unroll
-    for (int k = 0; k < kPtNsub; ++k) pt_substep_free(R, h, err);
-  } else {
-    for (int k = 0; k < kPtNsub; ++k) substep_full(C, R, h, err);
+    for (int d = 0; d < 3; ++d) R.v[d] += h * a[d];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) R.q[d] += h * R.v[d];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) if (bad_val(R.q[d]) || bad_val(R.v[d]) || bad_val(a[d])) err = 1;
+    time += h;
   }
-#pragma unroll
-  for (int k = 0; k < kPtNsub; ++k) time += h;
-  double rew[2] = {0.0, 0.0};
-  double cst = 0.0;
+  EndOut O;
+  end_of_step(C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
   unsigned char dn = 0;
-  PostOut P;
-  forward_any(C, R, P);  // :76
-  if (err || P.err) {    // :73-75 PhysicsError
-    rew[0] = -10.0; cst = 0.0; dn = 1; fl |= F_PHYS_ERROR;
-  } else {
-    if (compute_reward(C, rng, R, T, P.touch, rew)) fl |= F_RESAMPLE_FAILED;  // :77
-    cst = compute_cost(C, R, P.touch);                                        // :78
-  }
-  write_obs(C, R, T, P.qacc, obs_s, ostride);  // :80
+  if (err || O.err) { dn = 1; fl |= F_PHYS_ERROR; }
+  if (O.resample_failed) fl |= F_RESAMPLE_FAILED;
   // bookkeeping
   int ns = D.nstep[e] + 1;
   if (D.max_episode_steps > 0 && ns >= D.max_episode_steps) fl |= F_NEEDS_RESET;
   if (dn) fl |= F_NEEDS_RESET;
   D.nstep[e] = ns;
-  D.epret[e] += rew[0];
-  D.epcost[e] += cst;
+  D.epret[e] += O.rew[0];
+  D.epcost[e] += O.cost;
   D.flags[e] = fl;
   D.time[e] = time;
-  D.clear[e] = P.clear;
+  D.clear[e] = O.clear;
+  D.movmask[e] = (int)O.mov;
   store_robot(D, e, R);
   store_task_state(D, e, T);
-  reward2[0] = rew[0]; reward2[1] = rew[1];
-  *cost = (unsigned char)(cst > 0.0);
+  reward2[0] = O.rew[0]; reward2[1] = O.rew[1];
+  *cost = (unsigned char)(O.cost > 0.0);
   *done = dn;
 }
 
-// observation at the current state (reset return value / state injection refresh)
+// observation at the current state (reset return value / refresh after state injection)
 SAG_HD void env_observe(const Dev& D, int e, float* obs_s, int ostride) {
   Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
   C.L = make_slots(C.sp);
@@ -1058,10 +1108,18 @@ SAG_HD void env_observe(const Dev& D, int e, float* obs_s, int ostride) {
   load_robot(D, e, C.sp, R);
   TaskState T;
   load_task_state(D, e, T);
-  PostOut P;
-  forward_any(C, R, P);
-  write_obs(C, R, T, P.qacc, obs_s, ostride);
-  D.clear[e] = P.clear;
+  Rng rng = {D.seed, D.gid_base + (uint32_t)e, D.episode[e]};
+  const PtConst K = pt_const(R.damp_xy, kPtH);
+  unsigned mov = 0;  // rebuilt from the velocities: state may have been injected
+  for (int s = C.L.v0; s < C.L.n; ++s) {
+    if (!kind_movable(slot_kind(C.sp, C.L, s))) continue;
+    size_t i = oidx(D, s, e);
+    if (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0) mov |= 1u << s;
+  }
+  EndOut O;
+  end_of_step(C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
+  D.clear[e] = O.clear;
+  D.movmask[e] = (int)mov;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1149,6 +1207,7 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
   store_task_state(D, e, T);
   D.episode[e] = episode; D.nstep[e] = 0; D.time[e] = 0.0; D.epret[e] = 0.0; D.epcost[e] = 0.0; D.flags[e] = fl;
   D.clear[e] = -1.0;
+  D.movmask[e] = 0;
 }
 
 }  // namespace sag

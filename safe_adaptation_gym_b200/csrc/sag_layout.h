@@ -21,7 +21,7 @@ inline SlabLayout slab_layout(int n, int stride, int obs_dim) {
   L.bytes[SAG_F_ROBOT] = 6 * st * sizeof(double);
   L.bytes[SAG_F_OBJECTS] = 6 * (size_t)SAG_MAX_SLOTS * st * sizeof(double);
   L.bytes[SAG_F_TASK_F64] = 12 * st * sizeof(double);
-  L.bytes[SAG_F_TASK_I32] = 9 * st * sizeof(int32_t);
+  L.bytes[SAG_F_TASK_I32] = 10 * st * sizeof(int32_t);
   L.bytes[SAG_F_FLAGS] = st;
   size_t total = 0;
   for (int f = 0; f < SAG_NUM_FIELDS; ++f) { L.off[f] = total; total += align_up(L.bytes[f], 256); }
@@ -47,7 +47,7 @@ inline void slab_bind(Dev& D, const SlabLayout& L, char* base) {
   D.time = t + 6 * st; D.clear = t + 7 * st; D.epret = t + 8 * st; D.epcost = t + 9 * st; D.ctrl0 = t + 10 * st; D.ctrl1 = t + 11 * st;
   int32_t* ii = (int32_t*)(base + L.off[SAG_F_TASK_I32]);
   D.task = ii; D.gbtn = ii + st; D.bstate = ii + 2 * st; D.btimer = ii + 3 * st; D.amask = ii + 4 * st; D.cgtimer = ii + 5 * st;
-  D.nstep = ii + 6 * st; D.ctr = (unsigned*)(ii + 7 * st); D.episode = (unsigned*)(ii + 8 * st);
+  D.nstep = ii + 6 * st; D.ctr = (unsigned*)(ii + 7 * st); D.episode = (unsigned*)(ii + 8 * st); D.movmask = ii + 9 * st;
   D.flags = (unsigned char*)(base + L.off[SAG_F_FLAGS]);
 }
 

@@ -258,7 +258,7 @@ class BatchedSafeAdaptationGym:
             raise ResamplingError('Failed to generate goal')  # go_to_goal.py:80
 
     _FIELDS = {'robot': (_abi.F_ROBOT, torch.float64, (6,)), 'objects': (_abi.F_OBJECTS, torch.float64, (6, _abi.MAX_SLOTS)),
-               'task_f64': (_abi.F_TASK_F64, torch.float64, (12,)), 'task_i32': (_abi.F_TASK_I32, torch.int32, (9,)),
+               'task_f64': (_abi.F_TASK_F64, torch.float64, (12,)), 'task_i32': (_abi.F_TASK_I32, torch.int32, (10,)),
                'flags': (_abi.F_FLAGS, torch.uint8, ())}
 
     def get_field(self, name: str) -> torch.Tensor:

@@ -225,6 +225,13 @@ class FakeBridge:
             pos = [float(t) for t in body.get("pos").split()]
             quat = [float(t) for t in body.get("quat").split()]
             yaw = 2.0 * np.arctan2(quat[3], quat[0])
+            # the XML carries rot2quat(theta) (utils.py:92-94); recover the exact drawn theta = 2*pi*u from the
+            # recorded draws so that the injected world is bit-identical to what the oracle's own reset builds
+            cands = [0.0 + (2 * np.pi - 0.0) * ev[1] for ev in EVENTS if ev[0] == "uniform"]
+            if cands:
+                best = min(cands, key=lambda c: abs(((c - yaw + np.pi) % (2 * np.pi)) - np.pi))
+                if abs(((best - yaw + np.pi) % (2 * np.pi)) - np.pi) < 1e-9:
+                    yaw = best
             geom = body.find("geom")
             type_ = next(t for p, t in _PREFIX_TYPE if name.startswith(p))
             group = int(float(geom.get("user")))

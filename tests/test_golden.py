@@ -72,7 +72,7 @@ def test_episode_matches_reference_step_loop(ep):
         assert e.reset(k) == 0
         np.testing.assert_allclose(e.robot_state, seg["layout"]["robot"], rtol=0, atol=1e-14)
         ref_objs = np.asarray(seg["layout"]["objects"])
-        np.testing.assert_allclose(e.objects()[:, 2:], ref_objs[:, 2:], rtol=0, atol=1e-13)
+        np.testing.assert_array_equal(e.objects()[:, 2:], ref_objs[:, 2:])
         np.testing.assert_array_equal(e.objects()[:, 1], ref_objs[:, 1])
         np.testing.assert_allclose(e.observation(), seg["obs0"], rtol=1e-12, atol=1e-13)
         for t, a in enumerate(seg["actions"]):
@@ -86,7 +86,7 @@ def test_episode_matches_reference_step_loop(ep):
             else:
                 np.testing.assert_allclose(rew[0], ref_r[0], rtol=1e-10, atol=1e-13, err_msg=msg)
             assert cost == seg["cost"][t], msg
-            np.testing.assert_allclose(obs, seg["obs"][t], rtol=1e-11, atol=1e-13, err_msg=msg)
+            np.testing.assert_allclose(obs, seg["obs"][t], rtol=1e-9, atol=1e-11, err_msg=msg)  # alias = frac(angle/bin) is ill-conditioned near 0
         np.testing.assert_allclose(e.objects()[:, 2:], np.asarray(seg["final_objects"])[:, 2:], rtol=0, atol=1e-11)
     assert e.replay_pos == len(ep["replay"])
 
