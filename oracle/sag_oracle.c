@@ -82,6 +82,7 @@ struct orc_env {
   int error;
   int tendon_slot; /* haul_box.py:21-30; -1 = none */
   int touched[ORC_MAX_OBJ]; /* movable body had an active constraint row in the last forward pass */
+  int overflow;             /* contact / body limit exceeded in the last forward pass: constraint solve skipped */
   /* world / task (world.py, tasks/ *.py) */
   double extents[4];
   int has_rect[ORC_MAX_OBJ];
@@ -334,7 +335,7 @@ static void obj_mass(const orc_env* e, int type, double* m, double* iz, double* 
  * ---------------------------------------------------------------------------------------- */
 static void add_contacts(orc_env* e, int n, const double* o, int ba, int bb, int sa, int sb, int ga, int gb) {
   for (int k = 0; k < n; ++k) {
-    if (e->ncon >= ORC_MAX_CON) { e->error = 1; return; }
+    if (e->ncon >= ORC_MAX_CON) { e->error = 1; e->overflow = 1; return; }
     orc_contact* c = &e->con[e->ncon++];
     c->ba = ba; c->bb = bb; c->sa = sa; c->sb = sb; c->ga = ga; c->gb = gb;
     c->nx = o[5 * k]; c->ny = o[5 * k + 1]; c->px = o[5 * k + 2]; c->py = o[5 * k + 3]; c->dist = o[5 * k + 4];
@@ -343,6 +344,7 @@ static void add_contacts(orc_env* e, int n, const double* o, int ba, int bb, int
 
 static void detect(orc_env* e) {
   e->ncon = 0;
+  e->overflow = 0;
   int active[ORC_MAX_OBJ];
   double o[10];
   for (int s = 0; s < e->nobj; ++s) {
@@ -537,6 +539,10 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
     if (!obj_movable(o->type)) continue;
     if (touched[s] || o->vx != 0.0 || o->vy != 0.0 || o->w != 0.0) flslot[nfl++] = s;
   }
+  /* capacity limits (the GPU keeps the solver's working set in shared memory): on overflow the step is a
+   * PhysicsError and this pass applies no constraint forces and moves no object */
+  if (nfl > ORC_MAX_BODIES) { e->error = 1; e->overflow = 1; }
+  if (e->overflow) { nrow = 0; nfl = 0; tendon_row = -1; for (int s = 0; s < e->nobj; ++s) touched[s] = 0; }
   const double rr = (1.0 - IMP_D0) / IMP_D0;
   /* Projected Gauss-Seidel.  Row update: f <- proj(f - (J a - aref + R f) / (A_ii + R)); the reciprocal of the
    * denominator is taken once per row.  Terminates after PGS_SWEEPS sweeps or when one sweep changes the forces by
@@ -627,6 +633,7 @@ void orc_phys_step(orc_env* e, int nstep) {
       if (!obj_movable(o->type)) continue;
       int touched = e->touched[s];
       if (!(touched || o->vx != 0.0 || o->vy != 0.0 || o->w != 0.0)) continue;
+      if (e->overflow) continue;
       o->vx += e->h * e->oacc[s][0]; o->vy += e->h * e->oacc[s][1]; o->w += e->h * e->oacc[s][2];
       if (!touched && o->vx * o->vx + o->vy * o->vy < SLEEP_V * SLEEP_V && fabs(o->w) < SLEEP_V) { o->vx = o->vy = o->w = 0.0; }
       o->x += e->h * o->vx; o->y += e->h * o->vy; o->yaw += e->h * o->w;

@@ -30,7 +30,8 @@ extern "C" {
 #endif
 
 #define ORC_MAX_OBJ 32
-#define ORC_MAX_CON 24
+#define ORC_MAX_CON 16      /* contacts per forward pass; more -> PhysicsError (MuJoCo: nconmax) */
+#define ORC_MAX_BODIES 8    /* movable bodies with constraint rows per forward pass; more -> PhysicsError */
 #define ORC_MAX_PARTS 5
 #define ORC_NUM_LIDAR_BINS 16   /* safe_adaptation_gym.py:22 */
 #define ORC_OBS_MAX 72          /* car: 48 + 24 */

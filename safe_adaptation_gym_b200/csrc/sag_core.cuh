@@ -21,6 +21,13 @@
 #define SAG_HD_NOINLINE
 #endif
 
+#if defined(SAG_PROFILE) && !defined(__CUDACC__)
+extern long* sag_prof_ptr;  // tests/hostemu instrumentation: per-env work counters [n][8]
+#define SAG_PROF(e, i, n) do { if (sag_prof_ptr) sag_prof_ptr[(size_t)(e) * 8 + (i)] += (n); } while (0)
+#else
+#define SAG_PROF(e, i, n) do { } while (0)
+#endif
+
 namespace sag {
 
 // ------------------------------------------------------------------------------------------------
@@ -59,7 +66,7 @@ constexpr int kSweeps = 10;
 constexpr double kPgsTol = 1e-8;
 constexpr double kSleepV = 1e-8;
 constexpr int kMaxObj = 32;
-constexpr int kMaxCon = 24;
+constexpr int kMaxCon = 16;
 constexpr double kRobotReach = 0.16;    // >= |hinge -> far arrow corner| = hypot(0.15, 0.05)
 
 // point robot mass properties (MuJoCo uniform-density rule, density 1, point.xml:5,18-19)
@@ -391,12 +398,24 @@ SAG_HD double impedance(double r) {
 // collision detection in the oracle's canonical order, soft-constraint rows, projected Gauss-Seidel,
 // optional integration of the movable bodies.  Work is proportional to the objects actually involved.
 // ------------------------------------------------------------------------------------------------
-struct Con { int ba, bb; double nx, ny, px, py, dist; };
+struct Con { int ba, bb; double nx, ny, px, py, dist; };  // ba/bb: -1 static, 0 robot, 1 + slot movable object
 struct Row {  // one contact (normal k=0, tangent k=1) or the tendon limit (k=0 only)
-  int ba, bb;
+  int ba, bb;                 // indices into Scratch::acc (-1 static, 0 robot, 1 + compact body id)
   double ja[2][3], jb[2][3];  // Jacobian rows w.r.t. body a / b
   double wa[2][3], wb[2][3];  // M^-1 J^T, precomputed
   double aref[2], R[2], inv[2], f[2];
+};
+constexpr int kMaxBodies = 8;  // movable bodies with constraint rows in one forward pass
+
+// Working set of the contact solver.  On the device one Scratch lives in shared memory per WARP and the lanes
+// that need the contact path take turns (k_step's warp_contact_pass): local memory would put every access of
+// this latency-bound code on an L2/DRAM round trip.
+struct Scratch {
+  Con con[kMaxCon];
+  Row rows[kMaxCon + 1];
+  double acc[kMaxBodies + 1][3];
+  double ffl[kMaxBodies][3];
+  int bslot[kMaxBodies];
 };
 
 struct Ctx {  // per-thread view of one environment
@@ -416,21 +435,30 @@ struct Phys {
 };
 
 SAG_HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+SAG_HD int ctz32(unsigned m) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
 
 SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, double cs, const PtConst& K, const double* fs,
-                                  unsigned mov, bool integrate, double h, Phys& P) {
+                                  unsigned mov, bool integrate, double h, Scratch& S, Phys& P) {
   const Dev& D = C.D;
   const int e = C.e;
   const double p = -kPtMc * sn, q = kPtMc * cs;
-  Con con[kMaxCon];
+  Con* con = S.con;
   int ncon = 0;
   unsigned active = mov, touch = 0;
+  bool overflow = false;
   P.err = 0;
   Geom gr[2];
   gr[0].is_box = 0; gr[0].cx = R.q[0]; gr[0].cy = R.q[1]; gr[0].c = cs; gr[0].s = sn; gr[0].r = kPtR; gr[0].hx = gr[0].hy = 0.0;
   gr[1].is_box = 1; gr[1].cx = R.q[0] + kPtArrowOff * cs; gr[1].cy = R.q[1] + kPtArrowOff * sn; gr[1].c = cs; gr[1].s = sn;
   gr[1].hx = gr[1].hy = kPtArrowH; gr[1].r = 0.0;
   Hit hits[2];
+  SAG_PROF(e, 0, 1);
   // ---- phase 1: robot geoms vs objects, slot order
   for (int s = C.L.v0; s < C.L.n; ++s) {
     int kind = slot_kind(C.sp, C.L, s);
@@ -447,8 +475,9 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
         Geom go;
         obj_geom(D, kind, pt, x, y, oc, os, go);
         int n = collide(gr[rg], go, hits);
+        SAG_PROF(e, 1, 1);
         for (int k = 0; k < n; ++k) {
-          if (ncon >= kMaxCon) { P.err = 1; break; }
+          if (ncon >= kMaxCon) { overflow = true; break; }
           Con& c = con[ncon++];
           c.ba = 0; c.bb = mvb ? 1 + s : -1;
           c.nx = hits[k].nx; c.ny = hits[k].ny; c.px = hits[k].px; c.py = hits[k].py; c.dist = hits[k].dist;
@@ -470,13 +499,14 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
       bool mj = kind_movable(kj);
       double cj = 1.0, sj = 0.0;
       bool have_j = false;
-      for (int i = C.L.v0; i < j; ++i) {
-        if (!((cand >> i) & 1u)) continue;
+      for (unsigned cm = cand; cm; cm &= cm - 1) {
+        int i = ctz32(cm);
         int ki = slot_kind(C.sp, C.L, i);
         if (!kind_collidable(ki)) continue;
         size_t ii = oidx(D, i, e);
         double xi = D.ox[ii], yi = D.oy[ii];
         double dx = xj - xi, dy = yj - yi, reach = bj + kind_bound(D, ki);
+        SAG_PROF(e, 6, 1);
         if (dx * dx + dy * dy > reach * reach) continue;
         bool mi = kind_movable(ki);
         double ci = 1.0, si = 0.0;
@@ -489,8 +519,9 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
             Geom gj;
             obj_geom(D, kj, pj, xj, yj, cj, sj, gj);
             int n = collide(gi, gj, hits);
+            SAG_PROF(e, 1, 1);
             for (int k = 0; k < n; ++k) {
-              if (ncon >= kMaxCon) { P.err = 1; break; }
+              if (ncon >= kMaxCon) { overflow = true; break; }
               Con& c = con[ncon++];
               c.ba = mi ? 1 + i : -1; c.bb = mj ? 1 + j : -1;
               c.nx = hits[k].nx; c.ny = hits[k].ny; c.px = hits[k].px; c.py = hits[k].py; c.dist = hits[k].dist;
@@ -502,10 +533,19 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
   }
   P.touch = touch;
   P.mov = mov;
+  SAG_PROF(e, 2, ncon);
   P.fc[0] = P.fc[1] = P.fc[2] = 0.0;
   // ---- which constraint rows exist?
-  int nact = 0;
-  for (int i = 0; i < ncon; ++i) if (con[i].dist < 0.0 && !(con[i].ba < 0 && con[i].bb < 0)) ++nact;
+  unsigned touched = 0;
+  for (int i = 0; i < ncon; ++i) {
+    const Con& c = con[i];
+    if (!(c.dist < 0.0) || (c.ba < 0 && c.bb < 0)) continue;
+    touched |= 0x80000000u;  // marker: at least one active row (slot 31 is never a movable body)
+    if (c.ba > 0) touched |= 1u << (c.ba - 1);
+    if (c.bb > 0) touched |= 1u << (c.bb - 1);
+  }
+  const bool any_row = (touched & 0x80000000u) != 0;
+  touched &= 0x7fffffffu;
   double tdx = 0.0, tdy = 0.0, tlen = 0.0, tdist = 0.0;
   bool tendon = false;
   if (C.task == T_HAUL_BOX) {  // tendon length limit, haul_box.py:21-30
@@ -515,21 +555,30 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
     tlen = sqrt(tdx * tdx + tdy * tdy + dz * dz);
     tdist = kTendonMax - tlen;
     tendon = tdist < 0.0;
+    if (tendon) touched |= 1u << C.L.box;
   }
   double racc[3];
   pt_solve(p, q, K.ia0, K.is0, fs, racc);
-  if (nact == 0 && !tendon && mov == 0) {  // nothing to solve, nothing to move
-    P.qacc[0] = racc[0]; P.qacc[1] = racc[1]; P.qacc[2] = racc[2];
-    return;
-  }
-  // ---- body tables (only involved bodies are ever touched)
-  double vim, vii, vrf, bim, bii, brf;
-  { double m, iz; kind_mass(D, K_VASE, m, iz, vrf); vim = 1.0 / m; vii = 1.0 / iz; }
-  { double m, iz; kind_mass(D, K_BOX, m, iz, brf); bim = 1.0 / m; bii = 1.0 / iz; }
-  auto is_box_body = [&](int body) { return body - 1 == C.L.box; };
+  P.qacc[0] = racc[0]; P.qacc[1] = racc[1]; P.qacc[2] = racc[2];
+  const unsigned fl = touched | mov;  // floor-friction bodies: awake or touched, slot order
+  // capacity limits: a PhysicsError; no constraint forces, no object motion in this pass
+  int nb = 0;
+  for (unsigned m = fl; m; m &= m - 1) ++nb;
+  if (nb > kMaxBodies) overflow = true;
+  if (overflow) { P.err = 1; return; }
+  if (!any_row && !tendon && mov == 0) return;  // nothing to solve, nothing to move
+  // ---- body table: compact ids in slot order
+  nb = 0;
+  for (unsigned m = fl; m; m &= m - 1) S.bslot[nb++] = ctz32(m);
+  auto cid = [&](int slot) { int k = 0; while (S.bslot[k] != slot) ++k; return k; };
+  double vim, vii, vrf, bim, bii, brf, vmass, bmass;
+  { double iz; kind_mass(D, K_VASE, vmass, iz, vrf); vim = 1.0 / vmass; vii = 1.0 / iz; }
+  { double iz; kind_mass(D, K_BOX, bmass, iz, brf); bim = 1.0 / bmass; bii = 1.0 / iz; }
+  // body < 0 static, 0 robot, 1 + slot movable
   auto minv = [&](int body, const double* j, double* o) {
     if (body == 0) { pt_solve(p, q, K.ia0, K.is0, j, o); return; }
-    double im = is_box_body(body) ? bim : vim, ii = is_box_body(body) ? bii : vii;
+    const bool isb = body - 1 == C.L.box;
+    double im = isb ? bim : vim, ii = isb ? bii : vii;
     o[0] = j[0] * im; o[1] = j[1] * im; o[2] = j[2] * ii;
   };
   auto bvel = [&](int body, double* v) {
@@ -540,21 +589,20 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
     if (body == 0) { o[0] = R.q[0]; o[1] = R.q[1]; }
     else { size_t i = oidx(D, body - 1, e); o[0] = D.ox[i]; o[1] = D.oy[i]; }
   };
-  Row rows[kMaxCon + 1];
+  Row* rows = S.rows;
   int nrow = 0, tendon_row = -1;
-  unsigned touched = 0;
   const double bdamp = 2.0 / (kImpDmax * kSolTc);
   const double kbase = 1.0 / (kImpDmax * kImpDmax * kSolTc * kSolTc);
   for (int i = 0; i < ncon; ++i) {
-    const Con& c = con[i];
+    const Con c = con[i];
     if (!(c.dist < 0.0)) continue;
     if (c.ba < 0 && c.bb < 0) continue;
     Row& r = rows[nrow++];
-    r.ba = c.ba; r.bb = c.bb;
+    r.ba = c.ba > 0 ? 1 + cid(c.ba - 1) : c.ba; r.bb = c.bb > 0 ? 1 + cid(c.bb - 1) : c.bb;
     double tx = -c.ny, ty = c.nx;
     double pa[2] = {0, 0}, pb[2] = {0, 0}, va[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
-    if (c.ba >= 0) { bpos(c.ba, pa); bvel(c.ba, va); if (c.ba > 0) touched |= 1u << (c.ba - 1); }
-    if (c.bb >= 0) { bpos(c.bb, pb); bvel(c.bb, vb); if (c.bb > 0) touched |= 1u << (c.bb - 1); }
+    if (c.ba >= 0) { bpos(c.ba, pa); bvel(c.ba, va); }
+    if (c.bb >= 0) { bpos(c.bb, pb); bvel(c.bb, vb); }
     double rax = c.px - pa[0], ray = c.py - pa[1], rbx = c.px - pb[0], rby = c.py - pb[1];
     r.ja[0][0] = -c.nx; r.ja[0][1] = -c.ny; r.ja[0][2] = -(rax * c.ny - ray * c.nx);
     r.jb[0][0] = c.nx; r.jb[0][1] = c.ny; r.jb[0][2] = rbx * c.ny - rby * c.nx;
@@ -573,76 +621,75 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
   }
   if (tendon) {
     Row& r = rows[nrow]; tendon_row = nrow++;
-    r.ba = 0; r.bb = 1 + C.L.box;
+    const int bbox = 1 + C.L.box;
+    r.ba = 0; r.bb = 1 + cid(C.L.box);
     r.ja[0][0] = tdx / tlen; r.ja[0][1] = tdy / tlen; r.ja[0][2] = 0.0;
     r.jb[0][0] = -tdx / tlen; r.jb[0][1] = -tdy / tlen; r.jb[0][2] = 0.0;
     double va[3], vb[3], diag = 0.0;
-    bvel(0, va); bvel(r.bb, vb);
+    bvel(0, va); bvel(bbox, vb);
     minv(0, r.ja[0], r.wa[0]); diag += dot3(r.ja[0], r.wa[0]);
-    minv(r.bb, r.jb[0], r.wb[0]); diag += dot3(r.jb[0], r.wb[0]);
+    minv(bbox, r.jb[0], r.wb[0]); diag += dot3(r.jb[0], r.wb[0]);
     double d = impedance(tdist);
     r.R[0] = (1.0 - d) / d * diag;
     r.inv[0] = 1.0 / (diag + r.R[0]);
     r.aref[0] = -bdamp * (dot3(r.ja[0], va) + dot3(r.jb[0], vb)) - d * kbase * tdist;
     r.f[0] = 0.0;
-    touched |= 1u << C.L.box;
   }
-  // body accelerations: acc[0] = robot, acc[1 + slot] = movable object; only involved bodies are initialised
-  const unsigned fl = touched | mov;  // floor-friction bodies: awake or touched, slot order
-  double acc[kMaxObj + 1][3], ffl[kMaxObj][3];
+  // body accelerations: acc[0] = robot, acc[1 + compact id] = movable object
+  double (*acc)[3] = S.acc;
+  double (*ffl)[3] = S.ffl;
   acc[0][0] = racc[0]; acc[0][1] = racc[1]; acc[0][2] = racc[2];
-  for (unsigned m = fl; m; m &= m - 1) {
-    int s = 0; for (unsigned t = m; !(t & 1u); t >>= 1) ++s;
-    acc[1 + s][0] = acc[1 + s][1] = acc[1 + s][2] = 0.0; ffl[s][0] = ffl[s][1] = ffl[s][2] = 0.0;
-  }
+  for (int b = 0; b < nb; ++b) { acc[1 + b][0] = acc[1 + b][1] = acc[1 + b][2] = 0.0; ffl[b][0] = ffl[b][1] = ffl[b][2] = 0.0; }
   const double rr = (1.0 - kImpD0) / kImpD0;
   const double v_inv_lin = 1.0 / (vim + rr * vim), v_inv_tor = 1.0 / (vii + rr * vii);
   const double b_inv_lin = 1.0 / (bim + rr * bim), b_inv_tor = 1.0 / (bii + rr * bii);
-  double vmass, bmass;
-  { double iz, rf; kind_mass(D, K_VASE, vmass, iz, rf); kind_mass(D, K_BOX, bmass, iz, rf); }
   // projected Gauss-Seidel; stops after kSweeps sweeps or when a sweep changes the forces by < kPgsTol (relative, L1)
   for (int it = 0; it < kSweeps; ++it) {
     double sdf = 0.0, sf = 0.0;
     for (int i = 0; i < nrow; ++i) {
       Row& r = rows[i];
       const int nk = (i == tendon_row) ? 1 : 2;
+      const int ba = r.ba, bb = r.bb;
       for (int k = 0; k < nk; ++k) {
+        SAG_PROF(e, 4, 1);
         double a = 0.0;
-        if (r.ba >= 0) a += dot3(r.ja[k], acc[r.ba]);
-        if (r.bb >= 0) a += dot3(r.jb[k], acc[r.bb]);
-        double fn = r.f[k] - (a - r.aref[k] + r.R[k] * r.f[k]) * r.inv[k];
+        if (ba >= 0) a += dot3(r.ja[k], acc[ba]);
+        if (bb >= 0) a += dot3(r.jb[k], acc[bb]);
+        const double fo = r.f[k];
+        double fn = fo - (a - r.aref[k] + r.R[k] * fo) * r.inv[k];
         if (k == 0) { if (fn < 0.0) fn = 0.0; }
         else { double lim = kMu * r.f[0]; fn = clampd(fn, -lim, lim); }
-        double df = fn - r.f[k];
+        double df = fn - fo;
         r.f[k] = fn;
         sdf += fabs(df); sf += fabs(fn);
         if (df != 0.0) {
-          if (r.ba >= 0) { double* ac = acc[r.ba]; ac[0] += r.wa[k][0] * df; ac[1] += r.wa[k][1] * df; ac[2] += r.wa[k][2] * df; }
-          if (r.bb >= 0) { double* ac = acc[r.bb]; ac[0] += r.wb[k][0] * df; ac[1] += r.wb[k][1] * df; ac[2] += r.wb[k][2] * df; }
+          if (ba >= 0) { double* ac = acc[ba]; ac[0] += r.wa[k][0] * df; ac[1] += r.wa[k][1] * df; ac[2] += r.wa[k][2] * df; }
+          if (bb >= 0) { double* ac = acc[bb]; ac[0] += r.wb[k][0] * df; ac[1] += r.wb[k][1] * df; ac[2] += r.wb[k][2] * df; }
         }
       }
     }
-    for (unsigned m = fl; m; m &= m - 1) {
-      int s = 0; for (unsigned t = m; !(t & 1u); t >>= 1) ++s;
+    for (int b = 0; b < nb; ++b) {
+      SAG_PROF(e, 5, 1);
+      const int s = S.bslot[b];
       const bool isb = s == C.L.box;
       const double Al = isb ? bim : vim, At = isb ? bii : vii, rf = isb ? brf : vrf;
       const double inv_lin = isb ? b_inv_lin : v_inv_lin, inv_tor = isb ? b_inv_tor : v_inv_tor;
       const double lim = kMu * (isb ? bmass : vmass) * kGrav;
       size_t i = oidx(D, s, e);
       double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
-      double* ac = acc[1 + s];
-      double f0 = ffl[s][0] - (ac[0] + bdamp * vx + rr * Al * ffl[s][0]) * inv_lin;
-      double f1 = ffl[s][1] - (ac[1] + bdamp * vy + rr * Al * ffl[s][1]) * inv_lin;
+      double* ac = acc[1 + b];
+      double f0 = ffl[b][0] - (ac[0] + bdamp * vx + rr * Al * ffl[b][0]) * inv_lin;
+      double f1 = ffl[b][1] - (ac[1] + bdamp * vy + rr * Al * ffl[b][1]) * inv_lin;
       double nf = sqrt(f0 * f0 + f1 * f1);
       if (nf > lim) { double sc = lim / nf; f0 *= sc; f1 *= sc; }
-      double d0 = f0 - ffl[s][0], d1 = f1 - ffl[s][1];
+      double d0 = f0 - ffl[b][0], d1 = f1 - ffl[b][1];
       ac[0] += d0 * Al; ac[1] += d1 * Al;
-      ffl[s][0] = f0; ffl[s][1] = f1;
-      double f2 = ffl[s][2] - (ac[2] + bdamp * w + rr * At * ffl[s][2]) * inv_tor;
+      ffl[b][0] = f0; ffl[b][1] = f1;
+      double f2 = ffl[b][2] - (ac[2] + bdamp * w + rr * At * ffl[b][2]) * inv_tor;
       f2 = clampd(f2, -lim * rf, lim * rf);
-      double d2 = f2 - ffl[s][2];
+      double d2 = f2 - ffl[b][2];
       ac[2] += d2 * At;
-      ffl[s][2] = f2;
+      ffl[b][2] = f2;
       sdf += fabs(d0) + fabs(d1) + fabs(d2); sf += fabs(f0) + fabs(f1) + fabs(f2);
     }
     if (sdf <= kPgsTol * sf) break;
@@ -658,18 +705,37 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
   }
   if (!integrate) return;
   // ---- semi-implicit Euler for the awake / touched movable bodies (free joints: no damping)
-  for (unsigned m = fl; m; m &= m - 1) {
-    int s = 0; for (unsigned t = m; !(t & 1u); t >>= 1) ++s;
+  for (int b = 0; b < nb; ++b) {
+    const int s = S.bslot[b];
     size_t i = oidx(D, s, e);
     double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
     bool tch = (touched >> s) & 1u;
-    vx += h * acc[1 + s][0]; vy += h * acc[1 + s][1]; w += h * acc[1 + s][2];
+    vx += h * acc[1 + b][0]; vy += h * acc[1 + b][1]; w += h * acc[1 + b][2];
     if (!tch && vx * vx + vy * vy < kSleepV * kSleepV && fabs(w) < kSleepV) { vx = vy = w = 0.0; }
     double x = D.ox[i] + h * vx, y = D.oy[i] + h * vy, yaw = D.oyaw[i] + h * w;
     D.ovx[i] = vx; D.ovy[i] = vy; D.ow[i] = w; D.ox[i] = x; D.oy[i] = y; D.oyaw[i] = yaw;
     if (vx != 0.0 || vy != 0.0 || w != 0.0) P.mov |= 1u << s; else P.mov &= ~(1u << s);
     if (bad_val(x) || bad_val(y) || bad_val(vx) || bad_val(vy) || bad_val(w)) P.err = 1;
   }
+}
+
+// The lanes of a warp that need the contact path take turns on the warp's shared-memory Scratch.  `wmask` = lanes of
+// this warp that own an environment (all of them call this function together).  On the host there is one lane.
+SAG_HD void warp_contact_pass(unsigned wmask, bool need, const Ctx& C, const Robot& R, double sn, double cs, const PtConst& K,
+                              const double* fs, unsigned mov, bool integrate, double h, Scratch* S, Phys& P) {
+#if defined(__CUDA_ARCH__)
+  unsigned todo = __ballot_sync(wmask, need);
+  const int lane = threadIdx.x & 31;
+  while (todo) {
+    const int turn = __ffs((int)todo) - 1;
+    todo &= todo - 1;
+    if (lane == turn) contact_pass(C, R, sn, cs, K, fs, mov, integrate, h, *S, P);
+    __syncwarp(wmask);
+  }
+#else
+  (void)wmask;
+  if (need) contact_pass(C, R, sn, cs, K, fs, mov, integrate, h, *S, P);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -911,8 +977,8 @@ SAG_HD bool hazard_hit(double d2, double size) {  // world.py:151-152: ||robot_x
   return sqrt(d2) <= size;
 }
 
-SAG_HD void end_of_step(const Ctx& C, const Robot& R, TaskState& T, const Rng& rng, const PtConst& K, unsigned mov, bool phys_err,
-                        bool with_reward, float* obs_s, int ostride, EndOut& O) {
+SAG_HD void end_of_step(unsigned wmask, Scratch* S, const Ctx& C, const Robot& R, TaskState& T, const Rng& rng, const PtConst& K,
+                        unsigned mov, bool phys_err, bool with_reward, float* obs_s, int ostride, EndOut& O) {
   const Dev& D = C.D;
   const int e = C.e;
   double sn, cs;
@@ -960,16 +1026,15 @@ SAG_HD void end_of_step(const Ctx& C, const Robot& R, TaskState& T, const Rng& r
   unsigned touch = 0;
   O.err = 0;
   const bool tendon = C.task == T_HAUL_BOX;
-  if (clear > 0.0 && mov == 0 && !tendon) {
-    pt_solve(-kPtMc * sn, kPtMc * cs, K.ia0, K.is0, fs, qacc);
-  } else {
-    Phys P;
-    contact_pass(C, R, sn, cs, K, fs, mov, false, 0.0, P);
-    qacc[0] = P.qacc[0]; qacc[1] = P.qacc[1]; qacc[2] = P.qacc[2];
-    touch = P.touch;
-    O.err = P.err;
-    if (mov != 0 || tendon) clear = -1.0;
-  }
+  const bool need = !(clear > 0.0 && mov == 0 && !tendon);
+  Phys P;
+  P.err = 0; P.touch = 0;
+  if (!need) pt_solve(-kPtMc * sn, kPtMc * cs, K.ia0, K.is0, fs, P.qacc);
+  warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, P);
+  qacc[0] = P.qacc[0]; qacc[1] = P.qacc[1]; qacc[2] = P.qacc[2];
+  touch = P.touch;
+  O.err = P.err;
+  if (need && (mov != 0 || tendon)) clear = -1.0;
   O.clear = clear;
   O.mov = mov;
   // ---- reward (may resample the goal / change button groups) and cost
@@ -1018,8 +1083,8 @@ SAG_HD void store_robot(const Dev& D, int e, const Robot& R) {
 // ------------------------------------------------------------------------------------------------
 // SafeAdaptationGym.step for one environment (safe_adaptation_gym.py:56-83)
 // ------------------------------------------------------------------------------------------------
-SAG_HD void env_step(const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2, unsigned char* cost,
-                     unsigned char* done) {
+SAG_HD void env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2,
+                     unsigned char* cost, unsigned char* done) {
   Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
   C.L = make_slots(C.sp);
   Robot R;
@@ -1060,9 +1125,10 @@ SAG_HD void env_step(const Dev& D, int e, float a0, float a1, float* obs_s, int 
     double sn, cs, fs[3], fc[3] = {0.0, 0.0, 0.0}, rhs[3], a[3];
     sag_sincos(R.q[2], &sn, &cs);
     pt_smooth(R, sn, cs, fs);
-    if (!quiet) {
+    {
       Phys P;
-      contact_pass(C, R, sn, cs, K, fs, mov, true, h, P);
+      P.fc[0] = P.fc[1] = P.fc[2] = 0.0; P.mov = mov; P.err = 0;
+      warp_contact_pass(wmask, !quiet, C, R, sn, cs, K, fs, mov, true, h, S, P);
       fc[0] = P.fc[0]; fc[1] = P.fc[1]; fc[2] = P.fc[2];
       mov = P.mov;
       if (P.err) err = 1;
@@ -1078,7 +1144,7 @@ SAG_HD void env_step(const Dev& D, int e, float a0, float a1, float* obs_s, int 
     time += h;
   }
   EndOut O;
-  end_of_step(C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
+  end_of_step(wmask, S, C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
   unsigned char dn = 0;
   if (err || O.err) { dn = 1; fl |= F_PHYS_ERROR; }
   if (O.resample_failed) fl |= F_RESAMPLE_FAILED;
@@ -1101,7 +1167,7 @@ SAG_HD void env_step(const Dev& D, int e, float a0, float a1, float* obs_s, int 
 }
 
 // observation at the current state (reset return value / refresh after state injection)
-SAG_HD void env_observe(const Dev& D, int e, float* obs_s, int ostride) {
+SAG_HD void env_observe(unsigned wmask, Scratch* S, const Dev& D, int e, float* obs_s, int ostride) {
   Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
   C.L = make_slots(C.sp);
   Robot R;
@@ -1117,7 +1183,7 @@ SAG_HD void env_observe(const Dev& D, int e, float* obs_s, int ostride) {
     if (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0) mov |= 1u << s;
   }
   EndOut O;
-  end_of_step(C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
+  end_of_step(wmask, S, C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
   D.clear[e] = O.clear;
   D.movmask[e] = (int)mov;
 }

@@ -65,12 +65,14 @@ __global__ void __launch_bounds__(kBS) k_step(Dev D, const float* __restrict__ a
                                                double* __restrict__ reward, double* __restrict__ reward2,
                                                uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   __shared__ float tile[kObs * kTileStride];
+  __shared__ Scratch scratch[kBS / 32];  // contact-solver working set, one per warp
   const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
+  const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
   if (e < D.n) {
     float2 a = reinterpret_cast<const float2*>(act)[e];
     double rew[2];
     unsigned char c, d;
-    env_step(D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d);
+    env_step(wmask, &scratch[threadIdx.x >> 5], D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d);
     reward[e] = rew[0];
     if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
     cost[e] = c;
@@ -82,8 +84,10 @@ __global__ void __launch_bounds__(kBS) k_step(Dev D, const float* __restrict__ a
 
 __global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs) {
   __shared__ float tile[kObs * kTileStride];
+  __shared__ Scratch scratch[kBS / 32];
   const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
-  if (e < D.n) env_observe(D, e, tile + threadIdx.x, kTileStride);
+  const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
+  if (e < D.n) env_observe(wmask, &scratch[threadIdx.x >> 5], D, e, tile + threadIdx.x, kTileStride);
   __syncthreads();
   write_tile(tile, obs, e0, D.n);
 }
@@ -91,7 +95,9 @@ __global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs)
 __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __restrict__ obs, double* __restrict__ reward,
                                                   uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   __shared__ float tile[kObs * kTileStride];
+  __shared__ Scratch scratch[kBS / 32];
   const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
+  const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
   if (e < D.n) {
     double rew[2] = {0.0, 0.0};
     unsigned char c = 0, d = 0;
@@ -100,7 +106,8 @@ __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __re
     for (int k = 0; k < k_steps; ++k) {
       double u1, u2;
       rng.pair(2u, base + (uint32_t)k, u1, u2);
-      env_step(D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + threadIdx.x, kTileStride, rew, &c, &d);
+      env_step(wmask, &scratch[threadIdx.x >> 5], D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + threadIdx.x,
+               kTileStride, rew, &c, &d);
     }
     if (reward) reward[e] = rew[0];
     if (cost) cost[e] = c;

@@ -16,6 +16,11 @@
 #include "../../safe_adaptation_gym_b200/csrc/sag_core.cuh"
 #include "../../safe_adaptation_gym_b200/csrc/sag_layout.h"
 
+#ifdef SAG_PROFILE
+long* sag_prof_ptr = nullptr;
+extern "C" void sag_prof_set(long* p) { sag_prof_ptr = p; }
+#endif
+
 using namespace sag;
 
 namespace {
@@ -84,10 +89,11 @@ int sag_reset(void* h, const uint8_t* mask, int only_flagged, int new_task, void
 int sag_step(void* h, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done, void* s) {
   (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
   static float tile[kObs * kTileStride];
+  static Scratch scratch;
   for (int e0 = 0; e0 < D.n; e0 += kBS) {
     for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
       int e = e0 + t; double rew[2]; unsigned char c, d;
-      env_step(D, e, act[2 * e], act[2 * e + 1], tile + t, kTileStride, rew, &c, &d);
+      env_step(1u, &scratch, D, e, act[2 * e], act[2 * e + 1], tile + t, kTileStride, rew, &c, &d);
       reward[e] = rew[0];
       if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
       cost[e] = c; done[e] = d;
@@ -99,8 +105,9 @@ int sag_step(void* h, const float* act, float* obs, double* reward, double* rewa
 int sag_observe(void* h, float* obs, void* s) {
   (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
   static float tile[kObs * kTileStride];
+  static Scratch scratch;
   for (int e0 = 0; e0 < D.n; e0 += kBS) {
-    for (int t = 0; t < kBS && e0 + t < D.n; ++t) env_observe(D, e0 + t, tile + t, kTileStride);
+    for (int t = 0; t < kBS && e0 + t < D.n; ++t) env_observe(1u, &scratch, D, e0 + t, tile + t, kTileStride);
     write_tile(tile, obs, e0, D.n);
   }
   return 0;
@@ -108,6 +115,7 @@ int sag_observe(void* h, float* obs, void* s) {
 int sag_rollout(void* h, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* s) {
   (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
   static float tile[kObs * kTileStride];
+  static Scratch scratch;
   for (int e0 = 0; e0 < D.n; e0 += kBS) {
     for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
       int e = e0 + t; double rew[2] = {0, 0}; unsigned char c = 0, d = 0;
@@ -115,7 +123,7 @@ int sag_rollout(void* h, int k_steps, float* obs, double* reward, uint8_t* cost,
       uint32_t base = (uint32_t)D.nstep[e];
       for (int k = 0; k < k_steps; ++k) {
         double u1, u2; rng.pair(2u, base + (uint32_t)k, u1, u2);
-        env_step(D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + t, kTileStride, rew, &c, &d);
+        env_step(1u, &scratch, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + t, kTileStride, rew, &c, &d);
       }
       if (reward) reward[e] = rew[0];
       if (cost) cost[e] = c;
