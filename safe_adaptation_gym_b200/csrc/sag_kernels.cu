@@ -21,6 +21,8 @@ namespace {
 constexpr int kBS = 128;          // environments (threads) per CTA
 constexpr int kObs = SAG_OBS_POINT;
 constexpr int kTileStride = kBS + 1;
+constexpr size_t kTileBytes = (sizeof(float) * kObs * kTileStride + 15) / 16 * 16;
+constexpr size_t kSmemBytes = kTileBytes + sizeof(Scratch) * (kBS / 32);  // > 48 KB: opt-in dynamic shared memory
 
 thread_local char g_err[512] = "";
 
@@ -64,8 +66,9 @@ __device__ __forceinline__ void write_tile(const float* tile, float* out, int e0
 __global__ void __launch_bounds__(kBS) k_step(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                double* __restrict__ reward, double* __restrict__ reward2,
                                                uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
-  __shared__ float tile[kObs * kTileStride];
-  __shared__ Scratch scratch[kBS / 32];  // contact-solver working set, one per warp
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);                             // [kObs][kTileStride] observation tile
+  Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + kTileBytes);         // contact-solver working set, one per warp
   const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
   const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
   if (e < D.n) {
@@ -83,8 +86,9 @@ __global__ void __launch_bounds__(kBS) k_step(Dev D, const float* __restrict__ a
 }
 
 __global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs) {
-  __shared__ float tile[kObs * kTileStride];
-  __shared__ Scratch scratch[kBS / 32];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + kTileBytes);
   const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
   const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
   if (e < D.n) env_observe(wmask, &scratch[threadIdx.x >> 5], D, e, tile + threadIdx.x, kTileStride);
@@ -94,8 +98,9 @@ __global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs)
 
 __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __restrict__ obs, double* __restrict__ reward,
                                                   uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
-  __shared__ float tile[kObs * kTileStride];
-  __shared__ Scratch scratch[kBS / 32];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + kTileBytes);
   const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
   const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
   if (e < D.n) {
@@ -221,6 +226,9 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   if (cfg->robot != SAG_ROBOT_POINT) return fail("sag_create: only the point robot is implemented on the device path");
   if (cfg->robot_ctrl_range_scale != 0.0) return fail("sag_create: robot_ctrl_range_scale != 0 is not implemented");
   CK(cudaSetDevice(device));
+  CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  CK(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   Handle* H = new (std::nothrow) Handle();
   if (!H) return fail("sag_create: out of host memory");
   memset(H, 0, sizeof(*H));
@@ -298,7 +306,7 @@ int sag_step(void* handle, const float* act, float* obs, double* reward, double*
              void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !act || !obs || !reward || !cost || !done) return fail("sag_step: null argument");
-  k_step<<<grid_for(H->D.n), kBS, 0, (cudaStream_t)stream>>>(H->D, act, obs, reward, reward2, cost, done);
+  k_step<<<grid_for(H->D.n), kBS, kSmemBytes, (cudaStream_t)stream>>>(H->D, act, obs, reward, reward2, cost, done);
   CK(cudaGetLastError());
   return 0;
 }
@@ -306,7 +314,7 @@ int sag_step(void* handle, const float* act, float* obs, double* reward, double*
 int sag_observe(void* handle, float* obs, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !obs) return fail("sag_observe: null argument");
-  k_observe<<<grid_for(H->D.n), kBS, 0, (cudaStream_t)stream>>>(H->D, obs);
+  k_observe<<<grid_for(H->D.n), kBS, kSmemBytes, (cudaStream_t)stream>>>(H->D, obs);
   CK(cudaGetLastError());
   return 0;
 }
@@ -314,7 +322,7 @@ int sag_observe(void* handle, float* obs, void* stream) {
 int sag_rollout(void* handle, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || k_steps <= 0) return fail("sag_rollout: bad argument");
-  k_rollout<<<grid_for(H->D.n), kBS, 0, (cudaStream_t)stream>>>(H->D, k_steps, obs, reward, cost, done);
+  k_rollout<<<grid_for(H->D.n), kBS, kSmemBytes, (cudaStream_t)stream>>>(H->D, k_steps, obs, reward, cost, done);
   CK(cudaGetLastError());
   return 0;
 }
@@ -325,7 +333,7 @@ int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward
   cudaStream_t s = H->own_stream;
   const size_t n = (size_t)H->D.n;
   CK(cudaMemcpyAsync(H->act_d, act_h, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-  k_step<<<grid_for(H->D.n), kBS, 0, s>>>(H->D, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d);
+  k_step<<<grid_for(H->D.n), kBS, kSmemBytes, s>>>(H->D, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(obs_h, H->obs_d, n * kObs * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(reward_h, H->rew_d, n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -339,7 +347,7 @@ int sag_observe_host(void* handle, float* obs_h) {
   Handle* H = (Handle*)handle;
   if (!H || !obs_h) return fail("sag_observe_host: null argument");
   cudaStream_t s = H->own_stream;
-  k_observe<<<grid_for(H->D.n), kBS, 0, s>>>(H->D, H->obs_d);
+  k_observe<<<grid_for(H->D.n), kBS, kSmemBytes, s>>>(H->D, H->obs_d);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(obs_h, H->obs_d, (size_t)H->D.n * kObs * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
