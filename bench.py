@@ -158,19 +158,24 @@ def main():
     L, h = env._lib, env._h
     stream = torch.cuda.current_stream(dev)
     sp = C.c_void_p(stream.cuda_stream)
-    # synthetic actions, resident in HBM: a ring of 16 different U(-1,1) batches
+    # synthetic actions, resident in HBM: i.i.d. U(-1,1) per env per step (env.action_space.sample()), drawn on the device
+    # outside the timed event pair.  (A short cyclic ring of action batches would give every env a periodic action
+    # sequence, i.e. a systematic drift into obstacles -- not what a random policy does.)
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
-    ring = [(torch.rand((n, 2), device=dev, generator=g) * 2 - 1).contiguous() for _ in range(16)]
+    act_buf = torch.empty((n, 2), dtype=torch.float32, device=dev)
+
+    def new_actions():
+        act_buf.uniform_(-1.0, 1.0, generator=g)
     obs, rew, cost, done = env._obs, env._reward, env._cost, env._done
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     p = BatchedSafeAdaptationGym._p
 
     def launch(i):
-        L.check(L.L.sag_step(h, p(ring[i % 16]), p(obs), p(rew), None, p(cost), p(done), sp))
+        L.check(L.L.sag_step(h, p(act_buf), p(obs), p(rew), None, p(cost), p(done), sp))
 
     nstep = 0
     for i in range(W):
-        launch(i); nstep += 1
+        new_actions(); launch(i); nstep += 1
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -182,6 +187,7 @@ def main():
     launches = 0
     t_wall0 = time.perf_counter()
     for i in range(K):
+        new_actions()
         flush.zero_()  # L2 flush (not timed: outside the event pair)
         evs[i][0].record(stream)
         launch(W + i); launches += 1; nstep += 1
@@ -200,7 +206,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(K):
-        launch(i)
+        new_actions(); launch(i)
     e1.record(stream)
     torch.cuda.synchronize()
     warm_ms = e0.elapsed_time(e1)

@@ -304,6 +304,46 @@ SAG_HD int collide(const Geom& A, const Geom& B, Hit* o) {
   return hit_box_box(A, B, o);
 }
 
+// Overlap predicates: the first stage of the hit_* routines above with the same arithmetic, so "no overlap" here
+// implies that the full narrow phase would list no contact (the converse may fail for box-box: conservative).
+SAG_HD bool overlap_circle_circle(const Geom& A, const Geom& B) {
+  double dx = B.cx - A.cx, dy = B.cy - A.cy;
+  double len = sqrt(dx * dx + dy * dy);
+  double dist = len - A.r - B.r;
+  return !(dist > 0.0);
+}
+SAG_HD bool overlap_circle_box(const Geom& Cc, const Geom& B) {
+  double rx = Cc.cx - B.cx, ry = Cc.cy - B.cy;
+  double lx = rx * B.c + ry * B.s, ly = -rx * B.s + ry * B.c;
+  double qx = lx < -B.hx ? -B.hx : (lx > B.hx ? B.hx : lx);
+  double qy = ly < -B.hy ? -B.hy : (ly > B.hy ? B.hy : ly);
+  if (qx == lx && qy == ly) return true;
+  double ex = lx - qx, ey = ly - qy;
+  double len = sqrt(ex * ex + ey * ey);
+  double dist = len - Cc.r;
+  return !(dist > 0.0);
+}
+SAG_HD bool overlap_box_box(const Geom& A, const Geom& B) {
+  double dx = B.cx - A.cx, dy = B.cy - A.cy;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double ux = k == 0 ? A.c : (k == 1 ? -A.s : (k == 2 ? B.c : -B.s));
+    double uy = k == 0 ? A.s : (k == 1 ? A.c : (k == 2 ? B.s : B.c));
+    double dp = dx * ux + dy * uy;
+    double ra = A.hx * fabs(A.c * ux + A.s * uy) + A.hy * fabs(-A.s * ux + A.c * uy);
+    double rb = B.hx * fabs(B.c * ux + B.s * uy) + B.hy * fabs(-B.s * ux + B.c * uy);
+    double sep = fabs(dp) - (ra + rb);
+    if (sep > 0.0) return false;
+  }
+  return true;
+}
+SAG_HD bool overlap(const Geom& A, const Geom& B) {
+  if (!A.is_box && !B.is_box) return overlap_circle_circle(A, B);
+  if (!A.is_box) return overlap_circle_box(A, B);
+  if (!B.is_box) return overlap_circle_box(B, A);
+  return overlap_box_box(A, B);
+}
+
 SAG_HD bool kind_collidable(int k) { return k == K_VASE || k == K_GREMLIN || k == K_PILLAR || k == K_BUTTON || k == K_BOX; }
 SAG_HD bool kind_movable(int k) { return k == K_VASE || k == K_GREMLIN || k == K_BOX; }
 SAG_HD int kind_nparts(int k) { return k == K_BOX ? 5 : (kind_collidable(k) ? 1 : 0); }
@@ -719,6 +759,32 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
   }
 }
 
+// Cheap exact pre-test run by every non-quiet lane in parallel: does any robot geom overlap any object geom?
+// (same broad phase and first-stage arithmetic as contact_pass phase 1, so a `false` here means phase 1 lists nothing)
+SAG_HD bool robot_overlaps_any(const Ctx& C, const Robot& R, double sn, double cs) {
+  const Dev& D = C.D;
+  Geom gr[2];
+  gr[0].is_box = 0; gr[0].cx = R.q[0]; gr[0].cy = R.q[1]; gr[0].c = cs; gr[0].s = sn; gr[0].r = kPtR; gr[0].hx = gr[0].hy = 0.0;
+  gr[1].is_box = 1; gr[1].cx = R.q[0] + kPtArrowOff * cs; gr[1].cy = R.q[1] + kPtArrowOff * sn; gr[1].c = cs; gr[1].s = sn;
+  gr[1].hx = gr[1].hy = kPtArrowH; gr[1].r = 0.0;
+  for (int s = C.L.v0; s < C.L.n; ++s) {
+    int kind = slot_kind(C.sp, C.L, s);
+    if (!kind_collidable(kind)) continue;
+    size_t i = oidx(D, s, C.e);
+    double x = D.ox[i], y = D.oy[i];
+    double dx = x - R.q[0], dy = y - R.q[1], reach = kRobotReach + kind_bound(D, kind);
+    if (dx * dx + dy * dy > reach * reach) continue;
+    double oc = 1.0, os = 0.0;
+    if (kind_movable(kind)) sag_sincos(D.oyaw[i], &os, &oc);
+    for (int pt = 0; pt < kind_nparts(kind); ++pt) {
+      Geom go;
+      obj_geom(D, kind, pt, x, y, oc, os, go);
+      if (overlap(gr[0], go) || overlap(gr[1], go)) return true;
+    }
+  }
+  return false;
+}
+
 // The lanes of a warp that need the contact path take turns on the warp's shared-memory Scratch.  `wmask` = lanes of
 // this warp that own an environment (all of them call this function together).  On the host there is one lane.
 SAG_HD void warp_contact_pass(unsigned wmask, bool need, const Ctx& C, const Robot& R, double sn, double cs, const PtConst& K,
@@ -1026,7 +1092,8 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, const Ctx& C, const Robot& R
   unsigned touch = 0;
   O.err = 0;
   const bool tendon = C.task == T_HAUL_BOX;
-  const bool need = !(clear > 0.0 && mov == 0 && !tendon);
+  const bool near_ = !(clear > 0.0 && mov == 0 && !tendon);
+  const bool need = near_ && (mov != 0 || tendon || robot_overlaps_any(C, R, sn, cs));
   Phys P;
   P.err = 0; P.touch = 0;
   if (!need) pt_solve(-kPtMc * sn, kPtMc * cs, K.ia0, K.is0, fs, P.qacc);
@@ -1034,7 +1101,7 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, const Ctx& C, const Robot& R
   qacc[0] = P.qacc[0]; qacc[1] = P.qacc[1]; qacc[2] = P.qacc[2];
   touch = P.touch;
   O.err = P.err;
-  if (need && (mov != 0 || tendon)) clear = -1.0;
+  if (mov != 0 || tendon) clear = -1.0;
   O.clear = clear;
   O.mov = mov;
   // ---- reward (may resample the goal / change button groups) and cost
@@ -1128,7 +1195,8 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, 
     {
       Phys P;
       P.fc[0] = P.fc[1] = P.fc[2] = 0.0; P.mov = mov; P.err = 0;
-      warp_contact_pass(wmask, !quiet, C, R, sn, cs, K, fs, mov, true, h, S, P);
+      const bool need = !quiet && (mov != 0 || C.task == T_HAUL_BOX || robot_overlaps_any(C, R, sn, cs));
+      warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, P);
       fc[0] = P.fc[0]; fc[1] = P.fc[1]; fc[2] = P.fc[2];
       mov = P.mov;
       if (P.err) err = 1;
