@@ -1053,25 +1053,31 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, const Ctx& C, const Robot& R
   // ---- pass A: hazards / vases / gremlins / pillars -> obstacle lidar, hazard cost, clearance
   bool hz = false;
   double d2v = 1e300, d2p = 1e300, d2b = 1e300, d2x = 1e300;  // min squared centre distance per collidable kind
-  for (int s = C.L.h0; s < C.L.v0; ++s) {
-    size_t i = oidx(D, s, e);
-    double wx = D.ox[i] - R.q[0], wy = D.oy[i] - R.q[1];
-    hz = hz || hazard_hit(wx * wx + wy * wy, D.hazards_size);
-    lidar_apply(lidar_eval(wx, wy, cs, sn), obs_s, ostride);
-  }
-  for (int s = C.L.v0; s < C.L.p0; ++s) {  // vases (and gremlins: none in any shipped task)
-    size_t i = oidx(D, s, e);
-    double wx = D.ox[i] - R.q[0], wy = D.oy[i] - R.q[1];
-    double d2 = wx * wx + wy * wy;
-    if (d2 < d2v) d2v = d2;
-    lidar_apply(lidar_eval(wx, wy, cs, sn), obs_s, ostride);
-  }
-  for (int s = C.L.p0; s < C.L.t0; ++s) {
-    size_t i = oidx(D, s, e);
-    double wx = D.ox[i] - R.q[0], wy = D.oy[i] - R.q[1];
-    double d2 = wx * wx + wy * wy;
-    if (d2 < d2p) d2p = d2;
-    lidar_apply(lidar_eval(wx, wy, cs, sn), obs_s, ostride);
+  // obstacle slots [0, t0) in trips of three: loads and the sqrt / atan2 chains of a trip are independent, the
+  // shared-memory bin updates come last (the compiler has to keep those in order)
+  for (int s0 = 0; s0 < C.L.t0; s0 += 3) {
+    double wx[3], wy[3];
+    bool on[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int s = s0 + k;
+      on[k] = s < C.L.t0;
+      size_t i = oidx(D, on[k] ? s : s0, e);
+      wx[k] = D.ox[i] - R.q[0]; wy[k] = D.oy[i] - R.q[1];
+    }
+    LidarHit H[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) H[k] = lidar_eval(wx[k], wy[k], cs, sn);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (!on[k]) continue;
+      int s = s0 + k;
+      double d2 = wx[k] * wx[k] + wy[k] * wy[k];
+      if (s < C.L.v0) hz = hz || hazard_hit(d2, D.hazards_size);
+      else if (s < C.L.p0) { if (d2 < d2v) d2v = d2; }
+      else { if (d2 < d2p) d2p = d2; }
+      lidar_apply(H[k], obs_s, ostride);
+    }
   }
   for (int s = C.L.t0; s < C.L.n; ++s) {  // collidable task objects: buttons, push box
     int kind = slot_kind(C.sp, C.L, s);

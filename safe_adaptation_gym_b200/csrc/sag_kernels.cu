@@ -167,13 +167,36 @@ __global__ void __launch_bounds__(kBS) k_lidar(const double* __restrict__ robot,
     double rx = robot[e], ry = robot[(size_t)n + e], yaw = robot[2 * (size_t)n + e];
     double sn, cs;
     sag_sincos(yaw, &sn, &cs);
-    const double* oxp = obj_xy;
-    const double* oyp = obj_xy + (size_t)nslots * n;
-    for (int s = 0; s < nslots; ++s) {
-      int g = group[(size_t)s * n + e];
+    const double* oxp = obj_xy + e;
+    const double* oyp = obj_xy + (size_t)nslots * n + e;
+    const uint8_t* gp = group + e;
+    // four objects per trip: the loads and the four sqrt / atan2 chains are independent, the shared-memory bin
+    // updates (which the compiler must keep in order) come last
+    int s = 0;
+    for (; s + 4 <= nslots; s += 4) {
+      int g[4];
+      double wx[4], wy[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g[k] = gp[(size_t)(s + k) * n];
+        wx[k] = oxp[(size_t)(s + k) * n] - rx;
+        wy[k] = oyp[(size_t)(s + k) * n] - ry;
+      }
+      LidarHit H[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) H[k] = lidar_eval(wx[k], wy[k], cs, sn);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (g[k] == 0) continue;
+        int off = g[k] == 1 ? 0 : (g[k] == 3 ? 16 : 32);
+        lidar_apply(H[k], bins + off * kLidarTileStride, kLidarTileStride);
+      }
+    }
+    for (; s < nslots; ++s) {
+      int g = gp[(size_t)s * n];
       if (g == 0) continue;
       int off = g == 1 ? 0 : (g == 3 ? 16 : 32);
-      lidar_accum(rx, ry, cs, sn, oxp[(size_t)s * n + e], oyp[(size_t)s * n + e], bins + off * kLidarTileStride, kLidarTileStride);
+      lidar_accum(rx, ry, cs, sn, oxp[(size_t)s * n], oyp[(size_t)s * n], bins + off * kLidarTileStride, kLidarTileStride);
     }
   }
   __syncthreads();
@@ -194,9 +217,10 @@ __global__ void __launch_bounds__(256) k_cost(const double* __restrict__ robot_x
   bool hit = contact[e] != 0;                                        // world.py:146
   const float* hx = hazard_xy;
   const float* hy = hazard_xy + (size_t)nh * n;
+#pragma unroll 3
   for (int s = 0; s < nh; ++s) {                                     // world.py:148-153
     double dx = rx - (double)hx[(size_t)s * n + e], dy = ry - (double)hy[(size_t)s * n + e];
-    if (sqrt(dx * dx + dy * dy) <= hazard_size) hit = true;
+    hit = hit | hazard_hit(dx * dx + dy * dy, hazard_size);  // == (sqrt(d2) <= size), sqrt only near the boundary
   }
   out[e] = hit ? 1 : 0;                                              // world.py:155
 }
