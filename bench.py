@@ -190,7 +190,7 @@ def main():
         new_actions()
         flush.zero_()  # L2 flush (not timed: outside the event pair)
         evs[i][0].record(stream)
-        launch(W + i); launches += 1; nstep += 1
+        launch(W + i); launches += 2; nstep += 1  # k_plan + k_step
         if nstep % 1000 == 0:  # episode length used by the reference's tooling (tests/test_safety_gym.py:78)
             L.check(L.L.sag_reset(h, None, 0, 0, sp)); launches += 1
         evs[i][1].record(stream)

@@ -67,6 +67,7 @@ constexpr double kPgsTol = 1e-8;
 constexpr double kSleepV = 1e-8;
 constexpr int kMaxObj = 32;
 constexpr int kMaxCon = 16;
+constexpr double kHotMargin = 0.05;     // scheduling only: clearance below which an env is planned as "hot"
 constexpr double kRobotReach = 0.16;    // >= |hinge -> far arrow corner| = hypot(0.15, 0.05)
 
 // point robot mass properties (MuJoCo uniform-density rule, density 1, point.xml:5,18-19)
@@ -160,6 +161,9 @@ struct Dev {
   double *cgcur, *cgnext, *cgox, *cgoy;
   int* cgtimer;
   int* movmask;  // bit s: movable object s has a non-zero velocity (derived state, rebuilt by env_observe)
+  // scheduling hints (no effect on results): env is likely to need the contact path in its next step
+  int* hint;
+  int *hotlist, *coldlist, *counts;  // k_plan output: counts[0] = #hot
   double *time, *clear;
   unsigned *ctr, *episode;
   int* nstep;
@@ -1233,6 +1237,7 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, 
   D.time[e] = time;
   D.clear[e] = O.clear;
   D.movmask[e] = (int)O.mov;
+  D.hint[e] = (O.clear <= kHotMargin || O.mov != 0) ? 1 : 0;
   store_robot(D, e, R);
   store_task_state(D, e, T);
   reward2[0] = O.rew[0]; reward2[1] = O.rew[1];
@@ -1260,6 +1265,7 @@ SAG_HD void env_observe(unsigned wmask, Scratch* S, const Dev& D, int e, float* 
   end_of_step(wmask, S, C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
   D.clear[e] = O.clear;
   D.movmask[e] = (int)mov;
+  D.hint[e] = (O.clear <= kHotMargin || mov != 0) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1348,6 +1354,7 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
   D.episode[e] = episode; D.nstep[e] = 0; D.time[e] = 0.0; D.epret[e] = 0.0; D.epcost[e] = 0.0; D.flags[e] = fl;
   D.clear[e] = -1.0;
   D.movmask[e] = 0;
+  D.hint[e] = 1;
 }
 
 }  // namespace sag

@@ -63,15 +63,62 @@ __device__ __forceinline__ void write_tile(const float* tile, float* out, int e0
   }
 }
 
+// ---- tail balancing ---------------------------------------------------------------------------
+// The step time is set by the slowest warp, and a warp is slow when several of its lanes need the (serialised)
+// contact path.  k_plan splits the environments into "hot" (hinted by the previous step: something within 5 cm of
+// reach, or a moving body) and "cold" lists; k_step then gives every warp the same number of hot environments
+// (one per warp until there are more hot environments than warps) in its top lanes and fills the other lanes with
+// consecutive cold environments, which keeps the SoA accesses coalesced.  The mapping cannot change any result.
+__global__ void __launch_bounds__(256) k_plan(Dev D) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = e < D.n;
+  const bool hot = valid && D.hint[e] != 0;
+  const unsigned bh = __ballot_sync(0xffffffffu, hot), bc = __ballot_sync(0xffffffffu, valid && !hot);
+  const int lane = threadIdx.x & 31;
+  int base_h = 0, base_c = 0;
+  if (lane == 0) {
+    if (bh) base_h = atomicAdd(&D.counts[0], __popc(bh));
+    if (bc) base_c = atomicAdd(&D.counts[1], __popc(bc));
+  }
+  base_h = __shfl_sync(0xffffffffu, base_h, 0);
+  base_c = __shfl_sync(0xffffffffu, base_c, 0);
+  const unsigned lt = (1u << lane) - 1u;
+  if (hot) D.hotlist[base_h + __popc(bh & lt)] = e;
+  else if (valid) D.coldlist[base_c + __popc(bc & lt)] = e;
+}
+
+__device__ __forceinline__ int planned_env(const Dev& D, int t) {
+  const int W = (D.n + 31) >> 5, w = t >> 5, l = t & 31;
+  const int nh = D.counts[0], q = nh / W, r = nh - q * W;
+  const int kw = q + (w < r ? 1 : 0);
+  if (l >= 32 - kw) return D.hotlist[w + (31 - l) * W];
+  const int ci = 32 * w - (q * w + min(w, r)) + l;
+  return ci < D.n - nh ? D.coldlist[ci] : -1;
+}
+
+// per-warp write-out of 32 observation rows (the environments of a warp are not consecutive any more)
+__device__ __forceinline__ void write_rows(const float* tile, float* out, int e) {
+  const int lane = threadIdx.x & 31, col0 = threadIdx.x & ~31;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const int er = __shfl_sync(0xffffffffu, e, r);
+    if (er < 0) continue;
+    float* dst = out + (size_t)er * kObs;
+    const float* src = tile + col0 + r;
+    dst[lane] = src[lane * kTileStride];
+    if (lane + 32 < kObs) dst[lane + 32] = src[(lane + 32) * kTileStride];
+  }
+}
+
 __global__ void __launch_bounds__(kBS) k_step(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                double* __restrict__ reward, double* __restrict__ reward2,
                                                uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);                             // [kObs][kTileStride] observation tile
   Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + kTileBytes);         // contact-solver working set, one per warp
-  const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
-  const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
-  if (e < D.n) {
+  const int e = planned_env(D, blockIdx.x * kBS + threadIdx.x);
+  const unsigned wmask = __ballot_sync(0xffffffffu, e >= 0);
+  if (e >= 0) {
     float2 a = reinterpret_cast<const float2*>(act)[e];
     double rew[2];
     unsigned char c, d;
@@ -81,8 +128,8 @@ __global__ void __launch_bounds__(kBS) k_step(Dev D, const float* __restrict__ a
     cost[e] = c;
     done[e] = d;
   }
-  __syncthreads();
-  write_tile(tile, obs, e0, D.n);
+  __syncwarp();
+  write_rows(tile, obs, e);
 }
 
 __global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs) {
@@ -300,6 +347,13 @@ size_t sag_field_bytes(void* handle, int field) {
 
 static inline int grid_for(int n) { return (n + kBS - 1) / kBS; }
 
+static cudaError_t launch_plan(Handle* H, cudaStream_t s) {
+  cudaError_t ce = cudaMemsetAsync(H->D.counts, 0, 2 * sizeof(int), s);
+  if (ce != cudaSuccess) return ce;
+  k_plan<<<(H->D.n + 255) / 256, 256, 0, s>>>(H->D);
+  return cudaGetLastError();
+}
+
 int sag_set_tasks(void* handle, const int32_t* ids, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !ids) return fail("sag_set_tasks: null argument");
@@ -330,6 +384,7 @@ int sag_step(void* handle, const float* act, float* obs, double* reward, double*
              void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !act || !obs || !reward || !cost || !done) return fail("sag_step: null argument");
+  CK(launch_plan(H, (cudaStream_t)stream));
   k_step<<<grid_for(H->D.n), kBS, kSmemBytes, (cudaStream_t)stream>>>(H->D, act, obs, reward, reward2, cost, done);
   CK(cudaGetLastError());
   return 0;
@@ -357,6 +412,7 @@ int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward
   cudaStream_t s = H->own_stream;
   const size_t n = (size_t)H->D.n;
   CK(cudaMemcpyAsync(H->act_d, act_h, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+  CK(launch_plan(H, s));
   k_step<<<grid_for(H->D.n), kBS, kSmemBytes, s>>>(H->D, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(obs_h, H->obs_d, n * kObs * sizeof(float), cudaMemcpyDeviceToHost, s));

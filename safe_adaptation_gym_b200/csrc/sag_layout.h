@@ -12,7 +12,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct SlabLayout {
   size_t off[SAG_NUM_FIELDS], bytes[SAG_NUM_FIELDS];
-  size_t stats_off, act_off, obs_off, rew_off, cost_off, done_off, total;
+  size_t stats_off, sched_off, act_off, obs_off, rew_off, cost_off, done_off, total;
 };
 
 inline SlabLayout slab_layout(int n, int stride, int obs_dim) {
@@ -26,6 +26,7 @@ inline SlabLayout slab_layout(int n, int stride, int obs_dim) {
   size_t total = 0;
   for (int f = 0; f < SAG_NUM_FIELDS; ++f) { L.off[f] = total; total += align_up(L.bytes[f], 256); }
   L.stats_off = total; total += align_up(3 * st * sizeof(double), 256);
+  L.sched_off = total; total += align_up((3 * st + 64) * sizeof(int32_t), 256);
   L.act_off = total; total += align_up((size_t)n * 2 * sizeof(float), 256);
   L.obs_off = total; total += align_up((size_t)n * obs_dim * sizeof(float), 256);
   L.rew_off = total; total += align_up((size_t)n * sizeof(double), 256);
@@ -49,6 +50,8 @@ inline void slab_bind(Dev& D, const SlabLayout& L, char* base) {
   D.task = ii; D.gbtn = ii + st; D.bstate = ii + 2 * st; D.btimer = ii + 3 * st; D.amask = ii + 4 * st; D.cgtimer = ii + 5 * st;
   D.nstep = ii + 6 * st; D.ctr = (unsigned*)(ii + 7 * st); D.episode = (unsigned*)(ii + 8 * st); D.movmask = ii + 9 * st;
   D.flags = (unsigned char*)(base + L.off[SAG_F_FLAGS]);
+  int32_t* sc = (int32_t*)(base + L.sched_off);
+  D.hint = sc; D.hotlist = sc + st; D.coldlist = sc + 2 * st; D.counts = sc + 3 * st;
 }
 
 inline void dev_from_config(Dev& D, const SagConfig& c) {
