@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256) k_plan(Dev D) {
 
 __device__ __forceinline__ int planned_env(const Dev& D, int t) {
   const int W = (D.n + 31) >> 5, w = t >> 5, l = t & 31;
+  if (w >= W) return -1;  // the grid is rounded up to whole CTAs
   const int nh = D.counts[0], q = nh / W, r = nh - q * W;
   const int kw = q + (w < r ? 1 : 0);
   if (l >= 32 - kw) return D.hotlist[w + (31 - l) * W];
