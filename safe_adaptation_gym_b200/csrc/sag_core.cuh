@@ -1038,7 +1038,7 @@ SAG_HD void set_mocaps(const Ctx& C, const Rng& rng, TaskState& T, double time) 
 // objects (obstacle kinds before the reward, task objects after it because the reward may move the goal or
 // change button groups).  obs_s: this env's column of the CTA's shared-memory tile (stride ostride).
 // ------------------------------------------------------------------------------------------------
-struct EndOut { double rew[2]; double cost; double clear; unsigned mov; int err; int resample_failed; };
+struct EndOut { double rew[2]; double cost; double clear; unsigned mov, touch; int err; int resample_failed; };
 
 SAG_HD bool hazard_hit(double d2, double size) {  // world.py:151-152: ||robot_xy - hazard_xy|| <= size, exactly
   double lo = size * 0.999, hi = size * 1.001;
@@ -1114,6 +1114,7 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, const Ctx& C, const Robot& R
   if (mov != 0 || tendon) clear = -1.0;
   O.clear = clear;
   O.mov = mov;
+  O.touch = touch;
   // ---- reward (may resample the goal / change button groups) and cost
   O.rew[0] = O.rew[1] = 0.0; O.cost = 0.0; O.resample_failed = 0;
   if (with_reward) {
@@ -1237,7 +1238,7 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, 
   D.time[e] = time;
   D.clear[e] = O.clear;
   D.movmask[e] = (int)O.mov;
-  D.hint[e] = (O.clear <= kHotMargin || O.mov != 0) ? 1 : 0;
+  D.hint[e] = (O.mov != 0 || O.touch != 0 || O.clear <= 0.0) ? 2 : (O.clear <= kHotMargin ? 1 : 0);
   store_robot(D, e, R);
   store_task_state(D, e, T);
   reward2[0] = O.rew[0]; reward2[1] = O.rew[1];
@@ -1265,7 +1266,7 @@ SAG_HD void env_observe(unsigned wmask, Scratch* S, const Dev& D, int e, float* 
   end_of_step(wmask, S, C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
   D.clear[e] = O.clear;
   D.movmask[e] = (int)mov;
-  D.hint[e] = (O.clear <= kHotMargin || mov != 0) ? 1 : 0;
+  D.hint[e] = (mov != 0 || O.touch != 0 || O.clear <= 0.0) ? 2 : (O.clear <= kHotMargin ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------

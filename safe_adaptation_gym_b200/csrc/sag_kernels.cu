@@ -72,27 +72,37 @@ __device__ __forceinline__ void write_tile(const float* tile, float* out, int e0
 __global__ void __launch_bounds__(256) k_plan(Dev D) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = e < D.n;
-  const bool hot = valid && D.hint[e] != 0;
-  const unsigned bh = __ballot_sync(0xffffffffu, hot), bc = __ballot_sync(0xffffffffu, valid && !hot);
+  const int hint = valid ? D.hint[e] : 0;  // 2: in contact / bodies moving, 1: something within 5 cm of reach, 0: cold
+  const bool vhot = hint == 2, warm = hint == 1;
+  const unsigned bv = __ballot_sync(0xffffffffu, vhot), bw = __ballot_sync(0xffffffffu, warm),
+                 bc = __ballot_sync(0xffffffffu, valid && hint == 0);
   const int lane = threadIdx.x & 31;
-  int base_h = 0, base_c = 0;
+  int base_v = 0, base_w = 0, base_c = 0;
   if (lane == 0) {
-    if (bh) base_h = atomicAdd(&D.counts[0], __popc(bh));
+    if (bv) base_v = atomicAdd(&D.counts[0], __popc(bv));
     if (bc) base_c = atomicAdd(&D.counts[1], __popc(bc));
+    if (bw) base_w = atomicAdd(&D.counts[2], __popc(bw));
   }
-  base_h = __shfl_sync(0xffffffffu, base_h, 0);
+  base_v = __shfl_sync(0xffffffffu, base_v, 0);
+  base_w = __shfl_sync(0xffffffffu, base_w, 0);
   base_c = __shfl_sync(0xffffffffu, base_c, 0);
   const unsigned lt = (1u << lane) - 1u;
-  if (hot) D.hotlist[base_h + __popc(bh & lt)] = e;
+  // hot list = very hot entries from the front, warm entries from the back: the round-robin deal in planned_env
+  // then hands out the very hot (expensive) environments first, at most ceil(nv / #warps) per warp
+  if (vhot) D.hotlist[base_v + __popc(bv & lt)] = e;
+  else if (warm) D.hotlist[D.stride - 1 - (base_w + __popc(bw & lt))] = e;
   else if (valid) D.coldlist[base_c + __popc(bc & lt)] = e;
 }
 
 __device__ __forceinline__ int planned_env(const Dev& D, int t) {
   const int W = (D.n + 31) >> 5, w = t >> 5, l = t & 31;
   if (w >= W) return -1;  // the grid is rounded up to whole CTAs
-  const int nh = D.counts[0], q = nh / W, r = nh - q * W;
+  const int nv = D.counts[0], nh = nv + D.counts[2], q = nh / W, r = nh - q * W;
   const int kw = q + (w < r ? 1 : 0);
-  if (l >= 32 - kw) return D.hotlist[w + (31 - l) * W];
+  if (l >= 32 - kw) {
+    const int hi = w + (31 - l) * W;
+    return hi < nv ? D.hotlist[hi] : D.hotlist[D.stride - 1 - (hi - nv)];
+  }
   const int ci = 32 * w - (q * w + min(w, r)) + l;
   return ci < D.n - nh ? D.coldlist[ci] : -1;
 }
@@ -349,7 +359,7 @@ size_t sag_field_bytes(void* handle, int field) {
 static inline int grid_for(int n) { return (n + kBS - 1) / kBS; }
 
 static cudaError_t launch_plan(Handle* H, cudaStream_t s) {
-  cudaError_t ce = cudaMemsetAsync(H->D.counts, 0, 2 * sizeof(int), s);
+  cudaError_t ce = cudaMemsetAsync(H->D.counts, 0, 4 * sizeof(int), s);
   if (ce != cudaSuccess) return ce;
   k_plan<<<(H->D.n + 255) / 256, 256, 0, s>>>(H->D);
   return cudaGetLastError();
