@@ -161,9 +161,8 @@ struct Dev {
   double *cgcur, *cgnext, *cgox, *cgoy;
   int* cgtimer;
   int* movmask;  // bit s: movable object s has a non-zero velocity (derived state, rebuilt by env_observe)
-  // scheduling hints (no effect on results): env is likely to need the contact path in its next step
-  int* hint;
-  int *hotlist, *coldlist, *counts;  // k_plan output: counts[0] = #hot
+  // work list of the environments that are not quiet in the current step (k_step_quiet -> k_step_busy)
+  int *worklist, *counts;  // counts[0] = length
   double *time, *clear;
   unsigned *ctr, *episode;
   int* nstep;
@@ -451,16 +450,23 @@ struct Row {  // one contact (normal k=0, tangent k=1) or the tendon limit (k=0 
 };
 constexpr int kMaxBodies = 8;  // movable bodies with constraint rows in one forward pass
 
-// Working set of the contact solver.  On the device one Scratch lives in shared memory per WARP and the lanes
-// that need the contact path take turns (k_step's warp_contact_pass): local memory would put every access of
-// this latency-bound code on an L2/DRAM round trip.
-struct Scratch {
-  Con con[kMaxCon];
-  Row rows[kMaxCon + 1];
-  double acc[kMaxBodies + 1][3];
-  double ffl[kMaxBodies][3];
-  int bslot[kMaxBodies];
+// Working set of the contact solver, kept in shared memory (local memory would put every access of this
+// latency-bound code on an L2 / DRAM round trip).  Two sizes: every lane of a "busy" warp owns a SmallScratch that
+// covers the common case (<= 4 contacts, <= 2 bodies); a pass that does not fit re-runs on the warp's one big
+// Scratch, lanes taking turns.  sizeof / 8 is odd so that the lanes' doubles fall into distinct bank pairs.
+template <int NC, int NB>
+struct ScratchT {
+  static constexpr int kCon = NC, kBodies = NB;
+  Con con[NC];
+  Row rows[NC + 1];
+  double acc[NB + 1][3];
+  double ffl[NB][3];
+  int bslot[NB + (NB & 1)];
 };
+typedef ScratchT<kMaxCon, kMaxBodies> Scratch;
+constexpr int kSmallCon = 4, kSmallBodies = 2;
+typedef ScratchT<kSmallCon, kSmallBodies> SmallScratch;
+static_assert((sizeof(SmallScratch) / 8) % 2 == 1, "SmallScratch stride must be an odd number of 8-byte words");
 
 struct Ctx {  // per-thread view of one environment
   const Dev& D;
@@ -476,6 +482,7 @@ struct Phys {
   unsigned touch;  // bit s: a robot geom is in contact (dist <= 0) with object slot s
   unsigned mov;    // bit s: movable body s has a non-zero velocity (after integration, if any)
   int err;
+  int retry;       // the pass did not fit this scratch size and changed nothing: run it again on the big one
 };
 
 SAG_HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -487,8 +494,11 @@ SAG_HD int ctz32(unsigned m) {
 #endif
 }
 
+template <class ScratchType>
 SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, double cs, const PtConst& K, const double* fs,
-                                  unsigned mov, bool integrate, double h, Scratch& S, Phys& P) {
+                                  unsigned mov, bool integrate, double h, ScratchType& S, Phys& P) {
+  constexpr int kCapCon = ScratchType::kCon, kCapBodies = ScratchType::kBodies;
+  constexpr bool kIsBig = kCapCon == kMaxCon;
   const Dev& D = C.D;
   const int e = C.e;
   const double p = -kPtMc * sn, q = kPtMc * cs;
@@ -496,7 +506,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
   int ncon = 0;
   unsigned active = mov, touch = 0;
   bool overflow = false;
-  P.err = 0;
+  P.err = 0; P.retry = 0;
   Geom gr[2];
   gr[0].is_box = 0; gr[0].cx = R.q[0]; gr[0].cy = R.q[1]; gr[0].c = cs; gr[0].s = sn; gr[0].r = kPtR; gr[0].hx = gr[0].hy = 0.0;
   gr[1].is_box = 1; gr[1].cx = R.q[0] + kPtArrowOff * cs; gr[1].cy = R.q[1] + kPtArrowOff * sn; gr[1].c = cs; gr[1].s = sn;
@@ -521,7 +531,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
         int n = collide(gr[rg], go, hits);
         SAG_PROF(e, 1, 1);
         for (int k = 0; k < n; ++k) {
-          if (ncon >= kMaxCon) { overflow = true; break; }
+          if (ncon >= kCapCon) { overflow = true; break; }
           Con& c = con[ncon++];
           c.ba = 0; c.bb = mvb ? 1 + s : -1;
           c.nx = hits[k].nx; c.ny = hits[k].ny; c.px = hits[k].px; c.py = hits[k].py; c.dist = hits[k].dist;
@@ -565,7 +575,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
             int n = collide(gi, gj, hits);
             SAG_PROF(e, 1, 1);
             for (int k = 0; k < n; ++k) {
-              if (ncon >= kMaxCon) { overflow = true; break; }
+              if (ncon >= kCapCon) { overflow = true; break; }
               Con& c = con[ncon++];
               c.ba = mi ? 1 + i : -1; c.bb = mj ? 1 + j : -1;
               c.nx = hits[k].nx; c.ny = hits[k].ny; c.px = hits[k].px; c.py = hits[k].py; c.dist = hits[k].dist;
@@ -608,8 +618,11 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
   // capacity limits: a PhysicsError; no constraint forces, no object motion in this pass
   int nb = 0;
   for (unsigned m = fl; m; m &= m - 1) ++nb;
-  if (nb > kMaxBodies) overflow = true;
-  if (overflow) { P.err = 1; return; }
+  if (nb > kCapBodies) overflow = true;
+  if (overflow) {  // nothing has been modified yet
+    if (kIsBig) P.err = 1; else P.retry = 1;
+    return;
+  }
   if (!any_row && !tendon && mov == 0) return;  // nothing to solve, nothing to move
   // ---- body table: compact ids in slot order
   nb = 0;
@@ -789,12 +802,21 @@ SAG_HD bool robot_overlaps_any(const Ctx& C, const Robot& R, double sn, double c
   return false;
 }
 
-// The lanes of a warp that need the contact path take turns on the warp's shared-memory Scratch.  `wmask` = lanes of
-// this warp that own an environment (all of them call this function together).  On the host there is one lane.
+// Contact path of a warp.  Lanes that need it first run concurrently on their own SmallScratch (if the kernel
+// provides one); lanes whose pass did not fit, or all needing lanes when there is no SmallScratch, then take turns
+// on the warp's big Scratch.  `wmask` = lanes of this warp that own an environment (all of them call this together).
+// On the host there is a single lane.
 SAG_HD void warp_contact_pass(unsigned wmask, bool need, const Ctx& C, const Robot& R, double sn, double cs, const PtConst& K,
-                              const double* fs, unsigned mov, bool integrate, double h, Scratch* S, Phys& P) {
+                              const double* fs, unsigned mov, bool integrate, double h, Scratch* S, SmallScratch* small, Phys& P) {
+  bool big = need;
+  if (small) {
+    if (need) {
+      contact_pass(C, R, sn, cs, K, fs, mov, integrate, h, *small, P);
+      big = P.retry != 0;
+    }
+  }
 #if defined(__CUDA_ARCH__)
-  unsigned todo = __ballot_sync(wmask, need);
+  unsigned todo = __ballot_sync(wmask, big);
   const int lane = threadIdx.x & 31;
   while (todo) {
     const int turn = __ffs((int)todo) - 1;
@@ -804,7 +826,7 @@ SAG_HD void warp_contact_pass(unsigned wmask, bool need, const Ctx& C, const Rob
   }
 #else
   (void)wmask;
-  if (need) contact_pass(C, R, sn, cs, K, fs, mov, integrate, h, *S, P);
+  if (big) contact_pass(C, R, sn, cs, K, fs, mov, integrate, h, *S, P);
 #endif
 }
 
@@ -1047,7 +1069,8 @@ SAG_HD bool hazard_hit(double d2, double size) {  // world.py:151-152: ||robot_x
   return sqrt(d2) <= size;
 }
 
-SAG_HD void end_of_step(unsigned wmask, Scratch* S, const Ctx& C, const Robot& R, TaskState& T, const Rng& rng, const PtConst& K,
+template <bool QuietOnly>
+SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const Ctx& C, const Robot& R, TaskState& T, const Rng& rng, const PtConst& K,
                         unsigned mov, bool phys_err, bool with_reward, float* obs_s, int ostride, EndOut& O) {
   const Dev& D = C.D;
   const int e = C.e;
@@ -1102,12 +1125,16 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, const Ctx& C, const Robot& R
   unsigned touch = 0;
   O.err = 0;
   const bool tendon = C.task == T_HAUL_BOX;
-  const bool near_ = !(clear > 0.0 && mov == 0 && !tendon);
-  const bool need = near_ && (mov != 0 || tendon || robot_overlaps_any(C, R, sn, cs));
   Phys P;
-  P.err = 0; P.touch = 0;
-  if (!need) pt_solve(-kPtMc * sn, kPtMc * cs, K.ia0, K.is0, fs, P.qacc);
-  warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, P);
+  P.err = 0; P.touch = 0; P.retry = 0;
+  if (QuietOnly) {  // a quiet step ends with positive clearance: no contact is possible
+    pt_solve(-kPtMc * sn, kPtMc * cs, K.ia0, K.is0, fs, P.qacc);
+  } else {
+    const bool near_ = !(clear > 0.0 && mov == 0 && !tendon);
+    const bool need = near_ && (mov != 0 || tendon || robot_overlaps_any(C, R, sn, cs));
+    if (!need) pt_solve(-kPtMc * sn, kPtMc * cs, K.ia0, K.is0, fs, P.qacc);
+    warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, small, P);
+  }
   qacc[0] = P.qacc[0]; qacc[1] = P.qacc[1]; qacc[2] = P.qacc[2];
   touch = P.touch;
   O.err = P.err;
@@ -1158,10 +1185,23 @@ SAG_HD void store_robot(const Dev& D, int e, const Robot& R) {
   D.ctrl0[e] = R.ctrl[0]; D.ctrl1[e] = R.ctrl[1];
 }
 
+// "Quiet" environment: nothing can come within reach of the robot during the coming step and nothing is moving
+// (clearance cached by the previous end-of-step pass; -1 when a body moves or a tendon exists).  The bound on the
+// travel of the hinge point during one step is conservative.
+SAG_HD bool env_is_quiet(double clear, double vx, double vy, double w, double gear_x, double damp_xy) {
+  const double tstep = kPtNsub * kPtH;
+  double speed = sqrt(vx * vx + vy * vy), wabs = fabs(w);
+  double alpha_max = 750.0 + 200.0 * wabs, wmax = wabs + alpha_max * tstep;
+  double a_bound = 2.0 * (gear_x * kPtForceLim + damp_xy * speed) / kPtM + (kPtMc / kPtM) * (alpha_max + wmax * wmax);
+  double travel = tstep * speed + tstep * tstep * a_bound + 1e-3;
+  return clear > travel;
+}
+
 // ------------------------------------------------------------------------------------------------
 // SafeAdaptationGym.step for one environment (safe_adaptation_gym.py:56-83)
 // ------------------------------------------------------------------------------------------------
-SAG_HD void env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2,
+template <bool QuietOnly>
+SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2,
                      unsigned char* cost, unsigned char* done) {
   Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
   C.L = make_slots(C.sp);
@@ -1192,22 +1232,17 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, 
   // contact detection; the bound on the hinge point's travel is conservative.
   unsigned char fl = D.flags[e];
   int err = (fl & F_PHYS_ERROR) ? 1 : 0;  // a physics error is sticky until the env is reset
-  const double tstep = kPtNsub * kPtH;
-  double speed = sqrt(R.v[0] * R.v[0] + R.v[1] * R.v[1]), wabs = fabs(R.v[2]);
-  double alpha_max = 750.0 + 200.0 * wabs, wmax = wabs + alpha_max * tstep;
-  double a_bound = 2.0 * (R.gear_x * kPtForceLim + R.damp_xy * speed) / kPtM + (kPtMc / kPtM) * (alpha_max + wmax * wmax);
-  double travel = tstep * speed + tstep * tstep * a_bound + 1e-3;
-  const bool quiet = D.clear[e] > travel;
+  const bool quiet = QuietOnly ? true : env_is_quiet(D.clear[e], R.v[0], R.v[1], R.v[2], R.gear_x, R.damp_xy);
 #pragma unroll 1
   for (int k = 0; k < kPtNsub; ++k) {
     double sn, cs, fs[3], fc[3] = {0.0, 0.0, 0.0}, rhs[3], a[3];
     sag_sincos(R.q[2], &sn, &cs);
     pt_smooth(R, sn, cs, fs);
-    {
+    if (!QuietOnly) {
       Phys P;
-      P.fc[0] = P.fc[1] = P.fc[2] = 0.0; P.mov = mov; P.err = 0;
+      P.fc[0] = P.fc[1] = P.fc[2] = 0.0; P.mov = mov; P.err = 0; P.retry = 0;
       const bool need = !quiet && (mov != 0 || C.task == T_HAUL_BOX || robot_overlaps_any(C, R, sn, cs));
-      warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, P);
+      warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, small, P);
       fc[0] = P.fc[0]; fc[1] = P.fc[1]; fc[2] = P.fc[2];
       mov = P.mov;
       if (P.err) err = 1;
@@ -1223,7 +1258,7 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, 
     time += h;
   }
   EndOut O;
-  end_of_step(wmask, S, C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
+  end_of_step<QuietOnly>(wmask, S, small, C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
   unsigned char dn = 0;
   if (err || O.err) { dn = 1; fl |= F_PHYS_ERROR; }
   if (O.resample_failed) fl |= F_RESAMPLE_FAILED;
@@ -1238,7 +1273,6 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, 
   D.time[e] = time;
   D.clear[e] = O.clear;
   D.movmask[e] = (int)O.mov;
-  D.hint[e] = (O.mov != 0 || O.touch != 0 || O.clear <= 0.0) ? 2 : (O.clear <= kHotMargin ? 1 : 0);
   store_robot(D, e, R);
   store_task_state(D, e, T);
   reward2[0] = O.rew[0]; reward2[1] = O.rew[1];
@@ -1247,7 +1281,7 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, 
 }
 
 // observation at the current state (reset return value / refresh after state injection)
-SAG_HD void env_observe(unsigned wmask, Scratch* S, const Dev& D, int e, float* obs_s, int ostride) {
+SAG_HD void env_observe(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& D, int e, float* obs_s, int ostride) {
   Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
   C.L = make_slots(C.sp);
   Robot R;
@@ -1263,10 +1297,9 @@ SAG_HD void env_observe(unsigned wmask, Scratch* S, const Dev& D, int e, float* 
     if (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0) mov |= 1u << s;
   }
   EndOut O;
-  end_of_step(wmask, S, C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
+  end_of_step<false>(wmask, S, small, C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
   D.clear[e] = O.clear;
   D.movmask[e] = (int)mov;
-  D.hint[e] = (mov != 0 || O.touch != 0 || O.clear <= 0.0) ? 2 : (O.clear <= kHotMargin ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1355,7 +1388,6 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
   D.episode[e] = episode; D.nstep[e] = 0; D.time[e] = 0.0; D.epret[e] = 0.0; D.epcost[e] = 0.0; D.flags[e] = fl;
   D.clear[e] = -1.0;
   D.movmask[e] = 0;
-  D.hint[e] = 1;
 }
 
 }  // namespace sag

@@ -51,6 +51,7 @@ struct Handle {
   double* rew_d;
   uint8_t *cost_d, *done_d;
   cudaStream_t own_stream;
+  int busy_grid;  // CTAs of k_step_busy: resident CTAs per SM x SMs
 };
 
 // coalesced write-out of the CTA's observation tile: tile[k][t] -> out[(e0 + t) * kObs + k]
@@ -63,84 +64,94 @@ __device__ __forceinline__ void write_tile(const float* tile, float* out, int e0
   }
 }
 
-// ---- tail balancing ---------------------------------------------------------------------------
-// The step time is set by the slowest warp, and a warp is slow when several of its lanes need the (serialised)
-// contact path.  k_plan splits the environments into "hot" (hinted by the previous step: something within 5 cm of
-// reach, or a moving body) and "cold" lists; k_step then gives every warp the same number of hot environments
-// (one per warp until there are more hot environments than warps) in its top lanes and fills the other lanes with
-// consecutive cold environments, which keeps the SoA accesses coalesced.  The mapping cannot change any result.
-__global__ void __launch_bounds__(256) k_plan(Dev D) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = e < D.n;
-  const int hint = valid ? D.hint[e] : 0;  // 2: in contact / bodies moving, 1: something within 5 cm of reach, 0: cold
-  const bool vhot = hint == 2, warm = hint == 1;
-  const unsigned bv = __ballot_sync(0xffffffffu, vhot), bw = __ballot_sync(0xffffffffu, warm),
-                 bc = __ballot_sync(0xffffffffu, valid && hint == 0);
+// ---- the step: two kernels --------------------------------------------------------------------
+// k_step_quiet: one thread per environment over the whole batch.  Quiet environments (nothing within reach for the
+//   whole step, nothing moving: 88-100 % of them under a random policy) take the closed-form path with no contact
+//   code at all; the others are appended to a work list and left untouched.
+// k_step_busy: the work list, 32 environments per CTA of one warp, every lane with its own shared-memory SmallScratch
+//   so that the contact solvers of the 32 environments run concurrently (SIMT), plus one big Scratch for the rare pass
+//   that does not fit.  Putting the busy environments together is what makes their divergent code SIMT-efficient: in
+//   a mixed warp a contact environment runs with 1 of 32 lanes active.
+
+// per-warp write-out of up to 32 observation rows (tile column = lane)
+__device__ __forceinline__ void write_rows(const float* tile, int tstride, float* out, int e) {
   const int lane = threadIdx.x & 31;
-  int base_v = 0, base_w = 0, base_c = 0;
-  if (lane == 0) {
-    if (bv) base_v = atomicAdd(&D.counts[0], __popc(bv));
-    if (bc) base_c = atomicAdd(&D.counts[1], __popc(bc));
-    if (bw) base_w = atomicAdd(&D.counts[2], __popc(bw));
-  }
-  base_v = __shfl_sync(0xffffffffu, base_v, 0);
-  base_w = __shfl_sync(0xffffffffu, base_w, 0);
-  base_c = __shfl_sync(0xffffffffu, base_c, 0);
-  const unsigned lt = (1u << lane) - 1u;
-  // hot list = very hot entries from the front, warm entries from the back: the round-robin deal in planned_env
-  // then hands out the very hot (expensive) environments first, at most ceil(nv / #warps) per warp
-  if (vhot) D.hotlist[base_v + __popc(bv & lt)] = e;
-  else if (warm) D.hotlist[D.stride - 1 - (base_w + __popc(bw & lt))] = e;
-  else if (valid) D.coldlist[base_c + __popc(bc & lt)] = e;
-}
-
-__device__ __forceinline__ int planned_env(const Dev& D, int t) {
-  const int W = (D.n + 31) >> 5, w = t >> 5, l = t & 31;
-  if (w >= W) return -1;  // the grid is rounded up to whole CTAs
-  const int nv = D.counts[0], nh = nv + D.counts[2], q = nh / W, r = nh - q * W;
-  const int kw = q + (w < r ? 1 : 0);
-  if (l >= 32 - kw) {
-    const int hi = w + (31 - l) * W;
-    return hi < nv ? D.hotlist[hi] : D.hotlist[D.stride - 1 - (hi - nv)];
-  }
-  const int ci = 32 * w - (q * w + min(w, r)) + l;
-  return ci < D.n - nh ? D.coldlist[ci] : -1;
-}
-
-// per-warp write-out of 32 observation rows (the environments of a warp are not consecutive any more)
-__device__ __forceinline__ void write_rows(const float* tile, float* out, int e) {
-  const int lane = threadIdx.x & 31, col0 = threadIdx.x & ~31;
 #pragma unroll 4
   for (int r = 0; r < 32; ++r) {
     const int er = __shfl_sync(0xffffffffu, e, r);
     if (er < 0) continue;
     float* dst = out + (size_t)er * kObs;
-    const float* src = tile + col0 + r;
-    dst[lane] = src[lane * kTileStride];
-    if (lane + 32 < kObs) dst[lane + 32] = src[(lane + 32) * kTileStride];
+    const float* src = tile + r;
+    dst[lane] = src[lane * tstride];
+    if (lane + 32 < kObs) dst[lane + 32] = src[(lane + 32) * tstride];
   }
 }
 
-__global__ void __launch_bounds__(kBS) k_step(Dev D, const float* __restrict__ act, float* __restrict__ obs,
-                                               double* __restrict__ reward, double* __restrict__ reward2,
-                                               uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);                             // [kObs][kTileStride] observation tile
-  Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + kTileBytes);         // contact-solver working set, one per warp
-  const int e = planned_env(D, blockIdx.x * kBS + threadIdx.x);
-  const unsigned wmask = __ballot_sync(0xffffffffu, e >= 0);
+__global__ void __launch_bounds__(kBS) k_step_quiet(Dev D, const float* __restrict__ act, float* __restrict__ obs,
+                                                     double* __restrict__ reward, double* __restrict__ reward2,
+                                                     uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
+  __shared__ float tile[kObs * kTileStride];
+  int e = blockIdx.x * kBS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool quiet = false;
+  if (e < D.n) {
+    const TaskSpec sp = task_spec(D.task[e]);
+    quiet = !(D.flags[e] & F_PHYS_ERROR) && env_is_quiet(D.clear[e], D.rvx[e], D.rvy[e], D.rw[e], sp.gear_x, sp.damp_xy);
+  }
+  // work list append, one atomic per warp
+  const unsigned busy = __ballot_sync(0xffffffffu, e < D.n && !quiet);
+  if (busy) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&D.counts[0], __popc(busy));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((busy >> lane) & 1u) D.worklist[base + __popc(busy & ((1u << lane) - 1u))] = e;
+  }
+  if (!quiet) e = -1;
   if (e >= 0) {
     float2 a = reinterpret_cast<const float2*>(act)[e];
     double rew[2];
     unsigned char c, d;
-    env_step(wmask, &scratch[threadIdx.x >> 5], D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d);
+    env_step<true>(0u, nullptr, nullptr, D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d);
     reward[e] = rew[0];
     if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
     cost[e] = c;
     done[e] = d;
   }
   __syncwarp();
-  write_rows(tile, obs, e);
+  write_rows(tile + (threadIdx.x & ~31), kTileStride, obs, e);
+}
+
+constexpr int kBusyTileStride = 33;
+constexpr size_t kBusyTileBytes = (sizeof(float) * kObs * kBusyTileStride + 15) / 16 * 16;
+constexpr size_t kBusySmemBytes = kBusyTileBytes + sizeof(Scratch) + 32 * sizeof(SmallScratch);
+
+__global__ void __launch_bounds__(32) k_step_busy(Dev D, const float* __restrict__ act, float* __restrict__ obs,
+                                                   double* __restrict__ reward, double* __restrict__ reward2,
+                                                   uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  Scratch* big = reinterpret_cast<Scratch*>(smem_raw + kBusyTileBytes);
+  SmallScratch* small = reinterpret_cast<SmallScratch*>(smem_raw + kBusyTileBytes + sizeof(Scratch));
+  const int lane = threadIdx.x;
+  const int count = D.counts[0];
+  for (int chunk = blockIdx.x; chunk * 32 < count; chunk += gridDim.x) {
+    const int i = chunk * 32 + lane;
+    const int e = i < count ? D.worklist[i] : -1;
+    const unsigned wmask = __ballot_sync(0xffffffffu, e >= 0);
+    if (e >= 0) {
+      float2 a = reinterpret_cast<const float2*>(act)[e];
+      double rew[2];
+      unsigned char c, d;
+      env_step<false>(wmask, big, small + lane, D, e, a.x, a.y, tile + lane, kBusyTileStride, rew, &c, &d);
+      reward[e] = rew[0];
+      if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
+      cost[e] = c;
+      done[e] = d;
+    }
+    __syncwarp();
+    write_rows(tile, kBusyTileStride, obs, e);
+    __syncwarp();
+  }
 }
 
 __global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs) {
@@ -149,7 +160,7 @@ __global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs)
   Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + kTileBytes);
   const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
   const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
-  if (e < D.n) env_observe(wmask, &scratch[threadIdx.x >> 5], D, e, tile + threadIdx.x, kTileStride);
+  if (e < D.n) env_observe(wmask, &scratch[threadIdx.x >> 5], nullptr, D, e, tile + threadIdx.x, kTileStride);
   __syncthreads();
   write_tile(tile, obs, e0, D.n);
 }
@@ -169,8 +180,8 @@ __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __re
     for (int k = 0; k < k_steps; ++k) {
       double u1, u2;
       rng.pair(2u, base + (uint32_t)k, u1, u2);
-      env_step(wmask, &scratch[threadIdx.x >> 5], D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + threadIdx.x,
-               kTileStride, rew, &c, &d);
+      env_step<false>(wmask, &scratch[threadIdx.x >> 5], nullptr, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0),
+                      tile + threadIdx.x, kTileStride, rew, &c, &d);
     }
     if (reward) reward[e] = rew[0];
     if (cost) cost[e] = c;
@@ -308,13 +319,19 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   if (cfg->robot != SAG_ROBOT_POINT) return fail("sag_create: only the point robot is implemented on the device path");
   if (cfg->robot_ctrl_range_scale != 0.0) return fail("sag_create: robot_ctrl_range_scale != 0 is not implemented");
   CK(cudaSetDevice(device));
-  CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  CK(cudaFuncSetAttribute(k_step_busy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBusySmemBytes));
   CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   CK(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   Handle* H = new (std::nothrow) Handle();
   if (!H) return fail("sag_create: out of host memory");
   memset(H, 0, sizeof(*H));
   H->device = device;
+  {
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_busy, 32, kBusySmemBytes);
+    H->busy_grid = sms * (per_sm > 0 ? per_sm : 1);
+  }
   Dev& D = H->D;
   dev_from_config(D, *cfg);
   SlabLayout LY = slab_layout(D.n, D.stride, kObs);
@@ -358,10 +375,15 @@ size_t sag_field_bytes(void* handle, int field) {
 
 static inline int grid_for(int n) { return (n + kBS - 1) / kBS; }
 
-static cudaError_t launch_plan(Handle* H, cudaStream_t s) {
+static cudaError_t launch_step(Handle* H, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost,
+                               uint8_t* done, cudaStream_t s) {
   cudaError_t ce = cudaMemsetAsync(H->D.counts, 0, 4 * sizeof(int), s);
   if (ce != cudaSuccess) return ce;
-  k_plan<<<(H->D.n + 255) / 256, 256, 0, s>>>(H->D);
+  k_step_quiet<<<grid_for(H->D.n), kBS, 0, s>>>(H->D, act, obs, reward, reward2, cost, done);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return ce;
+  const int chunks = (H->D.n + 31) / 32;
+  k_step_busy<<<chunks < H->busy_grid ? chunks : H->busy_grid, 32, kBusySmemBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
   return cudaGetLastError();
 }
 
@@ -395,9 +417,7 @@ int sag_step(void* handle, const float* act, float* obs, double* reward, double*
              void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !act || !obs || !reward || !cost || !done) return fail("sag_step: null argument");
-  CK(launch_plan(H, (cudaStream_t)stream));
-  k_step<<<grid_for(H->D.n), kBS, kSmemBytes, (cudaStream_t)stream>>>(H->D, act, obs, reward, reward2, cost, done);
-  CK(cudaGetLastError());
+  CK(launch_step(H, act, obs, reward, reward2, cost, done, (cudaStream_t)stream));
   return 0;
 }
 
@@ -423,9 +443,7 @@ int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward
   cudaStream_t s = H->own_stream;
   const size_t n = (size_t)H->D.n;
   CK(cudaMemcpyAsync(H->act_d, act_h, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-  CK(launch_plan(H, s));
-  k_step<<<grid_for(H->D.n), kBS, kSmemBytes, s>>>(H->D, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d);
-  CK(cudaGetLastError());
+  CK(launch_step(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s));
   CK(cudaMemcpyAsync(obs_h, H->obs_d, n * kObs * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(reward_h, H->rew_d, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(cost_h, H->cost_d, n, cudaMemcpyDeviceToHost, s));

@@ -51,7 +51,7 @@ inline void slab_bind(Dev& D, const SlabLayout& L, char* base) {
   D.nstep = ii + 6 * st; D.ctr = (unsigned*)(ii + 7 * st); D.episode = (unsigned*)(ii + 8 * st); D.movmask = ii + 9 * st;
   D.flags = (unsigned char*)(base + L.off[SAG_F_FLAGS]);
   int32_t* sc = (int32_t*)(base + L.sched_off);
-  D.hint = sc; D.hotlist = sc + st; D.coldlist = sc + 2 * st; D.counts = sc + 3 * st;
+  D.worklist = sc; D.counts = sc + 3 * st;
 }
 
 inline void dev_from_config(Dev& D, const SagConfig& c) {

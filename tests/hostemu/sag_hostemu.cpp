@@ -90,10 +90,11 @@ int sag_step(void* h, const float* act, float* obs, double* reward, double* rewa
   (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
   static float tile[kObs * kTileStride];
   static Scratch scratch;
+  static SmallScratch small;
   for (int e0 = 0; e0 < D.n; e0 += kBS) {
     for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
       int e = e0 + t; double rew[2]; unsigned char c, d;
-      env_step(1u, &scratch, D, e, act[2 * e], act[2 * e + 1], tile + t, kTileStride, rew, &c, &d);
+      env_step<false>(1u, &scratch, &small, D, e, act[2 * e], act[2 * e + 1], tile + t, kTileStride, rew, &c, &d);
       reward[e] = rew[0];
       if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
       cost[e] = c; done[e] = d;
@@ -106,8 +107,9 @@ int sag_observe(void* h, float* obs, void* s) {
   (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
   static float tile[kObs * kTileStride];
   static Scratch scratch;
+  static SmallScratch small;
   for (int e0 = 0; e0 < D.n; e0 += kBS) {
-    for (int t = 0; t < kBS && e0 + t < D.n; ++t) env_observe(1u, &scratch, D, e0 + t, tile + t, kTileStride);
+    for (int t = 0; t < kBS && e0 + t < D.n; ++t) env_observe(1u, &scratch, nullptr, D, e0 + t, tile + t, kTileStride);
     write_tile(tile, obs, e0, D.n);
   }
   return 0;
@@ -116,6 +118,7 @@ int sag_rollout(void* h, int k_steps, float* obs, double* reward, uint8_t* cost,
   (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
   static float tile[kObs * kTileStride];
   static Scratch scratch;
+  static SmallScratch small;
   for (int e0 = 0; e0 < D.n; e0 += kBS) {
     for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
       int e = e0 + t; double rew[2] = {0, 0}; unsigned char c = 0, d = 0;
@@ -123,7 +126,7 @@ int sag_rollout(void* h, int k_steps, float* obs, double* reward, uint8_t* cost,
       uint32_t base = (uint32_t)D.nstep[e];
       for (int k = 0; k < k_steps; ++k) {
         double u1, u2; rng.pair(2u, base + (uint32_t)k, u1, u2);
-        env_step(1u, &scratch, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + t, kTileStride, rew, &c, &d);
+        env_step<false>(1u, &scratch, nullptr, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + t, kTileStride, rew, &c, &d);
       }
       if (reward) reward[e] = rew[0];
       if (cost) cost[e] = c;
