@@ -6,6 +6,7 @@
 // as one contiguous, fully coalesced block.  No tensor cores: nothing here is a dense contraction.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -52,6 +53,7 @@ struct Handle {
   uint8_t *cost_d, *done_d;
   cudaStream_t own_stream;
   int busy_grid;  // CTAs of k_step_busy: resident CTAs per SM x SMs
+  int busy_g;     // environments per warp in k_step_busy
 };
 
 // coalesced write-out of the CTA's observation tile: tile[k][t] -> out[(e0 + t) * kObs + k]
@@ -121,35 +123,48 @@ __global__ void __launch_bounds__(kBS) k_step_quiet(Dev D, const float* __restri
   write_rows(tile + (threadIdx.x & ~31), kTileStride, obs, e);
 }
 
-constexpr int kBusyTileStride = 33;
-constexpr size_t kBusyTileBytes = (sizeof(float) * kObs * kBusyTileStride + 15) / 16 * 16;
-constexpr size_t kBusySmemBytes = kBusyTileBytes + sizeof(Scratch) + 32 * sizeof(SmallScratch);
+// G = environments per warp (lanes 0..G-1 active).  A warp executes the union of its lanes' divergent paths and each
+// busy warp is latency-bound, so fewer environments per warp = shorter critical path, more warps = more latency hiding.
+template <int G>
+struct BusyCfg {
+  static constexpr int kTileStride = G + 1;
+  static constexpr size_t kTileBytes = (sizeof(float) * kObs * kTileStride + 15) / 16 * 16;
+  static constexpr size_t kSmemBytes = kTileBytes + sizeof(Scratch) + G * sizeof(SmallScratch);
+};
 
+template <int G>
 __global__ void __launch_bounds__(32) k_step_busy(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                    double* __restrict__ reward, double* __restrict__ reward2,
                                                    uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
-  Scratch* big = reinterpret_cast<Scratch*>(smem_raw + kBusyTileBytes);
-  SmallScratch* small = reinterpret_cast<SmallScratch*>(smem_raw + kBusyTileBytes + sizeof(Scratch));
+  Scratch* big = reinterpret_cast<Scratch*>(smem_raw + BusyCfg<G>::kTileBytes);
+  SmallScratch* small = reinterpret_cast<SmallScratch*>(smem_raw + BusyCfg<G>::kTileBytes + sizeof(Scratch));
   const int lane = threadIdx.x;
   const int count = D.counts[0];
-  for (int chunk = blockIdx.x; chunk * 32 < count; chunk += gridDim.x) {
-    const int i = chunk * 32 + lane;
-    const int e = i < count ? D.worklist[i] : -1;
+  for (int chunk = blockIdx.x; chunk * G < count; chunk += gridDim.x) {
+    const int i = chunk * G + lane;
+    const int e = (lane < G && i < count) ? D.worklist[i] : -1;
     const unsigned wmask = __ballot_sync(0xffffffffu, e >= 0);
     if (e >= 0) {
       float2 a = reinterpret_cast<const float2*>(act)[e];
       double rew[2];
       unsigned char c, d;
-      env_step<false>(wmask, big, small + lane, D, e, a.x, a.y, tile + lane, kBusyTileStride, rew, &c, &d);
+      env_step<false>(wmask, big, small + lane, D, e, a.x, a.y, tile + lane, BusyCfg<G>::kTileStride, rew, &c, &d);
       reward[e] = rew[0];
       if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
       cost[e] = c;
       done[e] = d;
     }
     __syncwarp();
-    write_rows(tile, kBusyTileStride, obs, e);
+#pragma unroll
+    for (int r = 0; r < G; ++r) {  // observation rows of this chunk, 60 floats each, all lanes help
+      const int er = __shfl_sync(0xffffffffu, e, r);
+      if (er < 0) continue;
+      float* dst = obs + (size_t)er * kObs;
+      dst[lane] = tile[lane * BusyCfg<G>::kTileStride + r];
+      if (lane + 32 < kObs) dst[lane + 32] = tile[(lane + 32) * BusyCfg<G>::kTileStride + r];
+    }
     __syncwarp();
   }
 }
@@ -319,7 +334,6 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   if (cfg->robot != SAG_ROBOT_POINT) return fail("sag_create: only the point robot is implemented on the device path");
   if (cfg->robot_ctrl_range_scale != 0.0) return fail("sag_create: robot_ctrl_range_scale != 0 is not implemented");
   CK(cudaSetDevice(device));
-  CK(cudaFuncSetAttribute(k_step_busy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBusySmemBytes));
   CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   CK(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   Handle* H = new (std::nothrow) Handle();
@@ -327,9 +341,21 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   memset(H, 0, sizeof(*H));
   H->device = device;
   {
+    // environments per busy warp: default 1 (measured best on B200); SAG_BUSY_G overrides for tuning
+    int G = 1;
+    const char* gs = getenv("SAG_BUSY_G");
+    if (gs) { int v = atoi(gs); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) G = v; }
+    H->busy_g = G;
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_busy, 32, kBusySmemBytes);
+#define SAG_SETUP_BUSY(GG)                                                                                                   \
+  {                                                                                                                          \
+    cudaFuncSetAttribute(k_step_busy<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BusyCfg<GG>::kSmemBytes);        \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_busy<GG>, 32, BusyCfg<GG>::kSmemBytes);                    \
+  }
+    if (G == 1) SAG_SETUP_BUSY(1) else if (G == 2) SAG_SETUP_BUSY(2) else if (G == 4) SAG_SETUP_BUSY(4)
+    else if (G == 8) SAG_SETUP_BUSY(8) else if (G == 16) SAG_SETUP_BUSY(16) else SAG_SETUP_BUSY(32)
+#undef SAG_SETUP_BUSY
     H->busy_grid = sms * (per_sm > 0 ? per_sm : 1);
   }
   Dev& D = H->D;
@@ -382,8 +408,13 @@ static cudaError_t launch_step(Handle* H, const float* act, float* obs, double* 
   k_step_quiet<<<grid_for(H->D.n), kBS, 0, s>>>(H->D, act, obs, reward, reward2, cost, done);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) return ce;
-  const int chunks = (H->D.n + 31) / 32;
-  k_step_busy<<<chunks < H->busy_grid ? chunks : H->busy_grid, 32, kBusySmemBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
+  const int G = H->busy_g;
+  const int chunks = (H->D.n + G - 1) / G;
+  const int grid = chunks < H->busy_grid ? chunks : H->busy_grid;
+#define SAG_LAUNCH_BUSY(GG) k_step_busy<GG><<<grid, 32, BusyCfg<GG>::kSmemBytes, s>>>(H->D, act, obs, reward, reward2, cost, done)
+  if (G == 1) SAG_LAUNCH_BUSY(1); else if (G == 2) SAG_LAUNCH_BUSY(2); else if (G == 4) SAG_LAUNCH_BUSY(4);
+  else if (G == 8) SAG_LAUNCH_BUSY(8); else if (G == 16) SAG_LAUNCH_BUSY(16); else SAG_LAUNCH_BUSY(32);
+#undef SAG_LAUNCH_BUSY
   return cudaGetLastError();
 }
 
