@@ -17,6 +17,10 @@
 
 using namespace sag;
 
+#ifndef SAG_BUSY_MIN_BLOCKS
+#define SAG_BUSY_MIN_BLOCKS 12
+#endif
+
 namespace {
 
 constexpr int kBS = 128;          // environments (threads) per CTA
@@ -133,7 +137,7 @@ struct BusyCfg {
 };
 
 template <int G>
-__global__ void __launch_bounds__(32) k_step_busy(Dev D, const float* __restrict__ act, float* __restrict__ obs,
+__global__ void __launch_bounds__(32, SAG_BUSY_MIN_BLOCKS) k_step_busy(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                    double* __restrict__ reward, double* __restrict__ reward2,
                                                    uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -341,8 +345,8 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   memset(H, 0, sizeof(*H));
   H->device = device;
   {
-    // environments per busy warp: default 1 (measured best on B200); SAG_BUSY_G overrides for tuning
-    int G = 1;
+    // environments per busy warp: 8 measured best on B200 (sweep 1/2/4/8/32 in DESIGN.md 7); SAG_BUSY_G overrides
+    int G = 8;
     const char* gs = getenv("SAG_BUSY_G");
     if (gs) { int v = atoi(gs); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) G = v; }
     H->busy_g = G;
