@@ -79,6 +79,8 @@ def lib():
     L.orc_env_get_robot.argtypes = [C.c_void_p, dp]
     L.orc_env_set_robot.argtypes = [C.c_void_p, dp]
     L.orc_env_get_obj.argtypes = [C.c_void_p, C.c_int, C.POINTER(Obj)]
+    L.orc_env_get_robot_ext.argtypes = [C.c_void_p, dp]
+    L.orc_env_set_robot_ext.argtypes = [C.c_void_p, dp]
     L.orc_env_set_obj.argtypes = [C.c_void_p, C.c_int, C.POINTER(Obj)]
     L.orc_env_get_task_state.argtypes = [C.c_void_p, dp]
     L.orc_env_set_task_state.argtypes = [C.c_void_p, dp]
@@ -194,6 +196,18 @@ class OracleEnv:
     def robot_state(self, v):
         v = np.ascontiguousarray(v, dtype=np.float64)
         self.L.orc_env_set_robot(self.h, _dp(v))
+
+    @property
+    def robot_ext(self):
+        """car extras: wheel rates (2), castor quaternion (4)"""
+        o = np.zeros(6)
+        self.L.orc_env_get_robot_ext(self.h, _dp(o))
+        return o
+
+    @robot_ext.setter
+    def robot_ext(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        self.L.orc_env_set_robot_ext(self.h, _dp(v))
 
     def get_obj(self, s):
         o = Obj()

@@ -55,6 +55,57 @@
 #define PGS_TOL 1e-8
 #define SLEEP_V 1e-8
 
+/* car.xml: timestep 0.008, frame_skip 10 (safe_adaptation_gym.py:18); default geom density 5 (car.xml:5) */
+#define CAR_TIMESTEP 0.008
+#define CAR_NSUB 10
+#define CAR_FORCE_LIM 0.02     /* car.xml:7 */
+#define CAR_WHEEL_R 0.05       /* car.xml:5 default size; fromto cylinders */
+#define CAR_WHEEL_DAMP 0.001   /* car.xml:6 */
+#define CAR_ARMATURE 0.00025   /* car.xml:22,26 */
+#define CAR_DENSITY 5.0
+#define CAR_NGEOM 8
+/* robot geoms in the body frame (x, y, half-x, half-y | radius), car.xml:16-31; wheels: x-axis cylinders -> footprints */
+static const double CAR_GEOM[CAR_NGEOM][5] = {
+    {0.0, 0.0, 0.1, 0.1, 0.0},       /* robot */
+    {0.0, 0.15, 0.1, 0.01, 0.0},     /* back_bumper */
+    {0.0, 0.125, 0.01, 0.025, 0.0},  /* back_connector */
+    {0.0, -0.165, 0.05, 0.01, 0.0},  /* front_bumper */
+    {0.0, -0.13, 0.05, 0.03, 0.0},   /* front_connector */
+    {-0.13, 0.1, 0.025, 0.05, 0.0},  /* left wheel footprint */
+    {0.13, 0.1, 0.025, 0.05, 0.0},   /* right wheel footprint */
+    {0.0, -0.1, 0.0, 0.0, 0.05},     /* rear castor sphere */
+};
+static const double CAR_GEOM_HZ[5] = {0.05, 0.05, 0.03, 0.05, 0.01}; /* box half heights (masses) */
+typedef struct { double M, mcx, mcy, Io, Iw, nwheel, nrear; } car_model;
+static car_model car_params(void) {
+  car_model c;
+  double M = 0.0, mx = 0.0, my = 0.0, Io = 0.0;
+  for (int g = 0; g < 5; ++g) { /* boxes */
+    double hx = CAR_GEOM[g][2], hy = CAR_GEOM[g][3], hz = CAR_GEOM_HZ[g];
+    double m = 8.0 * hx * hy * hz * CAR_DENSITY;
+    double x = CAR_GEOM[g][0], y = CAR_GEOM[g][1];
+    M += m; mx += m * x; my += m * y;
+    Io += m * (4.0 * hx * hx + 4.0 * hy * hy) / 12.0 + m * (x * x + y * y);
+  }
+  double mw = PI * CAR_WHEEL_R * CAR_WHEEL_R * 0.05 * CAR_DENSITY; /* cylinder radius .05 length .05 */
+  for (int g = 5; g < 7; ++g) {
+    double x = CAR_GEOM[g][0], y = CAR_GEOM[g][1];
+    M += mw; mx += mw * x; my += mw * y;
+    Io += mw * (3.0 * CAR_WHEEL_R * CAR_WHEEL_R + 0.05 * 0.05) / 12.0 + mw * (x * x + y * y);
+  }
+  double mb = 4.0 / 3.0 * PI * CAR_WHEEL_R * CAR_WHEEL_R * CAR_WHEEL_R * CAR_DENSITY;
+  { double x = CAR_GEOM[7][0], y = CAR_GEOM[7][1];
+    M += mb; mx += mb * x; my += mb * y;
+    Io += 0.4 * mb * CAR_WHEEL_R * CAR_WHEEL_R + mb * (x * x + y * y); }
+  c.M = M; c.mcx = mx; c.mcy = my; c.Io = Io;
+  c.Iw = 0.5 * mw * CAR_WHEEL_R * CAR_WHEEL_R + CAR_ARMATURE;
+  /* static normal loads on a level floor: wheels at y = +0.1, castor at y = -0.1 */
+  double yc = my / M;
+  c.nrear = M * GRAV * (0.1 - yc) / 0.2;
+  c.nwheel = (M * GRAV - c.nrear) / 2.0;
+  return c;
+}
+
 static double pt_mass(void) { return 4.0 / 3.0 * PI * PT_R * PT_R * PT_R + 8.0 * PT_ARROW_H * PT_ARROW_H * PT_ARROW_H; }
 static double pt_mc(void) { return 8.0 * PT_ARROW_H * PT_ARROW_H * PT_ARROW_H * PT_ARROW_OFF; } /* m * c */
 static double pt_inertia_o(void) {
@@ -73,6 +124,8 @@ struct orc_env {
   double damp_x, damp_y, damp_z, gear_x, gear_z;
   double ctrl[2], ctrl_lo[2], ctrl_hi[2];
   double q[3], v[3], qacc[3];
+  double wheel_w[2], wheel_tau[2]; /* car: wheel spin rates, constraint torque of the last forward pass */
+  double cq[4];                    /* car: castor ball orientation relative to the chassis (ball joint quaternion) */
   double time;
   int nobj;
   orc_obj obj[ORC_MAX_OBJ];
@@ -300,9 +353,16 @@ static void obj_geom(const orc_env* e, int slot, int part, geom2* g) {
     default: g->is_box = 0; break;
   }
 }
+static int robot_nparts(const orc_env* e) { return e->robot == ORC_CAR ? CAR_NGEOM : 2; }
 static void robot_geom(const orc_env* e, int part, geom2* g) {
   double c = sag_cos(e->q[2]), s = sag_sin(e->q[2]);
   g->c = c; g->s = s;
+  if (e->robot == ORC_CAR) {
+    const double* G = CAR_GEOM[part];
+    g->cx = e->q[0] + G[0] * c - G[1] * s; g->cy = e->q[1] + G[0] * s + G[1] * c;
+    g->is_box = G[4] == 0.0; g->hx = G[2]; g->hy = G[3]; g->r = G[4];
+    return;
+  }
   if (part == 0) { g->is_box = 0; g->cx = e->q[0]; g->cy = e->q[1]; g->r = PT_R; g->hx = g->hy = 0; }
   else { g->is_box = 1; g->cx = e->q[0] + PT_ARROW_OFF * c; g->cy = e->q[1] + PT_ARROW_OFF * s; g->hx = g->hy = PT_ARROW_H; g->r = 0; }
 }
@@ -351,7 +411,7 @@ static void detect(orc_env* e) {
     const orc_obj* ob = &e->obj[s];
     active[s] = obj_movable(ob->type) && (ob->vx != 0.0 || ob->vy != 0.0 || ob->w != 0.0);
     if (!obj_collidable(ob->type)) continue;
-    for (int rg = 0; rg < 2; ++rg) {
+    for (int rg = 0; rg < robot_nparts(e); ++rg) {
       geom2 gr; robot_geom(e, rg, &gr);
       for (int p = 0; p < obj_nparts(ob->type); ++p) {
         geom2 go; obj_geom(e, s, p, &go);
@@ -391,6 +451,14 @@ typedef struct { double p, q, ia, is; } pt_mat; /* M = [[a,0,p],[0,a,q],[p,q,I]]
 /* the two slide joints always share one damping value, so a == b and p^2 + q^2 == (m c)^2: the Schur
  * complement is a constant of the model and the solve needs no division per substep */
 static void pt_matrix(const orc_env* e, double hd, pt_mat* M) {
+  if (e->robot == ORC_CAR) { /* free joint: no damping; COM offset (cx, cy) in the body frame */
+    car_model c = car_params();
+    double sn = sag_sin(e->q[2]), cs = sag_cos(e->q[2]);
+    M->ia = 1.0 / c.M;
+    M->p = -(c.mcx * sn + c.mcy * cs); M->q = c.mcx * cs - c.mcy * sn;
+    M->is = 1.0 / (c.Io - (c.mcx * c.mcx + c.mcy * c.mcy) * M->ia);
+    return;
+  }
   double m = pt_mass(), mc = pt_mc();
   M->ia = 1.0 / (m + hd * e->damp_x);
   M->p = -mc * sag_sin(e->q[2]); M->q = mc * sag_cos(e->q[2]);
@@ -406,6 +474,14 @@ static void pt_solve(const pt_mat* M, const double* f, double* out) {
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 static void pt_smooth(const orc_env* e, double* f) {
+  if (e->robot == ORC_CAR) { /* chassis: no actuator, no damping; centripetal bias of the COM offset */
+    car_model cm = car_params();
+    double c = sag_cos(e->q[2]), s = sag_sin(e->q[2]), w = e->v[2];
+    f[0] = w * w * (cm.mcx * c - cm.mcy * s);
+    f[1] = w * w * (cm.mcx * s + cm.mcy * c);
+    f[2] = 0.0;
+    return;
+  }
   double mc = pt_mc(), c = sag_cos(e->q[2]), s = sag_sin(e->q[2]), w = e->v[2];
   /* actuators: motor 'x' (site transmission, gear 0.3 along body x) and velocity servo 'z' */
   double u0 = clampd(e->ctrl[0], e->ctrl_lo[0], e->ctrl_hi[0]);
@@ -415,6 +491,11 @@ static void pt_smooth(const orc_env* e, double* f) {
   f[0] = e->gear_x * fx * c - e->damp_x * e->v[0] + mc * w * w * c;
   f[1] = e->gear_x * fx * s - e->damp_y * e->v[1] + mc * w * w * s;
   f[2] = e->gear_z * fz - e->damp_z * w;
+}
+/* car wheel hinges: motor gear 1, forcerange +-0.02 (car.xml:7,51-54), joint damping 0.001 (car.xml:6) */
+static double car_wheel_smooth(const orc_env* e, int i) {
+  double u = clampd(e->ctrl[i], e->ctrl_lo[i], e->ctrl_hi[i]);
+  return clampd(u, -CAR_FORCE_LIM, CAR_FORCE_LIM) - CAR_WHEEL_DAMP * e->wheel_w[i];
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -431,16 +512,20 @@ static double impedance(double r) {
 
 typedef struct {
   pt_mat M;              /* robot mass matrix (no damping) */
-  double acc[1 + ORC_MAX_OBJ][3];
+  double acc[1 + ORC_MAX_OBJ + 2][3]; /* robot, objects, car wheels (1 DoF each, in [.][0]) */
   double im[ORC_MAX_OBJ], ii[ORC_MAX_OBJ];
+  double iw;                         /* 1 / wheel spin inertia */
 } solve_ctx;
+#define WHEEL_BODY(i) (1 + ORC_MAX_OBJ + (i))
 
 static void minv_mul(const solve_ctx* S, int body, const double* j, double* out) {
   if (body == 0) pt_solve(&S->M, j, out);
+  else if (body > ORC_MAX_OBJ) { out[0] = j[0] * S->iw; out[1] = 0.0; out[2] = 0.0; }
   else { out[0] = j[0] * S->im[body - 1]; out[1] = j[1] * S->im[body - 1]; out[2] = j[2] * S->ii[body - 1]; }
 }
 static void body_vel(const orc_env* e, int body, double* v) {
   if (body == 0) { v[0] = e->v[0]; v[1] = e->v[1]; v[2] = e->v[2]; }
+  else if (body > ORC_MAX_OBJ) { v[0] = e->wheel_w[body - 1 - ORC_MAX_OBJ]; v[1] = 0.0; v[2] = 0.0; }
   else { const orc_obj* o = &e->obj[body - 1]; v[0] = o->vx; v[1] = o->vy; v[2] = o->w; }
 }
 static void body_pos(const orc_env* e, int body, double* p) {
@@ -452,6 +537,8 @@ typedef struct {
   int ba, bb;
   double ja[2][3], jb[2][3]; /* row 0 normal, row 1 tangent */
   double aref[2], diag[2], R[2], f[2], inv[2];
+  int type;     /* 0 contact (normal, tangent), 2 wheel-floor friction (longitudinal, lateral; disc bound) */
+  double bound; /* type 2: mu * N */
 } crow;
 
 static double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -465,7 +552,7 @@ static void apply(solve_ctx* S, int body, const double* j, double df) {
 
 static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
   solve_ctx S;
-  crow rows[ORC_MAX_CON + 1];
+  crow rows[ORC_MAX_CON + 3];
   int nrow = 0;
   int touched[ORC_MAX_OBJ];
   double ffl[ORC_MAX_OBJ][3];
@@ -481,12 +568,42 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
   }
   const double bdamp = 2.0 / (IMP_DMAX * SOL_TC);
   const double kbase = 1.0 / (IMP_DMAX * IMP_DMAX * SOL_TC * SOL_TC * SOL_DR * SOL_DR);
+  const double rr0 = (1.0 - IMP_D0) / IMP_D0;
+  /* car: wheel-floor friction, always present.  Reduced model: the chassis stays level, normal loads
+   * are the static ones, each wheel has a longitudinal slip row (chassis point velocity along the rolling direction +
+   * r * wheel rate) and a lateral slip row, jointly bounded by mu * N; the rear castor rolls ideally. */
+  if (e->robot == ORC_CAR) {
+    car_model cm = car_params();
+    S.iw = 1.0 / cm.Iw;
+    double cs = sag_cos(e->q[2]), sn = sag_sin(e->q[2]);
+    for (int i = 0; i < 2; ++i) {
+      S.acc[WHEEL_BODY(i)][0] = car_wheel_smooth(e, i) * S.iw; S.acc[WHEEL_BODY(i)][1] = S.acc[WHEEL_BODY(i)][2] = 0.0;
+      double bx = i == 0 ? -0.1 : 0.1, by = 0.1;              /* wheel bodies, car.xml:21,25 */
+      double rx = bx * cs - by * sn, ry = bx * sn + by * cs;  /* lever arm in the world frame */
+      crow* r = &rows[nrow++];
+      r->type = 2; r->bound = FRICTION_MU * cm.nwheel;
+      r->ba = 0; r->bb = WHEEL_BODY(i);
+      r->ja[0][0] = -sn; r->ja[0][1] = cs; r->ja[0][2] = rx * cs - ry * -sn;  /* rolling direction = body y */
+      r->jb[0][0] = CAR_WHEEL_R; r->jb[0][1] = 0.0; r->jb[0][2] = 0.0;
+      r->ja[1][0] = cs; r->ja[1][1] = sn; r->ja[1][2] = rx * sn - ry * cs;    /* lateral = body x */
+      r->jb[1][0] = 0.0; r->jb[1][1] = 0.0; r->jb[1][2] = 0.0;
+      double va[3], vb[3];
+      body_vel(e, 0, va); body_vel(e, r->bb, vb);
+      for (int k = 0; k < 2; ++k) {
+        double t[3], diag = 0.0, vel = 0.0;
+        minv_mul(&S, 0, r->ja[k], t); diag += dot3(r->ja[k], t); vel += dot3(r->ja[k], va);
+        if (k == 0) { minv_mul(&S, r->bb, r->jb[k], t); diag += dot3(r->jb[k], t); vel += dot3(r->jb[k], vb); }
+        r->diag[k] = diag; r->R[k] = rr0 * diag; r->aref[k] = -bdamp * vel; r->f[k] = 0.0;
+      }
+    }
+  }
   /* contact rows (active only when penetrating: dist < 0) */
   for (int i = 0; i < e->ncon; ++i) {
     const orc_contact* c = &e->con[i];
     if (!(c->dist < 0.0)) continue;
     if (c->ba < 0 && c->bb < 0) continue;
     crow* r = &rows[nrow++];
+    r->type = 0; r->bound = 0.0;
     r->ba = c->ba; r->bb = c->bb;
     double tx = -c->ny, ty = c->nx;
     double pa[2] = {0, 0}, pb[2] = {0, 0}, va[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
@@ -517,6 +634,7 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
     double dist = TENDON_MAX - len;
     if (dist < 0.0) {
       crow* r = &rows[nrow]; tendon_row = nrow++;
+      r->type = 0; r->bound = 0.0;
       r->ba = 0; r->bb = 1 + e->tendon_slot;
       /* d(dist)/dq : robot +d/len, box -d/len */
       r->ja[0][0] = dx / len; r->ja[0][1] = dy / len; r->ja[0][2] = 0.0;
@@ -542,7 +660,7 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
   /* capacity limits (the GPU keeps the solver's working set in shared memory): on overflow the step is a
    * PhysicsError and this pass applies no constraint forces and moves no object */
   if (nfl > ORC_MAX_BODIES) { e->error = 1; e->overflow = 1; }
-  if (e->overflow) { nrow = 0; nfl = 0; tendon_row = -1; for (int s = 0; s < e->nobj; ++s) touched[s] = 0; }
+  if (e->overflow) { nrow = e->robot == ORC_CAR ? 2 : 0; nfl = 0; tendon_row = -1; for (int s = 0; s < e->nobj; ++s) touched[s] = 0; }
   const double rr = (1.0 - IMP_D0) / IMP_D0;
   /* Projected Gauss-Seidel.  Row update: f <- proj(f - (J a - aref + R f) / (A_ii + R)); the reciprocal of the
    * denominator is taken once per row.  Terminates after PGS_SWEEPS sweeps or when one sweep changes the forces by
@@ -556,6 +674,28 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
     for (int i = 0; i < nrow; ++i) {
       crow* r = &rows[i];
       int nk = (i == tendon_row) ? 1 : 2;
+      if (r->type == 2) { /* wheel: both slip rows, then project the pair onto the friction disc */
+        double fo[2] = {r->f[0], r->f[1]};
+        for (int k = 0; k < 2; ++k) {
+          double a = dot3(r->ja[k], S.acc[r->ba]);
+          if (k == 0) a += dot3(r->jb[k], S.acc[r->bb]);
+          double fn = r->f[k] - (a - r->aref[k] + r->R[k] * r->f[k]) * r->inv[k];
+          double df = fn - r->f[k];
+          r->f[k] = fn;
+          if (df != 0.0) { apply(&S, r->ba, r->ja[k], df); if (k == 0) apply(&S, r->bb, r->jb[k], df); }
+        }
+        double nf = sqrt(r->f[0] * r->f[0] + r->f[1] * r->f[1]);
+        if (nf > r->bound) {
+          double sc = r->bound / nf;
+          for (int k = 0; k < 2; ++k) {
+            double g = r->f[k] * sc, df = g - r->f[k];
+            r->f[k] = g;
+            if (df != 0.0) { apply(&S, r->ba, r->ja[k], df); if (k == 0) apply(&S, r->bb, r->jb[k], df); }
+          }
+        }
+        sdf += fabs(r->f[0] - fo[0]) + fabs(r->f[1] - fo[1]); sf += fabs(r->f[0]) + fabs(r->f[1]);
+        continue;
+      }
       for (int k = 0; k < nk; ++k) {
         double a = 0.0;
         if (r->ba >= 0) a += dot3(r->ja[k], S.acc[r->ba]);
@@ -604,6 +744,8 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
       if (r->bb == 0) for (int d = 0; d < 3; ++d) fcon_robot[d] += r->jb[k][d] * r->f[k];
     }
   }
+  e->wheel_tau[0] = e->wheel_tau[1] = 0.0;
+  for (int i = 0; i < nrow; ++i) if (rows[i].type == 2) e->wheel_tau[rows[i].bb - WHEEL_BODY(0)] = rows[i].jb[0][0] * rows[i].f[0];
   for (int s = 0; s < e->nobj; ++s) {
     e->oacc[s][0] = S.acc[1 + s][0]; e->oacc[s][1] = S.acc[1 + s][1]; e->oacc[s][2] = S.acc[1 + s][2];
     e->touched[s] = touched[s];
@@ -617,6 +759,47 @@ void orc_phys_forward(orc_env* e) {
 
 static int bad(double x) { return !(fabs(x) <= 1e10); } /* NaN or > mjMAXVAL [EXT] */
 
+/* castor ball (car.xml:29-32): ideal rolling.  Relative angular velocity of the ball joint in the child frame, from
+ * the chassis point velocity at the castor (mjSENS_BALLANGVEL semantics [EXT]). */
+static void car_castor_angvel(const orc_env* e, double* wc) {
+  double cs = sag_cos(e->q[2]), sn = sag_sin(e->q[2]);
+  double bx = 0.0, by = -0.1;
+  double rx = bx * cs - by * sn, ry = bx * sn + by * cs;
+  double vx = e->v[0] - e->v[2] * ry, vy = e->v[1] + e->v[2] * rx;  /* world velocity of the castor centre */
+  double wx = -vy / CAR_WHEEL_R, wy = vx / CAR_WHEEL_R;              /* rolling without slip; no spin relative to the chassis */
+  double px = wx * cs + wy * sn, py = -wx * sn + wy * cs, pz = 0.0;  /* parent (chassis) frame */
+  /* child frame: rotate by the inverse of the joint quaternion */
+  double w = e->cq[0], x = -e->cq[1], y = -e->cq[2], z = -e->cq[3];
+  double tx = 2.0 * (y * pz - z * py), ty = 2.0 * (z * px - x * pz), tz = 2.0 * (x * py - y * px);
+  wc[0] = px + w * tx + (y * tz - z * ty);
+  wc[1] = py + w * ty + (z * tx - x * tz);
+  wc[2] = pz + w * tz + (x * ty - y * tx);
+}
+/* wheels: implicit joint damping; castor: quaternion exponential-map update (mju_quatIntegrate [EXT]) */
+static void car_integrate_extra(orc_env* e) {
+  car_model cm = car_params();
+  for (int i = 0; i < 2; ++i) {
+    double al = (car_wheel_smooth(e, i) + e->wheel_tau[i]) / (cm.Iw + e->h * CAR_WHEEL_DAMP);
+    e->wheel_w[i] += e->h * al;
+    if (bad(e->wheel_w[i])) e->error = 1;
+  }
+  double wc[3];
+  car_castor_angvel(e, wc);
+  double wn = sqrt(wc[0] * wc[0] + wc[1] * wc[1] + wc[2] * wc[2]);
+  if (wn > 0.0) {
+    double sh, ch;
+    sag_sincos(0.5 * e->h * wn, &sh, &ch);
+    double ax = wc[0] / wn * sh, ay = wc[1] / wn * sh, az = wc[2] / wn * sh;
+    double a = e->cq[0], b = e->cq[1], c = e->cq[2], d = e->cq[3];
+    double q0 = a * ch - b * ax - c * ay - d * az;
+    double q1 = a * ax + b * ch + c * az - d * ay;
+    double q2 = a * ay - b * az + c * ch + d * ax;
+    double q3 = a * az + b * ay - c * ax + d * ch;
+    double n = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    e->cq[0] = q0 / n; e->cq[1] = q1 / n; e->cq[2] = q2 / n; e->cq[3] = q3 / n;
+  }
+}
+
 /* physics.step(nstep): nstep x (forward dynamics, semi-implicit Euler with implicit joint
  * damping), safe_adaptation_gym.py:72; SURVEY Appendix B.1-2 [EXT] */
 void orc_phys_step(orc_env* e, int nstep) {
@@ -628,6 +811,7 @@ void orc_phys_step(orc_env* e, int nstep) {
     pt_solve(&Mh, rhs, a);
     for (int k = 0; k < 3; ++k) { e->v[k] += e->h * a[k]; }
     for (int k = 0; k < 3; ++k) { e->q[k] += e->h * e->v[k]; }
+    if (e->robot == ORC_CAR) car_integrate_extra(e);
     for (int s = 0; s < e->nobj; ++s) {
       orc_obj* o = &e->obj[s];
       if (!obj_movable(o->type)) continue;
@@ -661,6 +845,13 @@ void orc_phys_sensors(const orc_env* e, double* out) {
   out[5] = 0.0;
   out[6] = 0.0; out[7] = 0.0; out[8] = e->v[2];  /* gyro */
   out[9] = -0.5 * s; out[10] = -0.5 * c; out[11] = 0.0; /* magnetometer: R^T (0,-0.5,0) */
+  if (e->robot == ORC_CAR) { /* ballangvel_rear (3) then quat2mat(ballquat_rear).ravel() (9): safe_adaptation_gym.py:228-236 */
+    car_castor_angvel(e, out + 12);
+    double w = e->cq[0], x = e->cq[1], y = e->cq[2], z = e->cq[3];
+    out[15] = w * w + x * x - y * y - z * z; out[16] = 2.0 * (x * y - w * z); out[17] = 2.0 * (x * z + w * y);
+    out[18] = 2.0 * (x * y + w * z); out[19] = w * w - x * x + y * y - z * z; out[20] = 2.0 * (y * z - w * x);
+    out[21] = 2.0 * (x * z - w * y); out[22] = 2.0 * (y * z + w * x); out[23] = w * w - x * x - y * y + z * z;
+  }
 }
 
 /* ==========================================================================================
@@ -813,7 +1004,8 @@ orc_env* orc_env_create(int robot, int task, const orc_config* cfg) {
   orc_env* e = (orc_env*)calloc(1, sizeof(orc_env));
   e->robot = robot; e->task = task;
   if (cfg) e->cfg = *cfg; else orc_default_config(&e->cfg);
-  e->h = PT_TIMESTEP; e->nsub = PT_NSUB;
+  e->h = robot == ORC_CAR ? CAR_TIMESTEP : PT_TIMESTEP; e->nsub = robot == ORC_CAR ? CAR_NSUB : PT_NSUB;
+  e->cq[0] = 1.0;
   e->ctrl_lo[0] = e->ctrl_lo[1] = -1.0; e->ctrl_hi[0] = e->ctrl_hi[1] = 1.0; /* point.xml:7-8 */
   e->bound = e->cfg.max_bound;                                               /* world.py:78 */
   /* task-instance state that survives env.reset() (catch_goal.py:12-18, press_buttons.py:20-24) */
@@ -954,6 +1146,7 @@ int orc_env_reset(orc_env* e, uint32_t episode) {
   /* MujocoBridge.rebuild: fresh physics, mujoco_bridge.py:170-175 */
   e->q[0] = rxy[0]; e->q[1] = rxy[1]; e->q[2] = e->robot_rot;
   e->v[0] = e->v[1] = e->v[2] = 0.0; e->ctrl[0] = e->ctrl[1] = 0.0;
+  e->wheel_w[0] = e->wheel_w[1] = 0.0; e->cq[0] = 1.0; e->cq[1] = e->cq[2] = e->cq[3] = 0.0;
   e->time = 0.0; e->error = 0;
   orc_phys_forward(e);
   /* World.reset -> task.reset, world.py:167-170 */
@@ -1011,10 +1204,12 @@ static int compute_reward(orc_env* e, double* reward) {
       r += 1.0;
     }
     if (e->task == ORC_T_UNSUPERVISED) {                   /* unsupervised.py:48-67 */
-      double c = pt_mc() / pt_mass();
+      double cx = pt_mc() / pt_mass(), cy = 0.0;
+      if (e->robot == ORC_CAR) { car_model cm = car_params(); cx = cm.mcx / cm.M; cy = cm.mcy / cm.M; }
       double cs = sag_cos(e->q[2]), sn = sag_sin(e->q[2]);
-      double x = e->q[0] + c * cs, y = e->q[1] + c * sn;   /* subtree_com */
-      double u = e->v[0] - c * e->v[2] * sn, v = e->v[1] + c * e->v[2] * cs; /* subtree_linvel */
+      double ox = cx * cs - cy * sn, oy = cx * sn + cy * cs;   /* COM offset in the world frame */
+      double x = e->q[0] + ox, y = e->q[1] + oy;               /* subtree_com */
+      double u = e->v[0] - e->v[2] * oy, v = e->v[1] + e->v[2] * ox; /* subtree_linvel */
       double radius = sqrt(x * x + y * y);
       reward[0] = (((-u * y + v * x) / radius) / (1.0 + fabs(radius - 1.5))) * 1e-1;
       reward[1] = r;
@@ -1127,6 +1322,8 @@ int orc_env_step(orc_env* e, const double* action, double* obs, double* reward, 
 int orc_env_nobj(const orc_env* e) { return e->nobj; }
 void orc_env_get_robot(const orc_env* e, double* o) { for (int k = 0; k < 3; ++k) { o[k] = e->q[k]; o[3 + k] = e->v[k]; } }
 void orc_env_set_robot(orc_env* e, const double* in) { for (int k = 0; k < 3; ++k) { e->q[k] = in[k]; e->v[k] = in[3 + k]; } }
+void orc_env_get_robot_ext(const orc_env* e, double* o) { o[0] = e->wheel_w[0]; o[1] = e->wheel_w[1]; for (int k = 0; k < 4; ++k) o[2 + k] = e->cq[k]; }
+void orc_env_set_robot_ext(orc_env* e, const double* in) { e->wheel_w[0] = in[0]; e->wheel_w[1] = in[1]; for (int k = 0; k < 4; ++k) e->cq[k] = in[2 + k]; }
 void orc_env_get_obj(const orc_env* e, int s, orc_obj* out) { *out = e->obj[s]; }
 void orc_env_set_obj(orc_env* e, int s, const orc_obj* in) { e->obj[s] = *in; }
 void orc_env_get_task_state(const orc_env* e, double* o) {
@@ -1146,6 +1343,7 @@ void orc_phys_clear(orc_env* e) {
   e->nobj = 0; e->goal_slot = e->box_slot = e->first_button = -1; e->nbuttons = 0; e->tendon_slot = -1;
   e->time = 0.0; e->error = 0; e->ncon = 0;
   e->v[0] = e->v[1] = e->v[2] = 0.0; e->ctrl[0] = e->ctrl[1] = 0.0;
+  e->wheel_w[0] = e->wheel_w[1] = 0.0; e->cq[0] = 1.0; e->cq[1] = e->cq[2] = e->cq[3] = 0.0;
 }
 int orc_phys_add_obj(orc_env* e, int type, double x, double y, double yaw, double keepout, int group) {
   if (e->nobj >= ORC_MAX_OBJ) return -1;

@@ -104,6 +104,9 @@ int orc_env_obs_dim(const orc_env* e);
 int orc_env_nobj(const orc_env* e);
 void orc_env_get_robot(const orc_env* e, double* out6);
 void orc_env_set_robot(orc_env* e, const double* in6);
+/* car extras: wheel rates (2), castor quaternion (4) */
+void orc_env_get_robot_ext(const orc_env* e, double* out6);
+void orc_env_set_robot_ext(orc_env* e, const double* in6);
 void orc_env_get_obj(const orc_env* e, int slot, orc_obj* out);
 void orc_env_set_obj(orc_env* e, int slot, const orc_obj* in);
 /* task scalars: [last_dist0,last_dist1, goal_button, btn_state, btn_timer, active_mask,

@@ -76,6 +76,12 @@ class _Elem:
 def install_stubs():
     dm = types.ModuleType("dm_control")
     mujoco = types.ModuleType("dm_control.mujoco")
+    def _quat2mat(m, q):  # mujoco.mju_quat2Mat [EXT]: row-major 3x3 of a unit quaternion (w, x, y, z)
+        w, x, y, z = q
+        m[:] = [w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y),
+                2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+                2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z]
+    mujoco.mju_quat2Mat = _quat2mat
     mjcf = types.ModuleType("dm_control.mjcf")
     mjcf.RootElement = _Elem
     rl = types.ModuleType("dm_control.rl")
@@ -160,22 +166,29 @@ def replay_stream(events):
 # --------------------------------------------------------------------------------------------
 # FakeRobot / FakeBridge: MujocoBridge's interface answered from the oracle physics
 # --------------------------------------------------------------------------------------------
-class FakeRobot:  # robot.py:8-59 evaluated on point.xml
+class FakeRobot:  # robot.py:8-59 evaluated on point.xml / car.xml
     def __init__(self, path):
         self.base_path = path
         self.name = os.path.splitext(os.path.basename(path))[0]
-        assert self.name == "point"
+        assert self.name in ("point", "car")
         self.z_height = 0.1
-        self.geom_names = {"robot", "pointarrow"}
-        self.nq = self.nv = 3
         self.nu = 2
         self.hinge_pos_names, self.hinge_vel_names, self.ballquat_names, self.ballangvel_names = [], [], [], []
+        if self.name == "point":
+            self.geom_names = {"robot", "pointarrow"}
+            self.nq = self.nv = 3
+        else:  # car.xml:16-31 geoms, :37-38 joint sensors
+            self.geom_names = {"robot", "back_bumper", "back_connector", "front_bumper", "front_connector", "left", "right", "rear"}
+            self.nq, self.nv = 13, 11
+            self.ballquat_names, self.ballangvel_names = ["ballquat_rear"], ["ballangvel_rear"]
 
 
+_ROBOT_GEOMS = {"point": ["robot", "pointarrow"],
+                "car": ["robot", "back_bumper", "back_connector", "front_bumper", "front_connector", "left", "right", "rear"]}
 _PREFIX_TYPE = [("hazards", O.HAZARD), ("vases", O.VASE), ("gremlins", O.GREMLIN), ("pillars", O.PILLAR),
                 ("goal", O.GOAL), ("buttons", O.BUTTON), ("box", O.BOX)]
 _SENSOR_SLICE = {"accelerometer": slice(0, 3), "velocimeter": slice(3, 6), "gyro": slice(6, 9),
-                 "magnetometer": slice(9, 12)}
+                 "magnetometer": slice(9, 12), "ballangvel_rear": slice(12, 15)}
 
 
 class _NamedView(dict):
@@ -204,7 +217,7 @@ class FakeBridge:
 
     def __init__(self, robot, addition_render_objects_specs=None, config=None):
         self.robot = robot
-        self.env = O.OracleEnv("point", FakeBridge.TASK)
+        self.env = O.OracleEnv(robot.name, FakeBridge.TASK)
         self.env.clear_world()
         self.physics = _Physics(self)
         self.names, self.z = [], {}
@@ -243,6 +256,7 @@ class FakeBridge:
             self.user_groups[name] = np.array([float(group)])
         rx, ry = config["robot_xy"]
         e.robot_state = [rx, ry, config["robot_rot"], 0, 0, 0]
+        e.robot_ext = [0, 0, 1, 0, 0, 0]
         if config.get("modify_tree"):  # go_to_goal_damping.py / go_to_goal_motor.py
             damp, gear = 0.01, 0.3
             for (ns, id_), (attr, value) in config["modify_tree"]:
@@ -262,6 +276,8 @@ class FakeBridge:
         return self.names.index(name)
 
     def get_sensor(self, name):
+        if name == "ballquat_rear":
+            return self.env.robot_ext[2:6]
         return self.env.sensors()[_SENSOR_SLICE[name]]
 
     def body_pos(self, name):
@@ -277,15 +293,24 @@ class FakeBridge:
         c, s = np.cos(th), np.sin(th)
         return np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
 
-    def body_com(self, name):  # subtree_com of the robot (point.xml:18-19 masses)
+    def _com_offset(self):  # body-frame COM offset of the whole robot (masses from point.xml / car.xml, density rule)
+        if self.robot.name == "point":
+            return 0.001 * 0.1 / (4.0 / 3.0 * np.pi * 0.1 ** 3 + 0.001), 0.0
+        m = np.array([0.02, 0.002, 3e-4, 0.001, 6e-4] + [np.pi * 0.05 ** 2 * 0.05 * 5] * 2 + [4 / 3 * np.pi * 0.05 ** 3 * 5])
+        y = np.array([0.0, 0.15, 0.125, -0.165, -0.13, 0.1, 0.1, -0.1])
+        x = np.array([0.0, 0.0, 0.0, 0.0, 0.0, -0.13, 0.13, 0.0])
+        return float((m * x).sum() / m.sum()), float((m * y).sum() / m.sum())
+
+    def body_com(self, name):  # subtree_com of the robot
         s = self.env.robot_state
-        c = 0.001 * 0.1 / (4.0 / 3.0 * np.pi * 0.1 ** 3 + 0.001)
-        return np.array([s[0] + c * np.cos(s[2]), s[1] + c * np.sin(s[2]), 0.1])
+        cx, cy = self._com_offset()
+        return np.array([s[0] + cx * np.cos(s[2]) - cy * np.sin(s[2]), s[1] + cx * np.sin(s[2]) + cy * np.cos(s[2]), 0.1])
 
     def body_vel(self, name):  # subtree_linvel
         s = self.env.robot_state
-        c = 0.001 * 0.1 / (4.0 / 3.0 * np.pi * 0.1 ** 3 + 0.001)
-        return np.array([s[3] - c * s[5] * np.sin(s[2]), s[4] + c * s[5] * np.cos(s[2]), 0.0])
+        cx, cy = self._com_offset()
+        ox, oy = cx * np.cos(s[2]) - cy * np.sin(s[2]), cx * np.sin(s[2]) + cy * np.cos(s[2])
+        return np.array([s[3] - s[5] * oy, s[4] + s[5] * ox, 0.0])
 
     def robot_pos(self):
         return self.body_pos("robot")
@@ -311,7 +336,7 @@ class FakeBridge:
 
     def _geom_name(self, slot, part):
         if slot == -1:
-            return ["robot", "pointarrow"][part]
+            return _ROBOT_GEOMS[self.robot.name][part]
         n = self.names[slot]
         return n if part == 0 else "col%d" % part
 
@@ -336,7 +361,7 @@ class FakeBridge:
 # --------------------------------------------------------------------------------------------
 # harness
 # --------------------------------------------------------------------------------------------
-def make_env(task_key, config=None, seed=0):
+def make_env(task_key, config=None, seed=0, robot="point"):
     import safe_adaptation_gym.safe_adaptation_gym as sag
     from safe_adaptation_gym.benchmark import TASKS
 
@@ -345,7 +370,7 @@ def make_env(task_key, config=None, seed=0):
     FakeBridge.TASK = task_key
     np.random.RandomState = RecRS
     try:
-        env = sag.SafeAdaptationGym("xmls/point.xml", config=config, render_lidars_and_collision=False)
+        env = sag.SafeAdaptationGym("xmls/%s.xml" % robot, config=config, render_lidars_and_collision=False)
         del EVENTS[:]
         env.seed(seed)
         env.set_task(TASKS[task_key]())
@@ -378,14 +403,20 @@ def policy(env, rng, mode):
     if target is None or mode == "random":
         return rng.uniform(-1, 1, 2)
     d = target - s[:2]
+    if env.robot.name == "car":  # differential drive; the car's front is body -y (car.xml:19-20)
+        err = np.arctan2(d[1], d[0]) - (s[2] - np.pi / 2)
+        err = (err + np.pi) % (2 * np.pi) - np.pi
+        fwd = np.clip(1.0 - abs(err), 0.0, 1.0) * 0.02
+        a = np.array([fwd + 0.01 * np.clip(err, -1, 1), fwd - 0.01 * np.clip(err, -1, 1)])
+        return np.clip(a + 0.003 * rng.normal(size=2), -1, 1)
     err = np.arctan2(d[1], d[0]) - s[2]
     err = (err + np.pi) % (2 * np.pi) - np.pi
     a = np.array([np.clip(1.0 - abs(err), 0.02, 1.0), np.clip(2.0 * err, -1, 1)])
     return np.clip(a + 0.2 * rng.normal(size=2), -1, 1)
 
 
-def record_episode(task_key, seed, steps, mode="drive", config=None, second_reset=True):
-    env = make_env(task_key, config=config, seed=seed)
+def record_episode(task_key, seed, steps, mode="drive", config=None, second_reset=True, robot="point"):
+    env = make_env(task_key, config=config, seed=seed, robot=robot)
     b = env.mujoco_bridge
     rng = _RealRS(1234 + seed)
     segs = []
@@ -395,7 +426,7 @@ def record_episode(task_key, seed, steps, mode="drive", config=None, second_rese
             env.reset()  # safe_adaptation_gym.py:85-107: seed += 1, same task instance
         b.sync_groups()
         obs0 = env.observation
-        layout = {"robot": b.env.robot_state.tolist(), "objects": b.env.objects().tolist(),
+        layout = {"robot": b.env.robot_state.tolist(), "robot_ext": b.env.robot_ext.tolist(), "objects": b.env.objects().tolist(),
                   "task_state": b.env.task_state.tolist()}
         actions, obs, rew, cost, states = [], [], [], [], []
         for t in range(steps):
@@ -411,7 +442,7 @@ def record_episode(task_key, seed, steps, mode="drive", config=None, second_rese
         segs.append({"obs0": np.asarray(obs0).tolist(), "layout": layout, "actions": actions, "obs": obs,
                      "reward": rew, "cost": cost, "robot": states,
                      "final_objects": b.env.objects().tolist()})
-    out = {"task": task_key, "seed": seed, "config": config or {}, "replay": replay_stream(EVENTS),
+    out = {"task": task_key, "robot": robot, "seed": seed, "config": config or {}, "replay": replay_stream(EVENTS),
            "segments": segs, "sizes": [[n, t, s, z] for n, t, s, z in b.checked_sizes[:40]]}
     np.random.RandomState = _RealRS
     return out
@@ -518,9 +549,12 @@ def main():
             ("press_buttons", 10, 400, "drive"), ("press_buttons_scarce", 11, 300, "drive"),
             ("collect", 12, 400, "drive"), ("push_box", 13, 400, "drive"), ("push_box_scarce", 14, 300, "drive"),
             ("haul_box", 15, 300, "drive")]
-    for task_key, seed, steps, mode in plan:
-        ep = record_episode(task_key, seed, steps, mode, config={"action_noise": 0.01})
-        print(task_key, "return", sum(r[-1] for s in ep["segments"] for r in s["reward"]),
+    plan = [(t, s_, n, m, "point") for t, s_, n, m in plan] + [
+        ("go_to_goal", 21, 250, "drive", "car"), ("press_buttons", 22, 250, "drive", "car"), ("push_box", 23, 200, "drive", "car"),
+        ("haul_box", 24, 150, "drive", "car"), ("unsupervised", 25, 120, "random", "car")]
+    for task_key, seed, steps, mode, robot in plan:
+        ep = record_episode(task_key, seed, steps, mode, config={"action_noise": 0.01}, robot=robot)
+        print(robot, task_key, "return", sum(r[-1] for s in ep["segments"] for r in s["reward"]),
               "cost", sum(sum(s["cost"]) for s in ep["segments"]), "replay", len(ep["replay"]))
         episodes.append(ep)
     np.savez_compressed(os.path.join(HERE, "episodes.npz"), data=np.frombuffer(json.dumps(episodes).encode(), dtype=np.uint8))

@@ -61,12 +61,12 @@ def test_layout_sampler_matches_reference_world():
     assert n >= 60
 
 
-@pytest.mark.parametrize("ep", EPISODES, ids=[f"{e['task']}-{e['seed']}" for e in EPISODES])
+@pytest.mark.parametrize("ep", EPISODES, ids=[f"{e.get('robot', 'point')}-{e['task']}-{e['seed']}" for e in EPISODES])
 def test_episode_matches_reference_step_loop(ep):
     """safe_adaptation_gym.py:56-107 + world.py + tasks/*.py executed by the reference over oracle physics,
     vs the oracle's own restatement of that logic, on the same recorded random stream."""
     cfg = dict(ep["config"])
-    e = O.OracleEnv("point", ep["task"], config=cfg)
+    e = O.OracleEnv(ep.get("robot", "point"), ep["task"], config=cfg)
     e.set_replay(ep["replay"])
     for k, seg in enumerate(ep["segments"]):
         assert e.reset(k) == 0
