@@ -25,6 +25,7 @@ extern "C" {
 #define SAG_ABI_VERSION 1
 #define SAG_LIDAR_BINS 16   /* safe_adaptation_gym.py:22 */
 #define SAG_OBS_POINT 60    /* 3*16 lidar + 12 sensor floats, safe_adaptation_gym.py:120-139,225-237 */
+#define SAG_OBS_CAR 72      /* + ballangvel_rear (3) + quat2mat(ballquat_rear) (9), car.xml:37-38 */
 #define SAG_MAX_SLOTS 32
 
 enum { SAG_ROBOT_POINT = 0, SAG_ROBOT_CAR = 1 };
@@ -62,6 +63,7 @@ enum {
   SAG_F_TASK_I32 = 3, /* int32 [10][stride]: task, goal_button, btn_state, btn_timer, active_mask, cg_timer, n_step, step_ctr, episode,
                          moving_mask (derived; rebuilt by sag_observe after an injection) */
   SAG_F_FLAGS = 4,    /* uint8 [stride] */
+  SAG_F_ROBOT_EXT = 5,/* double [6][stride]: car only -- wheel rates (2), castor ball-joint quaternion w,x,y,z (4) */
   SAG_NUM_FIELDS
 };
 

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SAG_B200_LIB") or os.path.join(_HERE, "csrc", "libsag
 
 NUM_TASKS = 14
 MAX_SLOTS = 32
-F_ROBOT, F_OBJECTS, F_TASK_F64, F_TASK_I32, F_FLAGS = range(5)
+F_ROBOT, F_OBJECTS, F_TASK_F64, F_TASK_I32, F_FLAGS, F_ROBOT_EXT = range(6)
 FLAG_PHYSICS_ERROR, FLAG_RESAMPLE_FAILED, FLAG_NEEDS_RESET = 1, 2, 4
 
 

@@ -14,9 +14,11 @@
 #include "../../include/sag_detmath.h"
 
 #if defined(__CUDACC__)
+#define SAG_DEV_CONST __device__
 #define SAG_HD __host__ __device__ __forceinline__
 #define SAG_HD_NOINLINE __host__ __device__ __noinline__
 #else
+#define SAG_DEV_CONST
 #define SAG_HD inline
 #define SAG_HD_NOINLINE
 #endif
@@ -152,6 +154,7 @@ struct Dev {
   // robot
   double *rx, *ry, *ryaw, *rvx, *rvy, *rw;
   double *ctrl0, *ctrl1;
+  double* rext;  // car extras [6][stride]: wheel rates (2), castor ball-joint quaternion (4)
   // objects [slot][env]
   double *ox, *oy, *oyaw, *ovx, *ovy, *ow;
   // task / bookkeeping
@@ -415,17 +418,138 @@ SAG_HD void pt_solve(double p, double q, double ia, double is, const double* f, 
 }
 SAG_HD double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-struct Robot { double q[3], v[3]; double ctrl[2]; double damp_xy, gear_x; };
-
-// qfrc_smooth = actuation + passive - bias  (SURVEY Appendix A.1 / B.2-3 [EXT])
-SAG_HD void pt_smooth(const Robot& R, double sn, double cs, double* f) {
-  double w = R.v[2];
-  double fx = clampd(R.ctrl[0], -kPtForceLim, kPtForceLim);
-  double fz = clampd(R.ctrl[1] - kPtGearZ * w, -kPtForceLim, kPtForceLim);
-  f[0] = R.gear_x * fx * cs - R.damp_xy * R.v[0] + kPtMc * w * w * cs;
-  f[1] = R.gear_x * fx * sn - R.damp_xy * R.v[1] + kPtMc * w * w * sn;
-  f[2] = kPtGearZ * fz - kPtDampZ * w;
+// ---- car (car.xml): reduced planar differential-drive model, DESIGN.md 4.  Mirrors oracle car_params().
+constexpr double kCarH = 0.008;          // car.xml:3
+constexpr int kCarNsub = 10;             // safe_adaptation_gym.py:18
+constexpr double kCarForceLim = 0.02;    // car.xml:7
+constexpr double kCarWheelR = 0.05;      // car.xml:5
+constexpr double kCarWheelDamp = 0.001;  // car.xml:6
+constexpr double kCarArmature = 0.00025; // car.xml:22,26
+constexpr double kCarDensity = 5.0;      // car.xml:5
+constexpr int kCarNGeom = 8;
+struct CarGeomTab { double v[kCarNGeom][5]; double hz[5]; };
+// body-frame x, y, half-x, half-y | radius (car.xml:16-31; wheels are x-axis cylinders -> footprints); box half heights
+constexpr CarGeomTab kCarGeomC = {{{0.0, 0.0, 0.1, 0.1, 0.0}, {0.0, 0.15, 0.1, 0.01, 0.0}, {0.0, 0.125, 0.01, 0.025, 0.0},
+                                  {0.0, -0.165, 0.05, 0.01, 0.0}, {0.0, -0.13, 0.05, 0.03, 0.0}, {-0.13, 0.1, 0.025, 0.05, 0.0},
+                                  {0.13, 0.1, 0.025, 0.05, 0.0}, {0.0, -0.1, 0.0, 0.0, 0.05}},
+                                 {0.05, 0.05, 0.03, 0.05, 0.01}};
+SAG_DEV_CONST constexpr CarGeomTab kCarGeom = kCarGeomC;  // run-time indexed copy (device memory under nvcc)
+struct CarModel { double M, mcx, mcy, Io, Iw, nwheel, nrear; };
+constexpr CarModel car_model() {
+  CarModel c = {0, 0, 0, 0, 0, 0, 0};
+  double M = 0.0, mx = 0.0, my = 0.0, Io = 0.0;
+  for (int g = 0; g < 5; ++g) {
+    double hx = kCarGeomC.v[g][2], hy = kCarGeomC.v[g][3], hz = kCarGeomC.hz[g];
+    double m = 8.0 * hx * hy * hz * kCarDensity;
+    double x = kCarGeomC.v[g][0], y = kCarGeomC.v[g][1];
+    M += m; mx += m * x; my += m * y;
+    Io += m * (4.0 * hx * hx + 4.0 * hy * hy) / 12.0 + m * (x * x + y * y);
+  }
+  double mw = kPi * kCarWheelR * kCarWheelR * 0.05 * kCarDensity;
+  for (int g = 5; g < 7; ++g) {
+    double x = kCarGeomC.v[g][0], y = kCarGeomC.v[g][1];
+    M += mw; mx += mw * x; my += mw * y;
+    Io += mw * (3.0 * kCarWheelR * kCarWheelR + 0.05 * 0.05) / 12.0 + mw * (x * x + y * y);
+  }
+  double mb = 4.0 / 3.0 * kPi * kCarWheelR * kCarWheelR * kCarWheelR * kCarDensity;
+  {
+    double x = kCarGeomC.v[7][0], y = kCarGeomC.v[7][1];
+    M += mb; mx += mb * x; my += mb * y;
+    Io += 0.4 * mb * kCarWheelR * kCarWheelR + mb * (x * x + y * y);
+  }
+  c.M = M; c.mcx = mx; c.mcy = my; c.Io = Io;
+  c.Iw = 0.5 * mw * kCarWheelR * kCarWheelR + kCarArmature;
+  double yc = my / M;
+  c.nrear = M * kGrav * (0.1 - yc) / 0.2;
+  c.nwheel = (M * kGrav - c.nrear) / 2.0;
+  return c;
 }
+constexpr CarModel kCar = car_model();
+
+struct PointRobot {
+  static constexpr int kKind = 0, kNGeom = 2, kNsub = kPtNsub, kObsDim = 60;
+  static constexpr double kH = kPtH, kReach = kRobotReach;
+  double q[3], v[3];
+  double ctrl[2];
+  double damp_xy, gear_x;
+  SAG_HD void pq(double sn, double cs, double& p, double& qq) const { p = -kPtMc * sn; qq = kPtMc * cs; }
+  SAG_HD PtConst consts(double h) const { return pt_const(damp_xy, h); }
+  // qfrc_smooth = actuation + passive - bias  (SURVEY Appendix A.1 / B.2-3 [EXT])
+  SAG_HD void smooth(double sn, double cs, double* f) const {
+    double w = v[2];
+    double fx = clampd(ctrl[0], -kPtForceLim, kPtForceLim);
+    double fz = clampd(ctrl[1] - kPtGearZ * w, -kPtForceLim, kPtForceLim);
+    f[0] = gear_x * fx * cs - damp_xy * v[0] + kPtMc * w * w * cs;
+    f[1] = gear_x * fx * sn - damp_xy * v[1] + kPtMc * w * w * sn;
+    f[2] = kPtGearZ * fz - kPtDampZ * w;
+  }
+  SAG_HD void geom(int part, double sn, double cs, Geom& g) const {
+    g.c = cs; g.s = sn;
+    if (part == 0) { g.is_box = 0; g.cx = q[0]; g.cy = q[1]; g.r = kPtR; g.hx = g.hy = 0.0; }
+    else { g.is_box = 1; g.cx = q[0] + kPtArrowOff * cs; g.cy = q[1] + kPtArrowOff * sn; g.hx = g.hy = kPtArrowH; g.r = 0.0; }
+  }
+  SAG_HD void com_offset(double& cx, double& cy) const { cx = kPtMc / kPtM; cy = 0.0; }
+  // conservative bound on how far any robot geom can travel during one env step
+  SAG_HD double travel_bound() const {
+    const double tstep = kPtNsub * kPtH;
+    double speed = sqrt(v[0] * v[0] + v[1] * v[1]), wabs = fabs(v[2]);
+    double alpha_max = 750.0 + 200.0 * wabs, wmax = wabs + alpha_max * tstep;
+    double a_bound = 2.0 * (gear_x * kPtForceLim + damp_xy * speed) / kPtM + (kPtMc / kPtM) * (alpha_max + wmax * wmax);
+    return tstep * speed + tstep * tstep * a_bound + 1e-3;
+  }
+};
+
+struct CarRobot {
+  static constexpr int kKind = 1, kNGeom = kCarNGeom, kNsub = kCarNsub, kObsDim = 72;
+  static constexpr double kH = kCarH, kReach = 0.22;  // >= farthest footprint corner (wheel: hypot(0.155, 0.15))
+  double q[3], v[3];
+  double ctrl[2];
+  double damp_xy, gear_x;  // unused (kept so that shared code can copy them)
+  double wheel[2];         // wheel spin rates
+  double cq[4];            // castor ball-joint quaternion
+  SAG_HD void pq(double sn, double cs, double& p, double& qq) const { p = -(kCar.mcx * sn + kCar.mcy * cs); qq = kCar.mcx * cs - kCar.mcy * sn; }
+  SAG_HD PtConst consts(double) const {  // free joint: no damping, so M + hD = M
+    PtConst K;
+    K.ia0 = 1.0 / kCar.M;
+    K.is0 = 1.0 / (kCar.Io - (kCar.mcx * kCar.mcx + kCar.mcy * kCar.mcy) * K.ia0);
+    K.iah = K.ia0; K.ish = K.is0;
+    return K;
+  }
+  SAG_HD void smooth(double sn, double cs, double* f) const {  // centripetal bias of the COM offset only
+    double w = v[2];
+    f[0] = w * w * (kCar.mcx * cs - kCar.mcy * sn);
+    f[1] = w * w * (kCar.mcx * sn + kCar.mcy * cs);
+    f[2] = 0.0;
+  }
+  SAG_HD double wheel_smooth(int i) const {  // motor (gear 1, forcerange +-0.02) - joint damping
+    return clampd(ctrl[i], -kCarForceLim, kCarForceLim) - kCarWheelDamp * wheel[i];
+  }
+  SAG_HD void geom(int part, double sn, double cs, Geom& g) const {
+    const double* G = kCarGeom.v[part];
+    g.c = cs; g.s = sn;
+    g.cx = q[0] + G[0] * cs - G[1] * sn; g.cy = q[1] + G[0] * sn + G[1] * cs;
+    g.is_box = G[4] == 0.0; g.hx = G[2]; g.hy = G[3]; g.r = G[4];
+  }
+  SAG_HD void com_offset(double& cx, double& cy) const { cx = kCar.mcx / kCar.M; cy = kCar.mcy / kCar.M; }
+  SAG_HD double travel_bound() const {  // traction-limited: |a| <= 2 mu g covers drive + contact pushes
+    const double tstep = kCarNsub * kCarH;
+    double speed = sqrt(v[0] * v[0] + v[1] * v[1]);
+    return tstep * speed + tstep * tstep * (2.0 * kMu * kGrav) + 1e-3;
+  }
+  // castor ball (car.xml:29-32), ideal rolling: joint angular velocity in the child frame (mjSENS_BALLANGVEL [EXT])
+  SAG_HD void castor_angvel(double sn, double cs, double* wc) const {
+    double bx = 0.0, by = -0.1;
+    double rx = bx * cs - by * sn, ry = bx * sn + by * cs;
+    double vx = v[0] - v[2] * ry, vy = v[1] + v[2] * rx;
+    double wx = -vy / kCarWheelR, wy = vx / kCarWheelR;
+    double px = wx * cs + wy * sn, py = -wx * sn + wy * cs, pz = 0.0;
+    double w = cq[0], x = -cq[1], y = -cq[2], z = -cq[3];
+    double tx = 2.0 * (y * pz - z * py), ty = 2.0 * (z * px - x * pz), tz = 2.0 * (x * py - y * px);
+    wc[0] = px + w * tx + (y * tz - z * ty);
+    wc[1] = py + w * ty + (z * tx - x * tz);
+    wc[2] = pz + w * tz + (x * ty - y * tx);
+  }
+};
 
 SAG_HD bool bad_val(double x) { return !(fabs(x) <= 1e10); }
 
@@ -442,8 +566,10 @@ SAG_HD double impedance(double r) {
 // optional integration of the movable bodies.  Work is proportional to the objects actually involved.
 // ------------------------------------------------------------------------------------------------
 struct Con { int ba, bb; double nx, ny, px, py, dist; };  // ba/bb: -1 static, 0 robot, 1 + slot movable object
-struct Row {  // one contact (normal k=0, tangent k=1) or the tendon limit (k=0 only)
-  int ba, bb;                 // indices into Scratch::acc (-1 static, 0 robot, 1 + compact body id)
+struct Row {  // one contact (normal k=0, tangent k=1), the tendon limit (k=0 only) or one car wheel (longitudinal, lateral)
+  int ba, bb;                 // indices into Scratch::acc (-1 static, 0 robot, 1 + compact body id, NB + 1 + wheel)
+  int type, pad_;             // 0 contact / tendon, 2 wheel-floor friction pair (disc bound)
+  double bound;               // type 2: mu * N
   double ja[2][3], jb[2][3];  // Jacobian rows w.r.t. body a / b
   double wa[2][3], wb[2][3];  // M^-1 J^T, precomputed
   double aref[2], R[2], inv[2], f[2];
@@ -458,8 +584,8 @@ template <int NC, int NB>
 struct ScratchT {
   static constexpr int kCon = NC, kBodies = NB;
   Con con[NC];
-  Row rows[NC + 1];
-  double acc[NB + 1][3];
+  Row rows[NC + 3];      // + tendon + two car wheels
+  double acc[NB + 3][3]; // robot, bodies, two car wheels (1 DoF each, in [.][0])
   double ffl[NB][3];
   int bslot[NB + (NB & 1)];
 };
@@ -483,6 +609,7 @@ struct Phys {
   unsigned mov;    // bit s: movable body s has a non-zero velocity (after integration, if any)
   int err;
   int retry;       // the pass did not fit this scratch size and changed nothing: run it again on the big one
+  double wtau[2];  // car: constraint torque on the wheels
 };
 
 SAG_HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -494,23 +621,105 @@ SAG_HD int ctz32(unsigned m) {
 #endif
 }
 
-template <class ScratchType>
-SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, double cs, const PtConst& K, const double* fs,
+// ---- car wheel-floor friction rows (always present for the car; oracle forward_dynamics "car:" block) ----------
+// Reduced model: level chassis, static normal loads; per wheel a longitudinal slip row (chassis point velocity along the
+// rolling direction + r * wheel rate) and a lateral slip row, jointly bounded by mu * N.
+SAG_HD void wheel_row_setup(const CarRobot& R, int i, double sn, double cs, double p, double q, const PtConst& K, int wheel_body, Row& r) {
+  const double iw = 1.0 / kCar.Iw;
+  const double bdamp = 2.0 / (kImpDmax * kSolTc), rr0 = (1.0 - kImpD0) / kImpD0;
+  double bx = i == 0 ? -0.1 : 0.1, by = 0.1;
+  double rx = bx * cs - by * sn, ry = bx * sn + by * cs;
+  r.type = 2; r.pad_ = 0; r.bound = kMu * kCar.nwheel;
+  r.ba = 0; r.bb = wheel_body;
+  r.ja[0][0] = -sn; r.ja[0][1] = cs; r.ja[0][2] = rx * cs - ry * -sn;
+  r.jb[0][0] = kCarWheelR; r.jb[0][1] = 0.0; r.jb[0][2] = 0.0;
+  r.ja[1][0] = cs; r.ja[1][1] = sn; r.ja[1][2] = rx * sn - ry * cs;
+  r.jb[1][0] = 0.0; r.jb[1][1] = 0.0; r.jb[1][2] = 0.0;
+  const double vb[3] = {R.wheel[i], 0.0, 0.0};
+  for (int k = 0; k < 2; ++k) {
+    double diag = 0.0, vel = 0.0;
+    pt_solve(p, q, K.ia0, K.is0, r.ja[k], r.wa[k]);
+    diag += dot3(r.ja[k], r.wa[k]); vel += dot3(r.ja[k], R.v);
+    r.wb[k][0] = r.wb[k][1] = r.wb[k][2] = 0.0;
+    if (k == 0) { r.wb[k][0] = r.jb[k][0] * iw; diag += dot3(r.jb[k], r.wb[k]); vel += dot3(r.jb[k], vb); }
+    r.R[k] = rr0 * diag;
+    r.inv[k] = 1.0 / (diag + r.R[k]);
+    r.aref[k] = -bdamp * vel;
+    r.f[k] = 0.0;
+  }
+}
+// one Gauss-Seidel visit of a wheel row pair: both slip rows, then projection onto the friction disc
+SAG_HD void wheel_row_update(Row& r, double* accR, double* accW, double& sdf, double& sf) {
+  const double fo0 = r.f[0], fo1 = r.f[1];
+  for (int k = 0; k < 2; ++k) {
+    double a = dot3(r.ja[k], accR);
+    if (k == 0) a += dot3(r.jb[k], accW);
+    double fn = r.f[k] - (a - r.aref[k] + r.R[k] * r.f[k]) * r.inv[k];
+    double df = fn - r.f[k];
+    r.f[k] = fn;
+    if (df != 0.0) {
+      accR[0] += r.wa[k][0] * df; accR[1] += r.wa[k][1] * df; accR[2] += r.wa[k][2] * df;
+      if (k == 0) { accW[0] += r.wb[k][0] * df; accW[1] += r.wb[k][1] * df; accW[2] += r.wb[k][2] * df; }
+    }
+  }
+  double nf = sqrt(r.f[0] * r.f[0] + r.f[1] * r.f[1]);
+  if (nf > r.bound) {
+    double sc = r.bound / nf;
+    for (int k = 0; k < 2; ++k) {
+      double g = r.f[k] * sc, df = g - r.f[k];
+      r.f[k] = g;
+      if (df != 0.0) {
+        accR[0] += r.wa[k][0] * df; accR[1] += r.wa[k][1] * df; accR[2] += r.wa[k][2] * df;
+        if (k == 0) { accW[0] += r.wb[k][0] * df; accW[1] += r.wb[k][1] * df; accW[2] += r.wb[k][2] * df; }
+      }
+    }
+  }
+  sdf += fabs(r.f[0] - fo0) + fabs(r.f[1] - fo1); sf += fabs(r.f[0]) + fabs(r.f[1]);
+}
+// the car's forward dynamics when nothing else constrains it: just the two wheel row pairs (registers only)
+struct CarFree { double qacc[3], fc[3], wtau[2]; };
+SAG_HD void car_free_solve(const CarRobot& R, double sn, double cs, const PtConst& K, const double* fs, CarFree& F) {
+  double p, q;
+  R.pq(sn, cs, p, q);
+  const double iw = 1.0 / kCar.Iw;
+  double accR[3], accW[2][3];
+  pt_solve(p, q, K.ia0, K.is0, fs, accR);
+  Row rows[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    accW[i][0] = R.wheel_smooth(i) * iw; accW[i][1] = accW[i][2] = 0.0;
+    wheel_row_setup(R, i, sn, cs, p, q, K, 0, rows[i]);
+  }
+  for (int it = 0; it < kSweeps; ++it) {
+    double sdf = 0.0, sf = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) wheel_row_update(rows[i], accR, accW[i], sdf, sf);
+    if (sdf <= kPgsTol * sf) break;
+  }
+  F.qacc[0] = accR[0]; F.qacc[1] = accR[1]; F.qacc[2] = accR[2];
+  F.fc[0] = F.fc[1] = F.fc[2] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    for (int k = 0; k < 2; ++k) for (int d = 0; d < 3; ++d) F.fc[d] += rows[i].ja[k][d] * rows[i].f[k];
+    F.wtau[i] = rows[i].jb[0][0] * rows[i].f[0];
+  }
+}
+
+template <class RB, class ScratchType>
+SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double cs, const PtConst& K, const double* fs,
                                   unsigned mov, bool integrate, double h, ScratchType& S, Phys& P) {
   constexpr int kCapCon = ScratchType::kCon, kCapBodies = ScratchType::kBodies;
   constexpr bool kIsBig = kCapCon == kMaxCon;
   const Dev& D = C.D;
   const int e = C.e;
-  const double p = -kPtMc * sn, q = kPtMc * cs;
+  double p, q;
+  R.pq(sn, cs, p, q);
   Con* con = S.con;
   int ncon = 0;
   unsigned active = mov, touch = 0;
   bool overflow = false;
   P.err = 0; P.retry = 0;
-  Geom gr[2];
-  gr[0].is_box = 0; gr[0].cx = R.q[0]; gr[0].cy = R.q[1]; gr[0].c = cs; gr[0].s = sn; gr[0].r = kPtR; gr[0].hx = gr[0].hy = 0.0;
-  gr[1].is_box = 1; gr[1].cx = R.q[0] + kPtArrowOff * cs; gr[1].cy = R.q[1] + kPtArrowOff * sn; gr[1].c = cs; gr[1].s = sn;
-  gr[1].hx = gr[1].hy = kPtArrowH; gr[1].r = 0.0;
+  constexpr bool kCarRobot = RB::kKind == 1;
   Hit hits[2];
   SAG_PROF(e, 0, 1);
   // ---- phase 1: robot geoms vs objects, slot order
@@ -519,16 +728,18 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
     if (!kind_collidable(kind)) continue;
     size_t i = oidx(D, s, e);
     double x = D.ox[i], y = D.oy[i];
-    double dx = x - R.q[0], dy = y - R.q[1], reach = kRobotReach + kind_bound(D, kind);
+    double dx = x - R.q[0], dy = y - R.q[1], reach = RB::kReach + kind_bound(D, kind);
     if (dx * dx + dy * dy > reach * reach) continue;
     bool mvb = kind_movable(kind);
     double oc = 1.0, os = 0.0;
     if (mvb) sag_sincos(D.oyaw[i], &os, &oc);
-    for (int rg = 0; rg < 2; ++rg)
+    for (int rg = 0; rg < RB::kNGeom; ++rg) {
+      Geom grg;
+      R.geom(rg, sn, cs, grg);
       for (int pt = 0; pt < kind_nparts(kind); ++pt) {
         Geom go;
         obj_geom(D, kind, pt, x, y, oc, os, go);
-        int n = collide(gr[rg], go, hits);
+        int n = collide(grg, go, hits);
         SAG_PROF(e, 1, 1);
         for (int k = 0; k < n; ++k) {
           if (ncon >= kCapCon) { overflow = true; break; }
@@ -538,6 +749,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
         }
         if (n) { touch |= 1u << s; if (mvb) active |= 1u << s; }
       }
+    }
   }
   // ---- phase 2: object pairs (j ascending, i < j ascending) with at least one awake / robot-touched movable body
   if (active) {
@@ -589,6 +801,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
   P.mov = mov;
   SAG_PROF(e, 2, ncon);
   P.fc[0] = P.fc[1] = P.fc[2] = 0.0;
+  P.wtau[0] = P.wtau[1] = 0.0;
   // ---- which constraint rows exist?
   unsigned touched = 0;
   for (int i = 0; i < ncon; ++i) {
@@ -619,14 +832,15 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
   int nb = 0;
   for (unsigned m = fl; m; m &= m - 1) ++nb;
   if (nb > kCapBodies) overflow = true;
-  if (overflow) {  // nothing has been modified yet
-    if (kIsBig) P.err = 1; else P.retry = 1;
-    return;
+  if (overflow && !kIsBig) { P.retry = 1; return; }  // nothing has been modified yet
+  if (overflow) P.err = 1;
+  if (!kCarRobot) {
+    if (overflow) return;
+    if (!any_row && !tendon && mov == 0) return;  // nothing to solve, nothing to move
   }
-  if (!any_row && !tendon && mov == 0) return;  // nothing to solve, nothing to move
   // ---- body table: compact ids in slot order
   nb = 0;
-  for (unsigned m = fl; m; m &= m - 1) S.bslot[nb++] = ctz32(m);
+  if (!overflow) for (unsigned m = fl; m; m &= m - 1) S.bslot[nb++] = ctz32(m);
   auto cid = [&](int slot) { int k = 0; while (S.bslot[k] != slot) ++k; return k; };
   double vim, vii, vrf, bim, bii, brf, vmass, bmass;
   { double iz; kind_mass(D, K_VASE, vmass, iz, vrf); vim = 1.0 / vmass; vii = 1.0 / iz; }
@@ -650,11 +864,22 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
   int nrow = 0, tendon_row = -1;
   const double bdamp = 2.0 / (kImpDmax * kSolTc);
   const double kbase = 1.0 / (kImpDmax * kImpDmax * kSolTc * kSolTc);
+  double (*acc)[3] = S.acc;
+  constexpr int kWheelBody = kCapBodies + 1;  // acc index of the left wheel
+  if constexpr (kCarRobot) {
+    const double iw = 1.0 / kCar.Iw;
+    for (int i = 0; i < 2; ++i) {
+      acc[kWheelBody + i][0] = R.wheel_smooth(i) * iw; acc[kWheelBody + i][1] = acc[kWheelBody + i][2] = 0.0;
+      wheel_row_setup(R, i, sn, cs, p, q, K, kWheelBody + i, rows[nrow++]);
+    }
+  }
+  if (overflow) { ncon = 0; tendon = false; }  // car: the wheel rows are still solved, nothing else
   for (int i = 0; i < ncon; ++i) {
     const Con c = con[i];
     if (!(c.dist < 0.0)) continue;
     if (c.ba < 0 && c.bb < 0) continue;
     Row& r = rows[nrow++];
+    r.type = 0; r.pad_ = 0; r.bound = 0.0;
     r.ba = c.ba > 0 ? 1 + cid(c.ba - 1) : c.ba; r.bb = c.bb > 0 ? 1 + cid(c.bb - 1) : c.bb;
     double tx = -c.ny, ty = c.nx;
     double pa[2] = {0, 0}, pb[2] = {0, 0}, va[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
@@ -678,6 +903,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
   }
   if (tendon) {
     Row& r = rows[nrow]; tendon_row = nrow++;
+    r.type = 0; r.pad_ = 0; r.bound = 0.0;
     const int bbox = 1 + C.L.box;
     r.ba = 0; r.bb = 1 + cid(C.L.box);
     r.ja[0][0] = tdx / tlen; r.ja[0][1] = tdy / tlen; r.ja[0][2] = 0.0;
@@ -693,7 +919,6 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
     r.f[0] = 0.0;
   }
   // body accelerations: acc[0] = robot, acc[1 + compact id] = movable object
-  double (*acc)[3] = S.acc;
   double (*ffl)[3] = S.ffl;
   acc[0][0] = racc[0]; acc[0][1] = racc[1]; acc[0][2] = racc[2];
   for (int b = 0; b < nb; ++b) { acc[1 + b][0] = acc[1 + b][1] = acc[1 + b][2] = 0.0; ffl[b][0] = ffl[b][1] = ffl[b][2] = 0.0; }
@@ -707,6 +932,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
       Row& r = rows[i];
       const int nk = (i == tendon_row) ? 1 : 2;
       const int ba = r.ba, bb = r.bb;
+      if (kCarRobot && r.type == 2) { wheel_row_update(r, acc[0], acc[bb], sdf, sf); continue; }
       for (int k = 0; k < nk; ++k) {
         SAG_PROF(e, 4, 1);
         double a = 0.0;
@@ -759,8 +985,9 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
       if (r.ba == 0) for (int d = 0; d < 3; ++d) P.fc[d] += r.ja[k][d] * r.f[k];
       if (r.bb == 0) for (int d = 0; d < 3; ++d) P.fc[d] += r.jb[k][d] * r.f[k];
     }
+    if (kCarRobot && r.type == 2) P.wtau[r.bb - kWheelBody] = r.jb[0][0] * r.f[0];
   }
-  if (!integrate) return;
+  if (!integrate || overflow) return;
   // ---- semi-implicit Euler for the awake / touched movable bodies (free joints: no damping)
   for (int b = 0; b < nb; ++b) {
     const int s = S.bslot[b];
@@ -778,25 +1005,26 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const Robot& R, double sn, doubl
 
 // Cheap exact pre-test run by every non-quiet lane in parallel: does any robot geom overlap any object geom?
 // (same broad phase and first-stage arithmetic as contact_pass phase 1, so a `false` here means phase 1 lists nothing)
-SAG_HD bool robot_overlaps_any(const Ctx& C, const Robot& R, double sn, double cs) {
+template <class RB>
+SAG_HD bool robot_overlaps_any(const Ctx& C, const RB& R, double sn, double cs) {
   const Dev& D = C.D;
-  Geom gr[2];
-  gr[0].is_box = 0; gr[0].cx = R.q[0]; gr[0].cy = R.q[1]; gr[0].c = cs; gr[0].s = sn; gr[0].r = kPtR; gr[0].hx = gr[0].hy = 0.0;
-  gr[1].is_box = 1; gr[1].cx = R.q[0] + kPtArrowOff * cs; gr[1].cy = R.q[1] + kPtArrowOff * sn; gr[1].c = cs; gr[1].s = sn;
-  gr[1].hx = gr[1].hy = kPtArrowH; gr[1].r = 0.0;
   for (int s = C.L.v0; s < C.L.n; ++s) {
     int kind = slot_kind(C.sp, C.L, s);
     if (!kind_collidable(kind)) continue;
     size_t i = oidx(D, s, C.e);
     double x = D.ox[i], y = D.oy[i];
-    double dx = x - R.q[0], dy = y - R.q[1], reach = kRobotReach + kind_bound(D, kind);
+    double dx = x - R.q[0], dy = y - R.q[1], reach = RB::kReach + kind_bound(D, kind);
     if (dx * dx + dy * dy > reach * reach) continue;
     double oc = 1.0, os = 0.0;
     if (kind_movable(kind)) sag_sincos(D.oyaw[i], &os, &oc);
     for (int pt = 0; pt < kind_nparts(kind); ++pt) {
       Geom go;
       obj_geom(D, kind, pt, x, y, oc, os, go);
-      if (overlap(gr[0], go) || overlap(gr[1], go)) return true;
+      for (int rg = 0; rg < RB::kNGeom; ++rg) {
+        Geom grg;
+        R.geom(rg, sn, cs, grg);
+        if (overlap(grg, go)) return true;
+      }
     }
   }
   return false;
@@ -806,7 +1034,8 @@ SAG_HD bool robot_overlaps_any(const Ctx& C, const Robot& R, double sn, double c
 // provides one); lanes whose pass did not fit, or all needing lanes when there is no SmallScratch, then take turns
 // on the warp's big Scratch.  `wmask` = lanes of this warp that own an environment (all of them call this together).
 // On the host there is a single lane.
-SAG_HD void warp_contact_pass(unsigned wmask, bool need, const Ctx& C, const Robot& R, double sn, double cs, const PtConst& K,
+template <class RB>
+SAG_HD void warp_contact_pass(unsigned wmask, bool need, const Ctx& C, const RB& R, double sn, double cs, const PtConst& K,
                               const double* fs, unsigned mov, bool integrate, double h, Scratch* S, SmallScratch* small, Phys& P) {
   bool big = need;
   if (small) {
@@ -930,7 +1159,8 @@ SAG_HD void store_task_state(const Dev& D, int e, const TaskState& T) {
   D.ctr[e] = T.ctr;
 }
 
-SAG_HD void sample_goal_button(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& ctr, const Robot& R, TaskState& T) {
+template <class RB>
+SAG_HD void sample_goal_button(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& ctr, const RB& R, TaskState& T) {
   double u1, u2;  // press_buttons.py:70-76
   rng.pair(stream, ctr++, u1, u2);
   int k = (int)(u1 * C.L.nbtn);
@@ -942,7 +1172,8 @@ SAG_HD void sample_goal_button(const Ctx& C, const Rng& rng, uint32_t stream, ui
 }
 
 // task.reset(): go_to_goal.py:50-57, push_box.py:94-100, press_buttons.py:65-68, collect.py:41-47, catch_goal.py:36-40
-SAG_HD int task_reset(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& ctr, const Robot& R, TaskState& T) {
+template <class RB>
+SAG_HD int task_reset(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& ctr, const RB& R, TaskState& T) {
   const Dev& D = C.D;
   if (C.sp.kind == 1) {
     if (C.task == T_COLLECT) T.amask = (1 << C.L.nbtn) - 1;
@@ -965,7 +1196,8 @@ SAG_HD int task_reset(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& c
 }
 
 // task.compute_reward family; touch = robot contact bitmask from the forward pass
-SAG_HD int compute_reward(const Ctx& C, const Rng& rng, const Robot& R, TaskState& T, unsigned touch, double* reward) {
+template <class RB>
+SAG_HD int compute_reward(const Ctx& C, const Rng& rng, const RB& R, TaskState& T, unsigned touch, double* reward) {
   const Dev& D = C.D;
   reward[0] = reward[1] = 0.0;
   if (C.sp.kind == 0) {  // go_to_goal.py:31-45
@@ -980,10 +1212,12 @@ SAG_HD int compute_reward(const Ctx& C, const Rng& rng, const Robot& R, TaskStat
       r += 1.0;
     }
     if (C.task == T_UNSUPERVISED) {  // unsupervised.py:48-67
-      const double c = kPtMc / kPtM;
+      double cx, cy;
+      R.com_offset(cx, cy);
       double cs = sag_cos(R.q[2]), sn = sag_sin(R.q[2]);
-      double x = R.q[0] + c * cs, y = R.q[1] + c * sn;
-      double u = R.v[0] - c * R.v[2] * sn, v = R.v[1] + c * R.v[2] * cs;
+      double ox = cx * cs - cy * sn, oy = cx * sn + cy * cs;
+      double x = R.q[0] + ox, y = R.q[1] + oy;
+      double u = R.v[0] - R.v[2] * oy, v = R.v[1] + R.v[2] * ox;
       double radius = sqrt(x * x + y * y);
       reward[0] = (((-u * y + v * x) / radius) / (1.0 + fabs(radius - 1.5))) * 1e-1;
       reward[1] = r;
@@ -1069,8 +1303,8 @@ SAG_HD bool hazard_hit(double d2, double size) {  // world.py:151-152: ||robot_x
   return sqrt(d2) <= size;
 }
 
-template <bool QuietOnly>
-SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const Ctx& C, const Robot& R, TaskState& T, const Rng& rng, const PtConst& K,
+template <bool QuietOnly, class RB>
+SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const Ctx& C, const RB& R, TaskState& T, const Rng& rng, const PtConst& K,
                         unsigned mov, bool phys_err, bool with_reward, float* obs_s, int ostride, EndOut& O) {
   const Dev& D = C.D;
   const int e = C.e;
@@ -1115,26 +1349,28 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
     if (kind == K_BUTTON) { if (d2 < d2b) d2b = d2; } else { if (d2 < d2x) d2x = d2; }
   }
   double clear = 1e30;
-  if (d2v < 1e299) clear = fmin(clear, sqrt(d2v) - (kRobotReach + kind_bound(D, K_VASE)));
-  if (d2p < 1e299) clear = fmin(clear, sqrt(d2p) - (kRobotReach + kind_bound(D, K_PILLAR)));
-  if (d2b < 1e299) clear = fmin(clear, sqrt(d2b) - (kRobotReach + kind_bound(D, K_BUTTON)));
-  if (d2x < 1e299) clear = fmin(clear, sqrt(d2x) - (kRobotReach + kind_bound(D, K_BOX)));
+  if (d2v < 1e299) clear = fmin(clear, sqrt(d2v) - (RB::kReach + kind_bound(D, K_VASE)));
+  if (d2p < 1e299) clear = fmin(clear, sqrt(d2p) - (RB::kReach + kind_bound(D, K_PILLAR)));
+  if (d2b < 1e299) clear = fmin(clear, sqrt(d2b) - (RB::kReach + kind_bound(D, K_BUTTON)));
+  if (d2x < 1e299) clear = fmin(clear, sqrt(d2x) - (RB::kReach + kind_bound(D, K_BOX)));
   // ---- forward(): contacts + acceleration at the final state (safe_adaptation_gym.py:76)
   double fs[3], qacc[3];
-  pt_smooth(R, sn, cs, fs);
+  R.smooth(sn, cs, fs);
   unsigned touch = 0;
   O.err = 0;
   const bool tendon = C.task == T_HAUL_BOX;
   Phys P;
   P.err = 0; P.touch = 0; P.retry = 0;
-  if (QuietOnly) {  // a quiet step ends with positive clearance: no contact is possible
-    pt_solve(-kPtMc * sn, kPtMc * cs, K.ia0, K.is0, fs, P.qacc);
-  } else {
+  bool need = false;
+  if (!QuietOnly) {  // (a quiet step ends with positive clearance: no contact is possible)
     const bool near_ = !(clear > 0.0 && mov == 0 && !tendon);
-    const bool need = near_ && (mov != 0 || tendon || robot_overlaps_any(C, R, sn, cs));
-    if (!need) pt_solve(-kPtMc * sn, kPtMc * cs, K.ia0, K.is0, fs, P.qacc);
-    warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, small, P);
+    need = near_ && (mov != 0 || tendon || robot_overlaps_any(C, R, sn, cs));
   }
+  if (!need) {
+    if constexpr (RB::kKind == 1) { CarFree F; car_free_solve(R, sn, cs, K, fs, F); P.qacc[0] = F.qacc[0]; P.qacc[1] = F.qacc[1]; P.qacc[2] = F.qacc[2]; }
+    else { double p, q; R.pq(sn, cs, p, q); pt_solve(p, q, K.ia0, K.is0, fs, P.qacc); }
+  }
+  if (!QuietOnly) warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, small, P);
   qacc[0] = P.qacc[0]; qacc[1] = P.qacc[1]; qacc[2] = P.qacc[2];
   touch = P.touch;
   O.err = P.err;
@@ -1171,49 +1407,62 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
   o[5 * ostride] = 0.0f;
   o[6 * ostride] = 0.0f; o[7 * ostride] = 0.0f; o[8 * ostride] = (float)R.v[2];  // gyro
   o[9 * ostride] = (float)(-0.5 * sn); o[10 * ostride] = (float)(-0.5 * cs); o[11 * ostride] = 0.0f;  // magnetometer
+  if constexpr (RB::kKind == 1) {  // ballangvel_rear (3), quat2mat(ballquat_rear).ravel() (9): safe_adaptation_gym.py:228-236
+    double wc[3];
+    R.castor_angvel(sn, cs, wc);
+    o[12 * ostride] = (float)wc[0]; o[13 * ostride] = (float)wc[1]; o[14 * ostride] = (float)wc[2];
+    const double w = R.cq[0], x = R.cq[1], y = R.cq[2], z = R.cq[3];
+    o[15 * ostride] = (float)(w * w + x * x - y * y - z * z); o[16 * ostride] = (float)(2.0 * (x * y - w * z)); o[17 * ostride] = (float)(2.0 * (x * z + w * y));
+    o[18 * ostride] = (float)(2.0 * (x * y + w * z)); o[19 * ostride] = (float)(w * w - x * x + y * y - z * z); o[20 * ostride] = (float)(2.0 * (y * z - w * x));
+    o[21 * ostride] = (float)(2.0 * (x * z - w * y)); o[22 * ostride] = (float)(2.0 * (y * z + w * x)); o[23 * ostride] = (float)(w * w - x * x - y * y + z * z);
+  }
 }
 
-SAG_HD void load_robot(const Dev& D, int e, const TaskSpec& sp, Robot& R) {
+template <class RB>
+SAG_HD void load_robot(const Dev& D, int e, const TaskSpec& sp, RB& R) {
   R.q[0] = D.rx[e]; R.q[1] = D.ry[e]; R.q[2] = D.ryaw[e];
   R.v[0] = D.rvx[e]; R.v[1] = D.rvy[e]; R.v[2] = D.rw[e];
   R.ctrl[0] = D.ctrl0[e]; R.ctrl[1] = D.ctrl1[e];
   R.damp_xy = sp.damp_xy; R.gear_x = sp.gear_x;
+  if constexpr (RB::kKind == 1) {
+    R.wheel[0] = D.rext[e]; R.wheel[1] = D.rext[(size_t)D.stride + e];
+    for (int k = 0; k < 4; ++k) R.cq[k] = D.rext[(size_t)(2 + k) * D.stride + e];
+  }
 }
-SAG_HD void store_robot(const Dev& D, int e, const Robot& R) {
+template <class RB>
+SAG_HD void store_robot(const Dev& D, int e, const RB& R) {
   D.rx[e] = R.q[0]; D.ry[e] = R.q[1]; D.ryaw[e] = R.q[2];
   D.rvx[e] = R.v[0]; D.rvy[e] = R.v[1]; D.rw[e] = R.v[2];
   D.ctrl0[e] = R.ctrl[0]; D.ctrl1[e] = R.ctrl[1];
+  if constexpr (RB::kKind == 1) {
+    D.rext[e] = R.wheel[0]; D.rext[(size_t)D.stride + e] = R.wheel[1];
+    for (int k = 0; k < 4; ++k) D.rext[(size_t)(2 + k) * D.stride + e] = R.cq[k];
+  }
 }
 
 // "Quiet" environment: nothing can come within reach of the robot during the coming step and nothing is moving
 // (clearance cached by the previous end-of-step pass; -1 when a body moves or a tendon exists).  The bound on the
 // travel of the hinge point during one step is conservative.
-SAG_HD bool env_is_quiet(double clear, double vx, double vy, double w, double gear_x, double damp_xy) {
-  const double tstep = kPtNsub * kPtH;
-  double speed = sqrt(vx * vx + vy * vy), wabs = fabs(w);
-  double alpha_max = 750.0 + 200.0 * wabs, wmax = wabs + alpha_max * tstep;
-  double a_bound = 2.0 * (gear_x * kPtForceLim + damp_xy * speed) / kPtM + (kPtMc / kPtM) * (alpha_max + wmax * wmax);
-  double travel = tstep * speed + tstep * tstep * a_bound + 1e-3;
-  return clear > travel;
-}
+template <class RB>
+SAG_HD bool env_is_quiet(double clear, const RB& R) { return clear > R.travel_bound(); }
 
 // ------------------------------------------------------------------------------------------------
 // SafeAdaptationGym.step for one environment (safe_adaptation_gym.py:56-83)
 // ------------------------------------------------------------------------------------------------
-template <bool QuietOnly>
+template <bool QuietOnly, class RB>
 SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2,
                      unsigned char* cost, unsigned char* done) {
   Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
   C.L = make_slots(C.sp);
-  Robot R;
+  RB R;
   load_robot(D, e, C.sp, R);
   TaskState T;
   load_task_state(D, e, T);
   Rng rng = {D.seed, D.gid_base + (uint32_t)e, D.episode[e]};
   double time = D.time[e];
   unsigned mov = (unsigned)D.movmask[e];
-  const double h = kPtH;
-  const PtConst K = pt_const(R.damp_xy, h);
+  const double h = RB::kH;
+  const PtConst K = R.consts(h);
   // action noise + clip (:58-67)
   double act0 = (double)a0, act1 = (double)a1;
   if (D.action_noise != 0.0) {
@@ -1232,33 +1481,66 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev&
   // contact detection; the bound on the hinge point's travel is conservative.
   unsigned char fl = D.flags[e];
   int err = (fl & F_PHYS_ERROR) ? 1 : 0;  // a physics error is sticky until the env is reset
-  const bool quiet = QuietOnly ? true : env_is_quiet(D.clear[e], R.v[0], R.v[1], R.v[2], R.gear_x, R.damp_xy);
+  const bool quiet = QuietOnly ? true : env_is_quiet(D.clear[e], R);
 #pragma unroll 1
-  for (int k = 0; k < kPtNsub; ++k) {
-    double sn, cs, fs[3], fc[3] = {0.0, 0.0, 0.0}, rhs[3], a[3];
+  for (int k = 0; k < RB::kNsub; ++k) {
+    double sn, cs, fs[3], fc[3] = {0.0, 0.0, 0.0}, wtau[2] = {0.0, 0.0}, rhs[3], a[3], p, q;
     sag_sincos(R.q[2], &sn, &cs);
-    pt_smooth(R, sn, cs, fs);
+    R.pq(sn, cs, p, q);
+    R.smooth(sn, cs, fs);
+    bool need = false;
+    if (!QuietOnly) need = !quiet && (mov != 0 || C.task == T_HAUL_BOX || robot_overlaps_any(C, R, sn, cs));
+    if constexpr (RB::kKind == 1) {  // car: the wheel-floor friction rows are always there
+      if (!need) {
+        CarFree F;
+        car_free_solve(R, sn, cs, K, fs, F);
+        fc[0] = F.fc[0]; fc[1] = F.fc[1]; fc[2] = F.fc[2]; wtau[0] = F.wtau[0]; wtau[1] = F.wtau[1];
+      }
+    }
     if (!QuietOnly) {
       Phys P;
-      P.fc[0] = P.fc[1] = P.fc[2] = 0.0; P.mov = mov; P.err = 0; P.retry = 0;
-      const bool need = !quiet && (mov != 0 || C.task == T_HAUL_BOX || robot_overlaps_any(C, R, sn, cs));
+      P.fc[0] = fc[0]; P.fc[1] = fc[1]; P.fc[2] = fc[2]; P.wtau[0] = wtau[0]; P.wtau[1] = wtau[1];
+      P.mov = mov; P.err = 0; P.retry = 0;
       warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, small, P);
-      fc[0] = P.fc[0]; fc[1] = P.fc[1]; fc[2] = P.fc[2];
+      fc[0] = P.fc[0]; fc[1] = P.fc[1]; fc[2] = P.fc[2]; wtau[0] = P.wtau[0]; wtau[1] = P.wtau[1];
       mov = P.mov;
       if (P.err) err = 1;
     }
     rhs[0] = fs[0] + fc[0]; rhs[1] = fs[1] + fc[1]; rhs[2] = fs[2] + fc[2];
-    pt_solve(-kPtMc * sn, kPtMc * cs, K.iah, K.ish, rhs, a);   // (M + hD) a = f: implicit joint damping
+    pt_solve(p, q, K.iah, K.ish, rhs, a);   // (M + hD) a = f: implicit joint damping
 #pragma unroll
     for (int d = 0; d < 3; ++d) R.v[d] += h * a[d];
 #pragma unroll
     for (int d = 0; d < 3; ++d) R.q[d] += h * R.v[d];
+    if constexpr (RB::kKind == 1) {  // wheels (implicit joint damping) and castor quaternion (mju_quatIntegrate [EXT])
+      for (int i = 0; i < 2; ++i) {
+        double al = (R.wheel_smooth(i) + wtau[i]) / (kCar.Iw + h * kCarWheelDamp);
+        R.wheel[i] += h * al;
+        if (bad_val(R.wheel[i])) err = 1;
+      }
+      double sn2, cs2, wc[3];
+      sag_sincos(R.q[2], &sn2, &cs2);
+      R.castor_angvel(sn2, cs2, wc);
+      double wn = sqrt(wc[0] * wc[0] + wc[1] * wc[1] + wc[2] * wc[2]);
+      if (wn > 0.0) {
+        double sh, ch;
+        sag_sincos(0.5 * h * wn, &sh, &ch);
+        double ax = wc[0] / wn * sh, ay = wc[1] / wn * sh, az = wc[2] / wn * sh;
+        double qa = R.cq[0], qb = R.cq[1], qc = R.cq[2], qd = R.cq[3];
+        double q0 = qa * ch - qb * ax - qc * ay - qd * az;
+        double q1 = qa * ax + qb * ch + qc * az - qd * ay;
+        double q2 = qa * ay - qb * az + qc * ch + qd * ax;
+        double q3 = qa * az + qb * ay - qc * ax + qd * ch;
+        double nq = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+        R.cq[0] = q0 / nq; R.cq[1] = q1 / nq; R.cq[2] = q2 / nq; R.cq[3] = q3 / nq;
+      }
+    }
 #pragma unroll
     for (int d = 0; d < 3; ++d) if (bad_val(R.q[d]) || bad_val(R.v[d]) || bad_val(a[d])) err = 1;
     time += h;
   }
   EndOut O;
-  end_of_step<QuietOnly>(wmask, S, small, C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
+  end_of_step<QuietOnly, RB>(wmask, S, small, C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
   unsigned char dn = 0;
   if (err || O.err) { dn = 1; fl |= F_PHYS_ERROR; }
   if (O.resample_failed) fl |= F_RESAMPLE_FAILED;
@@ -1281,15 +1563,16 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev&
 }
 
 // observation at the current state (reset return value / refresh after state injection)
+template <class RB>
 SAG_HD void env_observe(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& D, int e, float* obs_s, int ostride) {
   Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
   C.L = make_slots(C.sp);
-  Robot R;
+  RB R;
   load_robot(D, e, C.sp, R);
   TaskState T;
   load_task_state(D, e, T);
   Rng rng = {D.seed, D.gid_base + (uint32_t)e, D.episode[e]};
-  const PtConst K = pt_const(R.damp_xy, kPtH);
+  const PtConst K = R.consts(RB::kH);
   unsigned mov = 0;  // rebuilt from the velocities: state may have been injected
   for (int s = C.L.v0; s < C.L.n; ++s) {
     if (!kind_movable(slot_kind(C.sp, C.L, s))) continue;
@@ -1297,7 +1580,7 @@ SAG_HD void env_observe(unsigned wmask, Scratch* S, SmallScratch* small, const D
     if (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0) mov |= 1u << s;
   }
   EndOut O;
-  end_of_step<false>(wmask, S, small, C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
+  end_of_step<false, RB>(wmask, S, small, C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
   D.clear[e] = O.clear;
   D.movmask[e] = (int)mov;
 }
@@ -1311,6 +1594,7 @@ SAG_HD double slot_keepout(const Dev& D, const TaskSpec& sp, int kind) {
        : kind == K_PILLAR ? D.k_pillar : kind == K_GOAL ? kGoalKeepout : kind == K_BUTTON ? kButtonsKeepout : sp.box_keepout;
 }
 
+template <class RB>
 SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_task) {
   Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
   C.L = make_slots(C.sp);
@@ -1372,8 +1656,9 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
   if (C.sp.kind == 0 || C.sp.kind == 2) { rng.pair(0u, ctr++, u1, u2); D.oyaw[oidx(D, C.L.goal, e)] = kTwoPi * u1; }
   if (C.sp.kind == 2 && C.sp.box_kind == K_BOX) { rng.pair(0u, ctr++, u1, u2); D.oyaw[oidx(D, C.L.box, e)] = kTwoPi * u1; }
   if (C.sp.kind == 1) for (int i = 0; i < C.L.nbtn; ++i) { rng.pair(0u, ctr++, u1, u2); D.oyaw[oidx(D, C.L.btn0 + i, e)] = kTwoPi * u1; }
-  Robot R;
+  RB R;
   R.q[0] = rxy[0]; R.q[1] = rxy[1]; R.q[2] = robot_rot; R.v[0] = R.v[1] = R.v[2] = 0.0; R.ctrl[0] = R.ctrl[1] = 0.0;
+  if constexpr (RB::kKind == 1) { R.wheel[0] = R.wheel[1] = 0.0; R.cq[0] = 1.0; R.cq[1] = R.cq[2] = R.cq[3] = 0.0; }
   R.damp_xy = C.sp.damp_xy; R.gear_x = C.sp.gear_x;
   TaskState T;
   load_task_state(D, e, T);

@@ -24,10 +24,13 @@ using namespace sag;
 namespace {
 
 constexpr int kBS = 128;          // environments (threads) per CTA
-constexpr int kObs = SAG_OBS_POINT;
 constexpr int kTileStride = kBS + 1;
-constexpr size_t kTileBytes = (sizeof(float) * kObs * kTileStride + 15) / 16 * 16;
-constexpr size_t kSmemBytes = kTileBytes + sizeof(Scratch) * (kBS / 32);  // > 48 KB: opt-in dynamic shared memory
+template <class RB>
+struct TileCfg {
+  static constexpr int kObs = RB::kObsDim;
+  static constexpr size_t kTileBytes = (sizeof(float) * kObs * kTileStride + 15) / 16 * 16;
+  static constexpr size_t kSmemBytes = kTileBytes + sizeof(Scratch) * (kBS / 32);  // > 48 KB: opt-in dynamic shared memory
+};
 
 thread_local char g_err[512] = "";
 
@@ -61,6 +64,7 @@ struct Handle {
 };
 
 // coalesced write-out of the CTA's observation tile: tile[k][t] -> out[(e0 + t) * kObs + k]
+template <int kObs>
 __device__ __forceinline__ void write_tile(const float* tile, float* out, int e0, int n) {
   int cnt = min(kBS, n - e0) * kObs;
   float* dst = out + (size_t)e0 * kObs;
@@ -80,6 +84,7 @@ __device__ __forceinline__ void write_tile(const float* tile, float* out, int e0
 //   a mixed warp a contact environment runs with 1 of 32 lanes active.
 
 // per-warp write-out of up to 32 observation rows (tile column = lane)
+template <int kObs>
 __device__ __forceinline__ void write_rows(const float* tile, int tstride, float* out, int e) {
   const int lane = threadIdx.x & 31;
 #pragma unroll 4
@@ -88,21 +93,24 @@ __device__ __forceinline__ void write_rows(const float* tile, int tstride, float
     if (er < 0) continue;
     float* dst = out + (size_t)er * kObs;
     const float* src = tile + r;
-    dst[lane] = src[lane * tstride];
-    if (lane + 32 < kObs) dst[lane + 32] = src[(lane + 32) * tstride];
+    for (int k = lane; k < kObs; k += 32) dst[k] = src[k * tstride];
   }
 }
 
+template <class RB>
 __global__ void __launch_bounds__(kBS) k_step_quiet(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                      double* __restrict__ reward, double* __restrict__ reward2,
                                                      uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
-  __shared__ float tile[kObs * kTileStride];
+  constexpr int kObs = RB::kObsDim;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);  // [kObs][kTileStride]
   int e = blockIdx.x * kBS + threadIdx.x;
   const int lane = threadIdx.x & 31;
   bool quiet = false;
   if (e < D.n) {
-    const TaskSpec sp = task_spec(D.task[e]);
-    quiet = !(D.flags[e] & F_PHYS_ERROR) && env_is_quiet(D.clear[e], D.rvx[e], D.rvy[e], D.rw[e], sp.gear_x, sp.damp_xy);
+    RB R;
+    load_robot(D, e, task_spec(D.task[e]), R);
+    quiet = !(D.flags[e] & F_PHYS_ERROR) && env_is_quiet(D.clear[e], R);
   }
   // work list append, one atomic per warp
   const unsigned busy = __ballot_sync(0xffffffffu, e < D.n && !quiet);
@@ -117,33 +125,34 @@ __global__ void __launch_bounds__(kBS) k_step_quiet(Dev D, const float* __restri
     float2 a = reinterpret_cast<const float2*>(act)[e];
     double rew[2];
     unsigned char c, d;
-    env_step<true>(0u, nullptr, nullptr, D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d);
+    env_step<true, RB>(0u, nullptr, nullptr, D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d);
     reward[e] = rew[0];
     if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
     cost[e] = c;
     done[e] = d;
   }
   __syncwarp();
-  write_rows(tile + (threadIdx.x & ~31), kTileStride, obs, e);
+  write_rows<kObs>(tile + (threadIdx.x & ~31), kTileStride, obs, e);
 }
 
 // G = environments per warp (lanes 0..G-1 active).  A warp executes the union of its lanes' divergent paths and each
 // busy warp is latency-bound, so fewer environments per warp = shorter critical path, more warps = more latency hiding.
-template <int G>
+template <int G, class RB>
 struct BusyCfg {
+  static constexpr int kObs = RB::kObsDim;
   static constexpr int kTileStride = G + 1;
   static constexpr size_t kTileBytes = (sizeof(float) * kObs * kTileStride + 15) / 16 * 16;
   static constexpr size_t kSmemBytes = kTileBytes + sizeof(Scratch) + G * sizeof(SmallScratch);
 };
 
-template <int G>
+template <int G, class RB>
 __global__ void __launch_bounds__(32, SAG_BUSY_MIN_BLOCKS) k_step_busy(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                    double* __restrict__ reward, double* __restrict__ reward2,
                                                    uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
-  Scratch* big = reinterpret_cast<Scratch*>(smem_raw + BusyCfg<G>::kTileBytes);
-  SmallScratch* small = reinterpret_cast<SmallScratch*>(smem_raw + BusyCfg<G>::kTileBytes + sizeof(Scratch));
+  Scratch* big = reinterpret_cast<Scratch*>(smem_raw + BusyCfg<G, RB>::kTileBytes);
+  SmallScratch* small = reinterpret_cast<SmallScratch*>(smem_raw + BusyCfg<G, RB>::kTileBytes + sizeof(Scratch));
   const int lane = threadIdx.x;
   const int count = D.counts[0];
   for (int chunk = blockIdx.x; chunk * G < count; chunk += gridDim.x) {
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(32, SAG_BUSY_MIN_BLOCKS) k_step_busy(Dev D, co
       float2 a = reinterpret_cast<const float2*>(act)[e];
       double rew[2];
       unsigned char c, d;
-      env_step<false>(wmask, big, small + lane, D, e, a.x, a.y, tile + lane, BusyCfg<G>::kTileStride, rew, &c, &d);
+      env_step<false, RB>(wmask, big, small + lane, D, e, a.x, a.y, tile + lane, BusyCfg<G, RB>::kTileStride, rew, &c, &d);
       reward[e] = rew[0];
       if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
       cost[e] = c;
@@ -165,30 +174,31 @@ __global__ void __launch_bounds__(32, SAG_BUSY_MIN_BLOCKS) k_step_busy(Dev D, co
     for (int r = 0; r < G; ++r) {  // observation rows of this chunk, 60 floats each, all lanes help
       const int er = __shfl_sync(0xffffffffu, e, r);
       if (er < 0) continue;
-      float* dst = obs + (size_t)er * kObs;
-      dst[lane] = tile[lane * BusyCfg<G>::kTileStride + r];
-      if (lane + 32 < kObs) dst[lane + 32] = tile[(lane + 32) * BusyCfg<G>::kTileStride + r];
+      float* dst = obs + (size_t)er * BusyCfg<G, RB>::kObs;
+      for (int k = lane; k < BusyCfg<G, RB>::kObs; k += 32) dst[k] = tile[k * BusyCfg<G, RB>::kTileStride + r];
     }
     __syncwarp();
   }
 }
 
+template <class RB>
 __global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
-  Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + kTileBytes);
+  Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + TileCfg<RB>::kTileBytes);
   const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
   const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
-  if (e < D.n) env_observe(wmask, &scratch[threadIdx.x >> 5], nullptr, D, e, tile + threadIdx.x, kTileStride);
+  if (e < D.n) env_observe<RB>(wmask, &scratch[threadIdx.x >> 5], nullptr, D, e, tile + threadIdx.x, kTileStride);
   __syncthreads();
-  write_tile(tile, obs, e0, D.n);
+  write_tile<RB::kObsDim>(tile, obs, e0, D.n);
 }
 
+template <class RB>
 __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __restrict__ obs, double* __restrict__ reward,
                                                   uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
-  Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + kTileBytes);
+  Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + TileCfg<RB>::kTileBytes);
   const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
   const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
   if (e < D.n) {
@@ -199,7 +209,7 @@ __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __re
     for (int k = 0; k < k_steps; ++k) {
       double u1, u2;
       rng.pair(2u, base + (uint32_t)k, u1, u2);
-      env_step<false>(wmask, &scratch[threadIdx.x >> 5], nullptr, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0),
+      env_step<false, RB>(wmask, &scratch[threadIdx.x >> 5], nullptr, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0),
                       tile + threadIdx.x, kTileStride, rew, &c, &d);
     }
     if (reward) reward[e] = rew[0];
@@ -207,9 +217,10 @@ __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __re
     if (done) done[e] = d;
   }
   __syncthreads();
-  if (obs) write_tile(tile, obs, e0, D.n);
+  if (obs) write_tile<RB::kObsDim>(tile, obs, e0, D.n);
 }
 
+template <class RB>
 __global__ void __launch_bounds__(kBS) k_reset(Dev D, const uint8_t* __restrict__ mask, int only_flagged, int new_task,
                                                 double* sret, double* scost, double* sn) {
   const int e = blockIdx.x * kBS + threadIdx.x;
@@ -217,7 +228,7 @@ __global__ void __launch_bounds__(kBS) k_reset(Dev D, const uint8_t* __restrict_
   if (mask && !mask[e]) return;
   if (only_flagged && !(D.flags[e] & F_NEEDS_RESET)) return;
   if (D.nstep[e] > 0) { sret[e] += D.epret[e]; scost[e] += D.epcost[e]; sn[e] += 1.0; }
-  env_reset(D, e, D.episode[e] + 1u, new_task != 0);
+  env_reset<RB>(D, e, D.episode[e] + 1u, new_task != 0);
 }
 
 __global__ void k_set_tasks(Dev D, const int32_t* __restrict__ ids) {
@@ -313,6 +324,59 @@ __global__ void __launch_bounds__(256) k_cost(const double* __restrict__ robot_x
   out[e] = hit ? 1 : 0;                                              // world.py:155
 }
 
+static inline int grid_for(int n) { return (n + kBS - 1) / kBS; }
+
+// host-side launchers, one set per robot model
+template <class RB>
+struct Ops {
+  template <int G>
+  static cudaError_t setup_busy(int* per_sm) {
+    cudaError_t ce = cudaFuncSetAttribute(k_step_busy<G, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BusyCfg<G, RB>::kSmemBytes);
+    if (ce != cudaSuccess) return ce;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_step_busy<G, RB>, 32, BusyCfg<G, RB>::kSmemBytes);
+  }
+  static cudaError_t setup(Handle* H) {
+    cudaError_t ce = cudaFuncSetAttribute(k_observe<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_rollout<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
+    if (ce != cudaSuccess) return ce;
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, H->device);
+    const int G = H->busy_g;
+    ce = G == 1 ? setup_busy<1>(&per_sm) : G == 4 ? setup_busy<4>(&per_sm) : G == 32 ? setup_busy<32>(&per_sm) : setup_busy<8>(&per_sm);
+    H->busy_grid = sms * (per_sm > 0 ? per_sm : 1);
+    return ce;
+  }
+  static cudaError_t step(Handle* H, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done,
+                          cudaStream_t s) {
+    cudaError_t ce = cudaMemsetAsync(H->D.counts, 0, 4 * sizeof(int), s);
+    if (ce != cudaSuccess) return ce;
+    k_step_quiet<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kTileBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) return ce;
+    const int G = H->busy_g;
+    const int chunks = (H->D.n + G - 1) / G;
+    const int grid = chunks < H->busy_grid ? chunks : H->busy_grid;
+#define SAG_LAUNCH_BUSY(GG) k_step_busy<GG, RB><<<grid, 32, BusyCfg<GG, RB>::kSmemBytes, s>>>(H->D, act, obs, reward, reward2, cost, done)
+    if (G == 1) SAG_LAUNCH_BUSY(1); else if (G == 4) SAG_LAUNCH_BUSY(4); else if (G == 32) SAG_LAUNCH_BUSY(32); else SAG_LAUNCH_BUSY(8);
+#undef SAG_LAUNCH_BUSY
+    return cudaGetLastError();
+  }
+  static cudaError_t observe(Handle* H, float* obs, cudaStream_t s) {
+    k_observe<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kSmemBytes, s>>>(H->D, obs);
+    return cudaGetLastError();
+  }
+  static cudaError_t rollout(Handle* H, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, cudaStream_t s) {
+    k_rollout<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kSmemBytes, s>>>(H->D, k_steps, obs, reward, cost, done);
+    return cudaGetLastError();
+  }
+  static cudaError_t reset(Handle* H, const uint8_t* mask, int only_flagged, int new_task, cudaStream_t s) {
+    k_reset<RB><<<grid_for(H->D.n), kBS, 0, s>>>(H->D, mask, only_flagged, new_task, H->sret, H->scost, H->sn);
+    return cudaGetLastError();
+  }
+};
+
+#define SAG_DISPATCH(H, call) ((H)->D.robot == SAG_ROBOT_CAR ? Ops<CarRobot>::call : Ops<PointRobot>::call)
+
 }  // namespace
 
 // ================================================================================================
@@ -335,36 +399,26 @@ void sag_default_config(SagConfig* c) {
 int sag_create(const SagConfig* cfg, int device, void** handle) {
   if (!cfg || !handle) return fail("sag_create: null argument");
   if (cfg->n_envs <= 0) return fail("sag_create: n_envs must be positive");
-  if (cfg->robot != SAG_ROBOT_POINT) return fail("sag_create: only the point robot is implemented on the device path");
+  if (cfg->robot != SAG_ROBOT_POINT && cfg->robot != SAG_ROBOT_CAR) return fail("sag_create: robot must be point (0) or car (1)");
   if (cfg->robot_ctrl_range_scale != 0.0) return fail("sag_create: robot_ctrl_range_scale != 0 is not implemented");
   CK(cudaSetDevice(device));
-  CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  CK(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   Handle* H = new (std::nothrow) Handle();
   if (!H) return fail("sag_create: out of host memory");
   memset(H, 0, sizeof(*H));
   H->device = device;
+  Dev& D = H->D;
+  dev_from_config(D, *cfg);
   {
     // environments per busy warp: 8 measured best on B200 (sweep 1/2/4/8/32 in DESIGN.md 7); SAG_BUSY_G overrides
     int G = 8;
     const char* gs = getenv("SAG_BUSY_G");
-    if (gs) { int v = atoi(gs); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) G = v; }
+    if (gs) { int v = atoi(gs); if (v == 1 || v == 4 || v == 8 || v == 32) G = v; }
     H->busy_g = G;
-    int sms = 148, per_sm = 1;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-#define SAG_SETUP_BUSY(GG)                                                                                                   \
-  {                                                                                                                          \
-    cudaFuncSetAttribute(k_step_busy<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BusyCfg<GG>::kSmemBytes);        \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_busy<GG>, 32, BusyCfg<GG>::kSmemBytes);                    \
+    cudaError_t ce = SAG_DISPATCH(H, setup(H));
+    if (ce != cudaSuccess) { delete H; return fail("sag_create: kernel setup", ce); }
   }
-    if (G == 1) SAG_SETUP_BUSY(1) else if (G == 2) SAG_SETUP_BUSY(2) else if (G == 4) SAG_SETUP_BUSY(4)
-    else if (G == 8) SAG_SETUP_BUSY(8) else if (G == 16) SAG_SETUP_BUSY(16) else SAG_SETUP_BUSY(32)
-#undef SAG_SETUP_BUSY
-    H->busy_grid = sms * (per_sm > 0 ? per_sm : 1);
-  }
-  Dev& D = H->D;
-  dev_from_config(D, *cfg);
-  SlabLayout LY = slab_layout(D.n, D.stride, kObs);
+  const int obs_dim = D.robot == SAG_ROBOT_CAR ? SAG_OBS_CAR : SAG_OBS_POINT;
+  SlabLayout LY = slab_layout(D.n, D.stride, obs_dim);
   cudaError_t ce = cudaMalloc(&H->slab, LY.total);
   if (ce != cudaSuccess) { delete H; return fail("sag_create: cudaMalloc", ce); }
   H->slab_bytes = LY.total;
@@ -377,7 +431,7 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   H->sret = (double*)(base + LY.stats_off); H->scost = H->sret + st; H->sn = H->sret + 2 * st;
   H->act_d = (float*)(base + LY.act_off); H->obs_d = (float*)(base + LY.obs_off); H->rew_d = (double*)(base + LY.rew_off);
   H->cost_d = (uint8_t*)(base + LY.cost_off); H->done_d = (uint8_t*)(base + LY.done_off);
-  // default task: go_to_goal; episode counters start at 0xFFFFFFFF so that the first reset is episode 0
+  // episode counters start at 0xFFFFFFFF so that the first reset is episode 0
   ce = cudaMemset(D.episode, 0xFF, st * sizeof(unsigned));
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&H->own_stream, cudaStreamNonBlocking);
   if (ce != cudaSuccess) { cudaFree(H->slab); delete H; return fail("sag_create: init", ce); }
@@ -397,29 +451,10 @@ int sag_destroy(void* handle) {
 }
 
 int sag_stride(void* handle) { return ((Handle*)handle)->D.stride; }
-int sag_obs_dim(void* handle) { (void)handle; return kObs; }
+int sag_obs_dim(void* handle) { return ((Handle*)handle)->D.robot == SAG_ROBOT_CAR ? SAG_OBS_CAR : SAG_OBS_POINT; }
 size_t sag_field_bytes(void* handle, int field) {
   if (field < 0 || field >= SAG_NUM_FIELDS) return 0;
   return ((Handle*)handle)->field_bytes[field];
-}
-
-static inline int grid_for(int n) { return (n + kBS - 1) / kBS; }
-
-static cudaError_t launch_step(Handle* H, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost,
-                               uint8_t* done, cudaStream_t s) {
-  cudaError_t ce = cudaMemsetAsync(H->D.counts, 0, 4 * sizeof(int), s);
-  if (ce != cudaSuccess) return ce;
-  k_step_quiet<<<grid_for(H->D.n), kBS, 0, s>>>(H->D, act, obs, reward, reward2, cost, done);
-  ce = cudaGetLastError();
-  if (ce != cudaSuccess) return ce;
-  const int G = H->busy_g;
-  const int chunks = (H->D.n + G - 1) / G;
-  const int grid = chunks < H->busy_grid ? chunks : H->busy_grid;
-#define SAG_LAUNCH_BUSY(GG) k_step_busy<GG><<<grid, 32, BusyCfg<GG>::kSmemBytes, s>>>(H->D, act, obs, reward, reward2, cost, done)
-  if (G == 1) SAG_LAUNCH_BUSY(1); else if (G == 2) SAG_LAUNCH_BUSY(2); else if (G == 4) SAG_LAUNCH_BUSY(4);
-  else if (G == 8) SAG_LAUNCH_BUSY(8); else if (G == 16) SAG_LAUNCH_BUSY(16); else SAG_LAUNCH_BUSY(32);
-#undef SAG_LAUNCH_BUSY
-  return cudaGetLastError();
 }
 
 int sag_set_tasks(void* handle, const int32_t* ids, void* stream) {
@@ -443,8 +478,7 @@ int sag_seed(void* handle, uint64_t seed) {
 int sag_reset(void* handle, const uint8_t* mask, int only_flagged, int new_task, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H) return fail("sag_reset: null handle");
-  k_reset<<<grid_for(H->D.n), kBS, 0, (cudaStream_t)stream>>>(H->D, mask, only_flagged, new_task, H->sret, H->scost, H->sn);
-  CK(cudaGetLastError());
+  CK(SAG_DISPATCH(H, reset(H, mask, only_flagged, new_task, (cudaStream_t)stream)));
   return 0;
 }
 
@@ -452,23 +486,21 @@ int sag_step(void* handle, const float* act, float* obs, double* reward, double*
              void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !act || !obs || !reward || !cost || !done) return fail("sag_step: null argument");
-  CK(launch_step(H, act, obs, reward, reward2, cost, done, (cudaStream_t)stream));
+  CK(SAG_DISPATCH(H, step(H, act, obs, reward, reward2, cost, done, (cudaStream_t)stream)));
   return 0;
 }
 
 int sag_observe(void* handle, float* obs, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !obs) return fail("sag_observe: null argument");
-  k_observe<<<grid_for(H->D.n), kBS, kSmemBytes, (cudaStream_t)stream>>>(H->D, obs);
-  CK(cudaGetLastError());
+  CK(SAG_DISPATCH(H, observe(H, obs, (cudaStream_t)stream)));
   return 0;
 }
 
 int sag_rollout(void* handle, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || k_steps <= 0) return fail("sag_rollout: bad argument");
-  k_rollout<<<grid_for(H->D.n), kBS, kSmemBytes, (cudaStream_t)stream>>>(H->D, k_steps, obs, reward, cost, done);
-  CK(cudaGetLastError());
+  CK(SAG_DISPATCH(H, rollout(H, k_steps, obs, reward, cost, done, (cudaStream_t)stream)));
   return 0;
 }
 
@@ -478,8 +510,8 @@ int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward
   cudaStream_t s = H->own_stream;
   const size_t n = (size_t)H->D.n;
   CK(cudaMemcpyAsync(H->act_d, act_h, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-  CK(launch_step(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s));
-  CK(cudaMemcpyAsync(obs_h, H->obs_d, n * kObs * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(SAG_DISPATCH(H, step(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s)));
+  CK(cudaMemcpyAsync(obs_h, H->obs_d, n * (size_t)sag_obs_dim(H) * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(reward_h, H->rew_d, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(cost_h, H->cost_d, n, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(done_h, H->done_d, n, cudaMemcpyDeviceToHost, s));
@@ -491,9 +523,8 @@ int sag_observe_host(void* handle, float* obs_h) {
   Handle* H = (Handle*)handle;
   if (!H || !obs_h) return fail("sag_observe_host: null argument");
   cudaStream_t s = H->own_stream;
-  k_observe<<<grid_for(H->D.n), kBS, kSmemBytes, s>>>(H->D, H->obs_d);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(obs_h, H->obs_d, (size_t)H->D.n * kObs * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(SAG_DISPATCH(H, observe(H, H->obs_d, s)));
+  CK(cudaMemcpyAsync(obs_h, H->obs_d, (size_t)H->D.n * (size_t)sag_obs_dim(H) * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return 0;
 }

@@ -23,6 +23,7 @@ inline SlabLayout slab_layout(int n, int stride, int obs_dim) {
   L.bytes[SAG_F_TASK_F64] = 12 * st * sizeof(double);
   L.bytes[SAG_F_TASK_I32] = 10 * st * sizeof(int32_t);
   L.bytes[SAG_F_FLAGS] = st;
+  L.bytes[SAG_F_ROBOT_EXT] = 6 * st * sizeof(double);
   size_t total = 0;
   for (int f = 0; f < SAG_NUM_FIELDS; ++f) { L.off[f] = total; total += align_up(L.bytes[f], 256); }
   L.stats_off = total; total += align_up(3 * st * sizeof(double), 256);
@@ -50,6 +51,7 @@ inline void slab_bind(Dev& D, const SlabLayout& L, char* base) {
   D.task = ii; D.gbtn = ii + st; D.bstate = ii + 2 * st; D.btimer = ii + 3 * st; D.amask = ii + 4 * st; D.cgtimer = ii + 5 * st;
   D.nstep = ii + 6 * st; D.ctr = (unsigned*)(ii + 7 * st); D.episode = (unsigned*)(ii + 8 * st); D.movmask = ii + 9 * st;
   D.flags = (unsigned char*)(base + L.off[SAG_F_FLAGS]);
+  D.rext = (double*)(base + L.off[SAG_F_ROBOT_EXT]);
   int32_t* sc = (int32_t*)(base + L.sched_off);
   D.worklist = sc; D.counts = sc + 3 * st;
 }

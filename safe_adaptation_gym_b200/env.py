@@ -58,8 +58,8 @@ class BatchedSafeAdaptationGym:
         self.robot_name = _robot_name(robot_base)
         if self.robot_name not in _ROBOT_TO_CONTROL_FREQUENCY:
             raise KeyError(self.robot_name)
-        if self.robot_name != 'point':
-            raise NotImplementedError(f"robot '{self.robot_name}' is not implemented on the device path yet")
+        if self.robot_name not in ('point', 'car'):
+            raise NotImplementedError(f"robot '{self.robot_name}' is not implemented on the device path (3-D articulated body)")
         cfg = dict(WORLD_DEFAULT)
         for k, v in (config or {}).items():
             if k not in WORLD_DEFAULT and k not in _EXTRA_KEYS:
@@ -84,7 +84,7 @@ class BatchedSafeAdaptationGym:
         L = self._lib
         c = L.default_config()
         c.n_envs = self.num_envs
-        c.robot = 0
+        c.robot = 1 if self.robot_name == 'car' else 0
         c.env_id_base = int(env_id_base)
         c.max_episode_steps = int(max_episode_steps)
         c.max_layout_draws = int(cfg.get('max_layout_draws', 0))
@@ -259,7 +259,7 @@ class BatchedSafeAdaptationGym:
 
     _FIELDS = {'robot': (_abi.F_ROBOT, torch.float64, (6,)), 'objects': (_abi.F_OBJECTS, torch.float64, (6, _abi.MAX_SLOTS)),
                'task_f64': (_abi.F_TASK_F64, torch.float64, (12,)), 'task_i32': (_abi.F_TASK_I32, torch.int32, (10,)),
-               'flags': (_abi.F_FLAGS, torch.uint8, ())}
+               'flags': (_abi.F_FLAGS, torch.uint8, ()), 'robot_ext': (_abi.F_ROBOT_EXT, torch.float64, (6,))}
 
     def get_field(self, name: str) -> torch.Tensor:
         """Copy of an internal SoA state field, shape (*lead, stride) (see include/sag_b200.h SAG_F_*)."""

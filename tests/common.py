@@ -30,10 +30,10 @@ def hostemu_lib():
     return _hostemu
 
 
-def make_env(backend, n, task_names, seed, config=None, **kw):
+def make_env(backend, n, task_names, seed, config=None, robot="point", **kw):
     """backend: 'hostemu' (CPU, kernel body compiled by g++) or 'cuda' (the product library)."""
     lib = hostemu_lib() if backend == "hostemu" else None
-    env = BatchedSafeAdaptationGym("xmls/point.xml", config=config, num_envs=n, _test_lib=lib, **kw)
+    env = BatchedSafeAdaptationGym("xmls/%s.xml" % robot, config=config, num_envs=n, _test_lib=lib, **kw)
     env.seed(seed)
     if isinstance(task_names, str):
         task_names = [task_names] * n
@@ -41,31 +41,40 @@ def make_env(backend, n, task_names, seed, config=None, **kw):
     return env
 
 
-def make_oracles(n, task_names, seed, config=None, gid_base=0):
+def make_oracles(n, task_names, seed, config=None, gid_base=0, robot="point"):
     if isinstance(task_names, str):
         task_names = [task_names] * n
     cfg = {k: v for k, v in (config or {}).items()}
-    envs = [O.OracleEnv("point", task_names[e], config=cfg, seed=seed, env_gid=gid_base + e) for e in range(n)]
+    envs = [O.OracleEnv(robot, task_names[e], config=cfg, seed=seed, env_gid=gid_base + e) for e in range(n)]
     for e in envs:
         assert e.reset(0) == 0
     return envs
 
 
 def env_state(env):
-    """(robot [n,6], objects [n,32,6]) as numpy"""
+    """(robot [n,6] (+6 car extras), objects [n,32,6]) as numpy"""
     n = env.num_envs
     robot = env.get_field("robot").cpu().numpy()[:, :n].T.copy()
+    if env.robot_name == "car":
+        robot = np.concatenate([robot, env.get_field("robot_ext").cpu().numpy()[:, :n].T], axis=1)
     objs = env.get_field("objects").cpu().numpy()[:, :, :n].transpose(2, 1, 0).copy()
     return robot, objs
 
 
 def oracle_state(envs):
-    robot = np.stack([e.robot_state for e in envs])
+    robot = np.stack([np.concatenate([e.robot_state, e.robot_ext]) if e.robot == O.CAR else e.robot_state for e in envs])
     objs = np.zeros((len(envs), 32, 6))
     for i, e in enumerate(envs):
         o = e.objects()
         objs[i, :len(o)] = o[:, 2:8]
     return robot, objs
+
+
+def _car_action(err, rng):
+    """differential drive; the car's front is body -y (car.xml:19-20)"""
+    fwd = np.clip(1.0 - abs(err), 0.0, 1.0) * 0.02
+    a = np.array([fwd + 0.01 * np.clip(err, -1, 1), fwd - 0.01 * np.clip(err, -1, 1)])
+    return np.clip(a + 0.003 * rng.normal(size=2), -1, 1)
 
 
 def drive_action(oenv, rng, p_random=0.15):
@@ -92,12 +101,14 @@ def drive_action(oenv, rng, p_random=0.15):
     if target is None or rng.uniform() < p_random:
         return rng.uniform(-1, 1, 2)
     d = target - s[:2]
+    if oenv.robot == O.CAR:
+        return _car_action((np.arctan2(d[1], d[0]) - (s[2] - np.pi / 2) + np.pi) % (2 * np.pi) - np.pi, rng)
     err = (np.arctan2(d[1], d[0]) - s[2] + np.pi) % (2 * np.pi) - np.pi
     a = np.array([np.clip(1.0 - abs(err), 0.02, 1.0), np.clip(2.0 * err, -1, 1)])
     return np.clip(a + 0.2 * rng.normal(size=2), -1, 1)
 
 
-def run_parity(backend, task_names, n, steps, seed, config=None, policy="drive", check_every=1):
+def run_parity(backend, task_names, n, steps, seed, config=None, policy="drive", check_every=1, robot="point"):
     """Step the batched env and n oracle envs on identical actions and require BIT-EXACT agreement every step:
     robot / object state (float64), reward (float64), cost, done, and the float32 observation (== the oracle's
     float64 observation rounded to float32).  Exactness holds because both sides use only correctly rounded
@@ -105,8 +116,8 @@ def run_parity(backend, task_names, n, steps, seed, config=None, policy="drive",
     Returns summary statistics (so tests can assert that interesting events actually happened)."""
     cfg = dict(config or {})
     cfg.setdefault("action_noise", 0.0)
-    env = make_env(backend, n, task_names, seed, cfg)
-    orc = make_oracles(n, task_names, seed, cfg)
+    env = make_env(backend, n, task_names, seed, cfg, robot=robot)
+    orc = make_oracles(n, task_names, seed, cfg, robot=robot)
     r0, o0 = env_state(env)
     ro, oo = oracle_state(orc)
     np.testing.assert_array_equal(r0, ro)

@@ -24,7 +24,7 @@ extern "C" void sag_prof_set(long* p) { sag_prof_ptr = p; }
 using namespace sag;
 
 namespace {
-constexpr int kBS = 128, kObs = SAG_OBS_POINT, kTileStride = kBS + 1;
+constexpr int kBS = 128, kTileStride = kBS + 1, kObsMax = SAG_OBS_CAR;
 char g_err[512] = "";
 int fail(const char* w) { snprintf(g_err, sizeof(g_err), "%s", w); return 1; }
 struct Handle {
@@ -33,10 +33,70 @@ struct Handle {
   SlabLayout LY;
   double *sret, *scost, *sn;
 };
-void write_tile(const float* tile, float* out, int e0, int n) {
+void write_tile(const float* tile, float* out, int e0, int n, int kObs) {
   int cnt = (n - e0 < kBS ? n - e0 : kBS) * kObs;
   float* dst = out + (size_t)e0 * kObs;
   for (int i = 0; i < cnt; ++i) { int t = i / kObs, k = i - t * kObs; dst[i] = tile[k * kTileStride + t]; }
+}
+int obs_dim_of(const Dev& D) { return D.robot == SAG_ROBOT_CAR ? SAG_OBS_CAR : SAG_OBS_POINT; }
+
+template <class RB>
+void do_reset(Handle* H, const uint8_t* mask, int only_flagged, int new_task) {
+  Dev& D = H->D;
+  for (int e = 0; e < D.n; ++e) {
+    if (mask && !mask[e]) continue;
+    if (only_flagged && !(D.flags[e] & F_NEEDS_RESET)) continue;
+    if (D.nstep[e] > 0) { H->sret[e] += D.epret[e]; H->scost[e] += D.epcost[e]; H->sn[e] += 1.0; }
+    env_reset<RB>(D, e, D.episode[e] + 1u, new_task != 0);
+  }
+}
+template <class RB>
+void do_step(Handle* H, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done) {
+  Dev& D = H->D;
+  static float tile[kObsMax * kTileStride];
+  static Scratch scratch;
+  static SmallScratch small;
+  for (int e0 = 0; e0 < D.n; e0 += kBS) {
+    for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
+      int e = e0 + t; double rew[2]; unsigned char c, d;
+      env_step<false, RB>(1u, &scratch, &small, D, e, act[2 * e], act[2 * e + 1], tile + t, kTileStride, rew, &c, &d);
+      reward[e] = rew[0];
+      if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
+      cost[e] = c; done[e] = d;
+    }
+    write_tile(tile, obs, e0, D.n, RB::kObsDim);
+  }
+}
+template <class RB>
+void do_observe(Handle* H, float* obs) {
+  Dev& D = H->D;
+  static float tile[kObsMax * kTileStride];
+  static Scratch scratch;
+  for (int e0 = 0; e0 < D.n; e0 += kBS) {
+    for (int t = 0; t < kBS && e0 + t < D.n; ++t) env_observe<RB>(1u, &scratch, nullptr, D, e0 + t, tile + t, kTileStride);
+    write_tile(tile, obs, e0, D.n, RB::kObsDim);
+  }
+}
+template <class RB>
+void do_rollout(Handle* H, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done) {
+  Dev& D = H->D;
+  static float tile[kObsMax * kTileStride];
+  static Scratch scratch;
+  for (int e0 = 0; e0 < D.n; e0 += kBS) {
+    for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
+      int e = e0 + t; double rew[2] = {0, 0}; unsigned char c = 0, d = 0;
+      Rng rng = {D.seed, D.gid_base + (uint32_t)e, D.episode[e]};
+      uint32_t base = (uint32_t)D.nstep[e];
+      for (int k = 0; k < k_steps; ++k) {
+        double u1, u2; rng.pair(2u, base + (uint32_t)k, u1, u2);
+        env_step<false, RB>(1u, &scratch, nullptr, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + t, kTileStride, rew, &c, &d);
+      }
+      if (reward) reward[e] = rew[0];
+      if (cost) cost[e] = c;
+      if (done) done[e] = d;
+    }
+    if (obs) write_tile(tile, obs, e0, D.n, RB::kObsDim);
+  }
 }
 }  // namespace
 
@@ -57,7 +117,7 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   Handle* H = new Handle();
   memset(H, 0, sizeof(*H));
   dev_from_config(H->D, *cfg);
-  H->LY = slab_layout(H->D.n, H->D.stride, kObs);
+  H->LY = slab_layout(H->D.n, H->D.stride, obs_dim_of(H->D));
   H->slab = (char*)calloc(1, H->LY.total);
   slab_bind(H->D, H->LY, H->slab);
   size_t st = H->D.stride;
@@ -68,7 +128,7 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
 }
 int sag_destroy(void* h) { Handle* H = (Handle*)h; if (H) { free(H->slab); delete H; } return 0; }
 int sag_stride(void* h) { return ((Handle*)h)->D.stride; }
-int sag_obs_dim(void* h) { (void)h; return kObs; }
+int sag_obs_dim(void* h) { return obs_dim_of(((Handle*)h)->D); }
 size_t sag_field_bytes(void* h, int f) { return (f < 0 || f >= SAG_NUM_FIELDS) ? 0 : ((Handle*)h)->LY.bytes[f]; }
 int sag_set_tasks(void* h, const int32_t* ids, void* s) {
   (void)s; Handle* H = (Handle*)h;
@@ -77,63 +137,23 @@ int sag_set_tasks(void* h, const int32_t* ids, void* s) {
 }
 int sag_seed(void* h, uint64_t seed) { Handle* H = (Handle*)h; H->D.seed = seed; memset(H->D.episode, 0xFF, (size_t)H->D.stride * sizeof(unsigned)); return 0; }
 int sag_reset(void* h, const uint8_t* mask, int only_flagged, int new_task, void* s) {
-  (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
-  for (int e = 0; e < D.n; ++e) {
-    if (mask && !mask[e]) continue;
-    if (only_flagged && !(D.flags[e] & F_NEEDS_RESET)) continue;
-    if (D.nstep[e] > 0) { H->sret[e] += D.epret[e]; H->scost[e] += D.epcost[e]; H->sn[e] += 1.0; }
-    env_reset(D, e, D.episode[e] + 1u, new_task != 0);
-  }
+  (void)s; Handle* H = (Handle*)h;
+  if (H->D.robot == SAG_ROBOT_CAR) do_reset<CarRobot>(H, mask, only_flagged, new_task); else do_reset<PointRobot>(H, mask, only_flagged, new_task);
   return 0;
 }
 int sag_step(void* h, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done, void* s) {
-  (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
-  static float tile[kObs * kTileStride];
-  static Scratch scratch;
-  static SmallScratch small;
-  for (int e0 = 0; e0 < D.n; e0 += kBS) {
-    for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
-      int e = e0 + t; double rew[2]; unsigned char c, d;
-      env_step<false>(1u, &scratch, &small, D, e, act[2 * e], act[2 * e + 1], tile + t, kTileStride, rew, &c, &d);
-      reward[e] = rew[0];
-      if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
-      cost[e] = c; done[e] = d;
-    }
-    write_tile(tile, obs, e0, D.n);
-  }
+  (void)s; Handle* H = (Handle*)h;
+  if (H->D.robot == SAG_ROBOT_CAR) do_step<CarRobot>(H, act, obs, reward, reward2, cost, done); else do_step<PointRobot>(H, act, obs, reward, reward2, cost, done);
   return 0;
 }
 int sag_observe(void* h, float* obs, void* s) {
-  (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
-  static float tile[kObs * kTileStride];
-  static Scratch scratch;
-  static SmallScratch small;
-  for (int e0 = 0; e0 < D.n; e0 += kBS) {
-    for (int t = 0; t < kBS && e0 + t < D.n; ++t) env_observe(1u, &scratch, nullptr, D, e0 + t, tile + t, kTileStride);
-    write_tile(tile, obs, e0, D.n);
-  }
+  (void)s; Handle* H = (Handle*)h;
+  if (H->D.robot == SAG_ROBOT_CAR) do_observe<CarRobot>(H, obs); else do_observe<PointRobot>(H, obs);
   return 0;
 }
 int sag_rollout(void* h, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* s) {
-  (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
-  static float tile[kObs * kTileStride];
-  static Scratch scratch;
-  static SmallScratch small;
-  for (int e0 = 0; e0 < D.n; e0 += kBS) {
-    for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
-      int e = e0 + t; double rew[2] = {0, 0}; unsigned char c = 0, d = 0;
-      Rng rng = {D.seed, D.gid_base + (uint32_t)e, D.episode[e]};
-      uint32_t base = (uint32_t)D.nstep[e];
-      for (int k = 0; k < k_steps; ++k) {
-        double u1, u2; rng.pair(2u, base + (uint32_t)k, u1, u2);
-        env_step<false>(1u, &scratch, nullptr, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + t, kTileStride, rew, &c, &d);
-      }
-      if (reward) reward[e] = rew[0];
-      if (cost) cost[e] = c;
-      if (done) done[e] = d;
-    }
-    if (obs) write_tile(tile, obs, e0, D.n);
-  }
+  (void)s; Handle* H = (Handle*)h;
+  if (H->D.robot == SAG_ROBOT_CAR) do_rollout<CarRobot>(H, k_steps, obs, reward, cost, done); else do_rollout<PointRobot>(H, k_steps, obs, reward, cost, done);
   return 0;
 }
 int sag_read_field(void* h, int f, void* dst, void* s) { (void)s; Handle* H = (Handle*)h; memcpy(dst, H->slab + H->LY.off[f], H->LY.bytes[f]); return 0; }

@@ -195,3 +195,30 @@ def test_rollout_kernel_matches_stepping():
     rb, ob = env_state(b)
     np.testing.assert_array_equal(ra, rb)
     np.testing.assert_array_equal(oa, ob)
+
+
+@pytest.mark.parametrize("task", ["go_to_goal", "press_buttons", "push_box", "haul_box", "collect", "unsupervised", "catch_goal"])
+def test_car_tasks(task):
+    """BASELINE configs 3 / 4: car robot (reduced planar differential-drive model), bit-exact vs the oracle"""
+    s = run_parity("cuda", task, n=16, steps=250, seed=31, robot="car")
+    assert s["reward"] == s["reward"]
+
+
+def test_car_mixed_batch_random_actions_with_noise():
+    names = ["go_to_goal", "press_buttons", "push_box", "haul_box"] * 16
+    s = run_parity("cuda", names, n=64, steps=200, seed=7, policy="random", config={"action_noise": 0.01}, robot="car")
+    assert s["cost"] >= 0
+
+
+def test_car_observation_shape_and_full_size_smoke():
+    env = make_env("cuda", 32768, ["go_to_goal", "press_buttons"] * 16384, seed=666, robot="car")
+    obs = env.observation
+    assert tuple(obs.shape) == (32768, 72)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for _ in range(50):
+        obs, rew, done, info = env.step(torch.rand((32768, 2), device="cuda", generator=g) * 2 - 1)
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and not bool(done.any())
+    # ball-joint quaternion stays normalised; the 3x3 block of the obs is a rotation matrix
+    m = obs[:, 63:72].reshape(-1, 3, 3).double()
+    eye = torch.eye(3, device="cuda", dtype=torch.float64)
+    assert float((m @ m.transpose(1, 2) - eye).abs().max()) < 1e-5

@@ -25,3 +25,14 @@ def test_other_tasks(task):
 def test_mixed_task_batch_with_noise():
     names = ["go_to_goal", "press_buttons", "push_box", "collect", "catch_goal", "haul_box", "unsupervised", "go_to_goal_scarce"]
     run_parity("hostemu", names, n=8, steps=120, seed=3, config={"action_noise": 0.01})
+
+
+@pytest.mark.parametrize("task", ["go_to_goal", "press_buttons", "push_box", "haul_box", "collect", "unsupervised", "catch_goal"])
+def test_car_tasks(task):
+    s = run_parity("hostemu", task, n=3, steps=150, seed=31, robot="car")
+    assert s["reward"] == s["reward"]
+
+
+def test_car_random_actions_with_noise():
+    run_parity("hostemu", ["go_to_goal", "press_buttons", "push_box", "haul_box"], n=4, steps=120, seed=7, policy="random",
+               config={"action_noise": 0.01}, robot="car")
