@@ -25,6 +25,33 @@
 #define SAG_DM static inline
 #endif
 
+/* Polynomial coefficients.  On the device they live in constant memory so that DFMA/DMUL/DADD read them as constant-bank
+ * operands (as 64-bit immediates every use costs two extra UMOV instructions: 10 % of the lidar kernel's instructions). */
+#define SAG_DM_COEFFS                                                                                                     \
+  { /* 0..5 sin S1..S6 */                                                                                                 \
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06,     \
+    -2.50507602534068634195e-08, 1.58969099521155010221e-10,                                                              \
+    /* 6..11 cos C1..C6 */                                                                                                \
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07,     \
+    2.08757232129817482790e-09, -1.13596475577881948265e-11,                                                              \
+    /* 12..22 atan aT0..aT10 */                                                                                           \
+    3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01, -1.11111104054623557880e-01,     \
+    9.09088713343650656196e-02, -7.69187620504482999495e-02, 6.66107313738753120669e-02, -5.83357013379057348645e-02,     \
+    4.97687799461593236017e-02, -3.65315727442169155270e-02, 1.62858201153657823623e-02,                                  \
+    /* 23..29 log Lg1..Lg7 */                                                                                             \
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,               \
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01                                          \
+  }
+#if defined(__CUDACC__)
+static __constant__ double sag_dm_coeff_dev[30] = SAG_DM_COEFFS;
+#endif
+static const double sag_dm_coeff_host[30] = SAG_DM_COEFFS;
+#if defined(__CUDA_ARCH__)
+#define SAG_K(i) sag_dm_coeff_dev[i]
+#else
+#define SAG_K(i) sag_dm_coeff_host[i]
+#endif
+
 SAG_DM double sag_dm_from_bits(uint64_t b) {
 #if defined(__CUDA_ARCH__)
   return __longlong_as_double((long long)b);
@@ -56,13 +83,11 @@ SAG_DM void sag_sincos(double x, double* sn, double* cs) {
   double r = (x - dk * pio2_1) - dk * pio2_1t;
   double z = r * r;
   /* kernel sin */
-  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
-               S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+  const double S1 = SAG_K(0), S2 = SAG_K(1), S3 = SAG_K(2), S4 = SAG_K(3), S5 = SAG_K(4), S6 = SAG_K(5);
   double ps = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
   double ks = r + r * z * (S1 + z * ps);
   /* kernel cos */
-  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
-               C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+  const double C1 = SAG_K(6), C2 = SAG_K(7), C3 = SAG_K(8), C4 = SAG_K(9), C5 = SAG_K(10), C6 = SAG_K(11);
   double pc = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
   double hz = 0.5 * z;
   double w = 1.0 - hz;
@@ -78,27 +103,20 @@ SAG_DM void sag_sincos(double x, double* sn, double* cs) {
 SAG_DM double sag_sin(double x) { double s, c; sag_sincos(x, &s, &c); return s; }
 SAG_DM double sag_cos(double x) { double s, c; sag_sincos(x, &s, &c); return c; }
 
-/* atan(t), t >= 0 */
+/* atan(t), t >= 0.  fdlibm's four-way range reduction written without branches: the reduced argument is always one
+ * division num / den (num = t, den = 1 in the lowest range -- exact), and the reconstruction hi - ((x*s - lo) - x) with
+ * hi = lo = 0 equals x - x*s bit for bit.  No divergence between the lanes of a warp. */
 SAG_DM double sag_atan_pos(double t) {
-  const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01, aT2 = 1.42857142725034663711e-01,
-               aT3 = -1.11111104054623557880e-01, aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,
-               aT6 = 6.66107313738753120669e-02, aT7 = -5.83357013379057348645e-02, aT8 = 4.97687799461593236017e-02,
-               aT9 = -3.65315727442169155270e-02, aT10 = 1.62858201153657823623e-02;
-  double hi = 0.0, lo = 0.0, x;
-  int id;
-  if (t < 0.4375) { id = -1; x = t; }
-  else if (t < 1.1875) {
-    if (t < 0.6875) { id = 0; x = (2.0 * t - 1.0) / (2.0 + t); hi = 4.63647609000806093515e-01; lo = 2.26987774529616870924e-17; }
-    else { id = 1; x = (t - 1.0) / (t + 1.0); hi = 7.85398163397448278999e-01; lo = 3.06161699786838301793e-17; }
-  } else {
-    if (t < 2.4375) { id = 2; x = (t - 1.5) / (1.0 + 1.5 * t); hi = 9.82793723247329054082e-01; lo = 1.39033110312309984516e-17; }
-    else { id = 3; x = -1.0 / t; hi = 1.57079632679489655800e+00; lo = 6.12323399573676603587e-17; }
-  }
+  const int r1 = t >= 0.4375, r2 = t >= 0.6875, r3 = t >= 1.1875, r4 = t >= 2.4375;
+  double num = r4 ? -1.0 : (r3 ? t - 1.5 : (r2 ? t - 1.0 : (r1 ? 2.0 * t - 1.0 : t)));
+  double den = r4 ? t : (r3 ? 1.0 + 1.5 * t : (r2 ? t + 1.0 : (r1 ? 2.0 + t : 1.0)));
+  double hi = r4 ? 1.57079632679489655800e+00 : (r3 ? 9.82793723247329054082e-01 : (r2 ? 7.85398163397448278999e-01 : (r1 ? 4.63647609000806093515e-01 : 0.0)));
+  double lo = r4 ? 6.12323399573676603587e-17 : (r3 ? 1.39033110312309984516e-17 : (r2 ? 3.06161699786838301793e-17 : (r1 ? 2.26987774529616870924e-17 : 0.0)));
+  double x = num / den;
   double z = x * x;
   double w = z * z;
-  double s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
-  double s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
-  if (id < 0) return x - x * (s1 + s2);
+  double s1 = z * (SAG_K(12) + w * (SAG_K(14) + w * (SAG_K(16) + w * (SAG_K(18) + w * (SAG_K(20) + w * SAG_K(22))))));
+  double s2 = w * (SAG_K(13) + w * (SAG_K(15) + w * (SAG_K(17) + w * (SAG_K(19) + w * SAG_K(21)))));
   return hi - ((x * (s1 + s2) - lo) - x);
 }
 
@@ -116,9 +134,7 @@ SAG_DM double sag_atan2(double y, double x) {
 /* natural log of a positive normal double */
 SAG_DM double sag_log(double x) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
-  const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
-               Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
-               Lg7 = 1.479819860511658591e-01;
+  const double Lg1 = SAG_K(23), Lg2 = SAG_K(24), Lg3 = SAG_K(25), Lg4 = SAG_K(26), Lg5 = SAG_K(27), Lg6 = SAG_K(28), Lg7 = SAG_K(29);
   uint64_t b = sag_dm_bits(x);
   int32_t hx = (int32_t)(b >> 32);
   uint32_t lx = (uint32_t)b;

@@ -270,16 +270,16 @@ __global__ void __launch_bounds__(kBS) k_lidar(const double* __restrict__ robot,
     const double* oyp = obj_xy + (size_t)nslots * n + e;
     const uint8_t* gp = group + e;
     // four objects per trip: the loads and the four sqrt / atan2 chains are independent, the shared-memory bin
-    // updates (which the compiler must keep in order) come last
+    // updates (which the compiler must keep in order) come last.  Pointers are bumped by n per object (no 64-bit
+    // multiply per access).
     int s = 0;
     for (; s + 4 <= nslots; s += 4) {
       int g[4];
       double wx[4], wy[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        g[k] = gp[(size_t)(s + k) * n];
-        wx[k] = oxp[(size_t)(s + k) * n] - rx;
-        wy[k] = oyp[(size_t)(s + k) * n] - ry;
+        g[k] = *gp; wx[k] = *oxp - rx; wy[k] = *oyp - ry;
+        gp += n; oxp += n; oyp += n;
       }
       LidarHit H[4];
 #pragma unroll
@@ -292,10 +292,12 @@ __global__ void __launch_bounds__(kBS) k_lidar(const double* __restrict__ robot,
       }
     }
     for (; s < nslots; ++s) {
-      int g = gp[(size_t)s * n];
+      int g = *gp;
+      double px = *oxp, py = *oyp;
+      gp += n; oxp += n; oyp += n;
       if (g == 0) continue;
       int off = g == 1 ? 0 : (g == 3 ? 16 : 32);
-      lidar_accum(rx, ry, cs, sn, oxp[(size_t)s * n], oyp[(size_t)s * n], bins + off * kLidarTileStride, kLidarTileStride);
+      lidar_accum(rx, ry, cs, sn, px, py, bins + off * kLidarTileStride, kLidarTileStride);
     }
   }
   __syncthreads();
