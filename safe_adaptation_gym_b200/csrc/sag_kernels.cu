@@ -97,8 +97,9 @@ __device__ __forceinline__ void write_rows(const float* tile, int tstride, float
   }
 }
 
+// __launch_bounds__(kBS, 4): 4 CTAs / SM (<= 128 registers) so that the whole 65,536-env batch is one wave
 template <class RB>
-__global__ void __launch_bounds__(kBS) k_step_quiet(Dev D, const float* __restrict__ act, float* __restrict__ obs,
+__global__ void __launch_bounds__(kBS, 4) k_step_quiet(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                      double* __restrict__ reward, double* __restrict__ reward2,
                                                      uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   constexpr int kObs = RB::kObsDim;
