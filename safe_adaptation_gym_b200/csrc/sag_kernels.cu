@@ -310,19 +310,35 @@ __global__ void __launch_bounds__(kBS) k_lidar(const double* __restrict__ robot,
   }
 }
 
+// NH > 0: hazard count known at compile time -> all 2*NH loads of a thread are issued before the first use (HBM-bound
+// streaming kernel: memory-level parallelism is what matters); NH == 0: run-time count.
+template <int NH>
 __global__ void __launch_bounds__(256) k_cost(const double* __restrict__ robot_xy, const float* __restrict__ hazard_xy,
                                               const uint8_t* __restrict__ contact, int n, int nh, double hazard_size,
                                               uint8_t* __restrict__ out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  double rx = robot_xy[e], ry = robot_xy[(size_t)n + e];
-  bool hit = contact[e] != 0;                                        // world.py:146
-  const float* hx = hazard_xy;
-  const float* hy = hazard_xy + (size_t)nh * n;
-#pragma unroll 3
-  for (int s = 0; s < nh; ++s) {                                     // world.py:148-153
-    double dx = rx - (double)hx[(size_t)s * n + e], dy = ry - (double)hy[(size_t)s * n + e];
-    hit = hit | hazard_hit(dx * dx + dy * dy, hazard_size);  // == (sqrt(d2) <= size), sqrt only near the boundary
+  const float* hx = hazard_xy + e;
+  const float* hy = hazard_xy + (size_t)nh * n + e;
+  bool hit;
+  if (NH > 0) {
+    float fx[NH > 0 ? NH : 1], fy[NH > 0 ? NH : 1];
+#pragma unroll
+    for (int s = 0; s < NH; ++s) { fx[s] = hx[(size_t)s * n]; fy[s] = hy[(size_t)s * n]; }
+    const double rx = robot_xy[e], ry = robot_xy[(size_t)n + e];
+    hit = contact[e] != 0;                                           // world.py:146
+#pragma unroll
+    for (int s = 0; s < NH; ++s) {                                   // world.py:148-153
+      double dx = rx - (double)fx[s], dy = ry - (double)fy[s];
+      hit = hit | hazard_hit(dx * dx + dy * dy, hazard_size);        // == (sqrt(d2) <= size), sqrt only near the boundary
+    }
+  } else {
+    const double rx = robot_xy[e], ry = robot_xy[(size_t)n + e];
+    hit = contact[e] != 0;
+    for (int s = 0; s < nh; ++s) {
+      double dx = rx - (double)hx[(size_t)s * n], dy = ry - (double)hy[(size_t)s * n];
+      hit = hit | hazard_hit(dx * dx + dy * dy, hazard_size);
+    }
   }
   out[e] = hit ? 1 : 0;                                              // world.py:155
 }
@@ -573,7 +589,8 @@ int sag_lidar(const double* robot, const double* obj_xy, const uint8_t* group, i
 int sag_cost(const double* robot_xy, const float* hazard_xy, const uint8_t* contact, int n, int nh, double hazard_size,
              uint8_t* out, void* stream) {
   if (!robot_xy || !hazard_xy || !contact || !out || n <= 0 || nh < 0) return fail("sag_cost: bad argument");
-  k_cost<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(robot_xy, hazard_xy, contact, n, nh, hazard_size, out);
+  if (nh == 9) k_cost<9><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(robot_xy, hazard_xy, contact, n, nh, hazard_size, out);
+  else k_cost<0><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(robot_xy, hazard_xy, contact, n, nh, hazard_size, out);
   CK(cudaGetLastError());
   return 0;
 }

@@ -25,7 +25,7 @@ def hostemu_lib():
                 os.path.join(ROOT, "safe_adaptation_gym_b200", "csrc", "sag_layout.h"), os.path.join(ROOT, "include", "sag_b200.h"),
                 os.path.join(ROOT, "include", "sag_detmath.h")]
         if not os.path.exists(HOSTEMU_LIB) or os.path.getmtime(HOSTEMU_LIB) < max(os.path.getmtime(d) for d in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", HOSTEMU_LIB, HOSTEMU_SRC])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off"] + (["-mfma"] if "fma" in open("/proc/cpuinfo").read().split() else []) + ["-o", HOSTEMU_LIB, HOSTEMU_SRC])
         _hostemu = _abi.SagLib(HOSTEMU_LIB, host_api=False)
     return _hostemu
 
