@@ -1,9 +1,11 @@
 // sag_kernels.cu -- CUDA kernels (sm_100a) + the C ABI declared in include/sag_b200.h.
 //
-// Mapping: one thread per environment, 128 environments per CTA.  State is SoA / environment-minor so
-// that every global access of a warp is one contiguous 256-byte (fp64) segment.  Each CTA stages its
-// 128 x obs_dim observation tile in shared memory (lidar bins are accumulated there) and writes it out
-// as one contiguous, fully coalesced block.  No tensor cores: nothing here is a dense contraction.
+// The step is two kernels: k_step_quiet, one thread per environment over the whole batch (closed-form
+// path, appends the environments that are not quiet to a work list), and k_step_busy, the work list with a few
+// environments per warp and the contact solver's working set in shared memory.  State is SoA / environment-minor so
+// that every global access of a quiet warp is one contiguous 256-byte (fp64) segment; observation tiles (lidar bins
+// are accumulated in them) live in shared memory and are written out row by row.  No tensor cores: nothing here is
+// a dense contraction.  The per-environment logic is in sag_core.cuh; every kernel is templated on the robot model.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -16,10 +18,6 @@
 #include "sag_layout.h"
 
 using namespace sag;
-
-#ifndef SAG_BUSY_MIN_BLOCKS
-#define SAG_BUSY_MIN_BLOCKS 12
-#endif
 
 namespace {
 
@@ -147,7 +145,7 @@ struct BusyCfg {
 };
 
 template <int G, class RB>
-__global__ void __launch_bounds__(32, SAG_BUSY_MIN_BLOCKS) k_step_busy(Dev D, const float* __restrict__ act, float* __restrict__ obs,
+__global__ void __launch_bounds__(32) k_step_busy(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                    double* __restrict__ reward, double* __restrict__ reward2,
                                                    uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
