@@ -41,6 +41,18 @@
 #define BOX_SIZE 0.2           /* push_box.py:12 */
 #define BOX_DENSITY 0.001      /* push_box.py:15 */
 #define VASES_DENSITY 0.001    /* consts.py:21 */
+#define BALL_R 0.14            /* dribble_ball.py:11 */
+#define BALL_DENSITY (BOX_DENSITY / 2.0) /* dribble_ball.py:31 */
+#define BALL_SOL_TC 0.018      /* dribble_ball.py:34 solref = (0.018, 0.2) */
+#define BALL_SOL_DR 0.2
+#define BALL_ROLL 0.05         /* dribble_ball.py:32 friction = (slide 1.2, spin 0.003, roll 0.05); condim 6 */
+#define BALL_SPIN 0.003
+#define ROD_R 0.08             /* roll_rod.py:12 */
+#define ROD_HALF 0.3           /* roll_rod.py:11: cylinder size = (radius, half length) */
+#define ROD_DENSITY (BOX_DENSITY / 2.0)  /* roll_rod.py:35 */
+#define ROD_ROLL 0.05          /* roll_rod.py:36 friction = (1.2, 0.001, 0.05); floor condim 6 (point.xml:12) */
+#define PRIO_MU 1.2            /* ball / rod geoms have priority 1: their sliding friction wins the mix [EXT] */
+#define PI_D 3.14159265358979323846
 #define LIDAR_MAX_DIST 5.0     /* safe_adaptation_gym.py:23 */
 #define TENDON_MAX (BOX_SIZE * 3.75) /* haul_box.py:25 */
 
@@ -326,9 +338,12 @@ int orc_collide_box_box(double ax, double ay, double ayaw, double ahx, double ah
 typedef struct { int is_box; double cx, cy, c, s, hx, hy, r; } geom2;
 
 static int obj_collidable(int type) {
-  return type == ORC_VASE || type == ORC_GREMLIN || type == ORC_PILLAR || type == ORC_BUTTON || type == ORC_BOX;
+  return type == ORC_VASE || type == ORC_GREMLIN || type == ORC_PILLAR || type == ORC_BUTTON || type == ORC_BOX ||
+         type == ORC_ROD || type == ORC_BALL;
 }
-static int obj_movable(int type) { return type == ORC_VASE || type == ORC_GREMLIN || type == ORC_BOX; }
+static int obj_movable(int type) {
+  return type == ORC_VASE || type == ORC_GREMLIN || type == ORC_BOX || type == ORC_ROD || type == ORC_BALL;
+}
 static int obj_nparts(int type) { return type == ORC_BOX ? 5 : (obj_collidable(type) ? 1 : 0); }
 
 static void obj_geom(const orc_env* e, int slot, int part, geom2* g) {
@@ -350,6 +365,10 @@ static void obj_geom(const orc_env* e, int slot, int part, geom2* g) {
         g->cx = o->x + ox * c - oy * s; g->cy = o->y + ox * s + oy * c;
       }
     } break;
+    /* planar footprints: the sphere's great circle (dribble_ball.py:24-30); the lying cylinder's rectangle, axis along
+     * body y after euler = (90, 0, 0) (roll_rod.py:27-34) */
+    case ORC_BALL: g->is_box = 0; g->r = BALL_R; break;
+    case ORC_ROD: g->is_box = 1; g->hx = ROD_R; g->hy = ROD_HALF; break;
     default: g->is_box = 0; break;
   }
 }
@@ -374,18 +393,46 @@ static int collide(const geom2* A, const geom2* B, double* o) {
   return box_box(&a, &b, o);
 }
 
-static void obj_mass(const orc_env* e, int type, double* m, double* iz, double* reff) {
+/* Planar inertia and floor interaction of a movable body.
+ *   m     translational mass (isotropic bodies; for the ball the rolling-without-slipping effective mass 7/5 m)
+ *   iz    inertia about the vertical axis
+ *   flin  bound of the floor friction force (disc), ftor of the floor friction torque
+ *   bfl   damping rate of the floor rows' reference acceleration (2 / (dmax * timeconst) of the floor contact)
+ * The rod is anisotropic (aniso = 1): body x (across the axis) rolls -- effective mass 3/2 m, resistance
+ * roll / r * N -- and body y (along the axis) slides -- mass m, bound mu N; mx/my and fx/fy hold the two axes. */
+typedef struct { double m, iz, flin, ftor, bfl; int aniso; double mx, my, fx, fy; } body_par;
+
+static void obj_mass(const orc_env* e, int type, body_par* b) {
+  b->aniso = 0; b->mx = b->my = b->fx = b->fy = 0.0;
+  b->bfl = 2.0 / (IMP_DMAX * SOL_TC);
   if (type == ORC_VASE || type == ORC_GREMLIN) {
     double s = type == ORC_VASE ? e->cfg.vases_size : e->cfg.gremlins_size;
-    *m = 8.0 * s * s * s * VASES_DENSITY;            /* consts.py:21,31 */
-    *iz = *m * (2.0 / 3.0) * s * s;
-    *reff = s * sqrt(2.0);
+    b->m = 8.0 * s * s * s * VASES_DENSITY;            /* consts.py:21,31 */
+    b->iz = b->m * (2.0 / 3.0) * s * s;
+    b->flin = FRICTION_MU * b->m * GRAV;
+    b->ftor = b->flin * (s * sqrt(2.0));
+  } else if (type == ORC_BALL) { /* dribble_ball.py:24-38 */
+    double m0 = (4.0 / 3.0) * PI_D * BALL_R * BALL_R * BALL_R * BALL_DENSITY;
+    b->m = 1.4 * m0;
+    b->iz = 0.4 * m0 * BALL_R * BALL_R;
+    b->flin = BALL_ROLL * m0 * GRAV / BALL_R;
+    b->ftor = BALL_SPIN * m0 * GRAV;
+    b->bfl = 2.0 / (IMP_DMAX * BALL_SOL_TC);
+  } else if (type == ORC_ROD) { /* roll_rod.py:22-40 */
+    double m0 = PI_D * ROD_R * ROD_R * (2.0 * ROD_HALF) * ROD_DENSITY;
+    b->aniso = 1;
+    b->m = m0; b->mx = 1.5 * m0; b->my = m0;
+    b->iz = m0 * (3.0 * ROD_R * ROD_R + 4.0 * ROD_HALF * ROD_HALF) / 12.0;
+    b->fx = ROD_ROLL * m0 * GRAV / ROD_R; b->fy = PRIO_MU * m0 * GRAV;
+    b->flin = b->fy;
+    b->ftor = PRIO_MU * m0 * GRAV * ROD_HALF;   /* sliding friction at the two end contacts of the line [EXT] */
   } else { /* ORC_BOX: main cube + 4 columns, push_box.py:36-67 */
     double d = BOX_SIZE, wd = BOX_SIZE / 2;
     double m0 = 8.0 * d * d * d * BOX_DENSITY, mc = 8.0 * wd * wd * d * BOX_DENSITY;
-    *m = m0 + 4.0 * mc;
-    *iz = m0 * (2.0 / 3.0) * d * d + 4.0 * (mc * (2.0 / 3.0) * wd * wd + mc * (2.0 * d * d));
-    *reff = 1.5 * d;
+    b->m = m0 + 4.0 * mc;
+    b->iz = m0 * (2.0 / 3.0) * d * d + 4.0 * (mc * (2.0 / 3.0) * wd * wd + mc * (2.0 * d * d));
+    b->flin = FRICTION_MU * b->m * GRAV;
+    b->ftor = b->flin * (1.5 * d);
   }
 }
 
@@ -514,6 +561,8 @@ typedef struct {
   pt_mat M;              /* robot mass matrix (no damping) */
   double acc[1 + ORC_MAX_OBJ + 2][3]; /* robot, objects, car wheels (1 DoF each, in [.][0]) */
   double im[ORC_MAX_OBJ], ii[ORC_MAX_OBJ];
+  int aniso[ORC_MAX_OBJ];            /* rod: inverse mass R diag(imx, imy) R^T = [[ma, mb], [mb, mc]] */
+  double ma[ORC_MAX_OBJ], mb[ORC_MAX_OBJ], mc[ORC_MAX_OBJ];
   double iw;                         /* 1 / wheel spin inertia */
 } solve_ctx;
 #define WHEEL_BODY(i) (1 + ORC_MAX_OBJ + (i))
@@ -521,6 +570,10 @@ typedef struct {
 static void minv_mul(const solve_ctx* S, int body, const double* j, double* out) {
   if (body == 0) pt_solve(&S->M, j, out);
   else if (body > ORC_MAX_OBJ) { out[0] = j[0] * S->iw; out[1] = 0.0; out[2] = 0.0; }
+  else if (S->aniso[body - 1]) {
+    int b = body - 1;
+    out[0] = S->ma[b] * j[0] + S->mb[b] * j[1]; out[1] = S->mb[b] * j[0] + S->mc[b] * j[1]; out[2] = j[2] * S->ii[b];
+  }
   else { out[0] = j[0] * S->im[body - 1]; out[1] = j[1] * S->im[body - 1]; out[2] = j[2] * S->ii[body - 1]; }
 }
 static void body_vel(const orc_env* e, int body, double* v) {
@@ -563,8 +616,16 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
   for (int s = 0; s < e->nobj; ++s) {
     S.acc[1 + s][0] = S.acc[1 + s][1] = S.acc[1 + s][2] = 0.0;
     touched[s] = 0; ffl[s][0] = ffl[s][1] = ffl[s][2] = 0.0;
-    S.im[s] = S.ii[s] = 0.0;
-    if (obj_movable(e->obj[s].type)) { double m, iz, rf; obj_mass(e, e->obj[s].type, &m, &iz, &rf); S.im[s] = 1.0 / m; S.ii[s] = 1.0 / iz; }
+    S.im[s] = S.ii[s] = 0.0; S.aniso[s] = 0;
+    if (obj_movable(e->obj[s].type)) {
+      body_par bp; obj_mass(e, e->obj[s].type, &bp);
+      S.im[s] = 1.0 / bp.m; S.ii[s] = 1.0 / bp.iz;
+      if (bp.aniso) {
+        double c = sag_cos(e->obj[s].yaw), sn = sag_sin(e->obj[s].yaw), ix = 1.0 / bp.mx, iy = 1.0 / bp.my;
+        S.aniso[s] = 1;
+        S.ma[s] = ix * c * c + iy * sn * sn; S.mb[s] = (ix - iy) * c * sn; S.mc[s] = ix * sn * sn + iy * c * c;
+      }
+    }
   }
   const double bdamp = 2.0 / (IMP_DMAX * SOL_TC);
   const double kbase = 1.0 / (IMP_DMAX * IMP_DMAX * SOL_TC * SOL_TC * SOL_DR * SOL_DR);
@@ -603,8 +664,19 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
     if (!(c->dist < 0.0)) continue;
     if (c->ba < 0 && c->bb < 0) continue;
     crow* r = &rows[nrow++];
-    r->type = 0; r->bound = 0.0;
+    r->type = 0; r->bound = FRICTION_MU;
     r->ba = c->ba; r->bb = c->bb;
+    /* a ball / rod geom has priority 1 (dribble_ball.py:38, roll_rod.py:40): the contact takes its friction and
+     * solref instead of the max / default mix [EXT] */
+    double cb = bdamp, ck = kbase;
+    {
+      int ta = c->sa >= 0 ? e->obj[c->sa].type : ORC_NONE, tb = c->sb >= 0 ? e->obj[c->sb].type : ORC_NONE;
+      if (ta == ORC_ROD || tb == ORC_ROD || ta == ORC_BALL || tb == ORC_BALL) r->bound = PRIO_MU;
+      if (ta == ORC_BALL || tb == ORC_BALL) {
+        cb = 2.0 / (IMP_DMAX * BALL_SOL_TC);
+        ck = 1.0 / (IMP_DMAX * IMP_DMAX * BALL_SOL_TC * BALL_SOL_TC * BALL_SOL_DR * BALL_SOL_DR);
+      }
+    }
     double tx = -c->ny, ty = c->nx;
     double pa[2] = {0, 0}, pb[2] = {0, 0}, va[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
     if (c->ba >= 0) { body_pos(e, c->ba, pa); body_vel(e, c->ba, va); if (c->ba > 0) touched[c->ba - 1] = 1; }
@@ -621,7 +693,7 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
       if (c->bb >= 0) { minv_mul(&S, c->bb, r->jb[k], t); diag += dot3(r->jb[k], t); vel += dot3(r->jb[k], vb); }
       r->diag[k] = diag;
       r->R[k] = (1.0 - d) / d * diag;
-      r->aref[k] = -bdamp * vel - (k == 0 ? d * kbase * c->dist : 0.0);
+      r->aref[k] = -cb * vel - (k == 0 ? d * ck * c->dist : 0.0);
       r->f[k] = 0.0;
     }
   }
@@ -702,7 +774,7 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
         if (r->bb >= 0) a += dot3(r->jb[k], S.acc[r->bb]);
         double fn = r->f[k] - (a - r->aref[k] + r->R[k] * r->f[k]) * r->inv[k];
         if (k == 0) { if (fn < 0.0) fn = 0.0; }
-        else { double lim = FRICTION_MU * r->f[0]; fn = clampd(fn, -lim, lim); }
+        else { double lim = r->bound * r->f[0]; fn = clampd(fn, -lim, lim); }
         double df = fn - r->f[k];
         r->f[k] = fn;
         sdf += fabs(df); sf += fabs(fn);
@@ -712,20 +784,38 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
     for (int i = 0; i < nfl; ++i) {
       int s = flslot[i];
       const orc_obj* o = &e->obj[s];
-      double m, iz, rf; obj_mass(e, o->type, &m, &iz, &rf);
-      double lim = FRICTION_MU * m * GRAV;
+      body_par bp; obj_mass(e, o->type, &bp);
       double* ac = S.acc[1 + s];
-      double Al = S.im[s], At = S.ii[s];
-      double inv_lin = 1.0 / (Al + rr * Al), inv_tor = 1.0 / (At + rr * At);
-      double f0 = ffl[s][0] - (ac[0] + bdamp * o->vx + rr * Al * ffl[s][0]) * inv_lin;
-      double f1 = ffl[s][1] - (ac[1] + bdamp * o->vy + rr * Al * ffl[s][1]) * inv_lin;
-      double nf = sqrt(f0 * f0 + f1 * f1);
-      if (nf > lim) { double sc = lim / nf; f0 *= sc; f1 *= sc; }
-      double d0 = f0 - ffl[s][0], d1 = f1 - ffl[s][1];
-      ac[0] += d0 * Al; ac[1] += d1 * Al;
+      double At = S.ii[s];
+      double inv_tor = 1.0 / (At + rr * At);
+      double f0, f1, d0, d1;
+      if (bp.aniso) {
+        /* rod: one row across the axis (rolling, body x = u) and one along it (sliding, body y = w), each an
+         * eigen-direction of the inverse mass, clamped separately */
+        double c = sag_cos(o->yaw), sn = sag_sin(o->yaw);
+        double ix = 1.0 / bp.mx, iy = 1.0 / bp.my;
+        double inv_x = 1.0 / (ix + rr * ix), inv_y = 1.0 / (iy + rr * iy);
+        double au = ac[0] * c + ac[1] * sn, aw = -ac[0] * sn + ac[1] * c;
+        double vu = o->vx * c + o->vy * sn, vw = -o->vx * sn + o->vy * c;
+        f0 = ffl[s][0] - (au + bp.bfl * vu + rr * ix * ffl[s][0]) * inv_x;
+        f1 = ffl[s][1] - (aw + bp.bfl * vw + rr * iy * ffl[s][1]) * inv_y;
+        f0 = clampd(f0, -bp.fx, bp.fx); f1 = clampd(f1, -bp.fy, bp.fy);
+        d0 = f0 - ffl[s][0]; d1 = f1 - ffl[s][1];
+        double du = d0 * ix, dw = d1 * iy;
+        ac[0] += du * c - dw * sn; ac[1] += du * sn + dw * c;
+      } else {
+        double Al = S.im[s];
+        double inv_lin = 1.0 / (Al + rr * Al);
+        f0 = ffl[s][0] - (ac[0] + bp.bfl * o->vx + rr * Al * ffl[s][0]) * inv_lin;
+        f1 = ffl[s][1] - (ac[1] + bp.bfl * o->vy + rr * Al * ffl[s][1]) * inv_lin;
+        double nf = sqrt(f0 * f0 + f1 * f1);
+        if (nf > bp.flin) { double sc = bp.flin / nf; f0 *= sc; f1 *= sc; }
+        d0 = f0 - ffl[s][0]; d1 = f1 - ffl[s][1];
+        ac[0] += d0 * Al; ac[1] += d1 * Al;
+      }
       ffl[s][0] = f0; ffl[s][1] = f1;
-      double f2 = ffl[s][2] - (ac[2] + bdamp * o->w + rr * At * ffl[s][2]) * inv_tor;
-      f2 = clampd(f2, -lim * rf, lim * rf);
+      double f2 = ffl[s][2] - (ac[2] + bp.bfl * o->w + rr * At * ffl[s][2]) * inv_tor;
+      f2 = clampd(f2, -bp.ftor, bp.ftor);
       double d2 = f2 - ffl[s][2];
       ac[2] += d2 * At;
       ffl[s][2] = f2;

@@ -56,21 +56,37 @@ def _tolerance(x, bounds=(0.0, 0.0), margin=0.0, sigmoid="gaussian", value_at_ma
 
 
 class _Elem:
-    """Permissive stand-in for dm_control.mjcf elements (haul_box.py:16-29 only builds a tendon)."""
+    """Small stand-in for dm_control.mjcf elements: keeps the attributes and children a task adds and serialises
+    them, so the rod / ball bodies (roll_rod.py:24-41, dribble_ball.py:21-39) reach FakeBridge.rebuild as XML like
+    every other body; haul_box.py:16-29 only builds a tendon whose text is never parsed."""
 
-    def __init__(self, tag="root"):
-        self._tag = tag
+    def __init__(self, tag="root", **attrs):
+        self._tag, self._attrs, self._children = tag, attrs, []
 
     def __getattr__(self, k):
         if k.startswith("_"):
             raise AttributeError(k)
-        return _Elem(k)
+        child = _Elem(k)
+        self._children.append(child)
+        return child
 
     def add(self, tag, **kw):
-        return _Elem(tag)
+        child = _Elem(tag, **kw)
+        self._children.append(child)
+        return child
+
+    @staticmethod
+    def _text(v):
+        if isinstance(v, str):
+            return v
+        if isinstance(v, (list, tuple, np.ndarray)):
+            return " ".join(repr(float(t)) for t in np.asarray(v, dtype=np.float64).ravel())
+        return repr(v)
 
     def to_xml_string(self):
-        return "<%s/>" % self._tag
+        attrs = "".join(' %s="%s"' % (k, self._text(v)) for k, v in self._attrs.items())
+        inner = "".join(c.to_xml_string() for c in self._children)
+        return "<%s%s>%s</%s>" % (self._tag, attrs, inner, self._tag)
 
 
 def install_stubs():
@@ -236,8 +252,8 @@ class FakeBridge:
             if name == "circle":  # unsupervised.py:25-46: visual only, never in the layout
                 continue
             pos = [float(t) for t in body.get("pos").split()]
-            quat = [float(t) for t in body.get("quat").split()]
-            yaw = 2.0 * np.arctan2(quat[3], quat[0])
+            quat = [float(t) for t in body.get("quat").split()] if body.get("quat") else [1.0, 0.0, 0.0, 0.0]
+            yaw = 2.0 * np.arctan2(quat[3], quat[0])  # the rod's euler = "90 0 0" lays the cylinder along y: planar yaw 0
             # the XML carries rot2quat(theta) (utils.py:92-94); recover the exact drawn theta = 2*pi*u from the
             # recorded draws so that the injected world is bit-identical to what the oracle's own reset builds
             cands = [0.0 + (2 * np.pi - 0.0) * ev[1] for ev in EVENTS if ev[0] == "uniform"]
@@ -247,6 +263,8 @@ class FakeBridge:
                     yaw = best
             geom = body.find("geom")
             type_ = next(t for p, t in _PREFIX_TYPE if name.startswith(p))
+            if type_ == O.BOX:  # roll_rod.py:33 cylinder, dribble_ball.py:29 sphere
+                type_ = {"box": O.BOX, "cylinder": O.ROD, "sphere": O.BALL}[geom.get("type")]
             group = int(float(geom.get("user")))
             size = [float(t) for t in geom.get("size").split()]
             self.checked_sizes.append((name, geom.get("type"), size, pos[2]))
@@ -548,10 +566,11 @@ def main():
             ("catch_goal", 8, 300, "drive"), ("unsupervised", 9, 250, "drive"),
             ("press_buttons", 10, 400, "drive"), ("press_buttons_scarce", 11, 300, "drive"),
             ("collect", 12, 400, "drive"), ("push_box", 13, 400, "drive"), ("push_box_scarce", 14, 300, "drive"),
-            ("haul_box", 15, 300, "drive")]
+            ("haul_box", 15, 300, "drive"), ("roll_rod", 16, 400, "drive"), ("dribble_ball", 17, 400, "drive")]
     plan = [(t, s_, n, m, "point") for t, s_, n, m in plan] + [
         ("go_to_goal", 21, 250, "drive", "car"), ("press_buttons", 22, 250, "drive", "car"), ("push_box", 23, 200, "drive", "car"),
-        ("haul_box", 24, 150, "drive", "car"), ("unsupervised", 25, 120, "random", "car")]
+        ("haul_box", 24, 150, "drive", "car"), ("unsupervised", 25, 120, "random", "car"),
+        ("roll_rod", 26, 200, "drive", "car"), ("dribble_ball", 27, 200, "drive", "car")]
     for task_key, seed, steps, mode, robot in plan:
         ep = record_episode(task_key, seed, steps, mode, config={"action_noise": 0.01}, robot=robot)
         print(robot, task_key, "return", sum(r[-1] for s in ep["segments"] for r in s["reward"]),

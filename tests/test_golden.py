@@ -96,12 +96,19 @@ def test_geometry_constants_match_reference_xml():
     want = {"hazards": ("cylinder", [0.2, 0.01], 0.02), "vases": ("box", [0.1, 0.1, 0.1], 0.1 - 4e-5),
             "pillars": ("cylinder", [0.2, 0.5], 0.5), "goal": ("cylinder", [0.3, 0.15], 0.16),
             "buttons": ("sphere", [0.1, 0.1, 0.1], 0.1), "box": ("box", [0.2, 0.2, 0.2], 0.2)}
+    # the 'box' body of roll_rod.py:27-34 (cylinder radius 0.08, half length 0.3) and dribble_ball.py:24-30 (sphere 0.14)
+    box_by_task = {"roll_rod": ("cylinder", [0.08, 0.3], 0.08), "dribble_ball": ("sphere", [0.14], 0.14)}
     seen = set()
     for ep in EPISODES:
         for name, typ, size, z in ep["sizes"]:
             key = next(k for k in want if name.startswith(k))
+            if key == "box" and ep["task"] in box_by_task:
+                assert (typ, z) == (box_by_task[ep["task"]][0], box_by_task[ep["task"]][2])
+                np.testing.assert_allclose(size, box_by_task[ep["task"]][1], atol=1e-12)
+                seen.add(ep["task"])
+                continue
             assert typ == want[key][0]
             np.testing.assert_allclose(size, want[key][1], atol=1e-12)
             assert abs(z - want[key][2]) < 1e-12
             seen.add(key)
-    assert seen == set(want)
+    assert seen == set(want) | set(box_by_task)
