@@ -64,6 +64,11 @@ constexpr double kTendonMax = kBoxSize * 3.75;  // haul_box.py:25
 // MuJoCo default soft-constraint parameters [EXT]
 constexpr double kSolTc = 0.02, kImpD0 = 0.9, kImpDmax = 0.95, kImpWidth = 0.001;
 constexpr double kMu = 1.0;
+// roll_rod.py:11-40 / dribble_ball.py:11-38 (oracle obj_mass / obj_geom carry the per-line citations)
+constexpr double kBallR = 0.14, kBallDensity = kBoxDensity / 2.0, kBallSolTc = 0.018, kBallSolDr = 0.2;
+constexpr double kBallRoll = 0.05, kBallSpin = 0.003;
+constexpr double kRodR = 0.08, kRodHalf = 0.3, kRodDensity = kBoxDensity / 2.0, kRodRoll = 0.05;
+constexpr double kPrioMu = 1.2;  // ball / rod geoms have priority 1: their sliding friction wins the mix
 constexpr int kSweeps = 10;
 constexpr double kPgsTol = 1e-8;
 constexpr double kSleepV = 1e-8;
@@ -350,8 +355,8 @@ SAG_HD bool overlap(const Geom& A, const Geom& B) {
   return overlap_box_box(A, B);
 }
 
-SAG_HD bool kind_collidable(int k) { return k == K_VASE || k == K_GREMLIN || k == K_PILLAR || k == K_BUTTON || k == K_BOX; }
-SAG_HD bool kind_movable(int k) { return k == K_VASE || k == K_GREMLIN || k == K_BOX; }
+SAG_HD bool kind_collidable(int k) { return k == K_VASE || k == K_GREMLIN || k == K_PILLAR || k == K_BUTTON || k >= K_BOX; }
+SAG_HD bool kind_movable(int k) { return k == K_VASE || k == K_GREMLIN || k >= K_BOX; }
 SAG_HD int kind_nparts(int k) { return k == K_BOX ? 5 : (kind_collidable(k) ? 1 : 0); }
 // bounding radius about the body centre (for the broad phase); select chain, no jump table
 SAG_HD double kind_bound(const Dev& D, int k) {
@@ -359,21 +364,48 @@ SAG_HD double kind_bound(const Dev& D, int k) {
        : k == K_PILLAR ? D.pillars_size
        : k == K_BUTTON ? kButtonSize
        : k == K_BOX ? kBoxSize * 1.5 * 1.4142135623730951 + 1e-9
+       : k == K_BALL ? kBallR
+       : k == K_ROD ? 0.31048349392520047 + 1e-9  // sqrt(kRodR^2 + kRodHalf^2)
        : k == K_GREMLIN ? D.gremlins_size * 1.4142135623730951 + 1e-9 : 0.0;
 }
-SAG_HD void kind_mass(const Dev& D, int k, double& m, double& iz, double& reff) {
+// Planar inertia and floor interaction of a movable body (oracle obj_mass): m translational mass (ball: rolling
+// effective mass 7/5 m), iz about the vertical, flin / ftor bounds of the floor friction force (disc) and torque, bfl
+// damping rate of the floor rows.  The rod is anisotropic: body x rolls (3/2 m, resistance roll / r * N), body y slides
+// (m, mu N), each with its own row.
+struct BodyPar { double m, iz, flin, ftor, bfl, mx, my, fx, fy; };
+SAG_HD BodyPar kind_body(const Dev& D, int k) {
+  BodyPar b;
+  b.mx = b.my = b.fx = b.fy = 0.0;
+  b.bfl = 2.0 / (kImpDmax * kSolTc);
   if (k == K_BOX) {
     const double d = kBoxSize, wd = kBoxSize / 2;
     const double m0 = 8.0 * d * d * d * kBoxDensity, mc = 8.0 * wd * wd * d * kBoxDensity;
-    m = m0 + 4.0 * mc;
-    iz = m0 * (2.0 / 3.0) * d * d + 4.0 * (mc * (2.0 / 3.0) * wd * wd + mc * (2.0 * d * d));
-    reff = 1.5 * d;
+    b.m = m0 + 4.0 * mc;
+    b.iz = m0 * (2.0 / 3.0) * d * d + 4.0 * (mc * (2.0 / 3.0) * wd * wd + mc * (2.0 * d * d));
+    b.flin = kMu * b.m * kGrav;
+    b.ftor = b.flin * (1.5 * d);
+  } else if (k == K_BALL) {
+    const double m0 = (4.0 / 3.0) * kPi * kBallR * kBallR * kBallR * kBallDensity;
+    b.m = 1.4 * m0;
+    b.iz = 0.4 * m0 * kBallR * kBallR;
+    b.flin = kBallRoll * m0 * kGrav / kBallR;
+    b.ftor = kBallSpin * m0 * kGrav;
+    b.bfl = 2.0 / (kImpDmax * kBallSolTc);
+  } else if (k == K_ROD) {
+    const double m0 = kPi * kRodR * kRodR * (2.0 * kRodHalf) * kRodDensity;
+    b.m = m0; b.mx = 1.5 * m0; b.my = m0;
+    b.iz = m0 * (3.0 * kRodR * kRodR + 4.0 * kRodHalf * kRodHalf) / 12.0;
+    b.fx = kRodRoll * m0 * kGrav / kRodR; b.fy = kPrioMu * m0 * kGrav;
+    b.flin = b.fy;
+    b.ftor = kPrioMu * m0 * kGrav * kRodHalf;
   } else {
     double s = k == K_VASE ? D.vases_size : D.gremlins_size;
-    m = 8.0 * s * s * s * kVaseDensity;
-    iz = m * (2.0 / 3.0) * s * s;
-    reff = s * sqrt(2.0);
+    b.m = 8.0 * s * s * s * kVaseDensity;
+    b.iz = b.m * (2.0 / 3.0) * s * s;
+    b.flin = kMu * b.m * kGrav;
+    b.ftor = b.flin * (s * sqrt(2.0));
   }
+  return b;
 }
 
 SAG_HD void obj_geom(const Dev& D, int kind, int part, double x, double y, double c, double s, Geom& g) {
@@ -392,6 +424,8 @@ SAG_HD void obj_geom(const Dev& D, int kind, int part, double x, double y, doubl
       g.cx = x + ox * c - oy * s; g.cy = y + ox * s + oy * c;
     }
   }
+  else if (kind == K_BALL) { g.r = kBallR; }
+  else if (kind == K_ROD) { g.is_box = 1; g.hx = kRodR; g.hy = kRodHalf; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -842,13 +876,21 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   nb = 0;
   if (!overflow) for (unsigned m = fl; m; m &= m - 1) S.bslot[nb++] = ctz32(m);
   auto cid = [&](int slot) { int k = 0; while (S.bslot[k] != slot) ++k; return k; };
-  double vim, vii, vrf, bim, bii, brf, vmass, bmass;
-  { double iz; kind_mass(D, K_VASE, vmass, iz, vrf); vim = 1.0 / vmass; vii = 1.0 / iz; }
-  { double iz; kind_mass(D, K_BOX, bmass, iz, brf); bim = 1.0 / bmass; bii = 1.0 / iz; }
+  const int bkind = C.sp.box_kind;  // kind of the task's movable body: push box, rod or ball (0: none)
+  const BodyPar VP = kind_body(D, K_VASE), BP = kind_body(D, bkind ? bkind : K_BOX);
+  const double vim = 1.0 / VP.m, vii = 1.0 / VP.iz, bim = 1.0 / BP.m, bii = 1.0 / BP.iz;
+  const bool rod = bkind == K_ROD;
+  double rc = 1.0, rs = 0.0, rix = 0.0, riy = 0.0, rma = 0.0, rmb = 0.0, rmc = 0.0;  // rod: R diag(1/mx, 1/my) R^T
+  if (rod) {
+    sag_sincos(D.oyaw[oidx(D, C.L.box, e)], &rs, &rc);
+    rix = 1.0 / BP.mx; riy = 1.0 / BP.my;
+    rma = rix * rc * rc + riy * rs * rs; rmb = (rix - riy) * rc * rs; rmc = rix * rs * rs + riy * rc * rc;
+  }
   // body < 0 static, 0 robot, 1 + slot movable
   auto minv = [&](int body, const double* j, double* o) {
     if (body == 0) { pt_solve(p, q, K.ia0, K.is0, j, o); return; }
     const bool isb = body - 1 == C.L.box;
+    if (isb && rod) { o[0] = rma * j[0] + rmb * j[1]; o[1] = rmb * j[0] + rmc * j[1]; o[2] = j[2] * bii; return; }
     double im = isb ? bim : vim, ii = isb ? bii : vii;
     o[0] = j[0] * im; o[1] = j[1] * im; o[2] = j[2] * ii;
   };
@@ -879,7 +921,15 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
     if (!(c.dist < 0.0)) continue;
     if (c.ba < 0 && c.bb < 0) continue;
     Row& r = rows[nrow++];
-    r.type = 0; r.pad_ = 0; r.bound = 0.0;
+    r.type = 0; r.pad_ = 0; r.bound = kMu;  // contact rows: friction coefficient of the pair
+    double cb = bdamp, ck = kbase;
+    if (bkind > K_BOX && (c.ba - 1 == C.L.box || c.bb - 1 == C.L.box)) {  // priority-1 geom: its friction / solref
+      r.bound = kPrioMu;
+      if (bkind == K_BALL) {
+        cb = 2.0 / (kImpDmax * kBallSolTc);
+        ck = 1.0 / (kImpDmax * kImpDmax * kBallSolTc * kBallSolTc * kBallSolDr * kBallSolDr);
+      }
+    }
     r.ba = c.ba > 0 ? 1 + cid(c.ba - 1) : c.ba; r.bb = c.bb > 0 ? 1 + cid(c.bb - 1) : c.bb;
     double tx = -c.ny, ty = c.nx;
     double pa[2] = {0, 0}, pb[2] = {0, 0}, va[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
@@ -897,7 +947,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
       if (c.bb >= 0) { minv(c.bb, r.jb[k], r.wb[k]); diag += dot3(r.jb[k], r.wb[k]); vel += dot3(r.jb[k], vb); }
       r.R[k] = (1.0 - d) / d * diag;
       r.inv[k] = 1.0 / (diag + r.R[k]);
-      r.aref[k] = -bdamp * vel - (k == 0 ? d * kbase * c.dist : 0.0);
+      r.aref[k] = -cb * vel - (k == 0 ? d * ck * c.dist : 0.0);
       r.f[k] = 0.0;
     }
   }
@@ -941,7 +991,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
         const double fo = r.f[k];
         double fn = fo - (a - r.aref[k] + r.R[k] * fo) * r.inv[k];
         if (k == 0) { if (fn < 0.0) fn = 0.0; }
-        else { double lim = kMu * r.f[0]; fn = clampd(fn, -lim, lim); }
+        else { double lim = r.bound * r.f[0]; fn = clampd(fn, -lim, lim); }
         double df = fn - fo;
         r.f[k] = fn;
         sdf += fabs(df); sf += fabs(fn);
@@ -955,21 +1005,34 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
       SAG_PROF(e, 5, 1);
       const int s = S.bslot[b];
       const bool isb = s == C.L.box;
-      const double Al = isb ? bim : vim, At = isb ? bii : vii, rf = isb ? brf : vrf;
+      const double Al = isb ? bim : vim, At = isb ? bii : vii;
       const double inv_lin = isb ? b_inv_lin : v_inv_lin, inv_tor = isb ? b_inv_tor : v_inv_tor;
-      const double lim = kMu * (isb ? bmass : vmass) * kGrav;
+      const double flin = isb ? BP.flin : VP.flin, ftor = isb ? BP.ftor : VP.ftor, bfl = isb ? BP.bfl : VP.bfl;
       size_t i = oidx(D, s, e);
       double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
       double* ac = acc[1 + b];
-      double f0 = ffl[b][0] - (ac[0] + bdamp * vx + rr * Al * ffl[b][0]) * inv_lin;
-      double f1 = ffl[b][1] - (ac[1] + bdamp * vy + rr * Al * ffl[b][1]) * inv_lin;
-      double nf = sqrt(f0 * f0 + f1 * f1);
-      if (nf > lim) { double sc = lim / nf; f0 *= sc; f1 *= sc; }
-      double d0 = f0 - ffl[b][0], d1 = f1 - ffl[b][1];
-      ac[0] += d0 * Al; ac[1] += d1 * Al;
+      double f0, f1, d0, d1;
+      if (isb && rod) {  // one row across the axis (rolling, body x) and one along it (sliding, body y), clamped separately
+        const double inv_x = 1.0 / (rix + rr * rix), inv_y = 1.0 / (riy + rr * riy);
+        double au = ac[0] * rc + ac[1] * rs, aw = -ac[0] * rs + ac[1] * rc;
+        double vu = vx * rc + vy * rs, vw = -vx * rs + vy * rc;
+        f0 = ffl[b][0] - (au + bfl * vu + rr * rix * ffl[b][0]) * inv_x;
+        f1 = ffl[b][1] - (aw + bfl * vw + rr * riy * ffl[b][1]) * inv_y;
+        f0 = clampd(f0, -BP.fx, BP.fx); f1 = clampd(f1, -BP.fy, BP.fy);
+        d0 = f0 - ffl[b][0]; d1 = f1 - ffl[b][1];
+        double du = d0 * rix, dw = d1 * riy;
+        ac[0] += du * rc - dw * rs; ac[1] += du * rs + dw * rc;
+      } else {
+        f0 = ffl[b][0] - (ac[0] + bfl * vx + rr * Al * ffl[b][0]) * inv_lin;
+        f1 = ffl[b][1] - (ac[1] + bfl * vy + rr * Al * ffl[b][1]) * inv_lin;
+        double nf = sqrt(f0 * f0 + f1 * f1);
+        if (nf > flin) { double sc = flin / nf; f0 *= sc; f1 *= sc; }
+        d0 = f0 - ffl[b][0]; d1 = f1 - ffl[b][1];
+        ac[0] += d0 * Al; ac[1] += d1 * Al;
+      }
       ffl[b][0] = f0; ffl[b][1] = f1;
-      double f2 = ffl[b][2] - (ac[2] + bdamp * w + rr * At * ffl[b][2]) * inv_tor;
-      f2 = clampd(f2, -lim * rf, lim * rf);
+      double f2 = ffl[b][2] - (ac[2] + bfl * w + rr * At * ffl[b][2]) * inv_tor;
+      f2 = clampd(f2, -ftor, ftor);
       double d2 = f2 - ffl[b][2];
       ac[2] += d2 * At;
       ffl[b][2] = f2;
@@ -1352,7 +1415,7 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
   if (d2v < 1e299) clear = fmin(clear, sqrt(d2v) - (RB::kReach + kind_bound(D, K_VASE)));
   if (d2p < 1e299) clear = fmin(clear, sqrt(d2p) - (RB::kReach + kind_bound(D, K_PILLAR)));
   if (d2b < 1e299) clear = fmin(clear, sqrt(d2b) - (RB::kReach + kind_bound(D, K_BUTTON)));
-  if (d2x < 1e299) clear = fmin(clear, sqrt(d2x) - (RB::kReach + kind_bound(D, K_BOX)));
+  if (d2x < 1e299) clear = fmin(clear, sqrt(d2x) - (RB::kReach + kind_bound(D, C.sp.box_kind)));
   // ---- forward(): contacts + acceleration at the final state (safe_adaptation_gym.py:76)
   double fs[3], qacc[3];
   R.smooth(sn, cs, fs);

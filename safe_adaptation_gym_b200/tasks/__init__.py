@@ -163,5 +163,5 @@ __all__ = [
     "Unsupervised", "GoToGoalScarce", "PressButtonsScarce", "PushBoxScarce", "GoToGoalDamping", "GoToGoalMotor",
 ]
 
-# tasks whose free-body object is not simulated on the device path yet (rolling contact): DESIGN.md "next"
-DEVICE_UNSUPPORTED = {"roll_rod", "dribble_ball"}
+# tasks the device path does not simulate (none: all 14 registry tasks run; kept for callers that filter on it)
+DEVICE_UNSUPPORTED = frozenset()

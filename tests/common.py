@@ -89,8 +89,8 @@ def drive_action(oenv, rng, p_random=0.15):
         groups = objs[btn, 1].astype(int)
         goal = btn[groups == 2]
         target = objs[goal[0], 2:4] if len(goal) else objs[btn[int(ts[2]) % len(btn)], 2:4]
-    elif (kinds == O.BOX).any() and oenv.task != O.TASK_ID["haul_box"]:
-        box = objs[kinds == O.BOX][0, 2:4]
+    elif (kinds >= O.BOX).any() and oenv.task != O.TASK_ID["haul_box"]:  # push box, rod or ball
+        box = objs[kinds >= O.BOX][0, 2:4]
         goal = objs[kinds == O.GOAL][0, 2:4]
         d = goal - box
         target = box - 0.35 * d / (np.linalg.norm(d) + 1e-9)

@@ -70,7 +70,6 @@ def test_reset_with_task_options_single_and_per_env_list():
     names, ids = [], []
     for name, task in benchmark.make("multitask", 6, 666).train_tasks:
         names.append(name); ids.append(task)
-    ids = [t if t.name not in tasks.DEVICE_UNSUPPORTED else tasks.GoToGoal() for t in ids]
     env.reset(options={"task": ids})
     ti = env.get_field("task_i32").numpy()
     assert ti[0, :6].tolist() == [t.task_id for t in ids]

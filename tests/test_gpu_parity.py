@@ -36,7 +36,8 @@ def test_go_to_goal_1000_step_trajectory_bit_exact():
 
 
 @pytest.mark.parametrize("task", ["go_to_goal_scarce", "go_to_goal_damping", "go_to_goal_motor", "catch_goal", "unsupervised",
-                                  "press_buttons", "press_buttons_scarce", "collect", "push_box", "push_box_scarce", "haul_box"])
+                                  "press_buttons", "press_buttons_scarce", "collect", "push_box", "push_box_scarce", "haul_box",
+                                  "roll_rod", "dribble_ball"])
 def test_other_tasks(task):
     s = run_parity("cuda", task, n=8, steps=300, seed=23)
     assert s["reward"] == s["reward"]
@@ -197,7 +198,8 @@ def test_rollout_kernel_matches_stepping():
     np.testing.assert_array_equal(oa, ob)
 
 
-@pytest.mark.parametrize("task", ["go_to_goal", "press_buttons", "push_box", "haul_box", "collect", "unsupervised", "catch_goal"])
+@pytest.mark.parametrize("task", ["go_to_goal", "press_buttons", "push_box", "haul_box", "collect", "unsupervised", "catch_goal",
+                                  "roll_rod", "dribble_ball"])
 def test_car_tasks(task):
     """BASELINE configs 3 / 4: car robot (reduced planar differential-drive model), bit-exact vs the oracle"""
     s = run_parity("cuda", task, n=16, steps=250, seed=31, robot="car")

@@ -16,7 +16,8 @@ def test_go_to_goal_drive_hits_goals_hazards_and_vases():
 
 
 @pytest.mark.parametrize("task", ["go_to_goal_scarce", "go_to_goal_damping", "go_to_goal_motor", "catch_goal", "unsupervised",
-                                  "press_buttons", "press_buttons_scarce", "collect", "push_box", "push_box_scarce", "haul_box"])
+                                  "press_buttons", "press_buttons_scarce", "collect", "push_box", "push_box_scarce", "haul_box",
+                                  "roll_rod", "dribble_ball"])
 def test_other_tasks(task):
     s = run_parity("hostemu", task, n=3, steps=250, seed=23)
     assert s["reward"] == s["reward"]
@@ -27,7 +28,8 @@ def test_mixed_task_batch_with_noise():
     run_parity("hostemu", names, n=8, steps=120, seed=3, config={"action_noise": 0.01})
 
 
-@pytest.mark.parametrize("task", ["go_to_goal", "press_buttons", "push_box", "haul_box", "collect", "unsupervised", "catch_goal"])
+@pytest.mark.parametrize("task", ["go_to_goal", "press_buttons", "push_box", "haul_box", "collect", "unsupervised", "catch_goal",
+                                  "roll_rod", "dribble_ball"])
 def test_car_tasks(task):
     s = run_parity("hostemu", task, n=3, steps=150, seed=31, robot="car")
     assert s["reward"] == s["reward"]
@@ -36,3 +38,12 @@ def test_car_tasks(task):
 def test_car_random_actions_with_noise():
     run_parity("hostemu", ["go_to_goal", "press_buttons", "push_box", "haul_box"], n=4, steps=120, seed=7, policy="random",
                config={"action_noise": 0.01}, robot="car")
+
+
+def test_multitask_sampler_batch_on_car():
+    """BASELINE config 5: one environment per task of benchmark.make('multitask', 30, 666).train_tasks, car robot --
+    covers all 14 registry tasks' device paths in one batch (README.md:59-63)"""
+    from safe_adaptation_gym_b200 import benchmark
+    names = [name for name, _ in benchmark.make("multitask", 30, 666).train_tasks]
+    assert len(names) == 30 and {"roll_rod", "dribble_ball"} & set(names)
+    run_parity("hostemu", names, n=30, steps=60, seed=666, config={"action_noise": 0.01}, robot="car")
