@@ -47,7 +47,7 @@ typedef struct SagConfig {
   uint32_t env_id_base;       /* global id of env 0 (multi-GPU sharding: results do not depend on the GPU count) */
   int32_t max_episode_steps;  /* 0 = never flag NEEDS_RESET on step count (reference behaviour) */
   int32_t max_layout_draws;   /* draw budget of one layout rejection sampling; 0 = 1<<22 */
-  int32_t reserved;
+  int32_t random_bound;       /* world.py:33,75-78: constraint bound ~ U(0, max_bound) per Task instance instead of max_bound */
   double placements_margin, robot_keepout;
   double hazards_size, vases_size, pillars_size, gremlins_size;
   double hazards_keepout, gremlins_keepout, vases_keepout, pillars_keepout;
@@ -59,7 +59,8 @@ typedef struct SagConfig {
 enum {
   SAG_F_ROBOT = 0,    /* double [6][stride]: x, y, yaw, vx, vy, w */
   SAG_F_OBJECTS = 1,  /* double [6][SAG_MAX_SLOTS][stride]: x, y, yaw, vx, vy, w per object slot */
-  SAG_F_TASK_F64 = 2, /* double [12][stride]: last0,last1,cg_cur,cg_next,cg_ox,cg_oy,time,clearance,ep_return,ep_cost,ctrl0,ctrl1 */
+  SAG_F_TASK_F64 = 2, /* double [15][stride]: last0,last1,cg_cur,cg_next,cg_ox,cg_oy,time,clearance,ep_return,ep_cost,ctrl0,ctrl1,
+                         ctrl_scale0,ctrl_scale1 (world.py:72-73),bound (world.py:75-78) */
   SAG_F_TASK_I32 = 3, /* int32 [10][stride]: task, goal_button, btn_state, btn_timer, active_mask, cg_timer, n_step, step_ctr, episode,
                          moving_mask (derived; rebuilt by sag_observe after an injection) */
   SAG_F_FLAGS = 4,    /* uint8 [stride] */

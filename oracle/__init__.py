@@ -88,6 +88,8 @@ def lib():
     L.orc_env_set_ctrlrange.argtypes = [C.c_void_p, dp, dp]
     L.orc_env_bound.restype = C.c_double
     L.orc_env_bound.argtypes = [C.c_void_p]
+    L.orc_env_new_task.argtypes = [C.c_void_p]
+    L.orc_env_get_ctrlrange.argtypes = [C.c_void_p, dp, dp]
     L.orc_phys_set_control.argtypes = [C.c_void_p, dp]
     L.orc_phys_step.argtypes = [C.c_void_p, C.c_int]
     L.orc_phys_forward.argtypes = [C.c_void_p]
@@ -158,6 +160,20 @@ class OracleEnv:
     @property
     def replay_pos(self):
         return self.L.orc_env_replay_pos(self.h)
+
+    def new_task(self):
+        """the next reset() belongs to a fresh Task instance: redraws ctrl-range scale / constraint bound (world.py:72-78)"""
+        self.L.orc_env_new_task(self.h)
+
+    @property
+    def bound(self):
+        return self.L.orc_env_bound(self.h)
+
+    @property
+    def ctrlrange(self):
+        lo, hi = np.zeros(2), np.zeros(2)
+        self.L.orc_env_get_ctrlrange(self.h, _dp(lo), _dp(hi))
+        return lo, hi
 
     # env API
     @property

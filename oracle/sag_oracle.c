@@ -153,6 +153,7 @@ struct orc_env {
   int has_rect[ORC_MAX_OBJ];
   double rect[ORC_MAX_OBJ][4];
   double robot_rot, bound;
+  int new_task;            /* the next reset builds the World of a fresh Task instance (world.py:72-78) */
   double last_dist[2];
   int goal_button, btn_state, btn_timer;
   unsigned active_mask;
@@ -1098,6 +1099,7 @@ orc_env* orc_env_create(int robot, int task, const orc_config* cfg) {
   e->cq[0] = 1.0;
   e->ctrl_lo[0] = e->ctrl_lo[1] = -1.0; e->ctrl_hi[0] = e->ctrl_hi[1] = 1.0; /* point.xml:7-8 */
   e->bound = e->cfg.max_bound;                                               /* world.py:78 */
+  e->new_task = 1;
   /* task-instance state that survives env.reset() (catch_goal.py:12-18, press_buttons.py:20-24) */
   e->cg_cur = 1.0; e->cg_next = 0.2; e->cg_timer = 0;
   e->btn_state = 1; /* State.NORMAL */ e->btn_timer = BUTTON_DELAY; e->goal_button = 0;
@@ -1111,6 +1113,7 @@ void orc_env_seed(orc_env* e, uint64_t seed, uint32_t gid) { e->seed = seed; e->
 void orc_env_set_replay(orc_env* e, const double* u, int n) { e->replay = u; e->rn = n; e->rpos = 0; e->replay_mode = 1; }
 int orc_env_replay_pos(const orc_env* e) { return e->rpos; }
 double orc_env_bound(const orc_env* e) { return e->bound; }
+void orc_env_new_task(orc_env* e) { e->new_task = 1; }
 
 /* utils.draw_placement, utils.py:22-25,28-70: constrain by keepout, x drawn before y */
 void orc_draw_placement(const double rect[4], double keepout, double u1, double u2, double* xy) {
@@ -1214,6 +1217,25 @@ int orc_env_reset(orc_env* e, uint32_t episode) {
   const task_spec* t = &TASKS[e->task];
   e->episode = episode; e->ctr[0] = e->ctr[1] = e->ctr[2] = 0;
   setup_slots(e);
+  /* World.__init__, world.py:72-78: Task.ctrl_scale (standard Cauchy per actuator, task.py:85-89) and
+   * Task.constraint_bound (U(0, max_bound), task.py:91-94) are drawn once per Task instance and cached on it, so they
+   * survive env.reset() and change with env.set_task / reset(options={'task': ...}).  Philox stream 3; Cauchy by
+   * inversion tan(pi (u - 1/2)).  Not drawn in replay mode (the golden harness injects the reference's ranges). */
+  if (e->new_task) {
+    e->new_task = 0;
+    if (!e->replay_mode) {
+      double u[2];
+      orc_philox_uniform2(e->seed, 0u, episode, e->gid, 3u, u);
+      for (int k = 0; k < 2; ++k) {
+        double sn, cs;
+        sag_sincos(PI_D * (u[k] - 0.5), &sn, &cs);
+        double sc = (sn / cs) * e->cfg.robot_ctrl_range_scale + 1.0;
+        e->ctrl_lo[k] = -1.0 * sc; e->ctrl_hi[k] = 1.0 * sc;         /* mujoco_bridge.py:164-166 */
+      }
+      orc_philox_uniform2(e->seed, 1u, episode, e->gid, 3u, u);
+      e->bound = e->cfg.random_bound ? 0.0 + (e->cfg.max_bound - 0.0) * u[0] : e->cfg.max_bound;
+    }
+  }
   e->draws_left = e->cfg.max_layout_draws > 0 ? e->cfg.max_layout_draws : (1L << 22);
   /* World._generate_new_layout, world.py:172-189 (10000 attempts; the extents-growth fallback is
    * broken in the reference -- quirk D12 -- and is treated as ResamplingError) */
@@ -1389,7 +1411,14 @@ int orc_env_step(orc_env* e, const double* action, double* obs, double* reward, 
     a[0] += e->cfg.action_noise * (rad * sag_cos(TWO_PI * u2));
     a[1] += e->cfg.action_noise * (rad * sag_sin(TWO_PI * u2));
   }
-  double u[2] = {clampd(a[0], e->ctrl_lo[0], e->ctrl_hi[0]), clampd(a[1], e->ctrl_lo[1], e->ctrl_hi[1])}; /* :66-67 */
+  /* :66-67 np.clip = minimum(maximum(a, lo), hi); MuJoCo's own ctrl clamp (x < lo ? lo : x > hi ? hi : x [EXT]) is
+   * applied once more where the actuator force is computed (pt_smooth / car_wheel_smooth).  The two differ only for
+   * an inverted range, which a Cauchy-scaled ctrlrange can be (lo > hi, world.py:72-73) */
+  double u[2];
+  for (int k = 0; k < 2; ++k) {
+    double t = a[k] > e->ctrl_lo[k] ? a[k] : e->ctrl_lo[k];
+    u[k] = t < e->ctrl_hi[k] ? t : e->ctrl_hi[k];
+  }
   orc_phys_set_control(e, u);
   set_mocaps(e);                                           /* :71 */
   orc_phys_step(e, e->nsub);                               /* :72 */
@@ -1427,6 +1456,7 @@ void orc_env_set_task_state(orc_env* e, const double* o) {
   e->ctr[1] = (uint32_t)o[11]; e->time = o[12]; e->robot_rot = o[13]; e->ctrl[0] = o[14]; e->ctrl[1] = o[15];
 }
 void orc_env_set_dyn_params(orc_env* e, double damp_xy, double gear_x) { e->damp_x = e->damp_y = damp_xy; e->gear_x = gear_x; }
+void orc_env_get_ctrlrange(const orc_env* e, double* lo, double* hi) { for (int k = 0; k < 2; ++k) { lo[k] = e->ctrl_lo[k]; hi[k] = e->ctrl_hi[k]; } }
 void orc_env_set_ctrlrange(orc_env* e, const double* lo, const double* hi) { for (int k = 0; k < 2; ++k) { e->ctrl_lo[k] = lo[k]; e->ctrl_hi[k] = hi[k]; } }
 
 void orc_phys_clear(orc_env* e) {

@@ -116,6 +116,10 @@ void orc_env_set_task_state(orc_env* e, const double* in16);
 void orc_env_set_dyn_params(orc_env* e, double damp_xy, double gear_x);
 void orc_env_set_ctrlrange(orc_env* e, const double* lo2, const double* hi2);
 double orc_env_bound(const orc_env* e);
+/* the next orc_env_reset builds the World of a fresh Task instance: redraws ctrl-range scale and constraint bound
+ * (world.py:72-78); set at creation */
+void orc_env_new_task(orc_env* e);
+void orc_env_get_ctrlrange(const orc_env* e, double* lo2, double* hi2);
 
 /* physics-level API: the stand-in for what MujocoBridge exposes (mujoco_bridge.py) */
 void orc_phys_set_control(orc_env* e, const double* u2);   /* mujoco_bridge.py:239-241 */

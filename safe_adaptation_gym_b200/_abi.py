@@ -20,7 +20,7 @@ FLAG_PHYSICS_ERROR, FLAG_RESAMPLE_FAILED, FLAG_NEEDS_RESET = 1, 2, 4
 class SagConfig(C.Structure):
     _fields_ = [
         ("n_envs", C.c_int32), ("robot", C.c_int32), ("seed", C.c_uint64), ("env_id_base", C.c_uint32),
-        ("max_episode_steps", C.c_int32), ("max_layout_draws", C.c_int32), ("reserved", C.c_int32),
+        ("max_episode_steps", C.c_int32), ("max_layout_draws", C.c_int32), ("random_bound", C.c_int32),
         ("placements_margin", C.c_double), ("robot_keepout", C.c_double),
         ("hazards_size", C.c_double), ("vases_size", C.c_double), ("pillars_size", C.c_double), ("gremlins_size", C.c_double),
         ("hazards_keepout", C.c_double), ("gremlins_keepout", C.c_double), ("vases_keepout", C.c_double),

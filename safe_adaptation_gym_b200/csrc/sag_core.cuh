@@ -152,13 +152,15 @@ struct Dev {
   double action_noise, placements_margin, robot_keepout;
   double hazards_size, vases_size, pillars_size, gremlins_size;
   double k_hazard, k_vase, k_gremlin, k_pillar;
-  double max_bound;
+  double max_bound, ctrl_range_scale;
+  int random_bound;
   unsigned long long seed;
   unsigned gid_base;
   int max_layout_draws, max_episode_steps;
   // robot
   double *rx, *ry, *ryaw, *rvx, *rvy, *rw;
   double *ctrl0, *ctrl1;
+  double *cscale0, *cscale1, *bound;  // per Task instance: ctrl-range scale per actuator, constraint bound (world.py:72-78)
   double* rext;  // car extras [6][stride]: wheel rates (2), castor ball-joint quaternion (4)
   // objects [slot][env]
   double *ox, *oy, *oyaw, *ovx, *ovy, *ow;
@@ -1537,8 +1539,19 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev&
     act0 += D.action_noise * (rad * nc);
     act1 += D.action_noise * (rad * ns);
   }
-  R.ctrl[0] = clampd(act0, -1.0, 1.0);
-  R.ctrl[1] = clampd(act1, -1.0, 1.0);
+  // np.clip = min(max(a, lo), hi) (:66-67), then MuJoCo's ctrl clamp; they differ only for an inverted range, which a
+  // Cauchy-scaled ctrlrange can be (world.py:72-73, mujoco_bridge.py:164-166).  Uniform branch: off in World.DEFAULT.
+  if (D.ctrl_range_scale != 0.0) {
+    const double sc0 = D.cscale0[e], sc1 = D.cscale1[e];
+    const double lo0 = -1.0 * sc0, hi0 = 1.0 * sc0, lo1 = -1.0 * sc1, hi1 = 1.0 * sc1;
+    double t0 = act0 > lo0 ? act0 : lo0, t1 = act1 > lo1 ? act1 : lo1;
+    t0 = t0 < hi0 ? t0 : hi0; t1 = t1 < hi1 ? t1 : hi1;
+    R.ctrl[0] = clampd(t0, lo0, hi0);
+    R.ctrl[1] = clampd(t1, lo1, hi1);
+  } else {
+    R.ctrl[0] = clampd(act0, -1.0, 1.0);
+    R.ctrl[1] = clampd(act1, -1.0, 1.0);
+  }
   set_mocaps(C, rng, T, time);  // :71
   // physics.step(nstep) (:72).  "Quiet" envs (nothing within reach for the whole step, nothing moving) skip
   // contact detection; the bound on the hinge point's travel is conservative.
@@ -1725,6 +1738,25 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
   R.damp_xy = C.sp.damp_xy; R.gear_x = C.sp.gear_x;
   TaskState T;
   load_task_state(D, e, T);
+  if (new_task) {
+    // World.__init__ (world.py:72-78): Task.ctrl_scale (standard Cauchy per actuator, task.py:85-89) and
+    // Task.constraint_bound (task.py:91-94) are drawn once per Task instance.  Philox stream 3, Cauchy by inversion.
+    double u[2];
+    rng.pair(3u, 0u, u[0], u[1]);
+    double sc[2];
+    for (int k = 0; k < 2; ++k) {
+      double tn, tc;
+      sag_sincos(kPi * (u[k] - 0.5), &tn, &tc);
+      sc[k] = (tn / tc) * D.ctrl_range_scale + 1.0;
+    }
+    D.cscale0[e] = sc[0]; D.cscale1[e] = sc[1];
+    rng.pair(3u, 1u, u[0], u[1]);
+    D.bound[e] = D.random_bound ? 0.0 + (D.max_bound - 0.0) * u[0] : D.max_bound;
+  }
+  if (D.ctrl_range_scale != 0.0) {  // MuJoCo clamps the zero control of a fresh physics into an inverted range, too
+    const double sc0 = D.cscale0[e], sc1 = D.cscale1[e];
+    R.ctrl[0] = clampd(0.0, -1.0 * sc0, 1.0 * sc0); R.ctrl[1] = clampd(0.0, -1.0 * sc1, 1.0 * sc1);
+  }
   if (new_task) {  // fresh Task instance (catch_goal.py:12-18, press_buttons.py:20-24, collect.py:15-16)
     T.cgcur = 1.0; T.cgnext = 0.2; T.cgtimer = 0; T.bstate = 1; T.btimer = kButtonDelay; T.gbtn = 0;
     T.amask = C.task == T_COLLECT ? (1 << C.L.nbtn) - 1 : 0; T.cgox = T.cgoy = 0.0; T.last0 = T.last1 = 0.0;

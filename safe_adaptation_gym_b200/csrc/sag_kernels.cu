@@ -417,7 +417,6 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   if (!cfg || !handle) return fail("sag_create: null argument");
   if (cfg->n_envs <= 0) return fail("sag_create: n_envs must be positive");
   if (cfg->robot != SAG_ROBOT_POINT && cfg->robot != SAG_ROBOT_CAR) return fail("sag_create: robot must be point (0) or car (1)");
-  if (cfg->robot_ctrl_range_scale != 0.0) return fail("sag_create: robot_ctrl_range_scale != 0 is not implemented");
   CK(cudaSetDevice(device));
   Handle* H = new (std::nothrow) Handle();
   if (!H) return fail("sag_create: out of host memory");

@@ -20,7 +20,7 @@ inline SlabLayout slab_layout(int n, int stride, int obs_dim) {
   const size_t st = (size_t)stride;
   L.bytes[SAG_F_ROBOT] = 6 * st * sizeof(double);
   L.bytes[SAG_F_OBJECTS] = 6 * (size_t)SAG_MAX_SLOTS * st * sizeof(double);
-  L.bytes[SAG_F_TASK_F64] = 12 * st * sizeof(double);
+  L.bytes[SAG_F_TASK_F64] = 15 * st * sizeof(double);
   L.bytes[SAG_F_TASK_I32] = 10 * st * sizeof(int32_t);
   L.bytes[SAG_F_FLAGS] = st;
   L.bytes[SAG_F_ROBOT_EXT] = 6 * st * sizeof(double);
@@ -47,6 +47,7 @@ inline void slab_bind(Dev& D, const SlabLayout& L, char* base) {
   double* t = (double*)(base + L.off[SAG_F_TASK_F64]);
   D.last0 = t; D.last1 = t + st; D.cgcur = t + 2 * st; D.cgnext = t + 3 * st; D.cgox = t + 4 * st; D.cgoy = t + 5 * st;
   D.time = t + 6 * st; D.clear = t + 7 * st; D.epret = t + 8 * st; D.epcost = t + 9 * st; D.ctrl0 = t + 10 * st; D.ctrl1 = t + 11 * st;
+  D.cscale0 = t + 12 * st; D.cscale1 = t + 13 * st; D.bound = t + 14 * st;
   int32_t* ii = (int32_t*)(base + L.off[SAG_F_TASK_I32]);
   D.task = ii; D.gbtn = ii + st; D.bstate = ii + 2 * st; D.btimer = ii + 3 * st; D.amask = ii + 4 * st; D.cgtimer = ii + 5 * st;
   D.nstep = ii + 6 * st; D.ctr = (unsigned*)(ii + 7 * st); D.episode = (unsigned*)(ii + 8 * st); D.movmask = ii + 9 * st;
@@ -67,7 +68,8 @@ inline void dev_from_config(Dev& D, const SagConfig& c) {
   D.k_vase = c.vases_keepout < c.vases_size ? c.vases_size : c.vases_keepout;
   D.k_gremlin = c.gremlins_keepout < c.gremlins_size ? c.gremlins_size : c.gremlins_keepout;
   D.k_pillar = c.pillars_keepout < c.pillars_size ? c.pillars_size : c.pillars_keepout;
-  D.max_bound = c.max_bound; D.seed = c.seed; D.gid_base = c.env_id_base;
+  D.max_bound = c.max_bound; D.ctrl_range_scale = c.robot_ctrl_range_scale; D.random_bound = c.random_bound;
+  D.seed = c.seed; D.gid_base = c.env_id_base;
   D.max_layout_draws = c.max_layout_draws; D.max_episode_steps = c.max_episode_steps;
 }
 

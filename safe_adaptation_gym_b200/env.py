@@ -65,8 +65,6 @@ class BatchedSafeAdaptationGym:
             if k not in WORLD_DEFAULT and k not in _EXTRA_KEYS:
                 raise KeyError(f'unknown config key {k!r}')
             cfg[k] = v
-        if cfg['random_bound'] or cfg['robot_ctrl_range_scale'] != 0.0:
-            raise NotImplementedError('random_bound / robot_ctrl_range_scale are not implemented on the device path yet')
         self.base_config = cfg
         self.num_envs = int(num_envs)
         if _test_lib is None:
@@ -88,6 +86,7 @@ class BatchedSafeAdaptationGym:
         c.env_id_base = int(env_id_base)
         c.max_episode_steps = int(max_episode_steps)
         c.max_layout_draws = int(cfg.get('max_layout_draws', 0))
+        c.random_bound = 1 if cfg['random_bound'] else 0
         for k in ('placements_margin', 'robot_keepout', 'hazards_size', 'vases_size', 'pillars_size', 'gremlins_size',
                   'hazards_keepout', 'gremlins_keepout', 'vases_keepout', 'pillars_keepout', 'gremlins_travel',
                   'robot_ctrl_range_scale', 'action_noise', 'max_bound'):
@@ -243,6 +242,8 @@ class BatchedSafeAdaptationGym:
         self._steps_to_expiry = self.max_episode_steps if (mask is None and self.max_episode_steps > 0) else None
         flags = self.get_field('flags')[:self.num_envs]
         bad = (flags & _abi.FLAG_RESAMPLE_FAILED) != 0
+        if new_task and self.base_config['random_bound']:  # world.py:75-78: drawn once per Task instance
+            self._bound = self.get_field('task_f64')[14, :self.num_envs].clone()
         if bool(bad.any()):
             raise ResamplingError('Failed to generate layout')  # world.py:189
 
@@ -258,7 +259,7 @@ class BatchedSafeAdaptationGym:
             raise ResamplingError('Failed to generate goal')  # go_to_goal.py:80
 
     _FIELDS = {'robot': (_abi.F_ROBOT, torch.float64, (6,)), 'objects': (_abi.F_OBJECTS, torch.float64, (6, _abi.MAX_SLOTS)),
-               'task_f64': (_abi.F_TASK_F64, torch.float64, (12,)), 'task_i32': (_abi.F_TASK_I32, torch.int32, (10,)),
+               'task_f64': (_abi.F_TASK_F64, torch.float64, (15,)), 'task_i32': (_abi.F_TASK_I32, torch.int32, (10,)),
                'flags': (_abi.F_FLAGS, torch.uint8, ()), 'robot_ext': (_abi.F_ROBOT_EXT, torch.float64, (6,))}
 
     def get_field(self, name: str) -> torch.Tensor:

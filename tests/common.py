@@ -134,6 +134,7 @@ def run_parity(backend, task_names, n, steps, seed, config=None, policy="drive",
             acts[e] = a.astype(np.float32)
         obs, rew, done, info = env.step(torch.from_numpy(acts))
         obs = obs.cpu().numpy(); rew = rew.cpu().numpy(); cost = info["cost"].cpu().numpy(); done = done.cpu().numpy()
+        np.testing.assert_array_equal(np.broadcast_to(torch.as_tensor(info["bound"]).cpu().numpy(), (n,)), [o.bound for o in orc])
         for e in range(n):
             oobs, orew, ocost, odone, rc = orc[e].step(acts[e].astype(np.float64))
             assert rc == 0

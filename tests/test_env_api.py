@@ -110,3 +110,25 @@ def test_car_observation_layout():
     assert obs.shape == (3, 72)
     np.testing.assert_allclose(obs[:, 50], 9.81, rtol=1e-6)                      # accelerometer z
     np.testing.assert_array_equal(obs[:, 63:72].reshape(3, 3, 3), np.broadcast_to(np.eye(3, dtype=np.float32), (3, 3, 3)))  # ballquat -> I
+
+
+def test_random_bound_and_ctrl_scale_are_per_task_instance():
+    """world.py:72-78 + task.py:85-94: drawn once per Task instance -- kept by reset(), redrawn by set_task /
+    reset(options={'task': ...}); bound ~ U(0, max_bound); ctrl-range scale = Cauchy * scale + 1"""
+    n = 512
+    env = _make(n=n, seed=9, config={"random_bound": True, "robot_ctrl_range_scale": 0.1, "max_bound": 10})
+    b0 = env.step(np.zeros((n, 2), np.float32))[3]["bound"].clone()
+    assert tuple(b0.shape) == (n,) and float(b0.min()) >= 0.0 and float(b0.max()) <= 10.0
+    assert 4.0 < float(b0.mean()) < 6.0 and float(b0.std()) > 2.0
+    sc0 = env.get_field("task_f64")[12:14, :n].clone()
+    q = np.percentile(sc0.numpy().ravel(), [25, 50, 75])
+    np.testing.assert_allclose(q, [0.9, 1.0, 1.1], atol=0.03)     # quartiles of a Cauchy(1, 0.1)
+    env.reset()
+    assert torch.equal(env.step(np.zeros((n, 2), np.float32))[3]["bound"], b0)
+    assert torch.equal(env.get_field("task_f64")[12:14, :n], sc0)
+    env.reset(options={"task": tasks.GoToGoal()})
+    b1 = env.step(np.zeros((n, 2), np.float32))[3]["bound"]
+    assert not torch.equal(b1, b0) and not torch.equal(env.get_field("task_f64")[12:14, :n], sc0)
+    # defaults: fixed bound, unit scale
+    env = _make(n=4, seed=9)
+    assert env.get_field("task_f64")[12:15, :4].T.tolist() == [[1.0, 1.0, 25.0]] * 4

@@ -224,3 +224,19 @@ def test_car_observation_shape_and_full_size_smoke():
     m = obs[:, 63:72].reshape(-1, 3, 3).double()
     eye = torch.eye(3, device="cuda", dtype=torch.float64)
     assert float((m @ m.transpose(1, 2) - eye).abs().max()) < 1e-5
+
+
+@pytest.mark.gpu
+def test_multitask_sampler_batch_on_car():
+    """BASELINE config 5: the 30 train tasks of benchmark.make('multitask', 30, 666), one env each, car robot"""
+    from safe_adaptation_gym_b200 import benchmark
+    names = [name for name, _ in benchmark.make("multitask", 30, 666).train_tasks]
+    run_parity("cuda", names, n=30, steps=100, seed=666, config={"action_noise": 0.01}, robot="car")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot", ["point", "car"])
+def test_adaptation_knobs_ctrl_range_scale_and_random_bound(robot):
+    cfg = {"robot_ctrl_range_scale": 0.6, "random_bound": True, "action_noise": 0.01}
+    run_parity("cuda", ["go_to_goal", "push_box", "press_buttons", "unsupervised"] * 8, n=32, steps=120, seed=41, config=cfg,
+               policy="random", robot=robot)

@@ -47,3 +47,11 @@ def test_multitask_sampler_batch_on_car():
     names = [name for name, _ in benchmark.make("multitask", 30, 666).train_tasks]
     assert len(names) == 30 and {"roll_rod", "dribble_ball"} & set(names)
     run_parity("hostemu", names, n=30, steps=60, seed=666, config={"action_noise": 0.01}, robot="car")
+
+
+@pytest.mark.parametrize("robot", ["point", "car"])
+def test_adaptation_knobs_ctrl_range_scale_and_random_bound(robot):
+    """world.py:72-78: Cauchy-scaled ctrlrange (incl. inverted ranges) and U(0, max_bound) constraint bound per Task instance"""
+    cfg = {"robot_ctrl_range_scale": 0.6, "random_bound": True, "action_noise": 0.01}
+    run_parity("hostemu", ["go_to_goal", "push_box", "press_buttons", "unsupervised"] * 4, n=16, steps=80, seed=41, config=cfg,
+               policy="random", robot=robot)
