@@ -137,6 +137,35 @@ SAG_DM double sag_atan2(double y, double x) {
   return y > 0.0 ? pi - (z - pi_lo) : (z - pi_lo) - pi;
 }
 
+/* Lidar angle -> (bin, alias) for 16 bins (safe_adaptation_gym.py:210-216): with t = (atan2(ey, ex) mod 2 pi) / (2 pi / 16),
+ * bin = floor(t) and alias = t - bin.  Instead of a full atan2 (two divisions, a four-way range reduction) the vector is
+ * folded into the first half-bin -- |.| of both components, a swap about 45 deg, a reflection about 22.5 deg whose
+ * tangent is (x - y) / (x + y) -- so that ONE division feeds the lowest-range atan polynomial (|r| <= tan(pi/8) < 0.4375,
+ * no reduction), and the folds are undone on the integer bin index.  A fold turns t into c - t: the fraction becomes
+ * 1 - a and the bin the one below.  On an exact bin edge this names the neighbouring bin with alias 1 instead of alias 0,
+ * which yields the same three lidar contributions (s, 1*s, 0*s).  Agrees with the literal formula to a few ulp of t
+ * (tests/test_detmath.py); the oracle keeps the literal one next to it (orc_lidar_literal). */
+SAG_DM void sag_lidar_bin16(double ex, double ey, int* bin, double* alias) {
+  const double tan_pi_8 = 4.1421356237309503e-01, eight_over_pi = 2.5464790894703255e+00;
+  double ax = fabs(ex), ay = fabs(ey);
+  const int s1 = ay > ax;
+  double x = s1 ? ay : ax, y = s1 ? ax : ay;
+  const int s2 = y > x * tan_pi_8;
+  double num = s2 ? x - y : y, den = s2 ? x + y : x;
+  double r = den > 0.0 ? num / den : 0.0; /* the zero vector has angle 0 like numpy.angle */
+  double z = r * r;
+  double w = z * z;
+  double p1 = z * SAG_FMA(w, SAG_FMA(w, SAG_FMA(w, SAG_FMA(w, SAG_FMA(w, SAG_K(22), SAG_K(20)), SAG_K(18)), SAG_K(16)), SAG_K(14)), SAG_K(12));
+  double p2 = w * SAG_FMA(w, SAG_FMA(w, SAG_FMA(w, SAG_FMA(w, SAG_K(21), SAG_K(19)), SAG_K(17)), SAG_K(15)), SAG_K(13));
+  double a = (r - r * (p1 + p2)) * eight_over_pi; /* atan(r) in bins */
+  int B = s2 ? 2 : 0, neg = s2;
+  if (s1) { B = 4 - B; neg ^= 1; }
+  if (ex < 0.0) { B = 8 - B; neg ^= 1; }
+  if (ey < 0.0) { B = 16 - B; neg ^= 1; }
+  *bin = neg ? B - 1 : B;
+  *alias = neg ? 1.0 - a : a;
+}
+
 /* natural log of a positive normal double */
 SAG_DM double sag_log(double x) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;

@@ -102,6 +102,7 @@ def lib():
     L.orc_phys_clear.argtypes = [C.c_void_p]
     L.orc_phys_add_obj.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
     L.orc_lidar.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, dp, dp, dp]
+    L.orc_lidar_literal.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, dp, dp, dp]
     L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.orc_philox_uniform2.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp]
     L.orc_draw_placement.argtypes = [dp, C.c_double, C.c_double, C.c_double, dp]
@@ -294,11 +295,13 @@ class OracleEnv:
         return self.L.orc_phys_add_obj(self.h, type_, x, y, yaw, keepout, group)
 
 
-def lidar(rx, ry, ryaw, xs, ys):
+def lidar(rx, ry, ryaw, xs, ys, literal=False):
+    """one 16-bin pseudo-lidar; literal=True evaluates the line-by-line form of safe_adaptation_gym.py:204-223,
+    the default the folded form the environment and the GPU use (include/sag_detmath.h: sag_lidar_bin16)"""
     xs = np.ascontiguousarray(xs, dtype=np.float64)
     ys = np.ascontiguousarray(ys, dtype=np.float64)
     out = np.zeros(16)
-    lib().orc_lidar(rx, ry, ryaw, len(xs), _dp(xs), _dp(ys), _dp(out))
+    (lib().orc_lidar_literal if literal else lib().orc_lidar)(rx, ry, ryaw, len(xs), _dp(xs), _dp(ys), _dp(out))
     return out
 
 

@@ -948,7 +948,8 @@ void orc_phys_sensors(const orc_env* e, double* out) {
 /* ==========================================================================================
  * Lidar: SafeAdaptationGym._lidar, safe_adaptation_gym.py:174-223
  * ======================================================================================== */
-static void lidar_accum(double rx, double ry, double c, double s, double px, double py, double* obs) {
+/* literal restatement, line by line; pinned by tests/golden/lidar_kat.json */
+static void lidar_accum_literal(double rx, double ry, double c, double s, double px, double py, double* obs) {
   /* ego_xy (:197-202): (pos - robot_pos) @ robot_mat, planar */
   double wx = px - rx, wy = py - ry;
   double ex = wx * c + wy * s, ey = -wx * s + wy * c;
@@ -969,10 +970,36 @@ static void lidar_accum(double rx, double ry, double c, double s, double px, dou
   if ((1.0 - alias) * sensor > obs[bm]) obs[bm] = (1.0 - alias) * sensor; /* :222 */
 }
 
+/* the form the environment (and the GPU, bit for bit) evaluates: same quantities, with (bin, alias) from
+ * sag_lidar_bin16 (one division, no full atan2 -- include/sag_detmath.h) and fused multiply-adds in the ego transform.
+ * Pinned by the same known answers and against the literal form on random inputs (tests/test_golden.py,
+ * tests/test_detmath.py). */
+static void lidar_accum(double rx, double ry, double c, double s, double px, double py, double* obs) {
+  double wx = px - rx, wy = py - ry;
+  double ex = SAG_FMA(wx, c, wy * s), ey = SAG_FMA(wy, c, -(wx * s)); /* :197-202 */
+  double dist = sqrt(SAG_FMA(ex, ex, ey * ey));                       /* :209 */
+  int bin;
+  double alias;
+  sag_lidar_bin16(ex, ey, &bin, &alias);                              /* :210-213,216 */
+  double sensor = LIDAR_MAX_DIST - dist;                              /* :214 */
+  if (sensor < 0.0) sensor = 0.0;
+  sensor *= 1.0 / LIDAR_MAX_DIST;
+  int b0 = bin & (ORC_NUM_LIDAR_BINS - 1);                            /* quirk D7: wrap instead of IndexError */
+  int bp = (bin + 1) & (ORC_NUM_LIDAR_BINS - 1), bm = (bin + ORC_NUM_LIDAR_BINS - 1) & (ORC_NUM_LIDAR_BINS - 1);
+  if (sensor > obs[b0]) obs[b0] = sensor;                             /* :215 */
+  if (alias * sensor > obs[bp]) obs[bp] = alias * sensor;             /* :221 */
+  if ((1.0 - alias) * sensor > obs[bm]) obs[bm] = (1.0 - alias) * sensor; /* :222 */
+}
+
 void orc_lidar(double rx, double ry, double ryaw, int n, const double* xs, const double* ys, double* out16) {
   double c = sag_cos(ryaw), s = sag_sin(ryaw);
   for (int i = 0; i < ORC_NUM_LIDAR_BINS; ++i) out16[i] = 0.0;
   for (int i = 0; i < n; ++i) lidar_accum(rx, ry, c, s, xs[i], ys[i], out16);
+}
+void orc_lidar_literal(double rx, double ry, double ryaw, int n, const double* xs, const double* ys, double* out16) {
+  double c = sag_cos(ryaw), s = sag_sin(ryaw);
+  for (int i = 0; i < ORC_NUM_LIDAR_BINS; ++i) out16[i] = 0.0;
+  for (int i = 0; i < n; ++i) lidar_accum_literal(rx, ry, c, s, xs[i], ys[i], out16);
 }
 
 /* observation: safe_adaptation_gym.py:120-139 -- [obstacles(16), objects(16), goal(16), sensors] */

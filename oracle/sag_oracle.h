@@ -136,6 +136,8 @@ int orc_phys_add_obj(orc_env* e, int type, double x, double y, double yaw, doubl
 
 /* pure functions (known-answer tests) */
 void orc_lidar(double rx, double ry, double ryaw, int n, const double* xs, const double* ys, double* out16);
+/* the line-by-line form of safe_adaptation_gym.py:204-223 (full atan2); orc_lidar evaluates the folded form */
+void orc_lidar_literal(double rx, double ry, double ryaw, int n, const double* xs, const double* ys, double* out16);
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void orc_philox_uniform2(uint64_t seed, uint32_t ctr, uint32_t episode, uint32_t gid, uint32_t stream, double* u2);
 void orc_draw_placement(const double rect[4], double keepout, double u1, double u2, double* xy);

@@ -1131,17 +1131,14 @@ SAG_HD void warp_contact_pass(unsigned wmask, bool need, const Ctx& C, const RB&
 struct LidarHit { int bin; float s0, sp, sm; };
 
 SAG_HD LidarHit lidar_eval(double wx, double wy, double cs, double sn) {
-  double ex = wx * cs + wy * sn, ey = -wx * sn + wy * cs;   // :197-202 ego frame
-  double dist = sqrt(ex * ex + ey * ey);                    // :209
-  double angle = sag_atan2(ey, ex);                         // :210
-  if (angle < 0.0) angle += kTwoPi;
-  const double inv_bin_size = kLidarBins / kTwoPi;          // :211
-  double t = angle * inv_bin_size;
-  int bin = (int)t;                                         // :212
-  double sensor = kLidarMax - dist;                         // :214
+  double ex = SAG_FMA(wx, cs, wy * sn), ey = SAG_FMA(wy, cs, -(wx * sn));  // :197-202 ego frame
+  double dist = sqrt(SAG_FMA(ex, ex, ey * ey));                             // :209
+  int bin;
+  double alias;
+  sag_lidar_bin16(ex, ey, &bin, &alias);                                    // :210-213,216 (folded form, sag_detmath.h)
+  double sensor = kLidarMax - dist;                                         // :214
   if (sensor < 0.0) sensor = 0.0;
   sensor *= 1.0 / kLidarMax;
-  double alias = t - (double)bin;                           // :213,216
   LidarHit H;
   H.bin = bin;
   H.s0 = (float)sensor; H.sp = (float)(alias * sensor); H.sm = (float)((1.0 - alias) * sensor);

@@ -35,3 +35,25 @@ def test_log_within_1ulp():
     ref = np.log(u)
     m = ref != 0
     assert _ulps(l[m], ref[m]).max() <= 1.0 and l[0] == 0.0
+
+
+def test_folded_lidar_equals_literal_lidar():
+    """sag_lidar_bin16 (one division, bin index from folds) vs the literal atan2 form of safe_adaptation_gym.py:204-223:
+    random scenes, objects exactly on bin edges (every multiple of pi/8), on the axes, and at the robot's own position"""
+    import oracle as O
+    rng = np.random.RandomState(5)
+    worst = 0.0
+    for i in range(6000):
+        n = rng.randint(1, 14)
+        rx, ry = rng.uniform(-2, 2, 2)
+        yaw = rng.uniform(-10, 10)
+        xs, ys = rng.uniform(-3.5, 3.5, n), rng.uniform(-3.5, 3.5, n)
+        if i % 5 == 0:   # bin edges in the ego frame
+            yaw = 0.0
+            k, d = rng.randint(0, 16, n), rng.uniform(0.05, 3.2, n)
+            xs, ys = rx + d * np.cos(k * np.pi / 8), ry + d * np.sin(k * np.pi / 8)
+        if i % 7 == 0:   # exactly on an axis / at the robot
+            xs[0], ys[0] = rx, ry + (rng.randint(-1, 2)) * 0.5
+        a, b = O.lidar(rx, ry, yaw, xs, ys), O.lidar(rx, ry, yaw, xs, ys, literal=True)
+        worst = max(worst, float(np.abs(a - b).max()))
+    assert worst < 1e-14, worst

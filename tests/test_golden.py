@@ -26,8 +26,9 @@ def test_lidar_matches_reference_lidar():
     assert len(cases) > 150
     for c in cases:
         pts = np.asarray(c["pts"])
-        out = O.lidar(c["robot"][0], c["robot"][1], c["robot"][2], pts[:, 0], pts[:, 1])
-        np.testing.assert_allclose(out, c["out"], rtol=1e-12, atol=1e-14)
+        for literal in (True, False):  # the line-by-line form and the folded form the env / GPU evaluate
+            out = O.lidar(c["robot"][0], c["robot"][1], c["robot"][2], pts[:, 0], pts[:, 1], literal=literal)
+            np.testing.assert_allclose(out, c["out"], rtol=1e-12, atol=1e-14)
 
 
 def test_layout_sampler_matches_reference_world():
