@@ -630,6 +630,10 @@ constexpr int kSmallCon = 4, kSmallBodies = 2;
 typedef ScratchT<kSmallCon, kSmallBodies> SmallScratch;
 static_assert((sizeof(SmallScratch) / 8) % 2 == 1, "SmallScratch stride must be an odd number of 8-byte words");
 
+// env_step / end_of_step modes: full scalar path (one thread = one environment, contact solver included), quiet-only
+// (no contact code), warp-cooperative (one warp = one environment, device only)
+constexpr int kStepFull = 0, kStepQuiet = 1, kStepCoop = 2;
+
 struct Ctx {  // per-thread view of one environment
   const Dev& D;
   int e;
@@ -741,7 +745,196 @@ SAG_HD void car_free_solve(const CarRobot& R, double sn, double cs, const PtCons
   }
 }
 
-template <class RB, class ScratchType>
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative variants (device only).  In the cooperative busy kernel ONE WARP owns one environment: all 32
+// lanes execute the step's scalar code redundantly (same registers, warp-uniform control flow, identical stores), and
+// the sections below split their independent work items over the lanes: the broad and narrow collision phases (one
+// slot / one pair / one geom pair per lane, results appended in the scalar code's canonical order by warp prefix sums),
+// the overlap pre-test and the lidar pass (one object per lane, bins reduced with shared-memory max).  Every item is
+// computed by the same arithmetic as in the scalar path, so results are bit-identical (tests/test_gpu_parity.py runs
+// the oracle against this path).
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+constexpr unsigned kFullWarp = 0xffffffffu;
+__device__ __forceinline__ int coop_lane() { return threadIdx.x & 31; }
+
+// Item expansion: lane o owns cnt_o items (cnt uniform-shuffled); item t (global index within this expansion) ->
+// (owner lane, local index).  Owners are visited in lane order, so items are numbered in canonical order.
+__device__ __forceinline__ bool coop_find_item(unsigned owners, int cnt, int t, int& owner, int& local) {
+  bool found = false;
+  owner = 0; local = 0;
+  for (unsigned m = owners; m; m &= m - 1) {
+    const int o = __ffs((int)m) - 1;
+    const int c = __shfl_sync(kFullWarp, cnt, o);
+    if (!found && t >= 0 && t < c) { owner = o; local = t; found = true; }
+    t -= c;
+  }
+  return found;
+}
+
+// ordered append: lane order = canonical order; n in {0, 1, 2} hits per lane
+__device__ __forceinline__ void coop_append(Con* con, int cap, int& ncon, bool& overflow, int n, const Hit* hits, int ba, int bb) {
+  const int lane = coop_lane();
+  const unsigned m1 = __ballot_sync(kFullWarp, n >= 1), m2 = __ballot_sync(kFullWarp, n >= 2);
+  const unsigned lower = (1u << lane) - 1u;
+  const int off = ncon + __popc(m1 & lower) + __popc(m2 & lower);
+  for (int k = 0; k < n; ++k) {
+    const int idx = off + k;
+    if (idx < cap) {
+      Con& c = con[idx];
+      c.ba = ba; c.bb = bb;
+      c.nx = hits[k].nx; c.ny = hits[k].ny; c.px = hits[k].px; c.py = hits[k].py; c.dist = hits[k].dist;
+    }
+  }
+  const int tot = ncon + __popc(m1) + __popc(m2);
+  if (tot > cap) { overflow = true; ncon = cap; } else ncon = tot;
+}
+
+// Both collision phases of contact_pass, lane-parallel.  Same outputs: con[0..ncon) in canonical order, overflow, touch,
+// active.  (Scalar semantics on overflow: the list stops growing at the capacity, touch / active keep accumulating.)
+template <class RB>
+__device__ __noinline__ void detect_coop(const Ctx& C, const RB& R, double sn, double cs, unsigned mov, Con* con, int cap,
+                                         int& ncon_out, bool& overflow_out, unsigned& touch_out, unsigned& active_out) {
+  const Dev& D = C.D;
+  const int e = C.e, lane = coop_lane();
+  int ncon = 0;
+  bool overflow = false;
+  unsigned touch = 0, active = mov;
+  Hit hits[2];
+  // ---- phase 1 broad phase: lane <-> slot v0 + lane
+  const int s1 = C.L.v0 + lane;
+  int kind1 = K_NONE;
+  bool coll1 = false, near1 = false;
+  if (s1 < C.L.n) {
+    kind1 = slot_kind(C.sp, C.L, s1);
+    coll1 = kind_collidable(kind1);
+    if (coll1) {
+      size_t i = oidx(D, s1, e);
+      double dx = D.ox[i] - R.q[0], dy = D.oy[i] - R.q[1], reach = RB::kReach + kind_bound(D, kind1);
+      near1 = !(dx * dx + dy * dy > reach * reach);
+    }
+  }
+  const unsigned collm = __ballot_sync(kFullWarp, coll1) << C.L.v0;  // absolute slot bits
+  const unsigned near1m = __ballot_sync(kFullWarp, near1);           // lane bits
+  {
+    const int cnt = near1 ? RB::kNGeom * kind_nparts(kind1) : 0;
+    int total = cnt;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(kFullWarp, total, d);
+    for (int base = 0; base < total; base += 32) {
+      int owner, local;
+      const bool have = coop_find_item(near1m, cnt, base + lane, owner, local);
+      const int kind = __shfl_sync(kFullWarp, kind1, owner);
+      int n = 0, s = C.L.v0 + owner;
+      const bool mvb = kind_movable(kind);
+      if (have) {
+        const int np = kind_nparts(kind), rg = local / np, pt = local - rg * np;
+        size_t i = oidx(D, s, e);
+        double x = D.ox[i], y = D.oy[i], oc = 1.0, os = 0.0;
+        if (mvb) sag_sincos(D.oyaw[i], &os, &oc);
+        Geom grg, go;
+        R.geom(rg, sn, cs, grg);
+        obj_geom(D, kind, pt, x, y, oc, os, go);
+        n = collide(grg, go, hits);
+      }
+      coop_append(con, cap, ncon, overflow, n, hits, 0, mvb ? 1 + s : -1);
+      const unsigned tb = __reduce_or_sync(kFullWarp, n ? 1u << s : 0u);
+      touch |= tb;
+      active |= __reduce_or_sync(kFullWarp, (n && mvb) ? 1u << s : 0u);
+    }
+  }
+  // ---- phase 2: pairs (j ascending, i < j ascending) with at least one awake / robot-touched movable body
+  if (active) {
+    const unsigned lowcut = ~((1u << C.L.v0) - 1u);
+    // number of candidate pairs of every j, then the flattened pair list in canonical order, 32 per round
+    int total = 0;
+    for (unsigned jm = collm; jm; jm &= jm - 1) {
+      const int j = __ffs((int)jm) - 1;
+      const unsigned below = (1u << j) - 1u;
+      const unsigned cand = (((active >> j) & 1u) ? below : (active & below)) & lowcut & collm;
+      total += __popc(cand);
+    }
+    for (int base = 0; base < total; base += 32) {
+      int t = base + lane, pj = -1, pi = -1;
+      for (unsigned jm = collm; jm; jm &= jm - 1) {
+        const int j = __ffs((int)jm) - 1;
+        const unsigned below = (1u << j) - 1u;
+        const unsigned cand = (((active >> j) & 1u) ? below : (active & below)) & lowcut & collm;
+        const int c = __popc(cand);
+        if (pj < 0 && t >= 0 && t < c) { pj = j; pi = (int)__fns(cand, 0, t + 1); }
+        t -= c;
+      }
+      bool nearp = false;
+      int ki = K_NONE, kj = K_NONE;
+      if (pj >= 0) {
+        ki = slot_kind(C.sp, C.L, pi); kj = slot_kind(C.sp, C.L, pj);
+        size_t ii = oidx(D, pi, e), ij = oidx(D, pj, e);
+        double dx = D.ox[ij] - D.ox[ii], dy = D.oy[ij] - D.oy[ii], reach = kind_bound(D, kj) + kind_bound(D, ki);
+        nearp = !(dx * dx + dy * dy > reach * reach);
+      }
+      const unsigned nearm = __ballot_sync(kFullWarp, nearp);
+      const int cnt = nearp ? kind_nparts(ki) * kind_nparts(kj) : 0;
+      int items = cnt;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) items += __shfl_xor_sync(kFullWarp, items, d);
+      const int packed = (pi & 0xff) | ((pj & 0xff) << 8) | (ki << 16) | (kj << 24);
+      for (int ib = 0; ib < items; ib += 32) {
+        int owner, local;
+        const bool have = coop_find_item(nearm, cnt, ib + lane, owner, local);
+        const int pk = __shfl_sync(kFullWarp, packed, owner);
+        const int i = pk & 0xff, j = (pk >> 8) & 0xff, kki = (pk >> 16) & 0xff, kkj = (pk >> 24) & 0xff;
+        const bool mi = kind_movable(kki), mj = kind_movable(kkj);
+        int n = 0;
+        if (have) {
+          const int npj = kind_nparts(kkj), a = local / npj, b = local - a * npj;  // part of i (outer), part of j (inner)
+          size_t ii = oidx(D, i, e), ij = oidx(D, j, e);
+          double ci = 1.0, si = 0.0, cj = 1.0, sj = 0.0;
+          if (mi) sag_sincos(D.oyaw[ii], &si, &ci);
+          if (mj) sag_sincos(D.oyaw[ij], &sj, &cj);
+          Geom gi, gj;
+          obj_geom(D, kki, a, D.ox[ii], D.oy[ii], ci, si, gi);
+          obj_geom(D, kkj, b, D.ox[ij], D.oy[ij], cj, sj, gj);
+          n = collide(gi, gj, hits);
+        }
+        coop_append(con, cap, ncon, overflow, n, hits, mi ? 1 + i : -1, mj ? 1 + j : -1);
+      }
+    }
+  }
+  __syncwarp();
+  ncon_out = ncon; overflow_out = overflow; touch_out = touch; active_out = active;
+}
+
+template <class RB>
+__device__ __forceinline__ bool robot_overlaps_any_coop(const Ctx& C, const RB& R, double sn, double cs) {
+  const Dev& D = C.D;
+  const int s = C.L.v0 + coop_lane();
+  bool hit = false;
+  if (s < C.L.n) {
+    const int kind = slot_kind(C.sp, C.L, s);
+    if (kind_collidable(kind)) {
+      size_t i = oidx(D, s, C.e);
+      double x = D.ox[i], y = D.oy[i];
+      double dx = x - R.q[0], dy = y - R.q[1], reach = RB::kReach + kind_bound(D, kind);
+      if (!(dx * dx + dy * dy > reach * reach)) {
+        double oc = 1.0, os = 0.0;
+        if (kind_movable(kind)) sag_sincos(D.oyaw[i], &os, &oc);
+        for (int pt = 0; pt < kind_nparts(kind) && !hit; ++pt) {
+          Geom go;
+          obj_geom(D, kind, pt, x, y, oc, os, go);
+          for (int rg = 0; rg < RB::kNGeom; ++rg) {
+            Geom grg;
+            R.geom(rg, sn, cs, grg);
+            if (overlap(grg, go)) { hit = true; break; }
+          }
+        }
+      }
+    }
+  }
+  return __any_sync(kFullWarp, hit);
+}
+#endif  // __CUDA_ARCH__
+
+template <class RB, class ScratchType, bool Coop = false>
 SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double cs, const PtConst& K, const double* fs,
                                   unsigned mov, bool integrate, double h, ScratchType& S, Phys& P) {
   constexpr int kCapCon = ScratchType::kCon, kCapBodies = ScratchType::kBodies;
@@ -758,6 +951,11 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   constexpr bool kCarRobot = RB::kKind == 1;
   Hit hits[2];
   SAG_PROF(e, 0, 1);
+  if constexpr (Coop) {
+#if defined(__CUDA_ARCH__)
+    detect_coop<RB>(C, R, sn, cs, mov, con, kCapCon, ncon, overflow, touch, active);
+#endif
+  } else {
   // ---- phase 1: robot geoms vs objects, slot order
   for (int s = C.L.v0; s < C.L.n; ++s) {
     int kind = slot_kind(C.sp, C.L, s);
@@ -832,6 +1030,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
         }
       }
     }
+  }
   }
   P.touch = touch;
   P.mov = mov;
@@ -1054,6 +1253,32 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   }
   if (!integrate || overflow) return;
   // ---- semi-implicit Euler for the awake / touched movable bodies (free joints: no damping)
+  if constexpr (Coop) {
+#if defined(__CUDA_ARCH__)
+    // one body per lane (read-modify-write of global state: must not be replicated); mov / err combined by ballots
+    __syncwarp();
+    const int b = coop_lane();
+    bool moving = false, bad = false;
+    int sb = 0;
+    if (b < nb) {
+      sb = S.bslot[b];
+      size_t i = oidx(D, sb, e);
+      double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
+      bool tch = (touched >> sb) & 1u;
+      vx += h * acc[1 + b][0]; vy += h * acc[1 + b][1]; w += h * acc[1 + b][2];
+      if (!tch && vx * vx + vy * vy < kSleepV * kSleepV && fabs(w) < kSleepV) { vx = vy = w = 0.0; }
+      double x = D.ox[i] + h * vx, y = D.oy[i] + h * vy, yaw = D.oyaw[i] + h * w;
+      D.ovx[i] = vx; D.ovy[i] = vy; D.ow[i] = w; D.ox[i] = x; D.oy[i] = y; D.oyaw[i] = yaw;
+      moving = vx != 0.0 || vy != 0.0 || w != 0.0;
+      bad = bad_val(x) || bad_val(y) || bad_val(vx) || bad_val(vy) || bad_val(w);
+    }
+    const unsigned handled = __reduce_or_sync(kFullWarp, b < nb ? 1u << sb : 0u);
+    const unsigned nowmov = __reduce_or_sync(kFullWarp, moving ? 1u << sb : 0u);
+    P.mov = (P.mov & ~handled) | nowmov;
+    if (__any_sync(kFullWarp, bad)) P.err = 1;
+    __syncwarp();
+#endif
+  } else
   for (int b = 0; b < nb; ++b) {
     const int s = S.bslot[b];
     size_t i = oidx(D, s, e);
@@ -1365,9 +1590,53 @@ SAG_HD bool hazard_hit(double d2, double size) {  // world.py:151-152: ||robot_x
   return sqrt(d2) <= size;
 }
 
-template <bool QuietOnly, class RB>
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double coop_min(double v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v = fmin(v, __shfl_xor_sync(kFullWarp, v, d));
+  return v;
+}
+// max into a shared-memory bin; lidar values are >= 0 or tiny negatives / -0 that must not be stored, and for those
+// the signed-integer order of the float bits is the float order
+__device__ __forceinline__ void coop_lidar_apply(const LidarHit& H, float* bins, int bstride) {
+  int b0 = H.bin & (kLidarBins - 1), bp = (H.bin + 1) & (kLidarBins - 1), bm = (H.bin + kLidarBins - 1) & (kLidarBins - 1);
+  atomicMax(reinterpret_cast<int*>(bins + b0 * bstride), __float_as_int(H.s0));
+  atomicMax(reinterpret_cast<int*>(bins + bp * bstride), __float_as_int(H.sp));
+  atomicMax(reinterpret_cast<int*>(bins + bm * bstride), __float_as_int(H.sm));
+}
+// pass A of end_of_step with one object per lane: obstacle lidar, hazard flag, min squared distances per kind
+template <class RB>
+__device__ __forceinline__ void pass_a_coop(const Ctx& C, const RB& R, double cs, double sn, float* obs_s, int ostride, bool& hz,
+                                            double& d2v, double& d2p, double& d2b, double& d2x) {
+  const Dev& D = C.D;
+  const int s = coop_lane();
+  __syncwarp();  // the zeroed bins are visible
+  bool hzl = false;
+  double lv = 1e300, lp = 1e300, lb = 1e300, lx = 1e300;
+  if (s < C.L.n) {
+    size_t i = oidx(D, s, C.e);
+    double wx = D.ox[i] - R.q[0], wy = D.oy[i] - R.q[1];
+    double d2 = wx * wx + wy * wy;
+    if (s < C.L.t0) {
+      if (s < C.L.v0) hzl = hazard_hit(d2, D.hazards_size);
+      else if (s < C.L.p0) lv = d2;
+      else lp = d2;
+      coop_lidar_apply(lidar_eval(wx, wy, cs, sn), obs_s, ostride);
+    } else {
+      int kind = slot_kind(C.sp, C.L, s);
+      if (kind_collidable(kind)) { if (kind == K_BUTTON) lb = d2; else lx = d2; }
+    }
+  }
+  hz = __any_sync(kFullWarp, hzl);
+  d2v = coop_min(lv); d2p = coop_min(lp); d2b = coop_min(lb); d2x = coop_min(lx);
+  __syncwarp();
+}
+#endif
+
+template <int Mode, class RB>
 SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const Ctx& C, const RB& R, TaskState& T, const Rng& rng, const PtConst& K,
                         unsigned mov, bool phys_err, bool with_reward, float* obs_s, int ostride, EndOut& O) {
+  constexpr bool QuietOnly = Mode == kStepQuiet, Coop = Mode == kStepCoop;
   const Dev& D = C.D;
   const int e = C.e;
   double sn, cs;
@@ -1376,6 +1645,11 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
   // ---- pass A: hazards / vases / gremlins / pillars -> obstacle lidar, hazard cost, clearance
   bool hz = false;
   double d2v = 1e300, d2p = 1e300, d2b = 1e300, d2x = 1e300;  // min squared centre distance per collidable kind
+  if constexpr (Coop) {
+#if defined(__CUDA_ARCH__)
+    pass_a_coop(C, R, cs, sn, obs_s, ostride, hz, d2v, d2p, d2b, d2x);
+#endif
+  } else {
   // obstacle slots [0, t0) in trips of three: loads and the sqrt / atan2 chains of a trip are independent, the
   // shared-memory bin updates come last (the compiler has to keep those in order)
   for (int s0 = 0; s0 < C.L.t0; s0 += 3) {
@@ -1410,6 +1684,7 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
     double d2 = wx * wx + wy * wy;
     if (kind == K_BUTTON) { if (d2 < d2b) d2b = d2; } else { if (d2 < d2x) d2x = d2; }
   }
+  }
   double clear = 1e30;
   if (d2v < 1e299) clear = fmin(clear, sqrt(d2v) - (RB::kReach + kind_bound(D, K_VASE)));
   if (d2p < 1e299) clear = fmin(clear, sqrt(d2p) - (RB::kReach + kind_bound(D, K_PILLAR)));
@@ -1426,13 +1701,23 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
   bool need = false;
   if (!QuietOnly) {  // (a quiet step ends with positive clearance: no contact is possible)
     const bool near_ = !(clear > 0.0 && mov == 0 && !tendon);
-    need = near_ && (mov != 0 || tendon || robot_overlaps_any(C, R, sn, cs));
+    if constexpr (Coop) {
+#if defined(__CUDA_ARCH__)
+      need = near_ && (mov != 0 || tendon || robot_overlaps_any_coop(C, R, sn, cs));
+#endif
+    } else {
+      need = near_ && (mov != 0 || tendon || robot_overlaps_any(C, R, sn, cs));
+    }
   }
   if (!need) {
     if constexpr (RB::kKind == 1) { CarFree F; car_free_solve(R, sn, cs, K, fs, F); P.qacc[0] = F.qacc[0]; P.qacc[1] = F.qacc[1]; P.qacc[2] = F.qacc[2]; }
     else { double p, q; R.pq(sn, cs, p, q); pt_solve(p, q, K.ia0, K.is0, fs, P.qacc); }
   }
-  if (!QuietOnly) warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, small, P);
+  if constexpr (Coop) {
+    if (need) contact_pass<RB, Scratch, true>(C, R, sn, cs, K, fs, mov, false, 0.0, *S, P);
+  } else if (!QuietOnly) {
+    warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, small, P);
+  }
   qacc[0] = P.qacc[0]; qacc[1] = P.qacc[1]; qacc[2] = P.qacc[2];
   touch = P.touch;
   O.err = P.err;
@@ -1451,6 +1736,22 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
     }
   }
   // ---- pass B: task objects -> objects / goal lidar (safe_adaptation_gym.py:133-139, world.py:219-231)
+  if constexpr (Coop) {
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+    const int s = C.L.t0 + coop_lane();
+    if (s < C.L.n) {
+      int kind = slot_kind(C.sp, C.L, s);
+      int g = slot_group(C, s, kind, T.gbtn, T.bstate, T.amask);
+      if (g != 0) {
+        size_t i = oidx(D, s, e);
+        int off = g == 1 ? 0 : (g == 3 ? 16 : 32);
+        coop_lidar_apply(lidar_eval(D.ox[i] - R.q[0], D.oy[i] - R.q[1], cs, sn), obs_s + off * ostride, ostride);
+      }
+    }
+    __syncwarp();
+#endif
+  } else
   for (int s = C.L.t0; s < C.L.n; ++s) {
     int kind = slot_kind(C.sp, C.L, s);
     int g = slot_group(C, s, kind, T.gbtn, T.bstate, T.amask);
@@ -1511,9 +1812,10 @@ SAG_HD bool env_is_quiet(double clear, const RB& R) { return clear > R.travel_bo
 // ------------------------------------------------------------------------------------------------
 // SafeAdaptationGym.step for one environment (safe_adaptation_gym.py:56-83)
 // ------------------------------------------------------------------------------------------------
-template <bool QuietOnly, class RB>
+template <int Mode, class RB>
 SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2,
                      unsigned char* cost, unsigned char* done) {
+  constexpr bool QuietOnly = Mode == kStepQuiet, Coop = Mode == kStepCoop;
   Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
   C.L = make_slots(C.sp);
   RB R;
@@ -1555,6 +1857,7 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev&
   unsigned char fl = D.flags[e];
   int err = (fl & F_PHYS_ERROR) ? 1 : 0;  // a physics error is sticky until the env is reset
   const bool quiet = QuietOnly ? true : env_is_quiet(D.clear[e], R);
+  (void)Coop;
 #pragma unroll 1
   for (int k = 0; k < RB::kNsub; ++k) {
     double sn, cs, fs[3], fc[3] = {0.0, 0.0, 0.0}, wtau[2] = {0.0, 0.0}, rhs[3], a[3], p, q;
@@ -1562,7 +1865,13 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev&
     R.pq(sn, cs, p, q);
     R.smooth(sn, cs, fs);
     bool need = false;
-    if (!QuietOnly) need = !quiet && (mov != 0 || C.task == T_HAUL_BOX || robot_overlaps_any(C, R, sn, cs));
+    if constexpr (Coop) {
+#if defined(__CUDA_ARCH__)
+      need = !quiet && (mov != 0 || C.task == T_HAUL_BOX || robot_overlaps_any_coop(C, R, sn, cs));
+#endif
+    } else if (!QuietOnly) {
+      need = !quiet && (mov != 0 || C.task == T_HAUL_BOX || robot_overlaps_any(C, R, sn, cs));
+    }
     if constexpr (RB::kKind == 1) {  // car: the wheel-floor friction rows are always there
       if (!need) {
         CarFree F;
@@ -1574,7 +1883,11 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev&
       Phys P;
       P.fc[0] = fc[0]; P.fc[1] = fc[1]; P.fc[2] = fc[2]; P.wtau[0] = wtau[0]; P.wtau[1] = wtau[1];
       P.mov = mov; P.err = 0; P.retry = 0;
-      warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, small, P);
+      if constexpr (Coop) {
+        if (need) contact_pass<RB, Scratch, true>(C, R, sn, cs, K, fs, mov, true, h, *S, P);
+      } else {
+        warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, small, P);
+      }
       fc[0] = P.fc[0]; fc[1] = P.fc[1]; fc[2] = P.fc[2]; wtau[0] = P.wtau[0]; wtau[1] = P.wtau[1];
       mov = P.mov;
       if (P.err) err = 1;
@@ -1613,23 +1926,29 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev&
     time += h;
   }
   EndOut O;
-  end_of_step<QuietOnly, RB>(wmask, S, small, C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
+  end_of_step<Mode, RB>(wmask, S, small, C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
   unsigned char dn = 0;
   if (err || O.err) { dn = 1; fl |= F_PHYS_ERROR; }
   if (O.resample_failed) fl |= F_RESAMPLE_FAILED;
-  // bookkeeping
-  int ns = D.nstep[e] + 1;
-  if (D.max_episode_steps > 0 && ns >= D.max_episode_steps) fl |= F_NEEDS_RESET;
-  if (dn) fl |= F_NEEDS_RESET;
-  D.nstep[e] = ns;
-  D.epret[e] += O.rew[0];
-  D.epcost[e] += O.cost;
-  D.flags[e] = fl;
-  D.time[e] = time;
-  D.clear[e] = O.clear;
-  D.movmask[e] = (int)O.mov;
-  store_robot(D, e, R);
-  store_task_state(D, e, T);
+  // bookkeeping (cooperative mode: read-modify-write of global state by one lane only)
+  bool writer = true;
+#if defined(__CUDA_ARCH__)
+  if constexpr (Coop) { __syncwarp(); writer = coop_lane() == 0; }
+#endif
+  if (writer) {
+    int ns = D.nstep[e] + 1;
+    if (D.max_episode_steps > 0 && ns >= D.max_episode_steps) fl |= F_NEEDS_RESET;
+    if (dn) fl |= F_NEEDS_RESET;
+    D.nstep[e] = ns;
+    D.epret[e] += O.rew[0];
+    D.epcost[e] += O.cost;
+    D.flags[e] = fl;
+    D.time[e] = time;
+    D.clear[e] = O.clear;
+    D.movmask[e] = (int)O.mov;
+    store_robot(D, e, R);
+    store_task_state(D, e, T);
+  }
   reward2[0] = O.rew[0]; reward2[1] = O.rew[1];
   *cost = (unsigned char)(O.cost > 0.0);
   *done = dn;
@@ -1653,7 +1972,7 @@ SAG_HD void env_observe(unsigned wmask, Scratch* S, SmallScratch* small, const D
     if (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0) mov |= 1u << s;
   }
   EndOut O;
-  end_of_step<false, RB>(wmask, S, small, C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
+  end_of_step<kStepFull, RB>(wmask, S, small, C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
   D.clear[e] = O.clear;
   D.movmask[e] = (int)mov;
 }

@@ -180,6 +180,49 @@ __global__ void __launch_bounds__(32) k_step_busy(Dev D, const float* __restrict
   }
 }
 
+// k_step_coop: the work list with ONE WARP per environment (sag_core.cuh "warp-cooperative variants"): the lanes run the
+// step's scalar code redundantly and split the collision phases, the overlap pre-test and the lidar pass between them.
+// A contact environment's step is a long dependent chain (~60 k instructions when run by one thread); what bounds the
+// busy phase is that chain's latency, not throughput, so the lanes are spent on shortening it.
+constexpr int kCoopWarps = 4;  // warps (= environments in flight) per CTA
+template <class RB>
+struct CoopCfg {
+  static constexpr int kObs = RB::kObsDim;
+  static constexpr size_t kTileBytes = (sizeof(float) * kObs + 15) / 16 * 16;
+  static constexpr size_t kPerWarp = kTileBytes + (sizeof(Scratch) + 15) / 16 * 16;
+  static constexpr size_t kSmemBytes = kPerWarp * kCoopWarps;
+};
+
+template <class RB>
+__global__ void __launch_bounds__(32 * kCoopWarps) k_step_coop(const __grid_constant__ Dev D, const float* __restrict__ act,
+                                                              float* __restrict__ obs, double* __restrict__ reward,
+                                                              double* __restrict__ reward2, uint8_t* __restrict__ cost,
+                                                              uint8_t* __restrict__ done) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* mine = smem_raw + (size_t)warp * CoopCfg<RB>::kPerWarp;
+  float* tile = reinterpret_cast<float*>(mine);
+  Scratch* big = reinterpret_cast<Scratch*>(mine + CoopCfg<RB>::kTileBytes);
+  const int count = D.counts[0];
+  for (int i = blockIdx.x * kCoopWarps + warp; i < count; i += gridDim.x * kCoopWarps) {
+    const int e = D.worklist[i];
+    float2 a = reinterpret_cast<const float2*>(act)[e];
+    double rew[2];
+    unsigned char c, d;
+    env_step<kStepCoop, RB>(0xffffffffu, big, nullptr, D, e, a.x, a.y, tile, 1, rew, &c, &d);
+    __syncwarp();
+    if (lane == 0) {
+      reward[e] = rew[0];
+      if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
+      cost[e] = c;
+      done[e] = d;
+    }
+    float* dst = obs + (size_t)e * CoopCfg<RB>::kObs;
+    for (int k = lane; k < CoopCfg<RB>::kObs; k += 32) dst[k] = tile[k];
+    __syncwarp();
+  }
+}
+
 template <class RB>
 __global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -352,6 +395,11 @@ struct Ops {
     if (ce != cudaSuccess) return ce;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_step_busy<G, RB>, 32, BusyCfg<G, RB>::kSmemBytes);
   }
+  static cudaError_t setup_coop(int* per_sm) {
+    cudaError_t ce = cudaFuncSetAttribute(k_step_coop<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CoopCfg<RB>::kSmemBytes);
+    if (ce != cudaSuccess) return ce;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_step_coop<RB>, 32 * kCoopWarps, CoopCfg<RB>::kSmemBytes);
+  }
   static cudaError_t setup(Handle* H) {
     cudaError_t ce = cudaFuncSetAttribute(k_observe<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_rollout<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
@@ -359,7 +407,7 @@ struct Ops {
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, H->device);
     const int G = H->busy_g;
-    ce = G == 1 ? setup_busy<1>(&per_sm) : G == 4 ? setup_busy<4>(&per_sm) : G == 32 ? setup_busy<32>(&per_sm) : setup_busy<8>(&per_sm);
+    ce = G == 0 ? setup_coop(&per_sm) : G == 1 ? setup_busy<1>(&per_sm) : G == 4 ? setup_busy<4>(&per_sm) : G == 32 ? setup_busy<32>(&per_sm) : setup_busy<8>(&per_sm);
     H->busy_grid = sms * (per_sm > 0 ? per_sm : 1);
     return ce;
   }
@@ -371,6 +419,11 @@ struct Ops {
     ce = cudaGetLastError();
     if (ce != cudaSuccess) return ce;
     const int G = H->busy_g;
+    if (G == 0) {  // warp-cooperative busy path
+      const int need = (H->D.n + kCoopWarps - 1) / kCoopWarps;
+      k_step_coop<RB><<<need < H->busy_grid ? need : H->busy_grid, 32 * kCoopWarps, CoopCfg<RB>::kSmemBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
+      return cudaGetLastError();
+    }
     const int chunks = (H->D.n + G - 1) / G;
     const int grid = chunks < H->busy_grid ? chunks : H->busy_grid;
 #define SAG_LAUNCH_BUSY(GG) k_step_busy<GG, RB><<<grid, 32, BusyCfg<GG, RB>::kSmemBytes, s>>>(H->D, act, obs, reward, reward2, cost, done)
@@ -428,7 +481,7 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
     // environments per busy warp: 8 measured best on B200 (sweep 1/2/4/8/32 in DESIGN.md 7); SAG_BUSY_G overrides
     int G = 8;
     const char* gs = getenv("SAG_BUSY_G");
-    if (gs) { int v = atoi(gs); if (v == 1 || v == 4 || v == 8 || v == 32) G = v; }
+    if (gs) { int v = atoi(gs); if (v == 0 || v == 1 || v == 4 || v == 8 || v == 32) G = v; }
     H->busy_g = G;
     cudaError_t ce = SAG_DISPATCH(H, setup(H));
     if (ce != cudaSuccess) { delete H; return fail("sag_create: kernel setup", ce); }

@@ -9,6 +9,7 @@ from safe_adaptation_gym_b200 import tasks
 from safe_adaptation_gym_b200.env import BatchedSafeAdaptationGym
 
 n = 65536
+assert n // 32 >= 2048
 dev = torch.device("cuda:0")
 
 
@@ -28,7 +29,7 @@ def time_steps(env, act, steps=12):
     return ts
 
 
-for K, stride in ((0, 32), (1, 32), (64, 32), (2048, 32), (64, 1), (2048, 1), (8192, 8)):
+for K, stride in [(int(k), 32) for k in os.environ.get("PROBE_K", "0,1,64,2048").split(",")]:
     env = BatchedSafeAdaptationGym("xmls/point.xml", num_envs=n, device=dev, config={"action_noise": 0.0})
     env.seed(1); env.set_task(tasks.GoToGoal())
     _ = env.observation
