@@ -105,19 +105,29 @@ __global__ void __launch_bounds__(kBS, 4) k_step_quiet(Dev D, const float* __res
   float* tile = reinterpret_cast<float*>(smem_raw);  // [kObs][kTileStride]
   int e = blockIdx.x * kBS + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  bool quiet = false;
+  bool quiet = false, hot = false;
   if (e < D.n) {
     RB R;
     load_robot(D, e, task_spec(D.task[e]), R);
-    quiet = !(D.flags[e] & F_PHYS_ERROR) && env_is_quiet(D.clear[e], R);
+    const double clear = D.clear[e];
+    quiet = !(D.flags[e] & F_PHYS_ERROR) && env_is_quiet(clear, R);
+    hot = clear < kHotMargin;  // touching / moving bodies / tendon (clearance -1): the long contact steps, scheduled first
   }
-  // work list append, one atomic per warp
+  // work list append, one atomic per warp and segment: hot environments in [0, counts[0]), the merely near ones in
+  // [stride, stride + counts[1])
   const unsigned busy = __ballot_sync(0xffffffffu, e < D.n && !quiet);
   if (busy) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&D.counts[0], __popc(busy));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if ((busy >> lane) & 1u) D.worklist[base + __popc(busy & ((1u << lane) - 1u))] = e;
+    const unsigned bh = __ballot_sync(0xffffffffu, e < D.n && !quiet && hot), bc = busy & ~bh;
+    int baseh = 0, basec = 0;
+    if (lane == 0) {
+      if (bh) baseh = atomicAdd(&D.counts[0], __popc(bh));
+      if (bc) basec = atomicAdd(&D.counts[1], __popc(bc));
+    }
+    baseh = __shfl_sync(0xffffffffu, baseh, 0);
+    basec = __shfl_sync(0xffffffffu, basec, 0);
+    const unsigned lower = (1u << lane) - 1u;
+    if ((bh >> lane) & 1u) D.worklist[baseh + __popc(bh & lower)] = e;
+    if ((bc >> lane) & 1u) D.worklist[D.stride + basec + __popc(bc & lower)] = e;
   }
   if (!quiet) e = -1;
   if (e >= 0) {
@@ -153,10 +163,10 @@ __global__ void __launch_bounds__(32) k_step_busy(Dev D, const float* __restrict
   Scratch* big = reinterpret_cast<Scratch*>(smem_raw + BusyCfg<G, RB>::kTileBytes);
   SmallScratch* small = reinterpret_cast<SmallScratch*>(smem_raw + BusyCfg<G, RB>::kTileBytes + sizeof(Scratch));
   const int lane = threadIdx.x;
-  const int count = D.counts[0];
+  const int nhot = D.counts[0], count = nhot + D.counts[1];
   for (int chunk = blockIdx.x; chunk * G < count; chunk += gridDim.x) {
     const int i = chunk * G + lane;
-    const int e = (lane < G && i < count) ? D.worklist[i] : -1;
+    const int e = (lane < G && i < count) ? D.worklist[i < nhot ? i : D.stride + (i - nhot)] : -1;
     const unsigned wmask = __ballot_sync(0xffffffffu, e >= 0);
     if (e >= 0) {
       float2 a = reinterpret_cast<const float2*>(act)[e];
@@ -193,8 +203,11 @@ struct CoopCfg {
   static constexpr size_t kSmemBytes = kPerWarp * kCoopWarps;
 };
 
+#ifndef SAG_COOP_MINBLOCKS
+#define SAG_COOP_MINBLOCKS 1
+#endif
 template <class RB>
-__global__ void __launch_bounds__(32 * kCoopWarps) k_step_coop(const __grid_constant__ Dev D, const float* __restrict__ act,
+__global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_coop(const __grid_constant__ Dev D, const float* __restrict__ act,
                                                               float* __restrict__ obs, double* __restrict__ reward,
                                                               double* __restrict__ reward2, uint8_t* __restrict__ cost,
                                                               uint8_t* __restrict__ done) {
@@ -203,9 +216,14 @@ __global__ void __launch_bounds__(32 * kCoopWarps) k_step_coop(const __grid_cons
   unsigned char* mine = smem_raw + (size_t)warp * CoopCfg<RB>::kPerWarp;
   float* tile = reinterpret_cast<float*>(mine);
   Scratch* big = reinterpret_cast<Scratch*>(mine + CoopCfg<RB>::kTileBytes);
-  const int count = D.counts[0];
-  for (int i = blockIdx.x * kCoopWarps + warp; i < count; i += gridDim.x * kCoopWarps) {
-    const int e = D.worklist[i];
+  const int nhot = D.counts[0], count = nhot + D.counts[1];
+  // dynamic fetch (a contact environment takes ~15x a near one): hot entries first, so that the long steps start early
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&D.counts[2], 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= count) break;
+    const int e = D.worklist[i < nhot ? i : D.stride + (i - nhot)];
     float2 a = reinterpret_cast<const float2*>(act)[e];
     double rew[2];
     unsigned char c, d;
@@ -478,8 +496,9 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   Dev& D = H->D;
   dev_from_config(D, *cfg);
   {
-    // environments per busy warp: 8 measured best on B200 (sweep 1/2/4/8/32 in DESIGN.md 7); SAG_BUSY_G overrides
-    int G = 8;
+    // busy path: 0 = warp-cooperative kernel (one warp per environment; default, 1.6x the best scalar setting), else
+    // environments per warp of the scalar busy kernel (8 was the best of 1/4/8/32); SAG_BUSY_G overrides
+    int G = 0;
     const char* gs = getenv("SAG_BUSY_G");
     if (gs) { int v = atoi(gs); if (v == 0 || v == 1 || v == 4 || v == 8 || v == 32) G = v; }
     H->busy_g = G;
