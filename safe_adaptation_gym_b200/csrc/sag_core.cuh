@@ -1176,68 +1176,119 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   const double rr = (1.0 - kImpD0) / kImpD0;
   const double v_inv_lin = 1.0 / (vim + rr * vim), v_inv_tor = 1.0 / (vii + rr * vii);
   const double b_inv_lin = 1.0 / (bim + rr * bim), b_inv_tor = 1.0 / (bii + rr * bii);
+  // one Gauss-Seidel visit of a contact row pair (normal, tangent) or of the tendon row (nk = 1)
+  auto contact_row_update = [&](Row& r, int nk, double& sdf, double& sf) {
+    const int ba = r.ba, bb = r.bb;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k >= nk) break;
+      SAG_PROF(e, 4, 1);
+      double a = 0.0;
+      if (ba >= 0) a += dot3(r.ja[k], acc[ba]);
+      if (bb >= 0) a += dot3(r.jb[k], acc[bb]);
+      const double fo = r.f[k];
+      double fn = fo - (a - r.aref[k] + r.R[k] * fo) * r.inv[k];
+      if (k == 0) { if (fn < 0.0) fn = 0.0; }
+      else { double lim = r.bound * r.f[0]; fn = clampd(fn, -lim, lim); }
+      double df = fn - fo;
+      r.f[k] = fn;
+      sdf += fabs(df); sf += fabs(fn);
+      if (df != 0.0) {
+        if (ba >= 0) { double* ac = acc[ba]; ac[0] += r.wa[k][0] * df; ac[1] += r.wa[k][1] * df; ac[2] += r.wa[k][2] * df; }
+        if (bb >= 0) { double* ac = acc[bb]; ac[0] += r.wb[k][0] * df; ac[1] += r.wb[k][1] * df; ac[2] += r.wb[k][2] * df; }
+      }
+    }
+  };
+  // one visit of the floor-friction rows of body b (slot s): fl = its three row forces, (vx, vy, w) its velocity
+  auto floor_update = [&](int b, int s, double* fl, double vx, double vy, double w, double& sdf, double& sf) {
+    SAG_PROF(e, 5, 1);
+    const bool isb = s == C.L.box;
+    const double Al = isb ? bim : vim, At = isb ? bii : vii;
+    const double inv_lin = isb ? b_inv_lin : v_inv_lin, inv_tor = isb ? b_inv_tor : v_inv_tor;
+    const double flin = isb ? BP.flin : VP.flin, ftor = isb ? BP.ftor : VP.ftor, bfl = isb ? BP.bfl : VP.bfl;
+    double* ac = acc[1 + b];
+    double f0, f1, d0, d1;
+    if (isb && rod) {  // one row across the axis (rolling, body x) and one along it (sliding, body y), clamped separately
+      const double inv_x = 1.0 / (rix + rr * rix), inv_y = 1.0 / (riy + rr * riy);
+      double au = ac[0] * rc + ac[1] * rs, aw = -ac[0] * rs + ac[1] * rc;
+      double vu = vx * rc + vy * rs, vw = -vx * rs + vy * rc;
+      f0 = fl[0] - (au + bfl * vu + rr * rix * fl[0]) * inv_x;
+      f1 = fl[1] - (aw + bfl * vw + rr * riy * fl[1]) * inv_y;
+      f0 = clampd(f0, -BP.fx, BP.fx); f1 = clampd(f1, -BP.fy, BP.fy);
+      d0 = f0 - fl[0]; d1 = f1 - fl[1];
+      double du = d0 * rix, dw = d1 * riy;
+      ac[0] += du * rc - dw * rs; ac[1] += du * rs + dw * rc;
+    } else {
+      f0 = fl[0] - (ac[0] + bfl * vx + rr * Al * fl[0]) * inv_lin;
+      f1 = fl[1] - (ac[1] + bfl * vy + rr * Al * fl[1]) * inv_lin;
+      double nf = sqrt(f0 * f0 + f1 * f1);
+      if (nf > flin) { double sc = flin / nf; f0 *= sc; f1 *= sc; }
+      d0 = f0 - fl[0]; d1 = f1 - fl[1];
+      ac[0] += d0 * Al; ac[1] += d1 * Al;
+    }
+    fl[0] = f0; fl[1] = f1;
+    double f2 = fl[2] - (ac[2] + bfl * w + rr * At * fl[2]) * inv_tor;
+    f2 = clampd(f2, -ftor, ftor);
+    double d2 = f2 - fl[2];
+    ac[2] += d2 * At;
+    fl[2] = f2;
+    sdf += fabs(d0) + fabs(d1) + fabs(d2); sf += fabs(f0) + fabs(f1) + fabs(f2);
+  };
   // projected Gauss-Seidel; stops after kSweeps sweeps or when a sweep changes the forces by < kPgsTol (relative, L1)
+  bool pgs_done = false;
+  if constexpr (Coop) {
+#if defined(__CUDA_ARCH__)
+    // Lane-distributed: lane i keeps row i (its Jacobians, M^-1 J^T, forces) and the floor rows of body i in registers for
+    // all sweeps; the visits stay strictly sequential (Gauss-Seidel), only the owner lane of the visited row runs, the
+    // body accelerations live in shared memory, and the running sums sdf / sf travel from owner to owner by shuffle so
+    // that they are accumulated in the scalar order.  Removes the per-visit reload of ~32 row constants.
+    if (nrow <= 32 && nb <= 32) {
+      pgs_done = true;
+      __syncwarp();
+      const int lane = coop_lane();
+      Row my;
+      if (lane < nrow) my = rows[lane];
+      double fl[3] = {0.0, 0.0, 0.0}, bvx = 0.0, bvy = 0.0, bw = 0.0;
+      int bs = 0;
+      if (lane < nb) { bs = S.bslot[lane]; size_t i = oidx(D, bs, e); bvx = D.ovx[i]; bvy = D.ovy[i]; bw = D.ow[i]; }
+      for (int it = 0; it < kSweeps; ++it) {
+        double sdf = 0.0, sf = 0.0;
+        int last = 0;
+        for (int i = 0; i < nrow; ++i) {
+          sdf = __shfl_sync(kFullWarp, sdf, last); sf = __shfl_sync(kFullWarp, sf, last);
+          if (lane == i) {
+            if (kCarRobot && my.type == 2) wheel_row_update(my, acc[0], acc[my.bb], sdf, sf);
+            else contact_row_update(my, (i == tendon_row) ? 1 : 2, sdf, sf);
+          }
+          __syncwarp();
+          last = i;
+        }
+        for (int b = 0; b < nb; ++b) {
+          sdf = __shfl_sync(kFullWarp, sdf, last); sf = __shfl_sync(kFullWarp, sf, last);
+          if (lane == b) floor_update(b, bs, fl, bvx, bvy, bw, sdf, sf);
+          __syncwarp();
+          last = b;
+        }
+        sdf = __shfl_sync(kFullWarp, sdf, last); sf = __shfl_sync(kFullWarp, sf, last);
+        if (sdf <= kPgsTol * sf) break;
+      }
+      if (lane < nrow) { rows[lane].f[0] = my.f[0]; rows[lane].f[1] = my.f[1]; }
+      __syncwarp();
+    }
+#endif
+  }
+  if (!pgs_done)
   for (int it = 0; it < kSweeps; ++it) {
     double sdf = 0.0, sf = 0.0;
     for (int i = 0; i < nrow; ++i) {
       Row& r = rows[i];
-      const int nk = (i == tendon_row) ? 1 : 2;
-      const int ba = r.ba, bb = r.bb;
-      if (kCarRobot && r.type == 2) { wheel_row_update(r, acc[0], acc[bb], sdf, sf); continue; }
-      for (int k = 0; k < nk; ++k) {
-        SAG_PROF(e, 4, 1);
-        double a = 0.0;
-        if (ba >= 0) a += dot3(r.ja[k], acc[ba]);
-        if (bb >= 0) a += dot3(r.jb[k], acc[bb]);
-        const double fo = r.f[k];
-        double fn = fo - (a - r.aref[k] + r.R[k] * fo) * r.inv[k];
-        if (k == 0) { if (fn < 0.0) fn = 0.0; }
-        else { double lim = r.bound * r.f[0]; fn = clampd(fn, -lim, lim); }
-        double df = fn - fo;
-        r.f[k] = fn;
-        sdf += fabs(df); sf += fabs(fn);
-        if (df != 0.0) {
-          if (ba >= 0) { double* ac = acc[ba]; ac[0] += r.wa[k][0] * df; ac[1] += r.wa[k][1] * df; ac[2] += r.wa[k][2] * df; }
-          if (bb >= 0) { double* ac = acc[bb]; ac[0] += r.wb[k][0] * df; ac[1] += r.wb[k][1] * df; ac[2] += r.wb[k][2] * df; }
-        }
-      }
+      if (kCarRobot && r.type == 2) { wheel_row_update(r, acc[0], acc[r.bb], sdf, sf); continue; }
+      contact_row_update(r, (i == tendon_row) ? 1 : 2, sdf, sf);
     }
     for (int b = 0; b < nb; ++b) {
-      SAG_PROF(e, 5, 1);
       const int s = S.bslot[b];
-      const bool isb = s == C.L.box;
-      const double Al = isb ? bim : vim, At = isb ? bii : vii;
-      const double inv_lin = isb ? b_inv_lin : v_inv_lin, inv_tor = isb ? b_inv_tor : v_inv_tor;
-      const double flin = isb ? BP.flin : VP.flin, ftor = isb ? BP.ftor : VP.ftor, bfl = isb ? BP.bfl : VP.bfl;
       size_t i = oidx(D, s, e);
-      double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
-      double* ac = acc[1 + b];
-      double f0, f1, d0, d1;
-      if (isb && rod) {  // one row across the axis (rolling, body x) and one along it (sliding, body y), clamped separately
-        const double inv_x = 1.0 / (rix + rr * rix), inv_y = 1.0 / (riy + rr * riy);
-        double au = ac[0] * rc + ac[1] * rs, aw = -ac[0] * rs + ac[1] * rc;
-        double vu = vx * rc + vy * rs, vw = -vx * rs + vy * rc;
-        f0 = ffl[b][0] - (au + bfl * vu + rr * rix * ffl[b][0]) * inv_x;
-        f1 = ffl[b][1] - (aw + bfl * vw + rr * riy * ffl[b][1]) * inv_y;
-        f0 = clampd(f0, -BP.fx, BP.fx); f1 = clampd(f1, -BP.fy, BP.fy);
-        d0 = f0 - ffl[b][0]; d1 = f1 - ffl[b][1];
-        double du = d0 * rix, dw = d1 * riy;
-        ac[0] += du * rc - dw * rs; ac[1] += du * rs + dw * rc;
-      } else {
-        f0 = ffl[b][0] - (ac[0] + bfl * vx + rr * Al * ffl[b][0]) * inv_lin;
-        f1 = ffl[b][1] - (ac[1] + bfl * vy + rr * Al * ffl[b][1]) * inv_lin;
-        double nf = sqrt(f0 * f0 + f1 * f1);
-        if (nf > flin) { double sc = flin / nf; f0 *= sc; f1 *= sc; }
-        d0 = f0 - ffl[b][0]; d1 = f1 - ffl[b][1];
-        ac[0] += d0 * Al; ac[1] += d1 * Al;
-      }
-      ffl[b][0] = f0; ffl[b][1] = f1;
-      double f2 = ffl[b][2] - (ac[2] + bfl * w + rr * At * ffl[b][2]) * inv_tor;
-      f2 = clampd(f2, -ftor, ftor);
-      double d2 = f2 - ffl[b][2];
-      ac[2] += d2 * At;
-      ffl[b][2] = f2;
-      sdf += fabs(d0) + fabs(d1) + fabs(d2); sf += fabs(f0) + fabs(f1) + fabs(f2);
+      floor_update(b, s, ffl[b], D.ovx[i], D.ovy[i], D.ow[i], sdf, sf);
     }
     if (sdf <= kPgsTol * sf) break;
   }
