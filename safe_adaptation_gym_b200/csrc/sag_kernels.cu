@@ -72,6 +72,21 @@ __device__ __forceinline__ void write_tile(const float* tile, float* out, int e0
   }
 }
 
+// vectorised variant: 16-byte stores, 4 tile reads each (kObs is a multiple of 4; e0 a multiple of kBS, so rows are
+// 16-byte aligned).  Writes every row of the CTA, including columns the caller did not fill.
+template <int kObs>
+__device__ __forceinline__ void write_tile4(const float* tile, float* out, int e0, int n) {
+  static_assert(kObs % 4 == 0, "observation rows are written as float4");
+  constexpr int kQ = kObs / 4;
+  const int cnt = min(kBS, n - e0) * kQ;
+  float4* dst = reinterpret_cast<float4*>(out + (size_t)e0 * kObs);
+  for (int j = threadIdx.x; j < cnt; j += kBS) {
+    const int t = j / kQ, q = j - t * kQ;
+    const float* src = tile + (4 * q) * kTileStride + t;
+    dst[j] = make_float4(src[0], src[kTileStride], src[2 * kTileStride], src[3 * kTileStride]);
+  }
+}
+
 // ---- the step: two kernels --------------------------------------------------------------------
 // k_step_quiet: one thread per environment over the whole batch.  Quiet environments (nothing within reach for the
 //   whole step, nothing moving: 88-100 % of them under a random policy) take the closed-form path with no contact
@@ -140,8 +155,10 @@ __global__ void __launch_bounds__(kBS, 4) k_step_quiet(Dev D, const float* __res
     cost[e] = c;
     done[e] = d;
   }
-  __syncwarp();
-  write_rows<kObs>(tile + (threadIdx.x & ~31), kTileStride, obs, e);
+  // all kBS rows of the CTA in one coalesced sweep.  The columns of the non-quiet environments hold stale shared memory:
+  // their rows are rewritten by the busy kernel, which always runs after this one on the same stream.
+  __syncthreads();
+  write_tile4<kObs>(tile, obs, blockIdx.x * kBS, D.n);
 }
 
 // G = environments per warp (lanes 0..G-1 active).  A warp executes the union of its lanes' divergent paths and each
