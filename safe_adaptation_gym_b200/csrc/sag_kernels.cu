@@ -57,6 +57,8 @@ struct Handle {
   double* rew_d;
   uint8_t *cost_d, *done_d;
   cudaStream_t own_stream;
+  cudaStream_t copy_stream;          // host-buffer API: bulk device-to-host copies that overlap the busy kernel
+  cudaEvent_t ev_quiet, ev_copied;
   int busy_grid;  // CTAs of k_step_busy: resident CTAs per SM x SMs
   int busy_g;     // environments per warp in k_step_busy
 };
@@ -419,6 +421,25 @@ __global__ void __launch_bounds__(256) k_cost(const double* __restrict__ robot_x
   out[e] = hit ? 1 : 0;                                              // world.py:155
 }
 
+// Host-buffer API: copies the rows of this step's busy environments (both work-list segments) from the device output
+// arrays into MAPPED pinned host buffers, one warp per row (240 / 288 contiguous bytes: full PCIe write bursts).
+template <int kObs>
+__global__ void __launch_bounds__(128) k_fixup_host(const __grid_constant__ Dev D, const float* __restrict__ obs,
+                                                    const double* __restrict__ reward, const uint8_t* __restrict__ cost,
+                                                    const uint8_t* __restrict__ done, float* __restrict__ obs_h,
+                                                    double* __restrict__ reward_h, uint8_t* __restrict__ cost_h,
+                                                    uint8_t* __restrict__ done_h) {
+  const int lane = threadIdx.x & 31, nw = gridDim.x * 4;
+  const int nhot = D.counts[0], count = nhot + D.counts[1];
+  for (int i = blockIdx.x * 4 + (threadIdx.x >> 5); i < count; i += nw) {
+    const int e = D.worklist[i < nhot ? i : D.stride + (i - nhot)];
+    const float* src = obs + (size_t)e * kObs;
+    float* dst = obs_h + (size_t)e * kObs;
+    for (int k = lane; k < kObs; k += 32) dst[k] = src[k];
+    if (lane == 0) { reward_h[e] = reward[e]; cost_h[e] = cost[e]; done_h[e] = done[e]; }
+  }
+}
+
 static inline int grid_for(int n) { return (n + kBS - 1) / kBS; }
 
 // host-side launchers, one set per robot model
@@ -448,11 +469,25 @@ struct Ops {
   }
   static cudaError_t step(Handle* H, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done,
                           cudaStream_t s) {
+    cudaError_t ce = step_quiet(H, act, obs, reward, reward2, cost, done, s);
+    if (ce != cudaSuccess) return ce;
+    return step_busy(H, act, obs, reward, reward2, cost, done, s);
+  }
+  static cudaError_t step_quiet(Handle* H, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost,
+                                uint8_t* done, cudaStream_t s) {
     cudaError_t ce = cudaMemsetAsync(H->D.counts, 0, 4 * sizeof(int), s);
     if (ce != cudaSuccess) return ce;
     k_step_quiet<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kTileBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
-    ce = cudaGetLastError();
-    if (ce != cudaSuccess) return ce;
+    return cudaGetLastError();
+  }
+  // rows of the busy environments -> mapped host buffers (after the bulk copy that carried the quiet rows)
+  static cudaError_t fixup_host(Handle* H, const float* obs, const double* reward, const uint8_t* cost, const uint8_t* done,
+                                float* obs_h, double* reward_h, uint8_t* cost_h, uint8_t* done_h, cudaStream_t s) {
+    k_fixup_host<RB::kObsDim><<<H->busy_grid, 128, 0, s>>>(H->D, obs, reward, cost, done, obs_h, reward_h, cost_h, done_h);
+    return cudaGetLastError();
+  }
+  static cudaError_t step_busy(Handle* H, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done,
+                               cudaStream_t s) {
     const int G = H->busy_g;
     if (G == 0) {  // warp-cooperative busy path
       const int need = (H->D.n + kCoopWarps - 1) / kCoopWarps;
@@ -539,6 +574,9 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   // episode counters start at 0xFFFFFFFF so that the first reset is episode 0
   ce = cudaMemset(D.episode, 0xFF, st * sizeof(unsigned));
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&H->own_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&H->copy_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&H->ev_quiet, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&H->ev_copied, cudaEventDisableTiming);
   if (ce != cudaSuccess) { cudaFree(H->slab); delete H; return fail("sag_create: init", ce); }
   *handle = H;
   return 0;
@@ -550,6 +588,9 @@ int sag_destroy(void* handle) {
   cudaSetDevice(H->device);
   cudaDeviceSynchronize();
   if (H->own_stream) cudaStreamDestroy(H->own_stream);
+  if (H->copy_stream) cudaStreamDestroy(H->copy_stream);
+  if (H->ev_quiet) cudaEventDestroy(H->ev_quiet);
+  if (H->ev_copied) cudaEventDestroy(H->ev_copied);
   cudaFree(H->slab);
   delete H;
   return 0;
@@ -609,14 +650,43 @@ int sag_rollout(void* handle, int k_steps, float* obs, double* reward, uint8_t* 
   return 0;
 }
 
+// device-visible alias of a pinned (page-locked, mapped) host pointer, or nullptr for pageable memory
+static void* mapped_alias(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return a.devicePointer;
+}
+
 int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward_h, uint8_t* cost_h, uint8_t* done_h) {
   Handle* H = (Handle*)handle;
   if (!H || !act_h || !obs_h || !reward_h || !cost_h || !done_h) return fail("sag_step_host: null argument");
   cudaStream_t s = H->own_stream;
-  const size_t n = (size_t)H->D.n;
+  const size_t n = (size_t)H->D.n, od = (size_t)sag_obs_dim(H);
   CK(cudaMemcpyAsync(H->act_d, act_h, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+  float* obs_m = (float*)mapped_alias(obs_h);
+  double* rew_m = (double*)mapped_alias(reward_h);
+  uint8_t *cost_m = (uint8_t*)mapped_alias(cost_h), *done_m = (uint8_t*)mapped_alias(done_h);
+  if (obs_m && rew_m && cost_m && done_m) {
+    // Pinned output buffers: the bulk device-to-host copy starts as soon as the quiet kernel is done and runs under the
+    // busy kernel; the rows the busy kernel produced (5-30 % of them) follow as direct writes into the mapped buffers.
+    cudaStream_t c = H->copy_stream;
+    CK(SAG_DISPATCH(H, step_quiet(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s)));
+    CK(cudaEventRecord(H->ev_quiet, s));
+    CK(cudaStreamWaitEvent(c, H->ev_quiet, 0));
+    CK(cudaMemcpyAsync(obs_h, H->obs_d, n * od * sizeof(float), cudaMemcpyDeviceToHost, c));
+    CK(cudaMemcpyAsync(reward_h, H->rew_d, n * sizeof(double), cudaMemcpyDeviceToHost, c));
+    CK(cudaMemcpyAsync(cost_h, H->cost_d, n, cudaMemcpyDeviceToHost, c));
+    CK(cudaMemcpyAsync(done_h, H->done_d, n, cudaMemcpyDeviceToHost, c));
+    CK(cudaEventRecord(H->ev_copied, c));
+    CK(SAG_DISPATCH(H, step_busy(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s)));
+    CK(cudaStreamWaitEvent(s, H->ev_copied, 0));
+    CK(SAG_DISPATCH(H, fixup_host(H, H->obs_d, H->rew_d, H->cost_d, H->done_d, obs_m, rew_m, cost_m, done_m, s)));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+  }
   CK(SAG_DISPATCH(H, step(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s)));
-  CK(cudaMemcpyAsync(obs_h, H->obs_d, n * (size_t)sag_obs_dim(H) * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(obs_h, H->obs_d, n * od * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(reward_h, H->rew_d, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(cost_h, H->cost_d, n, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(done_h, H->done_d, n, cudaMemcpyDeviceToHost, s));

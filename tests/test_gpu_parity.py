@@ -153,22 +153,30 @@ def test_standalone_cost_kernel_bit_exact(n):
 
 
 def test_host_buffer_api_matches_device_api():
+    """sag_step_host: pinned buffers take the overlapped path (bulk copy under the busy kernel + mapped-memory fix-up of
+    the busy rows), pageable buffers the plain one; both must return exactly what the device API returns"""
     from safe_adaptation_gym_b200 import _abi
-    a = make_env("cuda", 300, "go_to_goal", seed=4)
-    b = make_env("cuda", 300, "go_to_goal", seed=4)
+    n = 4096
+    tasks_ = ["go_to_goal", "push_box", "press_buttons", "go_to_goal"] * (n // 4)
+    a = make_env("cuda", n, tasks_, seed=4)
+    b = make_env("cuda", n, tasks_, seed=4)
     L = _abi.load()
-    n = 300
-    act_h = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-    obs_h = torch.empty((n, 60), dtype=torch.float32).pin_memory()
-    rew_h = torch.empty((n,), dtype=torch.float64).pin_memory()
-    cost_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
-    done_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
-    for t in range(10):
+    pinned = [torch.empty((n, 2), dtype=torch.float32).pin_memory(), torch.empty((n, 60), dtype=torch.float32).pin_memory(),
+              torch.empty((n,), dtype=torch.float64).pin_memory(), torch.empty((n,), dtype=torch.uint8).pin_memory(),
+              torch.empty((n,), dtype=torch.uint8).pin_memory()]
+    pageable = [torch.empty((n, 2), dtype=torch.float32), torch.empty((n, 60), dtype=torch.float32),
+                torch.empty((n,), dtype=torch.float64), torch.empty((n,), dtype=torch.uint8), torch.empty((n,), dtype=torch.uint8)]
+    busy_rows = 0
+    for t in range(160):
+        act_h, obs_h, rew_h, cost_h, done_h = pageable if t % 8 == 7 else pinned
         act_h.uniform_(-1, 1)
+        obs_h.fill_(-7.0)
         L.check(L.L.sag_step_host(a._h, act_h.data_ptr(), obs_h.data_ptr(), rew_h.data_ptr(), cost_h.data_ptr(), done_h.data_ptr()))
         obs, rew, done, info = b.step(act_h.cuda())
-        assert torch.equal(obs.cpu(), obs_h) and torch.equal(rew.cpu(), rew_h)
-        assert torch.equal(info["cost"].cpu().to(torch.uint8), cost_h)
+        assert torch.equal(obs.cpu(), obs_h) and torch.equal(rew.cpu(), rew_h), t
+        assert torch.equal(info["cost"].cpu().to(torch.uint8), cost_h) and torch.equal(done.cpu().to(torch.uint8), done_h), t
+        busy_rows += int((b.get_field("task_f64")[7, :n] < 0.05).sum())   # cached clearance: touching / moving / tendon
+    assert busy_rows > 1000   # the fix-up path really carried rows
 
 
 def test_auto_reset_and_task_stats():
