@@ -11,7 +11,7 @@ A "step" = one env.step over the whole batch (5 physics substeps per env, reward
 value        : env-steps/s with actions resident in HBM, timed per step with CUDA events on the launching
                stream, L2 flushed (256 MiB memset) between steps.
 e2e          : same metric through sag_step_host (C ABI, pinned HOST buffers): H2D of the actions and D2H of
-               obs/reward/cost/done inside the timed region, every step.
+               obs/reward/cost/done inside the timed region, every step (the bulk D2H overlaps the busy kernel).
 roofline     : algorithmic bytes per env-step (2582 B for the fused point go_to_goal step)
                x envs / average k_step duration vs the measured HBM copy bandwidth.
 cpu_baseline : the oracle port (oracle/sag_oracle.c, pthreads) on the box's host cores, bounded sample.
@@ -190,7 +190,7 @@ def main():
         new_actions()
         flush.zero_()  # L2 flush (not timed: outside the event pair)
         evs[i][0].record(stream)
-        launch(W + i); launches += 2; nstep += 1  # k_plan + k_step
+        launch(W + i); launches += 2; nstep += 1  # k_step_quiet + k_step_coop
         if nstep % 1000 == 0:  # episode length used by the reference's tooling (tests/test_safety_gym.py:78)
             L.check(L.L.sag_reset(h, None, 0, 0, sp)); launches += 1
         evs[i][1].record(stream)
@@ -284,7 +284,7 @@ def main():
                     "api": "sag_step_host (C ABI, pinned host buffers)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "fused step = k_step_quiet + k_step_busy", "b_alg_per_env_step": B_ALG_STEP,
+                         "traffic": traffic, "kernel": "fused step = k_step_quiet + k_step_coop", "b_alg_per_env_step": B_ALG_STEP,
                          "peak_source": peak_src,
                          "frac_quiet_phase": B_ALG_STEP * n / first10_s / 1e9 / peak},
             "clocks": clocks,
