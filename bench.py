@@ -128,7 +128,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 200)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 2000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -219,7 +219,7 @@ def main():
 
     # ---- end-to-end through the C ABI with pinned host buffers, on a second handle reset to the same episode so that
     # it covers the same episode phase (steps W .. W+Ke after reset) as `value`
-    Ke = args.e2e_steps or min(K, 200)
+    Ke = args.e2e_steps or min(K, 2000)
     env2 = BatchedSafeAdaptationGym("xmls/point.xml", num_envs=n, device=dev, env_id_base=rank * n, max_episode_steps=0)
     env2.seed(666)
     env2.set_task(tasks.GoToGoal())
