@@ -1,8 +1,9 @@
 // sag_kernels.cu -- CUDA kernels (sm_100a) + the C ABI declared in include/sag_b200.h.
 //
 // The step is two kernels: k_step_quiet, one thread per environment over the whole batch (closed-form
-// path, appends the environments that are not quiet to a work list), and k_step_busy, the work list with a few
-// environments per warp and the contact solver's working set in shared memory.  State is SoA / environment-minor so
+// path, appends the environments that are not quiet to a work list), and k_step_coop, the work list with ONE WARP per
+// environment, the lanes splitting the collision phases / overlap test / lidar pass and the contact solver's working
+// set in shared memory (k_step_busy<G>, its scalar predecessor, stays selectable).  State is SoA / environment-minor so
 // that every global access of a quiet warp is one contiguous 256-byte (fp64) segment; observation tiles (lidar bins
 // are accumulated in them) live in shared memory and are written out row by row.  No tensor cores: nothing here is
 // a dense contraction.  The per-environment logic is in sag_core.cuh; every kernel is templated on the robot model.
@@ -93,10 +94,8 @@ __device__ __forceinline__ void write_tile4(const float* tile, float* out, int e
 // k_step_quiet: one thread per environment over the whole batch.  Quiet environments (nothing within reach for the
 //   whole step, nothing moving: 88-100 % of them under a random policy) take the closed-form path with no contact
 //   code at all; the others are appended to a work list and left untouched.
-// k_step_busy: the work list, 32 environments per CTA of one warp, every lane with its own shared-memory SmallScratch
-//   so that the contact solvers of the 32 environments run concurrently (SIMT), plus one big Scratch for the rare pass
-//   that does not fit.  Putting the busy environments together is what makes their divergent code SIMT-efficient: in
-//   a mixed warp a contact environment runs with 1 of 32 lanes active.
+// k_step_coop (default) / k_step_busy<G>: the work list.  Taking the busy environments out of the batch kernel is what
+//   keeps the quiet path free of contact code (126 registers, no divergence); see the kernels' own comments.
 
 // per-warp write-out of up to 32 observation rows (tile column = lane)
 template <int kObs>
