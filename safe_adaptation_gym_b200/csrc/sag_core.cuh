@@ -2133,7 +2133,20 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
   store_robot(D, e, R);
   store_task_state(D, e, T);
   D.episode[e] = episode; D.nstep[e] = 0; D.time[e] = 0.0; D.epret[e] = 0.0; D.epcost[e] = 0.0; D.flags[e] = fl;
-  D.clear[e] = -1.0;
+  // clearance of the fresh layout (same definition as end_of_step's; scheduling hint only: without it the first step
+  // after a reset would send the whole batch down the contact path)
+  double clear = 1e30;
+  if (C.task == T_HAUL_BOX) clear = -1.0;
+  else {
+    for (int s = C.L.v0; s < C.L.n; ++s) {
+      const int kind = slot_kind(C.sp, C.L, s);
+      if (!kind_collidable(kind)) continue;
+      size_t i = oidx(D, s, e);
+      double dx = D.ox[i] - R.q[0], dy = D.oy[i] - R.q[1];
+      clear = fmin(clear, sqrt(dx * dx + dy * dy) - (RB::kReach + kind_bound(D, kind)));
+    }
+  }
+  D.clear[e] = clear;
   D.movmask[e] = 0;
 }
 

@@ -111,6 +111,15 @@ __device__ __forceinline__ void write_rows(const float* tile, int tstride, float
   }
 }
 
+// The work list of a step: three segments of D.worklist (3 x stride ints), lengths in D.counts[0..2], D.counts[3] = fetch
+// counter of the cooperative kernel.
+//   contact  [0, c0)                  a body moves / tendon / sticky physics error: needs the contact solver for certain
+//   warm     [stride, stride + c1)    nothing moves, clearance below kHotMargin: probably touching
+//   cold     [2 stride, 2 stride + c2) something within reach only
+// Entry i of "contact, warm, cold" in this order (the order in which the busy kernel fetches them):
+__device__ __forceinline__ int worklist_at(const Dev& D, int i, int c0, int c1) {
+  return D.worklist[i < c0 ? i : (i < c0 + c1 ? D.stride + (i - c0) : 2 * D.stride + (i - c0 - c1))];
+}
 // __launch_bounds__(kBS, 4): 4 CTAs / SM (<= 128 registers) so that the whole 65,536-env batch is one wave
 template <class RB>
 __global__ void __launch_bounds__(kBS, 4) k_step_quiet(Dev D, const float* __restrict__ act, float* __restrict__ obs,
@@ -121,29 +130,30 @@ __global__ void __launch_bounds__(kBS, 4) k_step_quiet(Dev D, const float* __res
   float* tile = reinterpret_cast<float*>(smem_raw);  // [kObs][kTileStride]
   int e = blockIdx.x * kBS + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  bool quiet = false, hot = false;
+  bool quiet = false;
+  int seg = 0;
   if (e < D.n) {
     RB R;
-    load_robot(D, e, task_spec(D.task[e]), R);
+    const int task = D.task[e];
+    load_robot(D, e, task_spec(task), R);
     const double clear = D.clear[e];
-    quiet = !(D.flags[e] & F_PHYS_ERROR) && env_is_quiet(clear, R);
-    hot = clear < kHotMargin;  // touching / moving bodies / tendon (clearance -1): the long contact steps, scheduled first
+    const unsigned char fl = D.flags[e];
+    quiet = !(fl & F_PHYS_ERROR) && env_is_quiet(clear, R);
+    const bool contact = (fl & F_PHYS_ERROR) || task == T_HAUL_BOX || D.movmask[e] != 0;
+    seg = contact ? 0 : (clear < kHotMargin ? 1 : 2);
   }
-  // work list append, one atomic per warp and segment: hot environments in [0, counts[0]), the merely near ones in
-  // [stride, stride + counts[1])
+  // work list append, one atomic per warp and segment
   const unsigned busy = __ballot_sync(0xffffffffu, e < D.n && !quiet);
   if (busy) {
-    const unsigned bh = __ballot_sync(0xffffffffu, e < D.n && !quiet && hot), bc = busy & ~bh;
-    int baseh = 0, basec = 0;
-    if (lane == 0) {
-      if (bh) baseh = atomicAdd(&D.counts[0], __popc(bh));
-      if (bc) basec = atomicAdd(&D.counts[1], __popc(bc));
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const unsigned m = __ballot_sync(0xffffffffu, e < D.n && !quiet && seg == g);
+      if (!m) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&D.counts[g], __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if ((m >> lane) & 1u) D.worklist[g * D.stride + base + __popc(m & ((1u << lane) - 1u))] = e;
     }
-    baseh = __shfl_sync(0xffffffffu, baseh, 0);
-    basec = __shfl_sync(0xffffffffu, basec, 0);
-    const unsigned lower = (1u << lane) - 1u;
-    if ((bh >> lane) & 1u) D.worklist[baseh + __popc(bh & lower)] = e;
-    if ((bc >> lane) & 1u) D.worklist[D.stride + basec + __popc(bc & lower)] = e;
   }
   if (!quiet) e = -1;
   if (e >= 0) {
@@ -181,10 +191,10 @@ __global__ void __launch_bounds__(32) k_step_busy(Dev D, const float* __restrict
   Scratch* big = reinterpret_cast<Scratch*>(smem_raw + BusyCfg<G, RB>::kTileBytes);
   SmallScratch* small = reinterpret_cast<SmallScratch*>(smem_raw + BusyCfg<G, RB>::kTileBytes + sizeof(Scratch));
   const int lane = threadIdx.x;
-  const int nhot = D.counts[0], count = nhot + D.counts[1];
+  const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + c1 + D.counts[2];
   for (int chunk = blockIdx.x; chunk * G < count; chunk += gridDim.x) {
     const int i = chunk * G + lane;
-    const int e = (lane < G && i < count) ? D.worklist[i < nhot ? i : D.stride + (i - nhot)] : -1;
+    const int e = (lane < G && i < count) ? worklist_at(D, i, c0, c1) : -1;
     const unsigned wmask = __ballot_sync(0xffffffffu, e >= 0);
     if (e >= 0) {
       float2 a = reinterpret_cast<const float2*>(act)[e];
@@ -234,14 +244,15 @@ __global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_co
   unsigned char* mine = smem_raw + (size_t)warp * CoopCfg<RB>::kPerWarp;
   float* tile = reinterpret_cast<float*>(mine);
   Scratch* big = reinterpret_cast<Scratch*>(mine + CoopCfg<RB>::kTileBytes);
-  const int nhot = D.counts[0], count = nhot + D.counts[1];
-  // dynamic fetch (a contact environment takes ~15x a near one): hot entries first, so that the long steps start early
+  const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + c1 + D.counts[2];
+  // dynamic fetch (a contact environment takes ~15x a near one): contact entries first, then the probably-touching ones,
+  // so that the long steps start early
   for (;;) {
     int i = 0;
-    if (lane == 0) i = atomicAdd(&D.counts[2], 1);
+    if (lane == 0) i = atomicAdd(&D.counts[3], 1);
     i = __shfl_sync(0xffffffffu, i, 0);
     if (i >= count) break;
-    const int e = D.worklist[i < nhot ? i : D.stride + (i - nhot)];
+    const int e = worklist_at(D, i, c0, c1);
     float2 a = reinterpret_cast<const float2*>(act)[e];
     double rew[2];
     unsigned char c, d;
@@ -429,9 +440,9 @@ __global__ void __launch_bounds__(128) k_fixup_host(const __grid_constant__ Dev 
                                                     double* __restrict__ reward_h, uint8_t* __restrict__ cost_h,
                                                     uint8_t* __restrict__ done_h) {
   const int lane = threadIdx.x & 31, nw = gridDim.x * 4;
-  const int nhot = D.counts[0], count = nhot + D.counts[1];
+  const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + c1 + D.counts[2];
   for (int i = blockIdx.x * 4 + (threadIdx.x >> 5); i < count; i += nw) {
-    const int e = D.worklist[i < nhot ? i : D.stride + (i - nhot)];
+    const int e = worklist_at(D, i, c0, c1);
     const float* src = obs + (size_t)e * kObs;
     float* dst = obs_h + (size_t)e * kObs;
     for (int k = lane; k < kObs; k += 32) dst[k] = src[k];
