@@ -632,7 +632,10 @@ static_assert((sizeof(SmallScratch) / 8) % 2 == 1, "SmallScratch stride must be 
 
 // env_step / end_of_step modes: full scalar path (one thread = one environment, contact solver included), quiet-only
 // (no contact code), warp-cooperative (one warp = one environment, device only)
-constexpr int kStepFull = 0, kStepQuiet = 1, kStepCoop = 2;
+// kStepNear: the quiet path plus the exact overlap pre-test in every substep -- for environments that have something within
+// reach but (usually) touch nothing; the step is abandoned (return 1, nothing written that the full path would not
+// write identically) as soon as a robot geom overlaps an object, and the environment is handed to the contact path.
+constexpr int kStepFull = 0, kStepQuiet = 1, kStepCoop = 2, kStepNear = 3;
 
 struct Ctx {  // per-thread view of one environment
   const Dev& D;
@@ -1632,7 +1635,7 @@ SAG_HD void set_mocaps(const Ctx& C, const Rng& rng, TaskState& T, double time) 
 // objects (obstacle kinds before the reward, task objects after it because the reward may move the goal or
 // change button groups).  obs_s: this env's column of the CTA's shared-memory tile (stride ostride).
 // ------------------------------------------------------------------------------------------------
-struct EndOut { double rew[2]; double cost; double clear; unsigned mov, touch; int err; int resample_failed; };
+struct EndOut { double rew[2]; double cost; double clear; unsigned mov, touch; int err; int resample_failed; int bail; };
 
 SAG_HD bool hazard_hit(double d2, double size) {  // world.py:151-152: ||robot_xy - hazard_xy|| <= size, exactly
   double lo = size * 0.999, hi = size * 1.001;
@@ -1687,9 +1690,10 @@ __device__ __forceinline__ void pass_a_coop(const Ctx& C, const RB& R, double cs
 template <int Mode, class RB>
 SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const Ctx& C, const RB& R, TaskState& T, const Rng& rng, const PtConst& K,
                         unsigned mov, bool phys_err, bool with_reward, float* obs_s, int ostride, EndOut& O) {
-  constexpr bool QuietOnly = Mode == kStepQuiet, Coop = Mode == kStepCoop;
+  constexpr bool QuietOnly = Mode == kStepQuiet || Mode == kStepNear, Coop = Mode == kStepCoop, Near = Mode == kStepNear;
   const Dev& D = C.D;
   const int e = C.e;
+  O.bail = 0;
   double sn, cs;
   sag_sincos(R.q[2], &sn, &cs);
   for (int k = 0; k < 48; ++k) obs_s[k * ostride] = 0.0f;
@@ -1750,6 +1754,9 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
   Phys P;
   P.err = 0; P.touch = 0; P.retry = 0;
   bool need = false;
+  if constexpr (Near) {  // forward() at the final state would list a contact: not a contact-free step after all
+    if (!(clear > 0.0) && robot_overlaps_any(C, R, sn, cs)) { O.bail = 1; return; }
+  }
   if (!QuietOnly) {  // (a quiet step ends with positive clearance: no contact is possible)
     const bool near_ = !(clear > 0.0 && mov == 0 && !tendon);
     if constexpr (Coop) {
@@ -1864,9 +1871,9 @@ SAG_HD bool env_is_quiet(double clear, const RB& R) { return clear > R.travel_bo
 // SafeAdaptationGym.step for one environment (safe_adaptation_gym.py:56-83)
 // ------------------------------------------------------------------------------------------------
 template <int Mode, class RB>
-SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2,
+SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2,
                      unsigned char* cost, unsigned char* done) {
-  constexpr bool QuietOnly = Mode == kStepQuiet, Coop = Mode == kStepCoop;
+  constexpr bool QuietOnly = Mode == kStepQuiet || Mode == kStepNear, Coop = Mode == kStepCoop, Near = Mode == kStepNear;
   Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
   C.L = make_slots(C.sp);
   RB R;
@@ -1923,6 +1930,9 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev&
     } else if (!QuietOnly) {
       need = !quiet && (mov != 0 || C.task == T_HAUL_BOX || robot_overlaps_any(C, R, sn, cs));
     }
+    if constexpr (Near) {
+      if (robot_overlaps_any(C, R, sn, cs)) return 1;
+    }
     if constexpr (RB::kKind == 1) {  // car: the wheel-floor friction rows are always there
       if (!need) {
         CarFree F;
@@ -1978,6 +1988,7 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev&
   }
   EndOut O;
   end_of_step<Mode, RB>(wmask, S, small, C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
+  if constexpr (Near) { if (O.bail) return 1; }
   unsigned char dn = 0;
   if (err || O.err) { dn = 1; fl |= F_PHYS_ERROR; }
   if (O.resample_failed) fl |= F_RESAMPLE_FAILED;
@@ -2003,6 +2014,7 @@ SAG_HD void env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev&
   reward2[0] = O.rew[0]; reward2[1] = O.rew[1];
   *cost = (unsigned char)(O.cost > 0.0);
   *done = dn;
+  return 0;
 }
 
 // observation at the current state (reset return value / refresh after state injection)

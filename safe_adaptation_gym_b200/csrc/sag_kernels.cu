@@ -172,6 +172,53 @@ __global__ void __launch_bounds__(kBS, 4) k_step_quiet(Dev D, const float* __res
   write_tile4<kObs>(tile, obs, blockIdx.x * kBS, D.n);
 }
 
+// k_step_near (car only): the warm + cold segments of the work list, one thread per environment like the quiet kernel.
+// Runs the quiet path with the exact overlap pre-test in front of every substep (and of the final forward pass); an
+// environment whose robot does touch something is abandoned before anything is stored and appended to the contact
+// segment.  A near step of the car -- ten substeps with the two-wheel friction solve -- costs ~70 us when a whole warp
+// runs it redundantly in the cooperative kernel and there are thousands of them (its travel bound is large); the point
+// robot's near steps are cheap and few, hide under the contact steps' latency there, and a third launch would only add
+// serial latency (measured: 2.25e8 -> 1.96e8 env-steps/s), so the point robot does not use this kernel.
+template <class RB>
+constexpr bool kNearKernel = RB::kKind == 1;
+
+template <class RB>
+__global__ void __launch_bounds__(kBS, 4) k_step_near(const __grid_constant__ Dev D, const float* __restrict__ act, float* __restrict__ obs,
+                                                    double* __restrict__ reward, double* __restrict__ reward2,
+                                                    uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
+  constexpr int kObs = RB::kObsDim;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);  // [kObs][kTileStride]
+  const int i = blockIdx.x * kBS + threadIdx.x;
+  const int c1 = D.counts[1], c2 = D.counts[2];
+  if (blockIdx.x * kBS >= c1 + c2) return;
+  const int lane = threadIdx.x & 31;
+  int e = i < c1 + c2 ? worklist_at(D, i, 0, c1) : -1;
+  bool bail = false;
+  if (e >= 0) {
+    float2 a = reinterpret_cast<const float2*>(act)[e];
+    double rew[2];
+    unsigned char c, d;
+    bail = env_step<kStepNear, RB>(0u, nullptr, nullptr, D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d) != 0;
+    if (!bail) {
+      reward[e] = rew[0];
+      if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
+      cost[e] = c;
+      done[e] = d;
+    }
+  }
+  const unsigned bm = __ballot_sync(0xffffffffu, bail);
+  if (bm) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&D.counts[0], __popc(bm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (bail) D.worklist[base + __popc(bm & ((1u << lane) - 1u))] = e;
+  }
+  if (bail) e = -1;
+  __syncwarp();
+  write_rows<kObs>(tile + (threadIdx.x & ~31), kTileStride, obs, e);
+}
+
 // G = environments per warp (lanes 0..G-1 active).  A warp executes the union of its lanes' divergent paths and each
 // busy warp is latency-bound, so fewer environments per warp = shorter critical path, more warps = more latency hiding.
 template <int G, class RB>
@@ -191,7 +238,7 @@ __global__ void __launch_bounds__(32) k_step_busy(Dev D, const float* __restrict
   Scratch* big = reinterpret_cast<Scratch*>(smem_raw + BusyCfg<G, RB>::kTileBytes);
   SmallScratch* small = reinterpret_cast<SmallScratch*>(smem_raw + BusyCfg<G, RB>::kTileBytes + sizeof(Scratch));
   const int lane = threadIdx.x;
-  const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + c1 + D.counts[2];
+  const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + (kNearKernel<RB> ? 0 : c1 + D.counts[2]);
   for (int chunk = blockIdx.x; chunk * G < count; chunk += gridDim.x) {
     const int i = chunk * G + lane;
     const int e = (lane < G && i < count) ? worklist_at(D, i, c0, c1) : -1;
@@ -244,7 +291,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_co
   unsigned char* mine = smem_raw + (size_t)warp * CoopCfg<RB>::kPerWarp;
   float* tile = reinterpret_cast<float*>(mine);
   Scratch* big = reinterpret_cast<Scratch*>(mine + CoopCfg<RB>::kTileBytes);
-  const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + c1 + D.counts[2];
+  const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + (kNearKernel<RB> ? 0 : c1 + D.counts[2]);
   // dynamic fetch (a contact environment takes ~15x a near one): contact entries first, then the probably-touching ones,
   // so that the long steps start early
   for (;;) {
@@ -498,6 +545,11 @@ struct Ops {
   }
   static cudaError_t step_busy(Handle* H, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done,
                                cudaStream_t s) {
+    if (kNearKernel<RB>) {
+      k_step_near<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kTileBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
+      cudaError_t ce = cudaGetLastError();
+      if (ce != cudaSuccess) return ce;
+    }
     const int G = H->busy_g;
     if (G == 0) {  // warp-cooperative busy path
       const int need = (H->D.n + kCoopWarps - 1) / kCoopWarps;
