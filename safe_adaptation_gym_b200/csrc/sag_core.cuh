@@ -776,7 +776,7 @@ __device__ __forceinline__ bool coop_find_item(unsigned owners, int cnt, int t, 
 }
 
 // ordered append: lane order = canonical order; n in {0, 1, 2} hits per lane
-__device__ __forceinline__ void coop_append(Con* con, int cap, int& ncon, bool& overflow, int n, const Hit* hits, int ba, int bb) {
+__device__ __forceinline__ bool coop_append(Con* con, int cap, int& ncon, bool& overflow, int n, const Hit* hits, int ba, int bb) {
   const int lane = coop_lane();
   const unsigned m1 = __ballot_sync(kFullWarp, n >= 1), m2 = __ballot_sync(kFullWarp, n >= 2);
   const unsigned lower = (1u << lane) - 1u;
@@ -791,6 +791,7 @@ __device__ __forceinline__ void coop_append(Con* con, int cap, int& ncon, bool& 
   }
   const int tot = ncon + __popc(m1) + __popc(m2);
   if (tot > cap) { overflow = true; ncon = cap; } else ncon = tot;
+  return n > 0 && off < cap;  // this lane's first hit is in the list
 }
 
 // Both collision phases of contact_pass, lane-parallel.  Same outputs: con[0..ncon) in canonical order, overflow, touch,
@@ -840,8 +841,8 @@ __device__ __noinline__ void detect_coop(const Ctx& C, const RB& R, double sn, d
         obj_geom(D, kind, pt, x, y, oc, os, go);
         n = collide(grg, go, hits);
       }
-      coop_append(con, cap, ncon, overflow, n, hits, 0, mvb ? 1 + s : -1);
-      const unsigned tb = __reduce_or_sync(kFullWarp, n ? 1u << s : 0u);
+      const bool stored = coop_append(con, cap, ncon, overflow, n, hits, 0, mvb ? 1 + s : -1);
+      const unsigned tb = __reduce_or_sync(kFullWarp, stored ? 1u << s : 0u);
       touch |= tb;
       active |= __reduce_or_sync(kFullWarp, (n && mvb) ? 1u << s : 0u);
     }
@@ -983,8 +984,9 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
           Con& c = con[ncon++];
           c.ba = 0; c.bb = mvb ? 1 + s : -1;
           c.nx = hits[k].nx; c.ny = hits[k].ny; c.px = hits[k].px; c.py = hits[k].py; c.dist = hits[k].dist;
+          touch |= 1u << s;  // robot_contacts() sees the contacts that made it into the list (mujoco_bridge.py:177-191)
         }
-        if (n) { touch |= 1u << s; if (mvb) active |= 1u << s; }
+        if (n && mvb) active |= 1u << s;
       }
     }
   }
@@ -1689,7 +1691,7 @@ __device__ __forceinline__ void pass_a_coop(const Ctx& C, const RB& R, double cs
 
 template <int Mode, class RB>
 SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const Ctx& C, const RB& R, TaskState& T, const Rng& rng, const PtConst& K,
-                        unsigned mov, bool phys_err, bool with_reward, float* obs_s, int ostride, EndOut& O) {
+                        unsigned mov, bool phys_err, const double* qacc_err, bool with_reward, float* obs_s, int ostride, EndOut& O) {
   constexpr bool QuietOnly = Mode == kStepQuiet || Mode == kStepNear, Coop = Mode == kStepCoop, Near = Mode == kStepNear;
   const Dev& D = C.D;
   const int e = C.e;
@@ -1757,7 +1759,10 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
   if constexpr (Near) {  // forward() at the final state would list a contact: not a contact-free step after all
     if (!(clear > 0.0) && robot_overlaps_any(C, R, sn, cs)) { O.bail = 1; return; }
   }
-  if (!QuietOnly) {  // (a quiet step ends with positive clearance: no contact is possible)
+  // A PhysicsError in physics.step returns the observation at once (safe_adaptation_gym.py:73-75): no forward(), the
+  // accelerometer shows the last substep's acceleration, no reward / cost evaluation.
+  const bool skip_forward = phys_err && qacc_err != nullptr;
+  if (!QuietOnly && !skip_forward) {  // (a quiet step ends with positive clearance: no contact is possible)
     const bool near_ = !(clear > 0.0 && mov == 0 && !tendon);
     if constexpr (Coop) {
 #if defined(__CUDA_ARCH__)
@@ -1767,7 +1772,9 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
       need = near_ && (mov != 0 || tendon || robot_overlaps_any(C, R, sn, cs));
     }
   }
-  if (!need) {
+  if (skip_forward) {
+    P.qacc[0] = qacc_err[0]; P.qacc[1] = qacc_err[1]; P.qacc[2] = qacc_err[2];
+  } else if (!need) {
     if constexpr (RB::kKind == 1) { CarFree F; car_free_solve(R, sn, cs, K, fs, F); P.qacc[0] = F.qacc[0]; P.qacc[1] = F.qacc[1]; P.qacc[2] = F.qacc[2]; }
     else { double p, q; R.pq(sn, cs, p, q); pt_solve(p, q, K.ia0, K.is0, fs, P.qacc); }
   }
@@ -1786,7 +1793,8 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
   // ---- reward (may resample the goal / change button groups) and cost
   O.rew[0] = O.rew[1] = 0.0; O.cost = 0.0; O.resample_failed = 0;
   if (with_reward) {
-    if (phys_err || O.err) { O.rew[0] = -10.0; }                            // :73-75
+    if (phys_err) { O.rew[0] = -10.0; }                                     // :73-75 (an error raised by forward() itself,
+                                                                            // O.err, is sticky and takes this path next step)
     else {
       if (compute_reward(C, rng, R, T, touch, O.rew)) O.resample_failed = 1;  // :77
       unsigned obstacle_mask = C.L.t0 >= 32 ? 0xffffffffu : ((1u << C.L.t0) - 1u);
@@ -1916,6 +1924,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
   int err = (fl & F_PHYS_ERROR) ? 1 : 0;  // a physics error is sticky until the env is reset
   const bool quiet = QuietOnly ? true : env_is_quiet(D.clear[e], R);
   (void)Coop;
+  double qacc_err[3] = {0.0, 0.0, 0.0};
 #pragma unroll 1
   for (int k = 0; k < RB::kNsub; ++k) {
     double sn, cs, fs[3], fc[3] = {0.0, 0.0, 0.0}, wtau[2] = {0.0, 0.0}, rhs[3], a[3], p, q;
@@ -1933,11 +1942,13 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
     if constexpr (Near) {
       if (robot_overlaps_any(C, R, sn, cs)) return 1;
     }
+    double subq[3] = {0.0, 0.0, 0.0};  // this substep's forward-dynamics acceleration, if a solve produced one
     if constexpr (RB::kKind == 1) {  // car: the wheel-floor friction rows are always there
       if (!need) {
         CarFree F;
         car_free_solve(R, sn, cs, K, fs, F);
         fc[0] = F.fc[0]; fc[1] = F.fc[1]; fc[2] = F.fc[2]; wtau[0] = F.wtau[0]; wtau[1] = F.wtau[1];
+        subq[0] = F.qacc[0]; subq[1] = F.qacc[1]; subq[2] = F.qacc[2];
       }
     }
     if (!QuietOnly) {
@@ -1952,6 +1963,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
       fc[0] = P.fc[0]; fc[1] = P.fc[1]; fc[2] = P.fc[2]; wtau[0] = P.wtau[0]; wtau[1] = P.wtau[1];
       mov = P.mov;
       if (P.err) err = 1;
+      if (need) { subq[0] = P.qacc[0]; subq[1] = P.qacc[1]; subq[2] = P.qacc[2]; }
     }
     rhs[0] = fs[0] + fc[0]; rhs[1] = fs[1] + fc[1]; rhs[2] = fs[2] + fc[2];
     pt_solve(p, q, K.iah, K.ish, rhs, a);   // (M + hD) a = f: implicit joint damping
@@ -1984,13 +1996,18 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d) if (bad_val(R.q[d]) || bad_val(R.v[d]) || bad_val(a[d])) err = 1;
+    if (err) {  // PhysicsError: the observation will show the acceleration of the last forward-dynamics pass of step()
+      if (RB::kKind == 0 && !need) pt_solve(p, q, K.ia0, K.is0, fs, subq);
+      qacc_err[0] = subq[0]; qacc_err[1] = subq[1]; qacc_err[2] = subq[2];
+    }
     time += h;
   }
   EndOut O;
-  end_of_step<Mode, RB>(wmask, S, small, C, R, T, rng, K, mov, err != 0, true, obs_s, ostride, O);
+  end_of_step<Mode, RB>(wmask, S, small, C, R, T, rng, K, mov, err != 0, qacc_err, true, obs_s, ostride, O);
   if constexpr (Near) { if (O.bail) return 1; }
   unsigned char dn = 0;
-  if (err || O.err) { dn = 1; fl |= F_PHYS_ERROR; }
+  if (err) { dn = 1; fl |= F_PHYS_ERROR; }
+  if (O.err) fl |= F_PHYS_ERROR;
   if (O.resample_failed) fl |= F_RESAMPLE_FAILED;
   // bookkeeping (cooperative mode: read-modify-write of global state by one lane only)
   bool writer = true;
@@ -2035,7 +2052,7 @@ SAG_HD void env_observe(unsigned wmask, Scratch* S, SmallScratch* small, const D
     if (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0) mov |= 1u << s;
   }
   EndOut O;
-  end_of_step<kStepFull, RB>(wmask, S, small, C, R, T, rng, K, mov, false, false, obs_s, ostride, O);
+  end_of_step<kStepFull, RB>(wmask, S, small, C, R, T, rng, K, mov, false, nullptr, false, obs_s, ostride, O);
   D.clear[e] = O.clear;
   D.movmask[e] = (int)mov;
 }

@@ -156,3 +156,44 @@ def run_parity(backend, task_names, n, steps, seed, config=None, policy="drive",
     stats["moved_objects"] = float(np.abs(oo[:, :, :2] - o0[:, :, :2]).max())
     env.close()
     return stats
+
+
+def run_overflow_case(backend, robot="point"):
+    """Capacity overflow = the reference's PhysicsError path (safe_adaptation_gym.py:73-75: reward -10, done, cost 0):
+    all ten vases of go_to_goal are stacked into one heap that the robot drives into, so the contact list (16) and the
+    constrained-body table (8) overflow.  Same injected state in the batched env and in the oracle; exact agreement."""
+    n = 4
+    cfg = {"action_noise": 0.0}
+    env = make_env(backend, n, "go_to_goal", 77, cfg, robot=robot)
+    orc = make_oracles(n, "go_to_goal", 77, cfg, robot=robot)
+    objs = env.get_field("objects")
+    rob = env.get_field("robot")
+    for e in range(n):
+        rx, ry = float(rob[0, e]), float(rob[1, e])
+        for k, s in enumerate(range(9, 19)):          # vase slots
+            x, y = rx + 0.16 + 0.03 * (k % 4) + 0.01 * e, ry + 0.03 * (k // 4) - 0.03
+            objs[0, s, e], objs[1, s, e], objs[2, s, e] = x, y, 0.1 * k
+            orc[e].set_obj(s, x=x, y=y, yaw=0.1 * k)
+        st = orc[e].robot_state; st[2] = 0.0; st[3] = 0.5
+        orc[e].robot_state = st
+        rob[2, e], rob[3, e] = 0.0, 0.5
+    env.set_field("objects", objs); env.set_field("robot", rob)
+    _ = env.observation
+    for o in orc:
+        o.forward()
+    dones = 0
+    for t in range(6):
+        acts = np.tile(np.array([[1.0, 0.0]], dtype=np.float32), (n, 1))
+        if robot == "car":
+            acts[:] = 0.02
+        obs, rew, done, info = env.step(torch.from_numpy(acts))
+        for e in range(n):
+            oobs, orew, ocost, odone, rc = orc[e].step(acts[e].astype(np.float64))
+            assert bool(done[e]) == odone and float(rew[e]) == orew[0] and float(info["cost"][e]) == ocost, (t, e)
+            np.testing.assert_array_equal(obs[e].cpu().numpy(), oobs.astype(np.float32))
+            dones += int(odone)
+        r1, o1 = env_state(env)
+        ro, oo = oracle_state(orc)
+        np.testing.assert_array_equal(r1, ro); np.testing.assert_array_equal(o1, oo)
+    env.close()
+    return dones

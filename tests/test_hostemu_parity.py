@@ -55,3 +55,9 @@ def test_adaptation_knobs_ctrl_range_scale_and_random_bound(robot):
     cfg = {"robot_ctrl_range_scale": 0.6, "random_bound": True, "action_noise": 0.01}
     run_parity("hostemu", ["go_to_goal", "push_box", "press_buttons", "unsupervised"] * 4, n=16, steps=80, seed=41, config=cfg,
                policy="random", robot=robot)
+
+
+@pytest.mark.parametrize("robot", ["point", "car"])
+def test_capacity_overflow_is_a_physics_error(robot):
+    from common import run_overflow_case
+    assert run_overflow_case("hostemu", robot) >= 4   # every env hit the PhysicsError path (sticky until reset)
