@@ -197,3 +197,59 @@ def run_overflow_case(backend, robot="point"):
         np.testing.assert_array_equal(r1, ro); np.testing.assert_array_equal(o1, oo)
     env.close()
     return dones
+
+
+def run_chain_case(backend, robot="point", task="go_to_goal", steps=60):
+    """Several movable bodies in one solve, below the capacity limits: the vases are lined up in front of the robot with
+    1 cm gaps (every second one rotated), the robot pushes the first into the second into the third ...  Exercises
+    multi-body Gauss-Seidel, the object-pair phase, floor rows of many bodies and sleeping, in every kernel variant."""
+    n = 6
+    cfg = {"action_noise": 0.0}
+    env = make_env(backend, n, task, 78, cfg, robot=robot)
+    orc = make_oracles(n, task, 78, cfg, robot=robot)
+    objs = env.get_field("objects")
+    rob = env.get_field("robot")
+    kinds = orc[0].objects()[:, 0].astype(int)
+    vases = [s for s in range(len(kinds)) if kinds[s] == O.VASE]
+    for e in range(n):
+        rx, ry = float(rob[0, e]), float(rob[1, e])
+        heading = 0.0 if robot == "point" else np.pi / 2   # the car drives along body -y: yaw pi/2 -> world +x
+        for k, s in enumerate(vases):
+            if k < 2 + e:   # 2 .. 7 vases in the chain
+                x, y, yaw = rx + 0.33 + 0.21 * k, ry + 0.004 * k, (0.3 if k % 2 else 0.0)
+            else:           # the rest far away
+                x, y, yaw = rx + 3.0 + 0.5 * k, ry + 3.0, 0.0
+            objs[0, s, e], objs[1, s, e], objs[2, s, e] = x, y, yaw
+            orc[e].set_obj(s, x=x, y=y, yaw=yaw)
+        for s in range(len(kinds)):   # everything else out of the way
+            if kinds[s] in (O.PILLAR, O.HAZARD, O.BUTTON, O.BOX):
+                x, y = rx - 3.0 - 0.3 * s, ry - 3.0
+                objs[0, s, e], objs[1, s, e] = x, y
+                orc[e].set_obj(s, x=x, y=y)
+        st = orc[e].robot_state; st[2] = heading
+        orc[e].robot_state = st
+        rob[2, e] = heading
+    env.set_field("objects", objs); env.set_field("robot", rob)
+    _ = env.observation
+    for o in orc:
+        o.forward()
+    moved, maxcon = 0.0, 0
+    o0 = oracle_state(orc)[1]
+    for t in range(steps):
+        acts = np.tile(np.array([[1.0, 0.0]], dtype=np.float32), (n, 1))
+        if robot == "car":
+            acts[:] = np.array([[0.02, 0.02]], dtype=np.float32)   # both wheels forward: the car drives along body -y
+        obs, rew, done, info = env.step(torch.from_numpy(acts))
+        for e in range(n):
+            oobs, orew, ocost, odone, rc = orc[e].step(acts[e].astype(np.float64))
+            assert bool(done[e]) == odone and float(info["cost"][e]) == ocost, (t, e)
+            np.testing.assert_array_equal(np.atleast_1d(rew[e].cpu().numpy()), orew[:1], err_msg=f"step {t} env {e}")
+            np.testing.assert_array_equal(obs[e].cpu().numpy(), oobs.astype(np.float32), err_msg=f"step {t} env {e}")
+            maxcon = max(maxcon, len(orc[e].contacts()))
+        r1, o1 = env_state(env)
+        ro, oo = oracle_state(orc)
+        np.testing.assert_array_equal(r1, ro, err_msg=f"step {t}"); np.testing.assert_array_equal(o1, oo, err_msg=f"step {t}")
+    moved = float(np.abs(oo[:, :, :2] - o0[:, :, :2]).max())
+    nmoved = int((np.abs(oo[:, :, :2] - o0[:, :, :2]).max(axis=2) > 1e-6).sum(axis=1).max())
+    env.close()
+    return moved, nmoved, maxcon

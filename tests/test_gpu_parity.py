@@ -255,3 +255,11 @@ def test_adaptation_knobs_ctrl_range_scale_and_random_bound(robot):
 def test_capacity_overflow_is_a_physics_error(robot):
     from common import run_overflow_case
     assert run_overflow_case("cuda", robot) >= 4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot", ["point", "car"])
+def test_chain_of_pushed_bodies(robot):
+    from common import run_chain_case
+    moved, nmoved, maxcon = run_chain_case("cuda", robot, steps=100)
+    assert moved > 0.05 and nmoved >= 3 and maxcon >= 4, (moved, nmoved, maxcon)
