@@ -172,7 +172,8 @@ struct Dev {
   int* cgtimer;
   int* movmask;  // bit s: movable object s has a non-zero velocity (derived state, rebuilt by env_observe)
   // work list of the environments that are not quiet in the current step (k_step_quiet -> k_step_busy)
-  int *worklist, *counts;  // counts[0] = length
+  int *worklist, *counts;  // work list segments and their lengths (sag_kernels.cu)
+  int* counts_next;        // the other counter set: zeroed by this step's quiet kernel for the next step
   double *time, *clear;
   unsigned *ctr, *episode;
   int* nstep;

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kBS, 4) k_step_quiet(Dev D, const float* __res
   float* tile = reinterpret_cast<float*>(smem_raw);  // [kObs][kTileStride]
   int e = blockIdx.x * kBS + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x < 4) D.counts_next[threadIdx.x] = 0;
   bool quiet = false;
   int seg = 0;
   if (e < D.n) {
@@ -532,8 +533,9 @@ struct Ops {
   }
   static cudaError_t step_quiet(Handle* H, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost,
                                 uint8_t* done, cudaStream_t s) {
-    cudaError_t ce = cudaMemsetAsync(H->D.counts, 0, 4 * sizeof(int), s);
-    if (ce != cudaSuccess) return ce;
+    // two counter sets used alternately: this step's is zero already (cleared by the previous step's quiet kernel, which
+    // saves a memset node per step); steps of one handle must be stream-ordered
+    int* t = H->D.counts; H->D.counts = H->D.counts_next; H->D.counts_next = t;
     k_step_quiet<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kTileBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
     return cudaGetLastError();
   }

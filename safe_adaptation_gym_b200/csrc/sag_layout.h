@@ -54,7 +54,7 @@ inline void slab_bind(Dev& D, const SlabLayout& L, char* base) {
   D.flags = (unsigned char*)(base + L.off[SAG_F_FLAGS]);
   D.rext = (double*)(base + L.off[SAG_F_ROBOT_EXT]);
   int32_t* sc = (int32_t*)(base + L.sched_off);
-  D.worklist = sc; D.counts = sc + 3 * st;
+  D.worklist = sc; D.counts = sc + 3 * st; D.counts_next = D.counts + 8;
 }
 
 inline void dev_from_config(Dev& D, const SagConfig& c) {
