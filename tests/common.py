@@ -221,8 +221,19 @@ def run_chain_case(backend, robot="point", task="go_to_goal", steps=60):
                 x, y, yaw = rx + 3.0 + 0.5 * k, ry + 3.0, 0.0
             objs[0, s, e], objs[1, s, e], objs[2, s, e] = x, y, yaw
             orc[e].set_obj(s, x=x, y=y, yaw=yaw)
+        boxes = [s for s in range(len(kinds)) if kinds[s] in (O.BOX, O.ROD, O.BALL)]
+        if boxes:   # the task's movable body goes first in the chain, the vases behind it
+            s = boxes[0]
+            x, y = rx + 0.45, ry + 0.01
+            objs[0, s, e], objs[1, s, e], objs[2, s, e] = x, y, 0.2 * e
+            orc[e].set_obj(s, x=x, y=y, yaw=0.2 * e)
+            for k, sv in enumerate(vases):
+                if k < 2 + e // 2:
+                    x, y, yaw = rx + 0.45 + 0.42 + 0.21 * k, ry + 0.004 * k, (0.3 if k % 2 else 0.0)
+                    objs[0, sv, e], objs[1, sv, e], objs[2, sv, e] = x, y, yaw
+                    orc[e].set_obj(sv, x=x, y=y, yaw=yaw)
         for s in range(len(kinds)):   # everything else out of the way
-            if kinds[s] in (O.PILLAR, O.HAZARD, O.BUTTON, O.BOX):
+            if kinds[s] in (O.PILLAR, O.HAZARD, O.BUTTON):
                 x, y = rx - 3.0 - 0.3 * s, ry - 3.0
                 objs[0, s, e], objs[1, s, e] = x, y
                 orc[e].set_obj(s, x=x, y=y)

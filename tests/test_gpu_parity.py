@@ -263,3 +263,12 @@ def test_chain_of_pushed_bodies(robot):
     from common import run_chain_case
     moved, nmoved, maxcon = run_chain_case("cuda", robot, steps=100)
     assert moved > 0.05 and nmoved >= 3 and maxcon >= 4, (moved, nmoved, maxcon)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["push_box", "roll_rod", "dribble_ball"])
+def test_chain_behind_the_task_body(task):
+    """the robot pushes the box / rod / ball, which pushes a row of vases"""
+    from common import run_chain_case
+    moved, nmoved, maxcon = run_chain_case("cuda", "point", task=task, steps=100)
+    assert moved > 0.05 and nmoved >= 2 and maxcon >= 2, (moved, nmoved, maxcon)
