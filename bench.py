@@ -279,6 +279,7 @@ def main():
                        "l2": "flushed between steps (256 MiB memset outside the event pair)", "action_noise": 0.01,
                        "episode_phase": f"steps {W}..{W + K} after reset (1000-step episodes)"},
             "value_l2_warm": value_warm,
+            "value_l2_warm_note": f"back-to-back steps without the flush, LATER episode phase (steps {W + K}..{W + 2 * K}): more contacts than `value`'s phase",
             "ms_per_step_first10": float(sum(ms[:10]) / max(1, len(ms[:10]))), "ms_per_step_last10": float(sum(ms[-10:]) / max(1, len(ms[-10:]))),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "api": "sag_step_host (C ABI, pinned host buffers)"},
