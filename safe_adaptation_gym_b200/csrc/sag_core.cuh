@@ -1123,11 +1123,27 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
     }
   }
   if (overflow) { ncon = 0; tendon = false; }  // car: the wheel rows are still solved, nothing else
-  for (int i = 0; i < ncon; ++i) {
+  // one row pair per active contact, in contact order.  Cooperative mode: contact i is set up by lane i (ncon <= 16),
+  // the row index is the rank of the contact among the active ones.
+  int i_begin = 0, i_end = ncon, my_row = 0;
+  (void)my_row;
+#if defined(__CUDA_ARCH__)
+  if constexpr (Coop) {
+    __syncwarp();
+    const int lane = coop_lane();
+    bool act = false;
+    if (lane < ncon) { const Con& c = con[lane]; act = c.dist < 0.0 && !(c.ba < 0 && c.bb < 0); }
+    const unsigned am = __ballot_sync(kFullWarp, act);
+    my_row = nrow + __popc(am & ((1u << lane) - 1u));
+    nrow += __popc(am);
+    i_begin = act ? lane : 0; i_end = act ? lane + 1 : 0;
+  }
+#endif
+  for (int i = i_begin; i < i_end; ++i) {
     const Con c = con[i];
     if (!(c.dist < 0.0)) continue;
     if (c.ba < 0 && c.bb < 0) continue;
-    Row& r = rows[nrow++];
+    Row& r = Coop ? rows[my_row] : rows[nrow++];
     r.type = 0; r.pad_ = 0; r.bound = kMu;  // contact rows: friction coefficient of the pair
     double cb = bdamp, ck = kbase;
     if (bkind > K_BOX && (c.ba - 1 == C.L.box || c.bb - 1 == C.L.box)) {  // priority-1 geom: its friction / solref
@@ -1158,6 +1174,9 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
       r.f[k] = 0.0;
     }
   }
+#if defined(__CUDA_ARCH__)
+  if constexpr (Coop) __syncwarp();
+#endif
   if (tendon) {
     Row& r = rows[nrow]; tendon_row = nrow++;
     r.type = 0; r.pad_ = 0; r.bound = 0.0;
