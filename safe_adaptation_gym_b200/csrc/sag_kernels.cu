@@ -292,6 +292,9 @@ __global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_co
   unsigned char* mine = smem_raw + (size_t)warp * CoopCfg<RB>::kPerWarp;
   float* tile = reinterpret_cast<float*>(mine);
   Scratch* big = reinterpret_cast<Scratch*>(mine + CoopCfg<RB>::kTileBytes);
+  // launched with programmatic stream serialization where possible (Ops::step_busy): the grid may be resident before the
+  // preceding kernel has finished; everything that kernel wrote is visible after this call (no-op otherwise)
+  cudaGridDependencySynchronize();
   const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + (kNearKernel<RB> ? 0 : c1 + D.counts[2]);
   // dynamic fetch (a contact environment takes ~15x a near one): contact entries first, then the probably-touching ones,
   // so that the long steps start early
@@ -555,8 +558,17 @@ struct Ops {
     const int G = H->busy_g;
     if (G == 0) {  // warp-cooperative busy path
       const int need = (H->D.n + kCoopWarps - 1) / kCoopWarps;
-      k_step_coop<RB><<<need < H->busy_grid ? need : H->busy_grid, 32 * kCoopWarps, CoopCfg<RB>::kSmemBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
-      return cudaGetLastError();
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(need < H->busy_grid ? need : H->busy_grid);
+      cfg.blockDim = dim3(32 * kCoopWarps);
+      cfg.dynamicSmemBytes = CoopCfg<RB>::kSmemBytes;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;  // hides this launch's latency behind the previous kernel's tail
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, k_step_coop<RB>, H->D, act, obs, reward, reward2, cost, done);
     }
     const int chunks = (H->D.n + G - 1) / G;
     const int grid = chunks < H->busy_grid ? chunks : H->busy_grid;
