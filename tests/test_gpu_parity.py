@@ -152,19 +152,21 @@ def test_standalone_cost_kernel_bit_exact(n):
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
 
 
-def test_host_buffer_api_matches_device_api():
+@pytest.mark.parametrize("robot", ["point", "car"])
+def test_host_buffer_api_matches_device_api(robot):
     """sag_step_host: pinned buffers take the overlapped path (bulk copy under the busy kernel + mapped-memory fix-up of
     the busy rows), pageable buffers the plain one; both must return exactly what the device API returns"""
     from safe_adaptation_gym_b200 import _abi
     n = 4096
+    od = 60 if robot == "point" else 72
     tasks_ = ["go_to_goal", "push_box", "press_buttons", "go_to_goal"] * (n // 4)
-    a = make_env("cuda", n, tasks_, seed=4)
-    b = make_env("cuda", n, tasks_, seed=4)
+    a = make_env("cuda", n, tasks_, seed=4, robot=robot)
+    b = make_env("cuda", n, tasks_, seed=4, robot=robot)
     L = _abi.load()
-    pinned = [torch.empty((n, 2), dtype=torch.float32).pin_memory(), torch.empty((n, 60), dtype=torch.float32).pin_memory(),
+    pinned = [torch.empty((n, 2), dtype=torch.float32).pin_memory(), torch.empty((n, od), dtype=torch.float32).pin_memory(),
               torch.empty((n,), dtype=torch.float64).pin_memory(), torch.empty((n,), dtype=torch.uint8).pin_memory(),
               torch.empty((n,), dtype=torch.uint8).pin_memory()]
-    pageable = [torch.empty((n, 2), dtype=torch.float32), torch.empty((n, 60), dtype=torch.float32),
+    pageable = [torch.empty((n, 2), dtype=torch.float32), torch.empty((n, od), dtype=torch.float32),
                 torch.empty((n,), dtype=torch.float64), torch.empty((n,), dtype=torch.uint8), torch.empty((n,), dtype=torch.uint8)]
     busy_rows = 0
     for t in range(160):
