@@ -1204,13 +1204,19 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   // one Gauss-Seidel visit of a contact row pair (normal, tangent) or of the tendon row (nk = 1)
   auto contact_row_update = [&](Row& r, int nk, double& sdf, double& sf) {
     const int ba = r.ba, bb = r.bb;
+    // the two bodies' accelerations stay in registers for the whole visit (one load and one store each instead of one
+    // per k; same arithmetic)
+    double aa[3] = {0.0, 0.0, 0.0}, ab[3] = {0.0, 0.0, 0.0};
+    if (ba >= 0) { aa[0] = acc[ba][0]; aa[1] = acc[ba][1]; aa[2] = acc[ba][2]; }
+    if (bb >= 0) { ab[0] = acc[bb][0]; ab[1] = acc[bb][1]; ab[2] = acc[bb][2]; }
+    bool changed = false;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       if (k >= nk) break;
       SAG_PROF(e, 4, 1);
       double a = 0.0;
-      if (ba >= 0) a += dot3(r.ja[k], acc[ba]);
-      if (bb >= 0) a += dot3(r.jb[k], acc[bb]);
+      if (ba >= 0) a += dot3(r.ja[k], aa);
+      if (bb >= 0) a += dot3(r.jb[k], ab);
       const double fo = r.f[k];
       double fn = fo - (a - r.aref[k] + r.R[k] * fo) * r.inv[k];
       if (k == 0) { if (fn < 0.0) fn = 0.0; }
@@ -1219,9 +1225,14 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
       r.f[k] = fn;
       sdf += fabs(df); sf += fabs(fn);
       if (df != 0.0) {
-        if (ba >= 0) { double* ac = acc[ba]; ac[0] += r.wa[k][0] * df; ac[1] += r.wa[k][1] * df; ac[2] += r.wa[k][2] * df; }
-        if (bb >= 0) { double* ac = acc[bb]; ac[0] += r.wb[k][0] * df; ac[1] += r.wb[k][1] * df; ac[2] += r.wb[k][2] * df; }
+        changed = true;
+        if (ba >= 0) { aa[0] += r.wa[k][0] * df; aa[1] += r.wa[k][1] * df; aa[2] += r.wa[k][2] * df; }
+        if (bb >= 0) { ab[0] += r.wb[k][0] * df; ab[1] += r.wb[k][1] * df; ab[2] += r.wb[k][2] * df; }
       }
+    }
+    if (changed) {
+      if (ba >= 0) { acc[ba][0] = aa[0]; acc[ba][1] = aa[1]; acc[ba][2] = aa[2]; }
+      if (bb >= 0) { acc[bb][0] = ab[0]; acc[bb][1] = ab[1]; acc[bb][2] = ab[2]; }
     }
   };
   // one visit of the floor-friction rows of body b (slot s): fl = its three row forces, (vx, vy, w) its velocity
