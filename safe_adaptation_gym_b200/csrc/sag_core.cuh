@@ -693,8 +693,10 @@ SAG_HD void wheel_row_setup(const CarRobot& R, int i, double sn, double cs, doub
   }
 }
 // one Gauss-Seidel visit of a wheel row pair: both slip rows, then projection onto the friction disc
-SAG_HD void wheel_row_update(Row& r, double* accR, double* accW, double& sdf, double& sf) {
+SAG_HD void wheel_row_update(Row& r, double* accR_, double* accW_, double& sdf, double& sf) {
   const double fo0 = r.f[0], fo1 = r.f[1];
+  // chassis / wheel accelerations in registers for the visit (accR_ / accW_ may be shared memory); the wheel has one DoF
+  double accR[3] = {accR_[0], accR_[1], accR_[2]}, accW[3] = {accW_[0], accW_[1], accW_[2]};
   for (int k = 0; k < 2; ++k) {
     double a = dot3(r.ja[k], accR);
     if (k == 0) a += dot3(r.jb[k], accW);
@@ -718,6 +720,8 @@ SAG_HD void wheel_row_update(Row& r, double* accR, double* accW, double& sdf, do
       }
     }
   }
+  accR_[0] = accR[0]; accR_[1] = accR[1]; accR_[2] = accR[2];
+  accW_[0] = accW[0]; accW_[1] = accW[1]; accW_[2] = accW[2];
   sdf += fabs(r.f[0] - fo0) + fabs(r.f[1] - fo1); sf += fabs(r.f[0]) + fabs(r.f[1]);
 }
 // the car's forward dynamics when nothing else constrains it: just the two wheel row pairs (registers only)
@@ -1242,7 +1246,8 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
     const double Al = isb ? bim : vim, At = isb ? bii : vii;
     const double inv_lin = isb ? b_inv_lin : v_inv_lin, inv_tor = isb ? b_inv_tor : v_inv_tor;
     const double flin = isb ? BP.flin : VP.flin, ftor = isb ? BP.ftor : VP.ftor, bfl = isb ? BP.bfl : VP.bfl;
-    double* ac = acc[1 + b];
+    double* acs = acc[1 + b];
+    double ac[3] = {acs[0], acs[1], acs[2]};  // registers for the visit, stored back at the end
     double f0, f1, d0, d1;
     if (isb && rod) {  // one row across the axis (rolling, body x) and one along it (sliding, body y), clamped separately
       const double inv_x = 1.0 / (rix + rr * rix), inv_y = 1.0 / (riy + rr * riy);
@@ -1268,6 +1273,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
     double d2 = f2 - fl[2];
     ac[2] += d2 * At;
     fl[2] = f2;
+    acs[0] = ac[0]; acs[1] = ac[1]; acs[2] = ac[2];
     sdf += fabs(d0) + fabs(d1) + fabs(d2); sf += fabs(f0) + fabs(f1) + fabs(f2);
   };
   // projected Gauss-Seidel; stops after kSweeps sweeps or when a sweep changes the forces by < kPgsTol (relative, L1)
