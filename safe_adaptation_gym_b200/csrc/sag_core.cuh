@@ -1464,9 +1464,18 @@ SAG_HD LidarHit lidar_eval(double wx, double wy, double cs, double sn) {
 }
 SAG_HD void lidar_apply(const LidarHit& H, float* bins, int bstride) {
   int b0 = H.bin & (kLidarBins - 1), bp = (H.bin + 1) & (kLidarBins - 1), bm = (H.bin + kLidarBins - 1) & (kLidarBins - 1);
+#if defined(__CUDA_ARCH__)
+  // bins live in shared memory: a max without return value instead of load / compare / store, so the thread does not
+  // wait for the round trip.  Values are >= 0 or tiny negatives / -0 that must not be stored, and for those the signed
+  // integer order of the float bits is the float order (bins start at +0).
+  atomicMax(reinterpret_cast<int*>(bins + b0 * bstride), __float_as_int(H.s0));   // :215
+  atomicMax(reinterpret_cast<int*>(bins + bp * bstride), __float_as_int(H.sp));   // :221
+  atomicMax(reinterpret_cast<int*>(bins + bm * bstride), __float_as_int(H.sm));   // :222
+#else
   if (H.s0 > bins[b0 * bstride]) bins[b0 * bstride] = H.s0;   // :215
   if (H.sp > bins[bp * bstride]) bins[bp * bstride] = H.sp;   // :221
   if (H.sm > bins[bm * bstride]) bins[bm * bstride] = H.sm;   // :222
+#endif
 }
 SAG_HD void lidar_accum(double rx, double ry, double cs, double sn, double px, double py, float* bins, int bstride) {
   LidarHit H = lidar_eval(px - rx, py - ry, cs, sn);
