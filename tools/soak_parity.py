@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""One-off soak: the CUDA path against the CPU oracle, bit for bit, over long episodes of every task and both robots
+(tests/common.run_parity with more environments and steps than the test-suite uses).  Test infrastructure, not product."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from common import run_parity  # noqa: E402
+
+TASKS = ["go_to_goal", "go_to_goal_scarce", "go_to_goal_damping", "go_to_goal_motor", "catch_goal", "unsupervised", "press_buttons",
+         "press_buttons_scarce", "collect", "push_box", "push_box_scarce", "haul_box", "roll_rod", "dribble_ball"]
+
+if __name__ == "__main__":
+    n = int(os.environ.get("SOAK_N", "48"))
+    steps = int(os.environ.get("SOAK_STEPS", "1000"))
+    for robot in ("point", "car"):
+        for i, task in enumerate(TASKS):
+            t0 = time.time()
+            for policy in ("drive", "random"):
+                s = run_parity("cuda", task, n=n, steps=steps if policy == "drive" else steps // 4, seed=1000 + i, policy=policy,
+                               check_every=5, robot=robot, config={"action_noise": 0.01})
+                print(robot, task, policy, {k: (round(float(v), 3) if not isinstance(v, int) else v) for k, v in s.items()},
+                      "%.0fs" % (time.time() - t0), flush=True)
+    print("soak ok")
