@@ -100,7 +100,10 @@ int sag_step(void* handle, const float* act, float* obs, double* reward, double*
 /* env.observation (safe_adaptation_gym.py:120-131) at the current state; also refreshes internal caches
  * after sag_write_field. */
 int sag_observe(void* handle, float* obs, void* stream);
-/* same as sag_step with HOST buffers (pinned for full speed: sag_host_alloc): H2D, kernel, D2H, sync. */
+/* same as sag_step with HOST buffers: H2D, kernels, D2H, sync; returns when the outputs are in the host buffers.
+ * Page-locked buffers (sag_host_alloc, cudaHostRegister, torch pin_memory) take the overlapped path: the bulk copy runs
+ * under the contact kernel and that kernel's rows follow as writes into the mapped buffers.  Steps of one handle must be
+ * issued in order (one stream, or externally ordered streams): consecutive steps alternate two work-list counter sets. */
 int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward_h, uint8_t* cost_h, uint8_t* done_h);
 int sag_observe_host(void* handle, float* obs_h);
 void* sag_host_alloc(size_t bytes);
