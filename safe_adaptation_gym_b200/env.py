@@ -278,6 +278,31 @@ class BatchedSafeAdaptationGym:
         if self.device.type == 'cuda':
             torch.cuda.current_stream(self.device).synchronize()  # `t` may be a temporary
 
+    # ---- checkpoint / resume ------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        """Everything a bit-exact continuation needs: the Philox key, every SoA state field (they carry the episode and
+        in-step draw counters, the task ids and the cached clearance), and the host-side step budget.  The
+        finished-episode statistics of `task_stats` are not part of it."""
+        return {'seed': self._seed, 'num_envs': self.num_envs, 'robot': self.robot_name,
+                'fields': {name: self.get_field(name).cpu() for name in self._FIELDS},
+                'steps_to_expiry': self._steps_to_expiry}
+
+    def load_state_dict(self, sd: dict):
+        if sd['num_envs'] != self.num_envs or sd['robot'] != self.robot_name:
+            raise ValueError('state_dict belongs to a different batch size / robot')
+        self.seed(sd['seed'])
+        for name, value in sd['fields'].items():
+            self.set_field(name, value)
+        ids = sd['fields']['task_i32'][0, :self.num_envs].to(torch.int32)
+        by_id = {cls.task_id: cls for cls in _tasks.TASK_CLASSES}
+        self._tasks = [by_id[int(i)]() for i in ids.tolist()]
+        self._task_ids = ids.to(self.device)
+        self._any_unsupervised = bool((ids == _tasks.Unsupervised.task_id).any())
+        self._observation_space = None
+        self._steps_to_expiry = sd['steps_to_expiry']
+        if self.base_config['random_bound']:
+            self._bound = self.get_field('task_f64')[14, :self.num_envs].clone()
+
     def rollout(self, k_steps: int):
         """K steps per launch with on-device Philox U(-1,1) actions; returns the last step's outputs."""
         L = self._lib

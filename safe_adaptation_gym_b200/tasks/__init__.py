@@ -165,3 +165,6 @@ __all__ = [
 
 # tasks the device path does not simulate (none: all 14 registry tasks run; kept for callers that filter on it)
 DEVICE_UNSUPPORTED = frozenset()
+
+# every concrete task class (task_id = index in the registry's alphabetical order, benchmark/__init__.py:16-20)
+TASK_CLASSES = tuple(sorted((globals()[n] for n in __all__), key=lambda c: c.task_id))

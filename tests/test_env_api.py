@@ -132,3 +132,30 @@ def test_random_bound_and_ctrl_scale_are_per_task_instance():
     # defaults: fixed bound, unit scale
     env = _make(n=4, seed=9)
     assert env.get_field("task_f64")[12:15, :4].T.tolist() == [[1.0, 1.0, 25.0]] * 4
+
+
+def test_state_dict_resume_is_bit_exact():
+    """checkpoint / resume: a restored env continues exactly like the original (mixed tasks, goal resamples, button
+    cooldowns, moving bodies and the Philox draw counters all live in the saved fields)"""
+    n = 24
+    names = ["go_to_goal", "press_buttons", "push_box", "catch_goal", "collect", "haul_box"] * 4
+    env = _make(n=n, seed=21)
+    by_name = {c.name: c for c in tasks.TASK_CLASSES}
+    env.set_task([by_name[t]() for t in names])
+    g = torch.Generator(); g.manual_seed(3)
+    for _ in range(40):
+        env.step(torch.rand((n, 2), generator=g) * 2 - 1)
+    sd = env.state_dict()
+    acts = [torch.rand((n, 2), generator=g) * 2 - 1 for _ in range(30)]
+    ref = []
+    for a in acts:
+        obs, rew, done, info = env.step(a)
+        ref.append((obs.clone(), rew.clone(), done.clone(), info["cost"].clone()))
+    other = _make(n=n, seed=99)           # a different env object, different seed and tasks
+    other.load_state_dict(sd)
+    assert [t.name for t in other._tasks] == names
+    for a, (o, r, d, c) in zip(acts, ref):
+        obs, rew, done, info = other.step(a)
+        assert torch.equal(obs, o) and torch.equal(rew, r) and torch.equal(done, d) and torch.equal(info["cost"], c)
+    with pytest.raises(ValueError):
+        _make(n=n + 1).load_state_dict(sd)
