@@ -274,3 +274,20 @@ def test_chain_behind_the_task_body(task):
     from common import run_chain_case
     moved, nmoved, maxcon = run_chain_case("cuda", "point", task=task, steps=100)
     assert moved > 0.05 and nmoved >= 2 and maxcon >= 2, (moved, nmoved, maxcon)
+
+
+def test_state_dict_resume_on_device():
+    n = 512
+    names = ["go_to_goal", "press_buttons", "push_box", "catch_goal"] * (n // 4)
+    env = make_env("cuda", n, names, seed=21)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    for _ in range(60):
+        env.step(torch.rand((n, 2), device="cuda", generator=g) * 2 - 1)
+    sd = env.state_dict()
+    acts = [torch.rand((n, 2), device="cuda", generator=g) * 2 - 1 for _ in range(40)]
+    ref = [tuple(t.clone() for t in env.step(a)[:3]) for a in acts]
+    other = make_env("cuda", n, "go_to_goal", seed=5)
+    other.load_state_dict(sd)
+    for a, (o, r, d) in zip(acts, ref):
+        obs, rew, done, _ = other.step(a)
+        assert torch.equal(obs, o) and torch.equal(rew, r) and torch.equal(done, d)
