@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Probe: how long is k_step when exactly K environments are in contact and all others are quiet?
-Puts the robot of the first K environments (spread one per warp, stride 32) next to their first vase, driving into it."""
+"""Probe: how long is a step when exactly K environments are in contact and all others are quiet?
+Puts the robot of K environments (env ids 0, 32, 64, ...) next to their first vase, driving into it, and times
+sag_step with CUDA events.  PROBE_K=0,256,2048 selects the K values; SAG_BUSY_G selects the busy kernel."""
 import ctypes as C
 import sys, os
 import torch
@@ -9,7 +10,6 @@ from safe_adaptation_gym_b200 import tasks
 from safe_adaptation_gym_b200.env import BatchedSafeAdaptationGym
 
 n = 65536
-assert n // 32 >= 2048
 dev = torch.device("cuda:0")
 
 
