@@ -16,12 +16,16 @@ TASKS = ["go_to_goal", "go_to_goal_scarce", "go_to_goal_damping", "go_to_goal_mo
 if __name__ == "__main__":
     n = int(os.environ.get("SOAK_N", "48"))
     steps = int(os.environ.get("SOAK_STEPS", "1000"))
+    seed0 = int(os.environ.get("SOAK_SEED", "1000"))
+    cfg = {"action_noise": 0.01}
+    if os.environ.get("SOAK_KNOBS"):   # adaptation knobs on: Cauchy-scaled ctrl ranges (incl. inverted ones), random bound
+        cfg.update({"robot_ctrl_range_scale": 0.5, "random_bound": True})
     for robot in ("point", "car"):
         for i, task in enumerate(TASKS):
             t0 = time.time()
             for policy in ("drive", "random"):
-                s = run_parity("cuda", task, n=n, steps=steps if policy == "drive" else steps // 4, seed=1000 + i, policy=policy,
-                               check_every=5, robot=robot, config={"action_noise": 0.01})
+                s = run_parity("cuda", task, n=n, steps=steps if policy == "drive" else steps // 4, seed=seed0 + i, policy=policy,
+                               check_every=5, robot=robot, config=cfg)
                 print(robot, task, policy, {k: (round(float(v), 3) if not isinstance(v, int) else v) for k, v in s.items()},
                       "%.0fs" % (time.time() - t0), flush=True)
     print("soak ok")
