@@ -1,20 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- env-steps/sec of the point go_to_goal hot path (BASELINE.json metric).
+"""bench.py -- env-steps/sec of the per-step environment loop (BASELINE.json metric), whole-episode average.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on all host cores
+    python bench.py --config car_gtg_pb | haul_push_point | haul_push_car   # the other BASELINE configs
 
-Workload (N=1): BASELINE.json configs[1] -- point go_to_goal, 65,536 environments per GPU, pseudo-lidar
-observation + hazard/vase/pillar cost, i.i.d. U(-1,1) actions, action_noise 0.01 (reference default).
-A "step" = one env.step over the whole batch (5 physics substeps per env, reward, cost, 60-float obs).
+Workload (default, N=1): BASELINE.json configs[1] -- point go_to_goal, 65,536 environments per GPU, pseudo-lidar
+observation + hazard/vase/pillar cost, i.i.d. U(-1,1) actions, action_noise 0.01 (reference default), 1000-step
+episodes (tests/test_safety_gym.py:78).  A "step" = one env.step over the whole batch.
 
-value        : env-steps/s with actions resident in HBM, timed per step with CUDA events on the launching
-               stream, L2 flushed (256 MiB memset) between steps.
-e2e          : same metric through sag_step_host (C ABI, pinned HOST buffers): H2D of the actions and D2H of
-               obs/reward/cost/done inside the timed region, every step (the bulk D2H overlaps the busy kernel).
-roofline     : algorithmic bytes per env-step (2582 B for the fused point go_to_goal step)
-               x envs / average k_step duration vs the measured HBM copy bandwidth.
-cpu_baseline : the oracle port (oracle/sag_oracle.c, pthreads) on the box's host cores, bounded sample.
+The cost of a step depends on the episode phase (no robot is near anything right after a reset; ~10 % of them
+are late in the episode), so the K timed steps are STRATIFIED over one whole episode: S = min(K, 20) windows
+of K/S consecutive steps centred at (i + 1/2) * 1000 / S, the steps between the windows run untimed with the
+same kernels (fast-forward), and the episode's reset (layout rejection sampling, timed with events) is added
+amortised as t_reset / 1000 per step.  `value` is therefore the whole-episode average the reference arm
+measures by running whole episodes.
+
+value        : env-steps/s with actions resident in HBM, each timed step bracketed by CUDA events on the launching
+               stream, L2 flushed (256 MiB memset) before every timed step.
+e2e          : same metric and strata through sag_step_host (C ABI, pinned HOST buffers): H2D of the actions and
+               D2H of obs/reward/cost/done inside the timed region, every step.
+roofline     : algorithmic bytes per env-step x envs / average step duration vs the measured HBM
+               copy bandwidth.
+cpu_baseline : the oracle port (oracle/sag_oracle.c, pthreads) on the box's host cores, whole episodes.
 """
 import argparse
 import ctypes as C
@@ -28,11 +36,22 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ENVS_PER_GPU = 65536
-B_ALG_STEP = 2582  # fused step, point go_to_goal, vases simulated [bytes / env-step]
-METRIC = "env_steps_per_sec_point_go_to_goal"
+EPISODE = 1000  # tests/test_safety_gym.py:78
 UNIT = "env-steps/s"
-WORKLOAD = "point go_to_goal, 65536 envs/GPU, lidar obs + hazard/vase/pillar cost, U(-1,1) actions"
+# algorithmic bytes per env-step of the fused step
+CONFIGS = {
+    "point_gtg": dict(robot="point", tasks=["go_to_goal"], envs=65536, b_alg=2582, metric="env_steps_per_sec_point_go_to_goal",
+                      workload="point go_to_goal, 65536 envs/GPU, lidar obs + hazard/vase/pillar cost, U(-1,1) actions"),
+    "car_gtg_pb": dict(robot="car", tasks=["go_to_goal", "press_buttons"], envs=32768, b_alg=2918,
+                       metric="env_steps_per_sec_car_go_to_goal_press_buttons",
+                       workload="car go_to_goal + press_buttons (alternating envs), 32768 envs/GPU, U(-1,1) actions"),
+    "haul_push_point": dict(robot="point", tasks=["haul_box", "push_box"], envs=16384, b_alg=1278,
+                            metric="env_steps_per_sec_point_haul_box_push_box",
+                            workload="point haul_box + push_box (alternating envs), 16384 envs/GPU, U(-1,1) actions"),
+    "haul_push_car": dict(robot="car", tasks=["haul_box", "push_box"], envs=16384, b_alg=1614,
+                          metric="env_steps_per_sec_car_haul_box_push_box",
+                          workload="car haul_box + push_box (alternating envs), 16384 envs/GPU, U(-1,1) actions"),
+}
 
 
 def peaks():
@@ -42,18 +61,35 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def strata(K):
+    """[(first step, length)] of the timed windows inside one EPISODE-step episode; lengths sum to min(K, EPISODE)."""
+    K = min(K, EPISODE)
+    S = min(K, 20)
+    out, used = [], 0
+    for i in range(S):
+        ln = (K * (i + 1)) // S - used
+        used += ln
+        centre = (i + 0.5) * EPISODE / S
+        a = int(round(centre - ln / 2.0))
+        a = max(a, out[-1][0] + out[-1][1] if out else 0)
+        a = min(a, EPISODE - (K - used) - ln)
+        out.append((a, ln))
+    return out
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the run (started before the warm-up)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t_marks = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -61,32 +97,38 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """summary over the samples taken in [t0, t1] (perf_counter; the GPU-timed region), all samples if none fall inside"""
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1)]
+        scope = "timed region"
+        if not rows:
+            rows, scope = [r for _, r in self.rows], "whole run (no sample fell inside the timed region)"
+        sm = sorted(float(r[1]) for r in rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             for k, nm in enumerate(names):
                 if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
-def cpu_oracle_rate(n_envs, steps, threads, seed=666):
-    """env-steps/s of the oracle port on `threads` host threads (bounded sample of the same workload)."""
+def cpu_oracle_rate(cfg, n_envs, steps, threads, seed=666):
+    """env-steps/s of the oracle port on `threads` host threads: n_envs whole-or-partial episodes from a reset."""
     import oracle as O
-    envs = [O.OracleEnv("point", "go_to_goal", seed=seed, env_gid=i) for i in range(n_envs)]
+    tasks = cfg["tasks"]
+    envs = [O.OracleEnv(cfg["robot"], tasks[i % len(tasks)], seed=seed, env_gid=i) for i in range(n_envs)]
     for e in envs:
         e.reset(0)
     t0 = time.perf_counter()
@@ -95,26 +137,28 @@ def cpu_oracle_rate(n_envs, steps, threads, seed=666):
     return count / dt, count, dt
 
 
-def run_reference(args, rank, world):
+def run_reference(args, cfg, rank, world):
+    """CPU arm: whole 1000-step episodes (= the same strata as the GPU arm's whole-episode average) of the oracle port."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_envs = 64 * cores
-    rates = []
-    for _ in range(args.warmup):
-        cpu_oracle_rate(n_envs, 20, cores)
-    t_total, c_total = 0.0, 0
-    sample_steps = 250
+    per_core = 16 if cfg["robot"] == "point" else 2
+    n_envs = per_core * cores
+    for _ in range(min(args.warmup, 2)):
+        cpu_oracle_rate(cfg, n_envs, 20, cores)
+    t_total, c_total, done = 0.0, 0, 0
     for _ in range(args.steps):
-        r, c, dt = cpu_oracle_rate(n_envs, sample_steps, cores)
-        rates.append(r); t_total += dt; c_total += c
-        if t_total > 120:
+        r, c, dt = cpu_oracle_rate(cfg, n_envs, EPISODE, cores)
+        t_total += dt; c_total += c; done += 1
+        if t_total > 150:
             break
     value = c_total / t_total
-    sample = f"{n_envs} envs x {sample_steps} steps per bench step, {len(rates)} bench steps, oracle port (C, pthreads)"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(rates),
-            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, len(rates)), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+    sample = (f"{n_envs} envs x {EPISODE} steps (whole episodes from a reset) per bench step, {done} bench steps, "
+              f"oracle port (C, pthreads, {cores} threads)")
+    line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, done), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "episode_phase": "whole 1000-step episodes", "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference's own stack (dm_control/MuJoCo) is not installable here; this arm times the CPU oracle port"}
@@ -127,179 +171,270 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 2000)")
+    ap.add_argument("--config", default="point_gtg", choices=sorted(CONFIGS))
+    ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stagger", action="store_true", help="extra: episodes staggered over all 1000 phases (auto-reset every step)")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg, rank, world)
         return
 
     import numpy as np
     import torch
     import torch.distributed as dist
-    from safe_adaptation_gym_b200 import _abi, tasks
+    from safe_adaptation_gym_b200.benchmark import TASKS
     from safe_adaptation_gym_b200.env import BatchedSafeAdaptationGym
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up, so that a short timed region still carries samples
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    n = args.envs_per_gpu
+    n = args.envs_per_gpu or cfg["envs"]
     K, W = args.steps, max(3, args.warmup)
-    env = BatchedSafeAdaptationGym("xmls/point.xml", num_envs=n, device=dev, env_id_base=rank * n, max_episode_steps=0)
-    env.seed(666)
-    env.set_task(tasks.GoToGoal())
+    n_ep = (K + EPISODE - 1) // EPISODE
+    windows = strata((K + n_ep - 1) // n_ep)
+    K = n_ep * sum(ln for _, ln in windows)
+    task_objs = [TASKS[t]() for t in cfg["tasks"]]
+
+    def make_env():
+        env = BatchedSafeAdaptationGym("xmls/%s.xml" % cfg["robot"], num_envs=n, device=dev, env_id_base=rank * n, max_episode_steps=0)
+        env.seed(666)
+        env.set_task([task_objs[(rank * n + e) % len(task_objs)] for e in range(n)])
+        return env
+
+    env = make_env()
     L, h = env._lib, env._h
     stream = torch.cuda.current_stream(dev)
     sp = C.c_void_p(stream.cuda_stream)
+    p = BatchedSafeAdaptationGym._p
+    launch_count = getattr(L.L, "sag_launch_count", None)
+
+    def launches_now(hh):
+        return int(launch_count(hh)) if launch_count is not None else 0
+
     # synthetic actions, resident in HBM: i.i.d. U(-1,1) per env per step (env.action_space.sample()), drawn on the device
-    # outside the timed event pair.  (A short cyclic ring of action batches would give every env a periodic action
-    # sequence, i.e. a systematic drift into obstacles -- not what a random policy does.)
+    # outside the timed event pairs
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
     act_buf = torch.empty((n, 2), dtype=torch.float32, device=dev)
-
-    def new_actions():
-        act_buf.uniform_(-1.0, 1.0, generator=g)
     obs, rew, cost, done = env._obs, env._reward, env._cost, env._done
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    p = BatchedSafeAdaptationGym._p
 
-    def launch(i):
-        L.check(L.L.sag_step(h, p(act_buf), p(obs), p(rew), None, p(cost), p(done), sp))
+    def step_dev(hh):
+        act_buf.uniform_(-1.0, 1.0, generator=g)
+        L.check(L.L.sag_step(hh, p(act_buf), p(obs), p(rew), None, p(cost), p(done), sp))
 
-    nstep = 0
-    for i in range(W):
-        new_actions(); launch(i); nstep += 1
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    # ---- warm-up: W steps of a throw-away episode, then a reset so that the timed episode starts at phase 0
+    for _ in range(W):
+        step_dev(h)
+    L.check(L.L.sag_reset(h, None, 0, 0, sp))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    launches = 0
+
+    # ---- value: stratified timed steps over whole episodes, untimed fast-forward in between
+    timed, ff_blocks, reset_evs = [], [], []
     t_wall0 = time.perf_counter()
-    for i in range(K):
-        new_actions()
-        flush.zero_()  # L2 flush (not timed: outside the event pair)
-        evs[i][0].record(stream)
-        launch(W + i); launches += 2; nstep += 1  # k_step_quiet + k_step_coop
-        if nstep % 1000 == 0:  # episode length used by the reference's tooling (tests/test_safety_gym.py:78)
-            L.check(L.L.sag_reset(h, None, 0, 0, sp)); launches += 1
-        evs[i][1].record(stream)
+    l0 = launches_now(h)
+    timed_launches = 0
+    for _ep in range(n_ep):
+        t = 0
+        for (a, ln) in windows + [(EPISODE, 0)]:
+            if a > t:  # fast-forward (warm L2, timed as one block for the value_l2_warm extra)
+                e0, e1 = ev(), ev()
+                e0.record(stream)
+                for _ in range(a - t):
+                    step_dev(h)
+                e1.record(stream)
+                ff_blocks.append((t, a - t, e0, e1))
+            for k in range(ln):
+                act_buf.uniform_(-1.0, 1.0, generator=g)
+                flush.zero_()  # L2 flush, outside the event pair
+                e0, e1 = ev(), ev()
+                lc = launches_now(h)
+                e0.record(stream)
+                L.check(L.L.sag_step(h, p(act_buf), p(obs), p(rew), None, p(cost), p(done), sp))
+                e1.record(stream)
+                timed_launches += launches_now(h) - lc
+                timed.append((a + k, e0, e1))
+            t = a + ln
+        e0, e1 = ev(), ev()
+        flush.zero_()
+        e0.record(stream)
+        L.check(L.L.sag_reset(h, None, 0, 0, sp))  # episode end: layout rejection sampling for all envs
+        e1.record(stream)
+        reset_evs.append((e0, e1))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
-    ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = float(sum(ms))
-    # warm-L2 back-to-back variant (state stays resident in the 126 MB L2, as in a real RL loop)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(K):
-        new_actions(); launch(i)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    warm_ms = e0.elapsed_time(e1)
-    t = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device=dev)
+    t_wall1 = time.perf_counter()
+    launches_total = launches_now(h) - l0
+    ms = [(ph, a.elapsed_time(b)) for ph, a, b in timed]
+    reset_ms = sum(a.elapsed_time(b) for a, b in reset_evs) / len(reset_evs)
+    steps_ms = float(sum(m for _, m in ms))
+    total_ms = steps_ms + K * reset_ms / EPISODE
+    ff_steps = sum(c for _, c, _, _ in ff_blocks)
+    ff_ms = float(sum(a.elapsed_time(b) for _, _, a, b in ff_blocks))
+    t = torch.tensor([total_ms, steps_ms, reset_ms, ff_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, warm_ms = float(t[0]), float(t[1])
+    total_ms, steps_ms, reset_ms, ff_ms = (float(x) for x in t)
     value = world * n * K / (total_ms * 1e-3)
-    value_warm = world * n * K / (warm_ms * 1e-3)
+    value_warm = world * n * ff_steps / (ff_ms * 1e-3) if ff_steps else None
+    win_ms = []
+    i = 0
+    for _ep in range(n_ep):
+        for (a, ln) in windows:
+            if ln:
+                w = [m for _, m in ms[i:i + ln]]
+                win_ms.append({"phase": a, "steps": ln, "ms_per_step": float(sum(w) / ln)})
+            i += ln
 
-    # ---- end-to-end through the C ABI with pinned host buffers, on a second handle reset to the same episode so that
-    # it covers the same episode phase (steps W .. W+Ke after reset) as `value`
-    Ke = args.e2e_steps or min(K, 2000)
-    env2 = BatchedSafeAdaptationGym("xmls/point.xml", num_envs=n, device=dev, env_id_base=rank * n, max_episode_steps=0)
-    env2.seed(666)
-    env2.set_task(tasks.GoToGoal())
-    h2 = env2._h
-    act_h = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-    obs_h = torch.empty((n, env.obs_dim), dtype=torch.float32).pin_memory()
-    rew_h = torch.empty((n,), dtype=torch.float64).pin_memory()
-    cost_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
-    done_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
-    cpu_gen = torch.Generator(); cpu_gen.manual_seed(99 + rank)
-    act_h.uniform_(-1, 1, generator=cpu_gen)
-    torch.cuda.synchronize()
-    for i in range(W):
-        L.check(L.L.sag_step_host(h2, p(act_h), p(obs_h), p(rew_h), p(cost_h), p(done_h)))
-    if world > 1:
-        dist.barrier()
-    te = 0.0
-    for i in range(Ke):
-        act_h.uniform_(-1, 1, generator=cpu_gen)   # the host policy's work is not timed
-        t0 = time.perf_counter()
-        L.check(L.L.sag_step_host(h2, p(act_h), p(obs_h), p(rew_h), p(cost_h), p(done_h)))  # H2D + kernels + D2H + sync
-        te += time.perf_counter() - t0
-    torch.cuda.synchronize()
-    t = torch.tensor([te], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    te = float(t[0])
-    e2e_value = world * n * Ke / te
-    h2d = n * 2 * 4
-    d2h = n * (env.obs_dim * 4 + 8 + 1 + 1)
-    env2.close()
+    # ---- optional extra: episodes staggered over all 1000 phases (every step some envs auto-reset)
+    stagger = None
+    if args.stagger:
+        env_s = BatchedSafeAdaptationGym("xmls/%s.xml" % cfg["robot"], num_envs=n, device=dev, env_id_base=rank * n,
+                                         max_episode_steps=EPISODE)
+        env_s.seed(666)
+        env_s.set_task([task_objs[(rank * n + e) % len(task_objs)] for e in range(n)])
+        hs = env_s._h
+        # spread the step counters: env e has already done (e mod 1000) steps of its episode after a 1000-step run-in
+        for _ in range(EPISODE):
+            step_dev(hs)
+        ti = env_s.get_field("task_i32")
+        ti[6, :n] = (torch.arange(n, device=dev) % EPISODE).to(torch.int32)
+        env_s.set_field("task_i32", ti)
+        for _ in range(EPISODE):  # run-in: one full period with auto-reset so that phases are mixed
+            step_dev(hs); L.check(L.L.sag_reset(hs, None, 1, 0, sp))
+        torch.cuda.synchronize()
+        Ks = min(K, 200)
+        e0, e1 = ev(), ev()
+        e0.record(stream)
+        for _ in range(Ks):
+            step_dev(hs); L.check(L.L.sag_reset(hs, None, 1, 0, sp))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        stagger = {"value": world * n * Ks / (e0.elapsed_time(e1) * 1e-3), "steps": Ks,
+                   "note": "warm L2, step + auto-reset of the ~n/1000 envs that expire every step"}
+        env_s.close()
+
+    # ---- end to end through the C ABI with pinned host buffers, on a second handle, same strata
+    e2e = None
+    if not args.no_e2e:
+        env2 = make_env()
+        h2 = env2._h
+        od = env.obs_dim
+        act_h = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+        obs_h = torch.empty((n, od), dtype=torch.float32).pin_memory()
+        rew_h = torch.empty((n,), dtype=torch.float64).pin_memory()
+        cost_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
+        done_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
+        cpu_gen = torch.Generator(); cpu_gen.manual_seed(99 + rank)
+        act_h.uniform_(-1, 1, generator=cpu_gen)
+        torch.cuda.synchronize()
+        for _ in range(W):
+            L.check(L.L.sag_step_host(h2, p(act_h), p(obs_h), p(rew_h), p(cost_h), p(done_h)))
+        L.check(L.L.sag_reset(h2, None, 0, 0, sp))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        te, ke = 0.0, 0
+        t = 0
+        for (a, ln) in windows:
+            for _ in range(a - t):
+                step_dev(h2)
+            torch.cuda.synchronize()
+            for _ in range(ln):
+                act_h.uniform_(-1, 1, generator=cpu_gen)   # the host policy's work is not timed
+                t0 = time.perf_counter()
+                L.check(L.L.sag_step_host(h2, p(act_h), p(obs_h), p(rew_h), p(cost_h), p(done_h)))  # H2D + kernels + D2H + sync
+                te += time.perf_counter() - t0
+                ke += 1
+            t = a + ln
+        for _ in range(EPISODE - t):
+            step_dev(h2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()  # episode end: reset + the first observation of the new episode to the host
+        L.check(L.L.sag_reset(h2, None, 0, 0, sp))
+        L.check(L.L.sag_observe_host(h2, p(obs_h)))
+        torch.cuda.synchronize()
+        t_reset_e2e = time.perf_counter() - t0
+        te_total = te + ke * t_reset_e2e / EPISODE
+        t = torch.tensor([te_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te_total = float(t[0])
+        e2e = {"value": world * n * ke / te_total, "unit": UNIT, "h2d_bytes_per_step": n * 2 * 4,
+               "d2h_bytes_per_step": n * (od * 4 + 8 + 1 + 1), "steps": ke, "reset_ms": 1e3 * t_reset_e2e,
+               "api": "sag_step_host (C ABI, pinned host buffers), same strata as `value`"}
+        env2.close()
 
     # ---- per-task statistics: the only collective on this path (NCCL all-reduce of a [14,3] fp64 buffer)
-    L.check(L.L.sag_reset(h, None, 0, 0, sp))
     stats = env.task_stats(reset=True)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     stats = stats.cpu().numpy()
 
     if rank == 0:
+        clocks = sampler.stop(t_wall0, t_wall1)
         peak, peak_src = peaks()
         avg_s = total_ms * 1e-3 / K
-        achieved = B_ALG_STEP * n / avg_s / 1e9
+        achieved = cfg["b_alg"] * n / avg_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.config == "point_gtg":
             try:
                 traffic = json.load(open(tp)).get("step_dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        first10_s = float(sum(ms[:10]) / max(1, len(ms[:10]))) * 1e-3
+        first_s = win_ms[0]["ms_per_step"] * 1e-3
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-shard x{world}",
-                       "l2": "flushed between steps (256 MiB memset outside the event pair)", "action_noise": 0.01,
-                       "episode_phase": f"steps {W}..{W + K} after reset (1000-step episodes)"},
+            "config": {"workload": cfg["workload"], "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-shard x{world}",
+                       "l2": "flushed before every timed step (256 MiB memset outside the event pair)", "action_noise": 0.01,
+                       "episode_phase": (f"stratified over whole {EPISODE}-step episodes: {len(windows)} windows of "
+                                         f"{windows[0][1]}..{windows[-1][1]} steps at phases {[a for a, _ in windows]}, untimed fast-forward "
+                                         f"in between, + reset {reset_ms:.3f} ms amortised / {EPISODE}")},
+            "ms_per_step_windows": win_ms, "reset_ms": reset_ms,
             "value_l2_warm": value_warm,
-            "value_l2_warm_note": f"back-to-back steps without the flush, LATER episode phase (steps {W + K}..{W + 2 * K}): more contacts than `value`'s phase",
-            "ms_per_step_first10": float(sum(ms[:10]) / max(1, len(ms[:10]))), "ms_per_step_last10": float(sum(ms[-10:]) / max(1, len(ms[-10:]))),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "api": "sag_step_host (C ABI, pinned host buffers)"},
-            "gpu_launches": launches,
+            "value_l2_warm_note": "the fast-forward steps between the windows (no flush, back to back), whole-episode coverage",
+            "e2e": e2e,
+            "gpu_launches": timed_launches + n_ep, "gpu_launches_incl_fast_forward": launches_total,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "fused step = k_step_quiet + k_step_coop", "b_alg_per_env_step": B_ALG_STEP,
-                         "peak_source": peak_src,
-                         "frac_quiet_phase": B_ALG_STEP * n / first10_s / 1e9 / peak},
+                         "traffic": traffic, "kernel": "fused step (free-motion kernel + contact kernel), whole-episode average",
+                         "b_alg_per_env_step": cfg["b_alg"], "peak_source": peak_src,
+                         "frac_quiet_phase": cfg["b_alg"] * n / first_s / 1e9 / peak},
             "clocks": clocks,
-            "episode_stats": {"go_to_goal": {"sum_return": float(stats[3, 0]), "sum_cost": float(stats[3, 1]),
-                                             "episodes": float(stats[3, 2])}},
-            "wall_s_timed_region": t_wall,
+            "episode_stats": {t: {"sum_return": float(stats[TASKS[t].task_id, 0]), "sum_cost": float(stats[TASKS[t].task_id, 1]),
+                                  "episodes": float(stats[TASKS[t].task_id, 2])} for t in cfg["tasks"]},
+            "wall_s_timed_region": t_wall1 - t_wall0,
         }
+        if stagger:
+            line["staggered_episodes"] = stagger
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            ne, ns = 64 * cores, 1000
-            r, c, dt = cpu_oracle_rate(ne, ns, cores)
+            ne = (16 if cfg["robot"] == "point" else 2) * cores
+            r, c, dt = cpu_oracle_rate(cfg, ne, EPISODE, cores)
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{ne} envs x {ns} steps = {c} env-steps in {dt:.1f}s, oracle port (C, pthreads); "
-                                              "the reference's MuJoCo stack is not installable here"}
+                                    "sample": f"{ne} envs x {EPISODE} steps (whole episodes) = {c} env-steps in {dt:.1f}s, oracle port "
+                                              "(C, pthreads); the reference's MuJoCo stack is not installable here"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

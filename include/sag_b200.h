@@ -78,6 +78,8 @@ int sag_destroy(void* handle);
 int sag_stride(void* handle);
 int sag_obs_dim(void* handle);
 size_t sag_field_bytes(void* handle, int field);
+/* number of CUDA kernels launched on behalf of this handle so far (bench.py's gpu_launches is a difference of two reads) */
+unsigned long long sag_launch_count(void* handle);
 
 /* env.set_task (safe_adaptation_gym.py:165-168): task_ids is a DEVICE int32[n_envs] array */
 int sag_set_tasks(void* handle, const int32_t* task_ids_dev, void* stream);

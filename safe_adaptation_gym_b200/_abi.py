@@ -39,7 +39,7 @@ class SagLib:
 
     SYMBOLS = [
         "sag_last_error", "sag_abi_version", "sag_default_config", "sag_create", "sag_destroy", "sag_stride",
-        "sag_obs_dim", "sag_field_bytes", "sag_set_tasks", "sag_seed", "sag_reset", "sag_step", "sag_observe",
+        "sag_obs_dim", "sag_field_bytes", "sag_launch_count", "sag_set_tasks", "sag_seed", "sag_reset", "sag_step", "sag_observe",
         "sag_step_host", "sag_observe_host", "sag_host_alloc", "sag_host_free", "sag_rollout", "sag_read_field",
         "sag_write_field", "sag_task_stats", "sag_lidar", "sag_cost",
     ]
@@ -59,6 +59,8 @@ class SagLib:
         L.sag_destroy.argtypes = [vp]
         L.sag_stride.argtypes = [vp]
         L.sag_obs_dim.argtypes = [vp]
+        L.sag_launch_count.restype = C.c_ulonglong
+        L.sag_launch_count.argtypes = [vp]
         L.sag_field_bytes.restype = C.c_size_t
         L.sag_field_bytes.argtypes = [vp, i32]
         L.sag_set_tasks.argtypes = [vp, vp, vp]

@@ -24,10 +24,23 @@
 #endif
 
 #if defined(SAG_PROFILE) && !defined(__CUDACC__)
-extern long* sag_prof_ptr;  // tests/hostemu instrumentation: per-env work counters [n][8]
-#define SAG_PROF(e, i, n) do { if (sag_prof_ptr) sag_prof_ptr[(size_t)(e) * 8 + (i)] += (n); } while (0)
+extern long* sag_prof_ptr;  // tests/hostemu instrumentation: per-env work counters [n][16]
+#define SAG_PROF(e, i, n) do { if (sag_prof_ptr) sag_prof_ptr[(size_t)(e) * 16 + (i)] += (n); } while (0)
+#define SAG_PROF_MAX(e, i, n) do { if (sag_prof_ptr && sag_prof_ptr[(size_t)(e) * 16 + (i)] < (n)) sag_prof_ptr[(size_t)(e) * 16 + (i)] = (n); } while (0)
 #else
 #define SAG_PROF(e, i, n) do { } while (0)
+#define SAG_PROF_MAX(e, i, n) do { } while (0)
+#endif
+
+// SAG_TIMING (tuning builds only): the cooperative kernel accumulates clock64() intervals per section into D.dbg[16]
+#if defined(SAG_TIMING) && defined(__CUDA_ARCH__)
+#define SAG_CLK_DECL long long clk_ = clock64()
+#define SAG_CLK_RESET do { clk_ = clock64(); } while (0)
+#define SAG_CLK(i) do { long long now_ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&D.dbg[i], (unsigned long long)(now_ - clk_)); clk_ = now_; } while (0)
+#else
+#define SAG_CLK_DECL do { } while (0)
+#define SAG_CLK_RESET do { } while (0)
+#define SAG_CLK(i) do { } while (0)
 #endif
 
 namespace sag {
@@ -174,6 +187,7 @@ struct Dev {
   // work list of the environments that are not quiet in the current step (k_step_quiet -> k_step_busy)
   int *worklist, *counts;  // work list segments and their lengths (sag_kernels.cu)
   int* counts_next;        // the other counter set: zeroed by this step's quiet kernel for the next step
+  unsigned long long* dbg; // [16] section clocks of SAG_TIMING builds
   double *time, *clear;
   unsigned *ctr, *episode;
   int* nstep;
@@ -182,6 +196,15 @@ struct Dev {
 };
 
 SAG_HD size_t oidx(const Dev& D, int slot, int e) { return (size_t)slot * D.stride + e; }
+
+// View of ONE environment's object arrays: field[slot * stride].  Global memory: pointers offset by the environment
+// index, stride = D.stride (coalesced across the environments of a warp).  The cooperative kernel stages the arrays in
+// the warp's shared-memory working set for the duration of a step (stride 1).
+struct ObjView { double *x, *y, *yaw, *vx, *vy, *w; int stride; };
+SAG_HD ObjView global_objects(const Dev& D, int e) {
+  ObjView O = {D.ox + e, D.oy + e, D.oyaw + e, D.ovx + e, D.ovy + e, D.ow + e, D.stride};
+  return O;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10, counter = (ctr, episode, global env id, stream), key = seed
@@ -613,29 +636,36 @@ struct Row {  // one contact (normal k=0, tangent k=1), the tendon limit (k=0 on
 };
 constexpr int kMaxBodies = 8;  // movable bodies with constraint rows in one forward pass
 
-// Working set of the contact solver, kept in shared memory (local memory would put every access of this
-// latency-bound code on an L2 / DRAM round trip).  Two sizes: every lane of a "busy" warp owns a SmallScratch that
-// covers the common case (<= 4 contacts, <= 2 bodies); a pass that does not fit re-runs on the warp's one big
-// Scratch, lanes taking turns.  sizeof / 8 is odd so that the lanes' doubles fall into distinct bank pairs.
-template <int NC, int NB>
-struct ScratchT {
-  static constexpr int kCon = NC, kBodies = NB;
-  Con con[NC];
-  Row rows[NC + 3];      // + tendon + two car wheels
-  double acc[NB + 3][3]; // robot, bodies, two car wheels (1 DoF each, in [.][0])
-  double ffl[NB][3];
-  int bslot[NB + (NB & 1)];
+// Constants of the contact solver that depend on the configuration and the task only (oracle obj_mass + the reciprocals
+// forward_dynamics takes of them): evaluated once per environment step, not once per forward pass.
+struct SolveConsts {
+  double vim, vii, bim, bii;                          // 1 / mass, 1 / inertia: vase, task body (push box / rod / ball)
+  double v_inv_lin, v_inv_tor, b_inv_lin, b_inv_tor;  // 1 / (A + R) of the floor-friction rows
+  double vflin, vftor, vbfl, bflin, bftor, bbfl;      // floor-friction bounds, damping rate of the floor rows
+  double rix, riy, bfx, bfy;                          // rod: 1 / mx, 1 / my, per-axis bounds
 };
-typedef ScratchT<kMaxCon, kMaxBodies> Scratch;
-constexpr int kSmallCon = 4, kSmallBodies = 2;
-typedef ScratchT<kSmallCon, kSmallBodies> SmallScratch;
-static_assert((sizeof(SmallScratch) / 8) % 2 == 1, "SmallScratch stride must be an odd number of 8-byte words");
+
+// Working set of the contact solver of ONE environment, kept in shared memory (local memory would put every access
+// of this latency-bound code on an L2 / DRAM round trip).
+struct Scratch {
+  static constexpr int kCon = kMaxCon, kBodies = kMaxBodies;
+  Con con[kMaxCon];
+  Row rows[kMaxCon + 3];         // + tendon + two car wheels
+  double acc[kMaxBodies + 3][3]; // robot, bodies, two car wheels (1 DoF each, in [.][0])
+  double ffl[kMaxBodies][3];
+  double bv[kMaxBodies][3];      // velocities of the bodies in the table (read once per pass)
+  int bslot[kMaxBodies];
+  SolveConsts Q;                 // cooperative kernel: this environment's constants (scalar paths keep them in registers)
+  double obj[6][kMaxObj];        // cooperative kernel: the environment's object arrays for the duration of a step (ObjView)
+};
 
 // env_step / end_of_step modes: full scalar path (one thread = one environment, contact solver included), quiet-only
 // (no contact code), warp-cooperative (one warp = one environment, device only)
-// kStepNear: the quiet path plus the exact overlap pre-test in every substep -- for environments that have something within
-// reach but (usually) touch nothing; the step is abandoned (return 1, nothing written that the full path would not
-// write identically) as soon as a robot geom overlaps an object, and the environment is handed to the contact path.
+// kStepNear: the contact-free path, with (run-time flag `pretest`) the exact overlap / tendon pre-test in front of every
+// substep and of the final forward pass -- for environments that have something within reach but (usually) touch
+// nothing; the step is abandoned (return 1, nothing written that the full path would not write identically) as soon as
+// a robot geom overlaps an object or the tendon is taut, and the environment is handed to the contact path.  With
+// pretest == false it is the quiet path.
 constexpr int kStepFull = 0, kStepQuiet = 1, kStepCoop = 2, kStepNear = 3;
 
 struct Ctx {  // per-thread view of one environment
@@ -644,7 +674,9 @@ struct Ctx {  // per-thread view of one environment
   TaskSpec sp;
   Slots L;
   int task;
+  ObjView O;
 };
+SAG_HD size_t oix(const Ctx& C, int slot) { return (size_t)slot * C.O.stride; }
 
 struct Phys {
   double fc[3];    // generalised constraint force on the robot
@@ -652,7 +684,6 @@ struct Phys {
   unsigned touch;  // bit s: a robot geom is in contact (dist <= 0) with object slot s
   unsigned mov;    // bit s: movable body s has a non-zero velocity (after integration, if any)
   int err;
-  int retry;       // the pass did not fit this scratch size and changed nothing: run it again on the big one
   double wtau[2];  // car: constraint torque on the wheels
 };
 
@@ -766,20 +797,6 @@ SAG_HD void car_free_solve(const CarRobot& R, double sn, double cs, const PtCons
 constexpr unsigned kFullWarp = 0xffffffffu;
 __device__ __forceinline__ int coop_lane() { return threadIdx.x & 31; }
 
-// Item expansion: lane o owns cnt_o items (cnt uniform-shuffled); item t (global index within this expansion) ->
-// (owner lane, local index).  Owners are visited in lane order, so items are numbered in canonical order.
-__device__ __forceinline__ bool coop_find_item(unsigned owners, int cnt, int t, int& owner, int& local) {
-  bool found = false;
-  owner = 0; local = 0;
-  for (unsigned m = owners; m; m &= m - 1) {
-    const int o = __ffs((int)m) - 1;
-    const int c = __shfl_sync(kFullWarp, cnt, o);
-    if (!found && t >= 0 && t < c) { owner = o; local = t; found = true; }
-    t -= c;
-  }
-  return found;
-}
-
 // ordered append: lane order = canonical order; n in {0, 1, 2} hits per lane
 __device__ __forceinline__ bool coop_append(Con* con, int cap, int& ncon, bool& overflow, int n, const Hit* hits, int ba, int bb) {
   const int lane = coop_lane();
@@ -801,112 +818,122 @@ __device__ __forceinline__ bool coop_append(Con* con, int cap, int& ncon, bool& 
 
 // Both collision phases of contact_pass, lane-parallel.  Same outputs: con[0..ncon) in canonical order, overflow, touch,
 // active.  (Scalar semantics on overflow: the list stops growing at the capacity, touch / active keep accumulating.)
+//   broad phases: lane <-> object slot.  Phase 1 tests every collidable slot against the robot's reach; phase 2 tests, for
+//     every awake / robot-touched movable body a, all slots against a in one step and records the near pairs as bit rows
+//     pm[j] = {i < j} held by lane j, so that walking j upwards and the bits of pm[j] upwards is the canonical pair order.
+//   narrow phase: ONE copy of the collide() code; each trip hands up to 32 geom pairs to the lanes -- phase 1: (robot geom,
+//     object part) items of all near objects in slot order (only the push box has more than one part and it is the last
+//     slot); phase 2: the part pairs of one near object pair.  Hits are appended in lane order (= canonical order).
 template <class RB>
 __device__ __noinline__ void detect_coop(const Ctx& C, const RB& R, double sn, double cs, unsigned mov, Con* con, int cap,
                                          int& ncon_out, bool& overflow_out, unsigned& touch_out, unsigned& active_out) {
   const Dev& D = C.D;
-  const int e = C.e, lane = coop_lane();
+  const int lane = coop_lane();
   int ncon = 0;
   bool overflow = false;
   unsigned touch = 0, active = mov;
-  Hit hits[2];
-  // ---- phase 1 broad phase: lane <-> slot v0 + lane
-  const int s1 = C.L.v0 + lane;
-  int kind1 = K_NONE;
-  bool coll1 = false, near1 = false;
-  if (s1 < C.L.n) {
-    kind1 = slot_kind(C.sp, C.L, s1);
-    coll1 = kind_collidable(kind1);
-    if (coll1) {
-      size_t i = oidx(D, s1, e);
-      double dx = D.ox[i] - R.q[0], dy = D.oy[i] - R.q[1], reach = RB::kReach + kind_bound(D, kind1);
-      near1 = !(dx * dx + dy * dy > reach * reach);
-    }
+  // ---- this lane's slot
+  int kind_l = K_NONE;
+  bool coll_l = false;
+  double x_l = 0.0, y_l = 0.0, bound_l = 0.0;
+  if (lane >= C.L.v0 && lane < C.L.n) {
+    kind_l = slot_kind(C.sp, C.L, lane);
+    coll_l = kind_collidable(kind_l);
+    if (coll_l) { size_t i = oix(C, lane); x_l = C.O.x[i]; y_l = C.O.y[i]; bound_l = kind_bound(D, kind_l); }
   }
-  const unsigned collm = __ballot_sync(kFullWarp, coll1) << C.L.v0;  // absolute slot bits
-  const unsigned near1m = __ballot_sync(kFullWarp, near1);           // lane bits
-  {
-    const int cnt = near1 ? RB::kNGeom * kind_nparts(kind1) : 0;
-    int total = cnt;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(kFullWarp, total, d);
-    for (int base = 0; base < total; base += 32) {
-      int owner, local;
-      const bool have = coop_find_item(near1m, cnt, base + lane, owner, local);
-      const int kind = __shfl_sync(kFullWarp, kind1, owner);
-      int n = 0, s = C.L.v0 + owner;
-      const bool mvb = kind_movable(kind);
-      if (have) {
-        const int np = kind_nparts(kind), rg = local / np, pt = local - rg * np;
-        size_t i = oidx(D, s, e);
-        double x = D.ox[i], y = D.oy[i], oc = 1.0, os = 0.0;
-        if (mvb) sag_sincos(D.oyaw[i], &os, &oc);
-        Geom grg, go;
-        R.geom(rg, sn, cs, grg);
-        obj_geom(D, kind, pt, x, y, oc, os, go);
-        n = collide(grg, go, hits);
-      }
-      const bool stored = coop_append(con, cap, ncon, overflow, n, hits, 0, mvb ? 1 + s : -1);
-      const unsigned tb = __reduce_or_sync(kFullWarp, stored ? 1u << s : 0u);
-      touch |= tb;
-      active |= __reduce_or_sync(kFullWarp, (n && mvb) ? 1u << s : 0u);
-    }
+  const unsigned collm = __ballot_sync(kFullWarp, coll_l);
+  // ---- phase 1 broad phase
+  bool near1 = false;
+  if (coll_l) {
+    double dx = x_l - R.q[0], dy = y_l - R.q[1], reach = RB::kReach + bound_l;
+    near1 = !(dx * dx + dy * dy > reach * reach);
   }
-  // ---- phase 2: pairs (j ascending, i < j ascending) with at least one awake / robot-touched movable body
-  if (active) {
-    const unsigned lowcut = ~((1u << C.L.v0) - 1u);
-    // number of candidate pairs of every j, then the flattened pair list in canonical order, 32 per round
-    int total = 0;
-    for (unsigned jm = collm; jm; jm &= jm - 1) {
-      const int j = __ffs((int)jm) - 1;
-      const unsigned below = (1u << j) - 1u;
-      const unsigned cand = (((active >> j) & 1u) ? below : (active & below)) & lowcut & collm;
-      total += __popc(cand);
-    }
-    for (int base = 0; base < total; base += 32) {
-      int t = base + lane, pj = -1, pi = -1;
-      for (unsigned jm = collm; jm; jm &= jm - 1) {
-        const int j = __ffs((int)jm) - 1;
-        const unsigned below = (1u << j) - 1u;
-        const unsigned cand = (((active >> j) & 1u) ? below : (active & below)) & lowcut & collm;
-        const int c = __popc(cand);
-        if (pj < 0 && t >= 0 && t < c) { pj = j; pi = (int)__fns(cand, 0, t + 1); }
-        t -= c;
+  const unsigned near1m = __ballot_sync(kFullWarp, near1);
+  const unsigned boxbit = (C.sp.box_kind == K_BOX) ? (1u << C.L.box) : 0u;  // the only multi-part object; always the last slot
+  const unsigned near_single = near1m & ~boxbit;
+  const int n_single = __popc(near_single) * RB::kNGeom;
+  const int total1 = n_single + ((near1m & boxbit) ? RB::kNGeom * 5 : 0);
+  // ---- narrow phase trips
+  int base1 = 0, phase = total1 > 0 ? 0 : 1;
+  unsigned pm = 0, jm = 0, pmj = 0;
+  int pj = -1;
+  bool pairs_built = false;
+  for (;;) {
+    // -- next trip: per-lane item (geom A of body ia / part pa, geom B of slot sb / part pb); ia < 0: robot geom pa
+    bool have = false;
+    int ia = -1, pa = 0, sb = 0, pb = 0;
+    if (phase == 0) {
+      if (base1 >= total1) { phase = 1; continue; }
+      const int t = base1 + lane;
+      base1 += 32;
+      if (t < total1) {
+        have = true;
+        if (t < n_single) { const int rank = t / RB::kNGeom; pa = t - rank * RB::kNGeom; sb = (int)__fns(near_single, 0, rank + 1); pb = 0; }
+        else { const int u = t - n_single; pa = u / 5; pb = u - pa * 5; sb = C.L.box; }
       }
-      bool nearp = false;
-      int ki = K_NONE, kj = K_NONE;
-      if (pj >= 0) {
-        ki = slot_kind(C.sp, C.L, pi); kj = slot_kind(C.sp, C.L, pj);
-        size_t ii = oidx(D, pi, e), ij = oidx(D, pj, e);
-        double dx = D.ox[ij] - D.ox[ii], dy = D.oy[ij] - D.oy[ii], reach = kind_bound(D, kj) + kind_bound(D, ki);
-        nearp = !(dx * dx + dy * dy > reach * reach);
-      }
-      const unsigned nearm = __ballot_sync(kFullWarp, nearp);
-      const int cnt = nearp ? kind_nparts(ki) * kind_nparts(kj) : 0;
-      int items = cnt;
-#pragma unroll
-      for (int d = 16; d; d >>= 1) items += __shfl_xor_sync(kFullWarp, items, d);
-      const int packed = (pi & 0xff) | ((pj & 0xff) << 8) | (ki << 16) | (kj << 24);
-      for (int ib = 0; ib < items; ib += 32) {
-        int owner, local;
-        const bool have = coop_find_item(nearm, cnt, ib + lane, owner, local);
-        const int pk = __shfl_sync(kFullWarp, packed, owner);
-        const int i = pk & 0xff, j = (pk >> 8) & 0xff, kki = (pk >> 16) & 0xff, kkj = (pk >> 24) & 0xff;
-        const bool mi = kind_movable(kki), mj = kind_movable(kkj);
-        int n = 0;
-        if (have) {
-          const int npj = kind_nparts(kkj), a = local / npj, b = local - a * npj;  // part of i (outer), part of j (inner)
-          size_t ii = oidx(D, i, e), ij = oidx(D, j, e);
-          double ci = 1.0, si = 0.0, cj = 1.0, sj = 0.0;
-          if (mi) sag_sincos(D.oyaw[ii], &si, &ci);
-          if (mj) sag_sincos(D.oyaw[ij], &sj, &cj);
-          Geom gi, gj;
-          obj_geom(D, kki, a, D.ox[ii], D.oy[ii], ci, si, gi);
-          obj_geom(D, kkj, b, D.ox[ij], D.oy[ij], cj, sj, gj);
-          n = collide(gi, gj, hits);
+    } else {
+      if (!pairs_built) {
+        pairs_built = true;
+        if (!active) break;
+        // phase 2 broad phase: one body a at a time against all slots
+        for (unsigned am = active & collm; am; am &= am - 1) {
+          const int a = __ffs((int)am) - 1;
+          const size_t ia_ = oix(C, a);
+          const double xa = C.O.x[ia_], ya = C.O.y[ia_], ba = kind_bound(D, slot_kind(C.sp, C.L, a));
+          bool nearp = false;
+          if (coll_l && lane != a) {
+            // canonical operands: (x_j - x_i) with i < j; the squares and the sum of the bounds do not depend on the order
+            double dx = lane > a ? x_l - xa : xa - x_l, dy = lane > a ? y_l - ya : ya - y_l;
+            double reach = lane > a ? bound_l + ba : ba + bound_l;
+            nearp = !(dx * dx + dy * dy > reach * reach);
+          }
+          if (nearp && lane > a) pm |= 1u << a;
+          const unsigned below = __ballot_sync(kFullWarp, nearp && lane < a);
+          if (lane == a) pm |= below;
         }
-        coop_append(con, cap, ncon, overflow, n, hits, mi ? 1 + i : -1, mj ? 1 + j : -1);
+        jm = __ballot_sync(kFullWarp, pm != 0);
       }
+      if (!pmj) {
+        if (!jm) break;
+        pj = __ffs((int)jm) - 1;
+        jm &= jm - 1;
+        pmj = __shfl_sync(kFullWarp, pm, pj);
+      }
+      const int pi = __ffs((int)pmj) - 1;
+      pmj &= pmj - 1;
+      const int ki = slot_kind(C.sp, C.L, pi), kj = slot_kind(C.sp, C.L, pj);
+      const int npj = kind_nparts(kj), items = kind_nparts(ki) * npj;  // part of i outer, part of j inner
+      if (lane < items) { have = true; ia = pi; pa = lane / npj; sb = pj; pb = lane - pa * npj; }
+    }
+    // -- narrow phase of this trip
+    Hit hits[2];
+    int n = 0;
+    bool mvb = false, mva = false;
+    if (have) {
+      Geom ga, gb;
+      const int kb = slot_kind(C.sp, C.L, sb);
+      mvb = kind_movable(kb);
+      {
+        const size_t i = oix(C, sb);
+        double oc = 1.0, os = 0.0;
+        if (mvb) sag_sincos(C.O.yaw[i], &os, &oc);
+        obj_geom(D, kb, pb, C.O.x[i], C.O.y[i], oc, os, gb);
+      }
+      if (ia < 0) R.geom(pa, sn, cs, ga);
+      else {
+        const int ka = slot_kind(C.sp, C.L, ia);
+        mva = kind_movable(ka);
+        const size_t i = oix(C, ia);
+        double oc = 1.0, os = 0.0;
+        if (mva) sag_sincos(C.O.yaw[i], &os, &oc);
+        obj_geom(D, ka, pa, C.O.x[i], C.O.y[i], oc, os, ga);
+      }
+      n = collide(ga, gb, hits);
+    }
+    const bool stored = coop_append(con, cap, ncon, overflow, n, hits, ia < 0 ? 0 : (mva ? 1 + ia : -1), mvb ? 1 + sb : -1);
+    if (phase == 0) {
+      touch |= __reduce_or_sync(kFullWarp, stored ? 1u << sb : 0u);
+      active |= __reduce_or_sync(kFullWarp, (n && mvb) ? 1u << sb : 0u);
     }
   }
   __syncwarp();
@@ -921,12 +948,12 @@ __device__ __forceinline__ bool robot_overlaps_any_coop(const Ctx& C, const RB& 
   if (s < C.L.n) {
     const int kind = slot_kind(C.sp, C.L, s);
     if (kind_collidable(kind)) {
-      size_t i = oidx(D, s, C.e);
-      double x = D.ox[i], y = D.oy[i];
+      size_t i = oix(C, s);
+      double x = C.O.x[i], y = C.O.y[i];
       double dx = x - R.q[0], dy = y - R.q[1], reach = RB::kReach + kind_bound(D, kind);
       if (!(dx * dx + dy * dy > reach * reach)) {
         double oc = 1.0, os = 0.0;
-        if (kind_movable(kind)) sag_sincos(D.oyaw[i], &os, &oc);
+        if (kind_movable(kind)) sag_sincos(C.O.yaw[i], &os, &oc);
         for (int pt = 0; pt < kind_nparts(kind) && !hit; ++pt) {
           Geom go;
           obj_geom(D, kind, pt, x, y, oc, os, go);
@@ -943,11 +970,34 @@ __device__ __forceinline__ bool robot_overlaps_any_coop(const Ctx& C, const RB& 
 }
 #endif  // __CUDA_ARCH__
 
-template <class RB, class ScratchType, bool Coop = false>
+// HaulBox tendon (haul_box.py:21-30): robot site <-> box site, length limited to kTendonMax; taut when dist < 0
+template <class RB>
+SAG_HD bool tendon_taut(const Ctx& C, const RB& R, double& tdx, double& tdy, double& tlen, double& tdist) {
+  size_t ib = oix(C, C.L.box);
+  tdx = C.O.x[ib] - R.q[0]; tdy = C.O.y[ib] - R.q[1];
+  double dz = kBoxSize - kPtZ;
+  tlen = sqrt(tdx * tdx + tdy * tdy + dz * dz);
+  tdist = kTendonMax - tlen;
+  return tdist < 0.0;
+}
+
+SAG_HD void solve_consts(const Dev& D, const TaskSpec& sp, SolveConsts& Q) {
+  const int bkind = sp.box_kind;
+  const BodyPar VP = kind_body(D, K_VASE), BP = kind_body(D, bkind ? bkind : K_BOX);
+  const double rr = (1.0 - kImpD0) / kImpD0;
+  Q.vim = 1.0 / VP.m; Q.vii = 1.0 / VP.iz; Q.bim = 1.0 / BP.m; Q.bii = 1.0 / BP.iz;
+  Q.v_inv_lin = 1.0 / (Q.vim + rr * Q.vim); Q.v_inv_tor = 1.0 / (Q.vii + rr * Q.vii);
+  Q.b_inv_lin = 1.0 / (Q.bim + rr * Q.bim); Q.b_inv_tor = 1.0 / (Q.bii + rr * Q.bii);
+  Q.vflin = VP.flin; Q.vftor = VP.ftor; Q.vbfl = VP.bfl; Q.bflin = BP.flin; Q.bftor = BP.ftor; Q.bbfl = BP.bfl;
+  Q.rix = Q.riy = 0.0;
+  if (bkind == K_ROD) { Q.rix = 1.0 / BP.mx; Q.riy = 1.0 / BP.my; }
+  Q.bfx = BP.fx; Q.bfy = BP.fy;
+}
+
+template <class RB, bool Coop>
 SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double cs, const PtConst& K, const double* fs,
-                                  unsigned mov, bool integrate, double h, ScratchType& S, Phys& P) {
-  constexpr int kCapCon = ScratchType::kCon, kCapBodies = ScratchType::kBodies;
-  constexpr bool kIsBig = kCapCon == kMaxCon;
+                                  unsigned mov, bool integrate, double h, Scratch& S, const SolveConsts& Q, Phys& P) {
+  constexpr int kCapCon = Scratch::kCon, kCapBodies = Scratch::kBodies;
   const Dev& D = C.D;
   const int e = C.e;
   double p, q;
@@ -956,26 +1006,27 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   int ncon = 0;
   unsigned active = mov, touch = 0;
   bool overflow = false;
-  P.err = 0; P.retry = 0;
+  P.err = 0;
   constexpr bool kCarRobot = RB::kKind == 1;
-  Hit hits[2];
   SAG_PROF(e, 0, 1);
+  SAG_CLK_DECL;
   if constexpr (Coop) {
 #if defined(__CUDA_ARCH__)
     detect_coop<RB>(C, R, sn, cs, mov, con, kCapCon, ncon, overflow, touch, active);
 #endif
   } else {
+  Hit hits[2];
   // ---- phase 1: robot geoms vs objects, slot order
   for (int s = C.L.v0; s < C.L.n; ++s) {
     int kind = slot_kind(C.sp, C.L, s);
     if (!kind_collidable(kind)) continue;
-    size_t i = oidx(D, s, e);
-    double x = D.ox[i], y = D.oy[i];
+    size_t i = oix(C, s);
+    double x = C.O.x[i], y = C.O.y[i];
     double dx = x - R.q[0], dy = y - R.q[1], reach = RB::kReach + kind_bound(D, kind);
     if (dx * dx + dy * dy > reach * reach) continue;
     bool mvb = kind_movable(kind);
     double oc = 1.0, os = 0.0;
-    if (mvb) sag_sincos(D.oyaw[i], &os, &oc);
+    if (mvb) sag_sincos(C.O.yaw[i], &os, &oc);
     for (int rg = 0; rg < RB::kNGeom; ++rg) {
       Geom grg;
       R.geom(rg, sn, cs, grg);
@@ -1004,8 +1055,8 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
       unsigned cand = aj ? ((1u << j) - 1u) : (active & ((1u << j) - 1u));
       cand &= ~((1u << C.L.v0) - 1u);
       if (!cand) continue;
-      size_t ij = oidx(D, j, e);
-      double xj = D.ox[ij], yj = D.oy[ij], bj = kind_bound(D, kj);
+      size_t ij = oix(C, j);
+      double xj = C.O.x[ij], yj = C.O.y[ij], bj = kind_bound(D, kj);
       bool mj = kind_movable(kj);
       double cj = 1.0, sj = 0.0;
       bool have_j = false;
@@ -1013,15 +1064,15 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
         int i = ctz32(cm);
         int ki = slot_kind(C.sp, C.L, i);
         if (!kind_collidable(ki)) continue;
-        size_t ii = oidx(D, i, e);
-        double xi = D.ox[ii], yi = D.oy[ii];
+        size_t ii = oix(C, i);
+        double xi = C.O.x[ii], yi = C.O.y[ii];
         double dx = xj - xi, dy = yj - yi, reach = bj + kind_bound(D, ki);
         SAG_PROF(e, 6, 1);
         if (dx * dx + dy * dy > reach * reach) continue;
         bool mi = kind_movable(ki);
         double ci = 1.0, si = 0.0;
-        if (mi) sag_sincos(D.oyaw[ii], &si, &ci);
-        if (mj && !have_j) { sag_sincos(D.oyaw[ij], &sj, &cj); have_j = true; }
+        if (mi) sag_sincos(C.O.yaw[ii], &si, &ci);
+        if (mj && !have_j) { sag_sincos(C.O.yaw[ij], &sj, &cj); have_j = true; }
         for (int pi = 0; pi < kind_nparts(ki); ++pi) {
           Geom gi;
           obj_geom(D, ki, pi, xi, yi, ci, si, gi);
@@ -1044,6 +1095,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   }
   P.touch = touch;
   P.mov = mov;
+  if constexpr (Coop) SAG_CLK(2);
   SAG_PROF(e, 2, ncon);
   P.fc[0] = P.fc[1] = P.fc[2] = 0.0;
   P.wtau[0] = P.wtau[1] = 0.0;
@@ -1061,12 +1113,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   double tdx = 0.0, tdy = 0.0, tlen = 0.0, tdist = 0.0;
   bool tendon = false;
   if (C.task == T_HAUL_BOX) {  // tendon length limit, haul_box.py:21-30
-    size_t ib = oidx(D, C.L.box, e);
-    tdx = D.ox[ib] - R.q[0]; tdy = D.oy[ib] - R.q[1];
-    double dz = kBoxSize - kPtZ;
-    tlen = sqrt(tdx * tdx + tdy * tdy + dz * dz);
-    tdist = kTendonMax - tlen;
-    tendon = tdist < 0.0;
+    tendon = tendon_taut(C, R, tdx, tdy, tlen, tdist);
     if (tendon) touched |= 1u << C.L.box;
   }
   double racc[3];
@@ -1077,41 +1124,43 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   int nb = 0;
   for (unsigned m = fl; m; m &= m - 1) ++nb;
   if (nb > kCapBodies) overflow = true;
-  if (overflow && !kIsBig) { P.retry = 1; return; }  // nothing has been modified yet
   if (overflow) P.err = 1;
   if (!kCarRobot) {
     if (overflow) return;
     if (!any_row && !tendon && mov == 0) return;  // nothing to solve, nothing to move
   }
-  // ---- body table: compact ids in slot order
+  // ---- body table: compact ids in slot order, velocities read once
   nb = 0;
-  if (!overflow) for (unsigned m = fl; m; m &= m - 1) S.bslot[nb++] = ctz32(m);
+  if (!overflow) for (unsigned m = fl; m; m &= m - 1) {
+    const int s = ctz32(m);
+    size_t i = oix(C, s);
+    S.bslot[nb] = s;
+    S.bv[nb][0] = C.O.vx[i]; S.bv[nb][1] = C.O.vy[i]; S.bv[nb][2] = C.O.w[i];
+    ++nb;
+  }
   auto cid = [&](int slot) { int k = 0; while (S.bslot[k] != slot) ++k; return k; };
   const int bkind = C.sp.box_kind;  // kind of the task's movable body: push box, rod or ball (0: none)
-  const BodyPar VP = kind_body(D, K_VASE), BP = kind_body(D, bkind ? bkind : K_BOX);
-  const double vim = 1.0 / VP.m, vii = 1.0 / VP.iz, bim = 1.0 / BP.m, bii = 1.0 / BP.iz;
   const bool rod = bkind == K_ROD;
-  double rc = 1.0, rs = 0.0, rix = 0.0, riy = 0.0, rma = 0.0, rmb = 0.0, rmc = 0.0;  // rod: R diag(1/mx, 1/my) R^T
+  double rc = 1.0, rs = 0.0, rma = 0.0, rmb = 0.0, rmc = 0.0;  // rod: R diag(1/mx, 1/my) R^T
   if (rod) {
-    sag_sincos(D.oyaw[oidx(D, C.L.box, e)], &rs, &rc);
-    rix = 1.0 / BP.mx; riy = 1.0 / BP.my;
-    rma = rix * rc * rc + riy * rs * rs; rmb = (rix - riy) * rc * rs; rmc = rix * rs * rs + riy * rc * rc;
+    sag_sincos(C.O.yaw[oix(C, C.L.box)], &rs, &rc);
+    rma = Q.rix * rc * rc + Q.riy * rs * rs; rmb = (Q.rix - Q.riy) * rc * rs; rmc = Q.rix * rs * rs + Q.riy * rc * rc;
   }
   // body < 0 static, 0 robot, 1 + slot movable
   auto minv = [&](int body, const double* j, double* o) {
     if (body == 0) { pt_solve(p, q, K.ia0, K.is0, j, o); return; }
     const bool isb = body - 1 == C.L.box;
-    if (isb && rod) { o[0] = rma * j[0] + rmb * j[1]; o[1] = rmb * j[0] + rmc * j[1]; o[2] = j[2] * bii; return; }
-    double im = isb ? bim : vim, ii = isb ? bii : vii;
+    if (isb && rod) { o[0] = rma * j[0] + rmb * j[1]; o[1] = rmb * j[0] + rmc * j[1]; o[2] = j[2] * Q.bii; return; }
+    double im = isb ? Q.bim : Q.vim, ii = isb ? Q.bii : Q.vii;
     o[0] = j[0] * im; o[1] = j[1] * im; o[2] = j[2] * ii;
   };
   auto bvel = [&](int body, double* v) {
     if (body == 0) { v[0] = R.v[0]; v[1] = R.v[1]; v[2] = R.v[2]; }
-    else { size_t i = oidx(D, body - 1, e); v[0] = D.ovx[i]; v[1] = D.ovy[i]; v[2] = D.ow[i]; }
+    else { size_t i = oix(C, body - 1); v[0] = C.O.vx[i]; v[1] = C.O.vy[i]; v[2] = C.O.w[i]; }
   };
   auto bpos = [&](int body, double* o) {
     if (body == 0) { o[0] = R.q[0]; o[1] = R.q[1]; }
-    else { size_t i = oidx(D, body - 1, e); o[0] = D.ox[i]; o[1] = D.oy[i]; }
+    else { size_t i = oix(C, body - 1); o[0] = C.O.x[i]; o[1] = C.O.y[i]; }
   };
   Row* rows = S.rows;
   int nrow = 0, tendon_row = -1;
@@ -1203,137 +1252,95 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   acc[0][0] = racc[0]; acc[0][1] = racc[1]; acc[0][2] = racc[2];
   for (int b = 0; b < nb; ++b) { acc[1 + b][0] = acc[1 + b][1] = acc[1 + b][2] = 0.0; ffl[b][0] = ffl[b][1] = ffl[b][2] = 0.0; }
   const double rr = (1.0 - kImpD0) / kImpD0;
-  const double v_inv_lin = 1.0 / (vim + rr * vim), v_inv_tor = 1.0 / (vii + rr * vii);
-  const double b_inv_lin = 1.0 / (bim + rr * bim), b_inv_tor = 1.0 / (bii + rr * bii);
-  // one Gauss-Seidel visit of a contact row pair (normal, tangent) or of the tendon row (nk = 1)
-  auto contact_row_update = [&](Row& r, int nk, double& sdf, double& sf) {
-    const int ba = r.ba, bb = r.bb;
-    // the two bodies' accelerations stay in registers for the whole visit (one load and one store each instead of one
-    // per k; same arithmetic)
-    double aa[3] = {0.0, 0.0, 0.0}, ab[3] = {0.0, 0.0, 0.0};
-    if (ba >= 0) { aa[0] = acc[ba][0]; aa[1] = acc[ba][1]; aa[2] = acc[ba][2]; }
-    if (bb >= 0) { ab[0] = acc[bb][0]; ab[1] = acc[bb][1]; ab[2] = acc[bb][2]; }
-    bool changed = false;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k >= nk) break;
-      SAG_PROF(e, 4, 1);
-      double a = 0.0;
-      if (ba >= 0) a += dot3(r.ja[k], aa);
-      if (bb >= 0) a += dot3(r.jb[k], ab);
-      const double fo = r.f[k];
-      double fn = fo - (a - r.aref[k] + r.R[k] * fo) * r.inv[k];
-      if (k == 0) { if (fn < 0.0) fn = 0.0; }
-      else { double lim = r.bound * r.f[0]; fn = clampd(fn, -lim, lim); }
-      double df = fn - fo;
-      r.f[k] = fn;
-      sdf += fabs(df); sf += fabs(fn);
-      if (df != 0.0) {
-        changed = true;
-        if (ba >= 0) { aa[0] += r.wa[k][0] * df; aa[1] += r.wa[k][1] * df; aa[2] += r.wa[k][2] * df; }
-        if (bb >= 0) { ab[0] += r.wb[k][0] * df; ab[1] += r.wb[k][1] * df; ab[2] += r.wb[k][2] * df; }
-      }
-    }
-    if (changed) {
-      if (ba >= 0) { acc[ba][0] = aa[0]; acc[ba][1] = aa[1]; acc[ba][2] = aa[2]; }
-      if (bb >= 0) { acc[bb][0] = ab[0]; acc[bb][1] = ab[1]; acc[bb][2] = ab[2]; }
-    }
-  };
-  // one visit of the floor-friction rows of body b (slot s): fl = its three row forces, (vx, vy, w) its velocity
-  auto floor_update = [&](int b, int s, double* fl, double vx, double vy, double w, double& sdf, double& sf) {
-    SAG_PROF(e, 5, 1);
-    const bool isb = s == C.L.box;
-    const double Al = isb ? bim : vim, At = isb ? bii : vii;
-    const double inv_lin = isb ? b_inv_lin : v_inv_lin, inv_tor = isb ? b_inv_tor : v_inv_tor;
-    const double flin = isb ? BP.flin : VP.flin, ftor = isb ? BP.ftor : VP.ftor, bfl = isb ? BP.bfl : VP.bfl;
-    double* acs = acc[1 + b];
-    double ac[3] = {acs[0], acs[1], acs[2]};  // registers for the visit, stored back at the end
-    double f0, f1, d0, d1;
-    if (isb && rod) {  // one row across the axis (rolling, body x) and one along it (sliding, body y), clamped separately
-      const double inv_x = 1.0 / (rix + rr * rix), inv_y = 1.0 / (riy + rr * riy);
-      double au = ac[0] * rc + ac[1] * rs, aw = -ac[0] * rs + ac[1] * rc;
-      double vu = vx * rc + vy * rs, vw = -vx * rs + vy * rc;
-      f0 = fl[0] - (au + bfl * vu + rr * rix * fl[0]) * inv_x;
-      f1 = fl[1] - (aw + bfl * vw + rr * riy * fl[1]) * inv_y;
-      f0 = clampd(f0, -BP.fx, BP.fx); f1 = clampd(f1, -BP.fy, BP.fy);
-      d0 = f0 - fl[0]; d1 = f1 - fl[1];
-      double du = d0 * rix, dw = d1 * riy;
-      ac[0] += du * rc - dw * rs; ac[1] += du * rs + dw * rc;
-    } else {
-      f0 = fl[0] - (ac[0] + bfl * vx + rr * Al * fl[0]) * inv_lin;
-      f1 = fl[1] - (ac[1] + bfl * vy + rr * Al * fl[1]) * inv_lin;
-      double nf = sqrt(f0 * f0 + f1 * f1);
-      if (nf > flin) { double sc = flin / nf; f0 *= sc; f1 *= sc; }
-      d0 = f0 - fl[0]; d1 = f1 - fl[1];
-      ac[0] += d0 * Al; ac[1] += d1 * Al;
-    }
-    fl[0] = f0; fl[1] = f1;
-    double f2 = fl[2] - (ac[2] + bfl * w + rr * At * fl[2]) * inv_tor;
-    f2 = clampd(f2, -ftor, ftor);
-    double d2 = f2 - fl[2];
-    ac[2] += d2 * At;
-    fl[2] = f2;
-    acs[0] = ac[0]; acs[1] = ac[1]; acs[2] = ac[2];
-    sdf += fabs(d0) + fabs(d1) + fabs(d2); sf += fabs(f0) + fabs(f1) + fabs(f2);
-  };
-  // projected Gauss-Seidel; stops after kSweeps sweeps or when a sweep changes the forces by < kPgsTol (relative, L1)
-  bool pgs_done = false;
-  if constexpr (Coop) {
-#if defined(__CUDA_ARCH__)
-    // Lane-distributed: lane i keeps row i (its Jacobians, M^-1 J^T, forces) and the floor rows of body i in registers for
-    // all sweeps; the visits stay strictly sequential (Gauss-Seidel), only the owner lane of the visited row runs, the
-    // body accelerations live in shared memory, and the running sums sdf / sf travel from owner to owner by shuffle so
-    // that they are accumulated in the scalar order.  Removes the per-visit reload of ~32 row constants.
-    if (nrow <= 32 && nb <= 32) {
-      pgs_done = true;
-      __syncwarp();
-      const int lane = coop_lane();
-      Row my;
-      if (lane < nrow) my = rows[lane];
-      double fl[3] = {0.0, 0.0, 0.0}, bvx = 0.0, bvy = 0.0, bw = 0.0;
-      int bs = 0;
-      if (lane < nb) { bs = S.bslot[lane]; size_t i = oidx(D, bs, e); bvx = D.ovx[i]; bvy = D.ovy[i]; bw = D.ow[i]; }
-      for (int it = 0; it < kSweeps; ++it) {
-        double sdf = 0.0, sf = 0.0;
-        int last = 0;
-        for (int i = 0; i < nrow; ++i) {
-          sdf = __shfl_sync(kFullWarp, sdf, last); sf = __shfl_sync(kFullWarp, sf, last);
-          if (lane == i) {
-            if (kCarRobot && my.type == 2) wheel_row_update(my, acc[0], acc[my.bb], sdf, sf);
-            else contact_row_update(my, (i == tendon_row) ? 1 : 2, sdf, sf);
-          }
-          __syncwarp();
-          last = i;
-        }
-        for (int b = 0; b < nb; ++b) {
-          sdf = __shfl_sync(kFullWarp, sdf, last); sf = __shfl_sync(kFullWarp, sf, last);
-          if (lane == b) floor_update(b, bs, fl, bvx, bvy, bw, sdf, sf);
-          __syncwarp();
-          last = b;
-        }
-        sdf = __shfl_sync(kFullWarp, sdf, last); sf = __shfl_sync(kFullWarp, sf, last);
-        if (sdf <= kPgsTol * sf) break;
-      }
-      if (lane < nrow) { rows[lane].f[0] = my.f[0]; rows[lane].f[1] = my.f[1]; }
-      __syncwarp();
-    }
-#endif
-  }
-  if (!pgs_done)
+  SAG_PROF(e, 9, nrow); SAG_PROF(e, 10, nb); SAG_PROF(e, 11, any_row ? 1 : 0);
+  SAG_PROF_MAX(e, 12, ncon); SAG_PROF_MAX(e, 13, nb); SAG_PROF_MAX(e, 14, nrow);
+  { int oo = 0; for (int i = 0; i < ncon; ++i) if (con[i].ba != 0) oo = 1; SAG_PROF_MAX(e, 15, oo); (void)oo; }
+  if constexpr (Coop) SAG_CLK(3);
+  // Projected Gauss-Seidel; stops after kSweeps sweeps or when a sweep changes the forces by < kPgsTol (relative, L1).
+  // Strictly sequential visits; in the cooperative kernel all lanes run them redundantly on the warp's shared-memory
+  // working set (broadcast reads, identical stores): the visit chain is latency-bound and has no parallelism to hand out.
+#pragma unroll 1
   for (int it = 0; it < kSweeps; ++it) {
     double sdf = 0.0, sf = 0.0;
+    SAG_PROF(e, 8, 1);
+#pragma unroll 1
     for (int i = 0; i < nrow; ++i) {
       Row& r = rows[i];
       if (kCarRobot && r.type == 2) { wheel_row_update(r, acc[0], acc[r.bb], sdf, sf); continue; }
-      contact_row_update(r, (i == tendon_row) ? 1 : 2, sdf, sf);
+      // one visit of a contact row pair (normal, tangent) or of the tendon row (one row): the two bodies' accelerations
+      // stay in registers for the whole visit
+      const int ba = r.ba, bb = r.bb, nk = (i == tendon_row) ? 1 : 2;
+      double aa[3] = {0.0, 0.0, 0.0}, ab[3] = {0.0, 0.0, 0.0};
+      if (ba >= 0) { aa[0] = acc[ba][0]; aa[1] = acc[ba][1]; aa[2] = acc[ba][2]; }
+      if (bb >= 0) { ab[0] = acc[bb][0]; ab[1] = acc[bb][1]; ab[2] = acc[bb][2]; }
+      bool changed = false;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (k >= nk) break;
+        SAG_PROF(e, 4, 1);
+        double a = 0.0;
+        if (ba >= 0) a += dot3(r.ja[k], aa);
+        if (bb >= 0) a += dot3(r.jb[k], ab);
+        const double fo = r.f[k];
+        double fn = fo - (a - r.aref[k] + r.R[k] * fo) * r.inv[k];
+        if (k == 0) { if (fn < 0.0) fn = 0.0; }
+        else { double lim = r.bound * r.f[0]; fn = clampd(fn, -lim, lim); }
+        double df = fn - fo;
+        r.f[k] = fn;
+        sdf += fabs(df); sf += fabs(fn);
+        if (df != 0.0) {
+          changed = true;
+          if (ba >= 0) { aa[0] += r.wa[k][0] * df; aa[1] += r.wa[k][1] * df; aa[2] += r.wa[k][2] * df; }
+          if (bb >= 0) { ab[0] += r.wb[k][0] * df; ab[1] += r.wb[k][1] * df; ab[2] += r.wb[k][2] * df; }
+        }
+      }
+      if (changed) {
+        if (ba >= 0) { acc[ba][0] = aa[0]; acc[ba][1] = aa[1]; acc[ba][2] = aa[2]; }
+        if (bb >= 0) { acc[bb][0] = ab[0]; acc[bb][1] = ab[1]; acc[bb][2] = ab[2]; }
+      }
     }
+    // floor-friction rows of every body in the table
+#pragma unroll 1
     for (int b = 0; b < nb; ++b) {
-      const int s = S.bslot[b];
-      size_t i = oidx(D, s, e);
-      floor_update(b, s, ffl[b], D.ovx[i], D.ovy[i], D.ow[i], sdf, sf);
+      SAG_PROF(e, 5, 1);
+      const bool isb = S.bslot[b] == C.L.box;
+      const double Al = isb ? Q.bim : Q.vim, At = isb ? Q.bii : Q.vii;
+      const double inv_lin = isb ? Q.b_inv_lin : Q.v_inv_lin, inv_tor = isb ? Q.b_inv_tor : Q.v_inv_tor;
+      const double flin = isb ? Q.bflin : Q.vflin, ftor = isb ? Q.bftor : Q.vftor, bfl = isb ? Q.bbfl : Q.vbfl;
+      const double vx = S.bv[b][0], vy = S.bv[b][1], w = S.bv[b][2];
+      double* acs = acc[1 + b];
+      double* flb = ffl[b];
+      double ac[3] = {acs[0], acs[1], acs[2]};  // registers for the visit, stored back at the end
+      double f0, f1, d0, d1;
+      if (isb && rod) {  // one row across the axis (rolling, body x) and one along it (sliding, body y), clamped separately
+        const double inv_x = 1.0 / (Q.rix + rr * Q.rix), inv_y = 1.0 / (Q.riy + rr * Q.riy);
+        double au = ac[0] * rc + ac[1] * rs, aw = -ac[0] * rs + ac[1] * rc;
+        double vu = vx * rc + vy * rs, vw = -vx * rs + vy * rc;
+        f0 = flb[0] - (au + bfl * vu + rr * Q.rix * flb[0]) * inv_x;
+        f1 = flb[1] - (aw + bfl * vw + rr * Q.riy * flb[1]) * inv_y;
+        f0 = clampd(f0, -Q.bfx, Q.bfx); f1 = clampd(f1, -Q.bfy, Q.bfy);
+        d0 = f0 - flb[0]; d1 = f1 - flb[1];
+        double du = d0 * Q.rix, dw = d1 * Q.riy;
+        ac[0] += du * rc - dw * rs; ac[1] += du * rs + dw * rc;
+      } else {
+        f0 = flb[0] - (ac[0] + bfl * vx + rr * Al * flb[0]) * inv_lin;
+        f1 = flb[1] - (ac[1] + bfl * vy + rr * Al * flb[1]) * inv_lin;
+        double nf = sqrt(f0 * f0 + f1 * f1);
+        if (nf > flin) { double sc = flin / nf; f0 *= sc; f1 *= sc; }
+        d0 = f0 - flb[0]; d1 = f1 - flb[1];
+        ac[0] += d0 * Al; ac[1] += d1 * Al;
+      }
+      double f2 = flb[2] - (ac[2] + bfl * w + rr * At * flb[2]) * inv_tor;
+      f2 = clampd(f2, -ftor, ftor);
+      double d2 = f2 - flb[2];
+      ac[2] += d2 * At;
+      flb[0] = f0; flb[1] = f1; flb[2] = f2;
+      acs[0] = ac[0]; acs[1] = ac[1]; acs[2] = ac[2];
+      sdf += fabs(d0) + fabs(d1) + fabs(d2); sf += fabs(f0) + fabs(f1) + fabs(f2);
     }
     if (sdf <= kPgsTol * sf) break;
   }
+  if constexpr (Coop) SAG_CLK(4);
   P.qacc[0] = acc[0][0]; P.qacc[1] = acc[0][1]; P.qacc[2] = acc[0][2];
   for (int i = 0; i < nrow; ++i) {
     const Row& r = rows[i];
@@ -1355,13 +1362,13 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
     int sb = 0;
     if (b < nb) {
       sb = S.bslot[b];
-      size_t i = oidx(D, sb, e);
-      double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
+      size_t i = oix(C, sb);
+      double vx = S.bv[b][0], vy = S.bv[b][1], w = S.bv[b][2];
       bool tch = (touched >> sb) & 1u;
       vx += h * acc[1 + b][0]; vy += h * acc[1 + b][1]; w += h * acc[1 + b][2];
       if (!tch && vx * vx + vy * vy < kSleepV * kSleepV && fabs(w) < kSleepV) { vx = vy = w = 0.0; }
-      double x = D.ox[i] + h * vx, y = D.oy[i] + h * vy, yaw = D.oyaw[i] + h * w;
-      D.ovx[i] = vx; D.ovy[i] = vy; D.ow[i] = w; D.ox[i] = x; D.oy[i] = y; D.oyaw[i] = yaw;
+      double x = C.O.x[i] + h * vx, y = C.O.y[i] + h * vy, yaw = C.O.yaw[i] + h * w;
+      C.O.vx[i] = vx; C.O.vy[i] = vy; C.O.w[i] = w; C.O.x[i] = x; C.O.y[i] = y; C.O.yaw[i] = yaw;
       moving = vx != 0.0 || vy != 0.0 || w != 0.0;
       bad = bad_val(x) || bad_val(y) || bad_val(vx) || bad_val(vy) || bad_val(w);
     }
@@ -1370,17 +1377,18 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
     P.mov = (P.mov & ~handled) | nowmov;
     if (__any_sync(kFullWarp, bad)) P.err = 1;
     __syncwarp();
+    SAG_CLK(5);
 #endif
   } else
   for (int b = 0; b < nb; ++b) {
     const int s = S.bslot[b];
-    size_t i = oidx(D, s, e);
-    double vx = D.ovx[i], vy = D.ovy[i], w = D.ow[i];
+    size_t i = oix(C, s);
+    double vx = S.bv[b][0], vy = S.bv[b][1], w = S.bv[b][2];
     bool tch = (touched >> s) & 1u;
     vx += h * acc[1 + b][0]; vy += h * acc[1 + b][1]; w += h * acc[1 + b][2];
     if (!tch && vx * vx + vy * vy < kSleepV * kSleepV && fabs(w) < kSleepV) { vx = vy = w = 0.0; }
-    double x = D.ox[i] + h * vx, y = D.oy[i] + h * vy, yaw = D.oyaw[i] + h * w;
-    D.ovx[i] = vx; D.ovy[i] = vy; D.ow[i] = w; D.ox[i] = x; D.oy[i] = y; D.oyaw[i] = yaw;
+    double x = C.O.x[i] + h * vx, y = C.O.y[i] + h * vy, yaw = C.O.yaw[i] + h * w;
+    C.O.vx[i] = vx; C.O.vy[i] = vy; C.O.w[i] = w; C.O.x[i] = x; C.O.y[i] = y; C.O.yaw[i] = yaw;
     if (vx != 0.0 || vy != 0.0 || w != 0.0) P.mov |= 1u << s; else P.mov &= ~(1u << s);
     if (bad_val(x) || bad_val(y) || bad_val(vx) || bad_val(vy) || bad_val(w)) P.err = 1;
   }
@@ -1394,12 +1402,12 @@ SAG_HD bool robot_overlaps_any(const Ctx& C, const RB& R, double sn, double cs) 
   for (int s = C.L.v0; s < C.L.n; ++s) {
     int kind = slot_kind(C.sp, C.L, s);
     if (!kind_collidable(kind)) continue;
-    size_t i = oidx(D, s, C.e);
-    double x = D.ox[i], y = D.oy[i];
+    size_t i = oix(C, s);
+    double x = C.O.x[i], y = C.O.y[i];
     double dx = x - R.q[0], dy = y - R.q[1], reach = RB::kReach + kind_bound(D, kind);
     if (dx * dx + dy * dy > reach * reach) continue;
     double oc = 1.0, os = 0.0;
-    if (kind_movable(kind)) sag_sincos(D.oyaw[i], &os, &oc);
+    if (kind_movable(kind)) sag_sincos(C.O.yaw[i], &os, &oc);
     for (int pt = 0; pt < kind_nparts(kind); ++pt) {
       Geom go;
       obj_geom(D, kind, pt, x, y, oc, os, go);
@@ -1413,32 +1421,24 @@ SAG_HD bool robot_overlaps_any(const Ctx& C, const RB& R, double sn, double cs) 
   return false;
 }
 
-// Contact path of a warp.  Lanes that need it first run concurrently on their own SmallScratch (if the kernel
-// provides one); lanes whose pass did not fit, or all needing lanes when there is no SmallScratch, then take turns
-// on the warp's big Scratch.  `wmask` = lanes of this warp that own an environment (all of them call this together).
-// On the host there is a single lane.
+// Contact path of a warp of the scalar (one thread = one environment) kernels: the lanes that need it take turns on the
+// warp's Scratch.  `wmask` = lanes of this warp that own an environment (all of them call this together).  On the host
+// there is a single lane.
 template <class RB>
 SAG_HD void warp_contact_pass(unsigned wmask, bool need, const Ctx& C, const RB& R, double sn, double cs, const PtConst& K,
-                              const double* fs, unsigned mov, bool integrate, double h, Scratch* S, SmallScratch* small, Phys& P) {
-  bool big = need;
-  if (small) {
-    if (need) {
-      contact_pass(C, R, sn, cs, K, fs, mov, integrate, h, *small, P);
-      big = P.retry != 0;
-    }
-  }
+                              const double* fs, unsigned mov, bool integrate, double h, Scratch* S, const SolveConsts& Q, Phys& P) {
 #if defined(__CUDA_ARCH__)
-  unsigned todo = __ballot_sync(wmask, big);
+  unsigned todo = __ballot_sync(wmask, need);
   const int lane = threadIdx.x & 31;
   while (todo) {
     const int turn = __ffs((int)todo) - 1;
     todo &= todo - 1;
-    if (lane == turn) contact_pass(C, R, sn, cs, K, fs, mov, integrate, h, *S, P);
+    if (lane == turn) contact_pass<RB, false>(C, R, sn, cs, K, fs, mov, integrate, h, *S, Q, P);
     __syncwarp(wmask);
   }
 #else
   (void)wmask;
-  if (big) contact_pass(C, R, sn, cs, K, fs, mov, integrate, h, *S, P);
+  if (need) contact_pass<RB, false>(C, R, sn, cs, K, fs, mov, integrate, h, *S, Q, P);
 #endif
 }
 
@@ -1513,8 +1513,8 @@ SAG_HD int resample_goal(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t
       int kind = slot_kind(C.sp, C.L, s);
       double ko = kind == K_HAZARD ? D.k_hazard : kind == K_VASE ? D.k_vase : kind == K_GREMLIN ? D.k_gremlin
                 : kind == K_PILLAR ? D.k_pillar : kind == K_BUTTON ? kButtonsKeepout : C.sp.box_keepout;
-      size_t i = oidx(D, s, C.e);
-      double dx = x - D.ox[i], dy = y - D.oy[i];
+      size_t i = oix(C, s);
+      double dx = x - C.O.x[i], dy = y - C.O.y[i];
       if (sqrt(dx * dx + dy * dy) < ko + kGoalKeepout) valid = false;
     }
     if (valid) { gx = x; gy = y; return 0; }
@@ -1556,8 +1556,8 @@ SAG_HD void sample_goal_button(const Ctx& C, const Rng& rng, uint32_t stream, ui
   if (k >= C.L.nbtn) k = C.L.nbtn - 1;
   T.gbtn = k;
   T.btimer = kButtonDelay;
-  size_t i = oidx(C.D, C.L.btn0 + k, C.e);
-  T.last0 = dist2d(R.q[0], R.q[1], C.D.ox[i], C.D.oy[i]);
+  size_t i = oix(C, C.L.btn0 + k);
+  T.last0 = dist2d(R.q[0], R.q[1], C.O.x[i], C.O.y[i]);
 }
 
 // task.reset(): go_to_goal.py:50-57, push_box.py:94-100, press_buttons.py:65-68, collect.py:41-47, catch_goal.py:36-40
@@ -1571,13 +1571,13 @@ SAG_HD int task_reset(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& c
   }
   double gx, gy;
   if (resample_goal(C, rng, stream, ctr, R.q[0], R.q[1], gx, gy)) return 1;
-  size_t ig = oidx(D, C.L.goal, C.e);
-  D.ox[ig] = gx; D.oy[ig] = gy;
+  size_t ig = oix(C, C.L.goal);
+  C.O.x[ig] = gx; C.O.y[ig] = gy;
   T.last0 = dist2d(R.q[0], R.q[1], gx, gy);
   if (C.task == T_CATCH_GOAL) { T.cgox = gx; T.cgoy = gy; }
   if (C.sp.kind == 2) {
-    size_t ib = oidx(D, C.L.box, C.e);
-    double bx = D.ox[ib], by = D.oy[ib];
+    size_t ib = oix(C, C.L.box);
+    double bx = C.O.x[ib], by = C.O.y[ib];
     T.last1 = dist2d(gx, gy, bx, by);
     T.last0 = dist2d(R.q[0], R.q[1], bx, by);
   }
@@ -1590,8 +1590,8 @@ SAG_HD int compute_reward(const Ctx& C, const Rng& rng, const RB& R, TaskState& 
   const Dev& D = C.D;
   reward[0] = reward[1] = 0.0;
   if (C.sp.kind == 0) {  // go_to_goal.py:31-45
-    size_t ig = oidx(D, C.L.goal, C.e);
-    double dx = R.q[0] - D.ox[ig], dy = R.q[1] - D.oy[ig], dz = kPtZ - kGoalZ;
+    size_t ig = oix(C, C.L.goal);
+    double dx = R.q[0] - C.O.x[ig], dy = R.q[1] - C.O.y[ig], dz = kPtZ - kGoalZ;
     double distance = sqrt(dx * dx + dy * dy + dz * dz);
     double r = T.last0 - distance;
     if (C.task == T_GO_TO_GOAL_SCARCE) r = ((distance >= 0.0 && distance <= kGoalSize * 1.5) ? 1.0 : 0.0) * r;
@@ -1622,8 +1622,8 @@ SAG_HD int compute_reward(const Ctx& C, const Rng& rng, const RB& R, TaskState& 
     return 0;
   }
   if (C.sp.kind == 1) {  // press_buttons.py:42-63, press_buttons_scarce.py:22-55
-    size_t ib = oidx(D, C.L.btn0 + T.gbtn, C.e);
-    double d = dist2d(R.q[0], R.q[1], D.ox[ib], D.oy[ib]);
+    size_t ib = oix(C, C.L.btn0 + T.gbtn);
+    double d = dist2d(R.q[0], R.q[1], C.O.x[ib], C.O.y[ib]);
     double r = C.task == T_PRESS_BUTTONS_SCARCE ? 0.0 : T.last0 - d;
     T.last0 = d;
     if ((touch >> (C.L.btn0 + T.gbtn)) & 1u) {
@@ -1639,8 +1639,8 @@ SAG_HD int compute_reward(const Ctx& C, const Rng& rng, const RB& R, TaskState& 
     return 0;
   }
   // push_box.py:74-92, push_box_scarce.py:22-50, haul_box.py:34-48
-  size_t ig = oidx(D, C.L.goal, C.e), ib = oidx(D, C.L.box, C.e);
-  double bx = D.ox[ib], by = D.oy[ib];
+  size_t ig = oix(C, C.L.goal), ib = oix(C, C.L.box);
+  double bx = C.O.x[ib], by = C.O.y[ib];
   double r = 0.0;
   if (C.task != T_HAUL_BOX) {
     double bd = dist2d(R.q[0], R.q[1], bx, by);
@@ -1649,7 +1649,7 @@ SAG_HD int compute_reward(const Ctx& C, const Rng& rng, const RB& R, TaskState& 
     r += sh;
     T.last0 = bd;
   }
-  double bg = dist2d(bx, by, D.ox[ig], D.oy[ig]);
+  double bg = dist2d(bx, by, C.O.x[ig], C.O.y[ig]);
   r += T.last1 - bg;
   T.last1 = bg;
   if (bg <= kGoalSize) {
@@ -1673,9 +1673,9 @@ SAG_HD void set_mocaps(const Ctx& C, const Rng& rng, TaskState& T, double time) 
   }
   double progress = (10 - T.cgtimer) / 10.0;
   double radius = progress * (T.cgnext - T.cgcur) + T.cgcur;
-  size_t ig = oidx(C.D, C.L.goal, C.e);
-  C.D.ox[ig] = T.cgox + sag_sin(time) * radius;
-  C.D.oy[ig] = T.cgoy + sag_cos(time) * radius;
+  size_t ig = oix(C, C.L.goal);
+  C.O.x[ig] = T.cgox + sag_sin(time) * radius;
+  C.O.y[ig] = T.cgoy + sag_cos(time) * radius;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1716,8 +1716,8 @@ __device__ __forceinline__ void pass_a_coop(const Ctx& C, const RB& R, double cs
   bool hzl = false;
   double lv = 1e300, lp = 1e300, lb = 1e300, lx = 1e300;
   if (s < C.L.n) {
-    size_t i = oidx(D, s, C.e);
-    double wx = D.ox[i] - R.q[0], wy = D.oy[i] - R.q[1];
+    size_t i = oix(C, s);
+    double wx = C.O.x[i] - R.q[0], wy = C.O.y[i] - R.q[1];
     double d2 = wx * wx + wy * wy;
     if (s < C.L.t0) {
       if (s < C.L.v0) hzl = hazard_hit(d2, D.hazards_size);
@@ -1736,12 +1736,13 @@ __device__ __forceinline__ void pass_a_coop(const Ctx& C, const RB& R, double cs
 #endif
 
 template <int Mode, class RB>
-SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const Ctx& C, const RB& R, TaskState& T, const Rng& rng, const PtConst& K,
+SAG_HD void end_of_step(unsigned wmask, Scratch* S, const SolveConsts& Q, const Ctx& C, const RB& R, TaskState& T, const Rng& rng, const PtConst& K,
                         unsigned mov, bool phys_err, const double* qacc_err, bool with_reward, float* obs_s, int ostride, EndOut& O) {
   constexpr bool QuietOnly = Mode == kStepQuiet || Mode == kStepNear, Coop = Mode == kStepCoop, Near = Mode == kStepNear;
   const Dev& D = C.D;
   const int e = C.e;
   O.bail = 0;
+  SAG_CLK_DECL;
   double sn, cs;
   sag_sincos(R.q[2], &sn, &cs);
   for (int k = 0; k < 48; ++k) obs_s[k * ostride] = 0.0f;
@@ -1762,8 +1763,8 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
     for (int k = 0; k < 3; ++k) {
       int s = s0 + k;
       on[k] = s < C.L.t0;
-      size_t i = oidx(D, on[k] ? s : s0, e);
-      wx[k] = D.ox[i] - R.q[0]; wy[k] = D.oy[i] - R.q[1];
+      size_t i = oix(C, on[k] ? s : s0);
+      wx[k] = C.O.x[i] - R.q[0]; wy[k] = C.O.y[i] - R.q[1];
     }
     LidarHit H[3];
 #pragma unroll
@@ -1782,8 +1783,8 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
   for (int s = C.L.t0; s < C.L.n; ++s) {  // collidable task objects: buttons, push box
     int kind = slot_kind(C.sp, C.L, s);
     if (!kind_collidable(kind)) continue;
-    size_t i = oidx(D, s, e);
-    double wx = D.ox[i] - R.q[0], wy = D.oy[i] - R.q[1];
+    size_t i = oix(C, s);
+    double wx = C.O.x[i] - R.q[0], wy = C.O.y[i] - R.q[1];
     double d2 = wx * wx + wy * wy;
     if (kind == K_BUTTON) { if (d2 < d2b) d2b = d2; } else { if (d2 < d2x) d2x = d2; }
   }
@@ -1793,29 +1794,35 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
   if (d2p < 1e299) clear = fmin(clear, sqrt(d2p) - (RB::kReach + kind_bound(D, K_PILLAR)));
   if (d2b < 1e299) clear = fmin(clear, sqrt(d2b) - (RB::kReach + kind_bound(D, K_BUTTON)));
   if (d2x < 1e299) clear = fmin(clear, sqrt(d2x) - (RB::kReach + kind_bound(D, C.sp.box_kind)));
+  // HaulBox: the tendon's slack bounds the clearance too (a slack tendon adds no constraint row: haul_box.py:21-30)
+  bool taut = false;
+  if (C.task == T_HAUL_BOX) {
+    double tdx, tdy, tlen, tdist;
+    taut = tendon_taut(C, R, tdx, tdy, tlen, tdist);
+    clear = fmin(clear, tdist);
+  }
   // ---- forward(): contacts + acceleration at the final state (safe_adaptation_gym.py:76)
   double fs[3], qacc[3];
   R.smooth(sn, cs, fs);
   unsigned touch = 0;
   O.err = 0;
-  const bool tendon = C.task == T_HAUL_BOX;
   Phys P;
-  P.err = 0; P.touch = 0; P.retry = 0;
+  P.err = 0; P.touch = 0;
   bool need = false;
   if constexpr (Near) {  // forward() at the final state would list a contact: not a contact-free step after all
-    if (!(clear > 0.0) && robot_overlaps_any(C, R, sn, cs)) { O.bail = 1; return; }
+    if (!(clear > 0.0) && (taut || robot_overlaps_any(C, R, sn, cs))) { O.bail = 1; return; }
   }
   // A PhysicsError in physics.step returns the observation at once (safe_adaptation_gym.py:73-75): no forward(), the
   // accelerometer shows the last substep's acceleration, no reward / cost evaluation.
   const bool skip_forward = phys_err && qacc_err != nullptr;
   if (!QuietOnly && !skip_forward) {  // (a quiet step ends with positive clearance: no contact is possible)
-    const bool near_ = !(clear > 0.0 && mov == 0 && !tendon);
+    const bool near_ = !(clear > 0.0 && mov == 0);
     if constexpr (Coop) {
 #if defined(__CUDA_ARCH__)
-      need = near_ && (mov != 0 || tendon || robot_overlaps_any_coop(C, R, sn, cs));
+      need = near_ && (mov != 0 || taut || robot_overlaps_any_coop(C, R, sn, cs));
 #endif
     } else {
-      need = near_ && (mov != 0 || tendon || robot_overlaps_any(C, R, sn, cs));
+      need = near_ && (mov != 0 || taut || robot_overlaps_any(C, R, sn, cs));
     }
   }
   if (skip_forward) {
@@ -1825,14 +1832,16 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
     else { double p, q; R.pq(sn, cs, p, q); pt_solve(p, q, K.ia0, K.is0, fs, P.qacc); }
   }
   if constexpr (Coop) {
-    if (need) contact_pass<RB, Scratch, true>(C, R, sn, cs, K, fs, mov, false, 0.0, *S, P);
+    SAG_CLK(7);
+    if (need) contact_pass<RB, true>(C, R, sn, cs, K, fs, mov, false, 0.0, *S, Q, P);
+    SAG_CLK_RESET;
   } else if (!QuietOnly) {
-    warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, small, P);
+    warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, Q, P);
   }
   qacc[0] = P.qacc[0]; qacc[1] = P.qacc[1]; qacc[2] = P.qacc[2];
   touch = P.touch;
   O.err = P.err;
-  if (mov != 0 || tendon) clear = -1.0;
+  if (mov != 0) clear = -1.0;
   O.clear = clear;
   O.mov = mov;
   O.touch = touch;
@@ -1856,9 +1865,9 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
       int kind = slot_kind(C.sp, C.L, s);
       int g = slot_group(C, s, kind, T.gbtn, T.bstate, T.amask);
       if (g != 0) {
-        size_t i = oidx(D, s, e);
+        size_t i = oix(C, s);
         int off = g == 1 ? 0 : (g == 3 ? 16 : 32);
-        coop_lidar_apply(lidar_eval(D.ox[i] - R.q[0], D.oy[i] - R.q[1], cs, sn), obs_s + off * ostride, ostride);
+        coop_lidar_apply(lidar_eval(C.O.x[i] - R.q[0], C.O.y[i] - R.q[1], cs, sn), obs_s + off * ostride, ostride);
       }
     }
     __syncwarp();
@@ -1868,9 +1877,9 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
     int kind = slot_kind(C.sp, C.L, s);
     int g = slot_group(C, s, kind, T.gbtn, T.bstate, T.amask);
     if (g == 0) continue;
-    size_t i = oidx(D, s, e);
+    size_t i = oix(C, s);
     int off = g == 1 ? 0 : (g == 3 ? 16 : 32);
-    lidar_apply(lidar_eval(D.ox[i] - R.q[0], D.oy[i] - R.q[1], cs, sn), obs_s + off * ostride, ostride);
+    lidar_apply(lidar_eval(C.O.x[i] - R.q[0], C.O.y[i] - R.q[1], cs, sn), obs_s + off * ostride, ostride);
   }
   // ---- sensors (safe_adaptation_gym.py:225-237; semantics SURVEY App. B.6 [EXT])
   float* o = obs_s + 48 * ostride;
@@ -1891,6 +1900,7 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, SmallScratch* small, const C
     o[18 * ostride] = (float)(2.0 * (x * y + w * z)); o[19 * ostride] = (float)(w * w - x * x + y * y - z * z); o[20 * ostride] = (float)(2.0 * (y * z - w * x));
     o[21 * ostride] = (float)(2.0 * (x * z - w * y)); o[22 * ostride] = (float)(2.0 * (y * z + w * x)); o[23 * ostride] = (float)(w * w - x * x - y * y + z * z);
   }
+  if constexpr (Coop) SAG_CLK(9);
 }
 
 template <class RB>
@@ -1925,11 +1935,25 @@ SAG_HD bool env_is_quiet(double clear, const RB& R) { return clear > R.travel_bo
 // SafeAdaptationGym.step for one environment (safe_adaptation_gym.py:56-83)
 // ------------------------------------------------------------------------------------------------
 template <int Mode, class RB>
-SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2,
-                     unsigned char* cost, unsigned char* done) {
+SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, float a1, float* obs_s, int ostride, double* reward2,
+                     unsigned char* cost, unsigned char* done, bool pretest = true) {
   constexpr bool QuietOnly = Mode == kStepQuiet || Mode == kStepNear, Coop = Mode == kStepCoop, Near = Mode == kStepNear;
-  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
+  SAG_CLK_DECL;
+  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
+#if defined(__CUDA_ARCH__)
+  if constexpr (Coop) {  // stage the object arrays in the warp's working set, one slot per lane; written back at the end
+    const int s = coop_lane();
+    if (s < C.L.n) {
+      const size_t i = oix(C, s);
+      S->obj[0][s] = C.O.x[i]; S->obj[1][s] = C.O.y[i]; S->obj[2][s] = C.O.yaw[i];
+      S->obj[3][s] = C.O.vx[i]; S->obj[4][s] = C.O.vy[i]; S->obj[5][s] = C.O.w[i];
+    }
+    C.O.x = S->obj[0]; C.O.y = S->obj[1]; C.O.yaw = S->obj[2]; C.O.vx = S->obj[3]; C.O.vy = S->obj[4]; C.O.w = S->obj[5];
+    C.O.stride = 1;
+    __syncwarp();
+  }
+#endif
   RB R;
   load_robot(D, e, C.sp, R);
   TaskState T;
@@ -1939,6 +1963,13 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
   unsigned mov = (unsigned)D.movmask[e];
   const double h = RB::kH;
   const PtConst K = R.consts(h);
+  // constants of the contact solver: the cooperative kernel keeps them in the warp's shared-memory working set (every
+  // lane writes the same values), the scalar path in registers / local memory; the contact-free modes need none
+  SolveConsts Qloc;
+  if constexpr (Mode == kStepFull) solve_consts(D, C.sp, Qloc);
+  if constexpr (Coop) solve_consts(D, C.sp, S->Q);
+  const SolveConsts& Q = Coop ? S->Q : Qloc;
+  const bool tendon_task = C.task == T_HAUL_BOX;
   // action noise + clip (:58-67)
   double act0 = (double)a0, act1 = (double)a1;
   if (D.action_noise != 0.0) {
@@ -1970,7 +2001,9 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
   int err = (fl & F_PHYS_ERROR) ? 1 : 0;  // a physics error is sticky until the env is reset
   const bool quiet = QuietOnly ? true : env_is_quiet(D.clear[e], R);
   (void)Coop;
+  SAG_PROF(e, 7, quiet ? 0 : 1);
   double qacc_err[3] = {0.0, 0.0, 0.0};
+  if constexpr (Coop) SAG_CLK(0);
 #pragma unroll 1
   for (int k = 0; k < RB::kNsub; ++k) {
     double sn, cs, fs[3], fc[3] = {0.0, 0.0, 0.0}, wtau[2] = {0.0, 0.0}, rhs[3], a[3], p, q;
@@ -1978,16 +2011,22 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
     R.pq(sn, cs, p, q);
     R.smooth(sn, cs, fs);
     bool need = false;
+    bool taut = false;
+    if (tendon_task && (Near ? pretest : (Mode != kStepQuiet && !quiet))) {
+      double tdx, tdy, tlen, tdist;
+      taut = tendon_taut(C, R, tdx, tdy, tlen, tdist);
+    }
     if constexpr (Coop) {
 #if defined(__CUDA_ARCH__)
-      need = !quiet && (mov != 0 || C.task == T_HAUL_BOX || robot_overlaps_any_coop(C, R, sn, cs));
+      need = !quiet && (mov != 0 || taut || robot_overlaps_any_coop(C, R, sn, cs));
 #endif
     } else if (!QuietOnly) {
-      need = !quiet && (mov != 0 || C.task == T_HAUL_BOX || robot_overlaps_any(C, R, sn, cs));
+      need = !quiet && (mov != 0 || taut || robot_overlaps_any(C, R, sn, cs));
     }
     if constexpr (Near) {
-      if (robot_overlaps_any(C, R, sn, cs)) return 1;
+      if (pretest && (taut || robot_overlaps_any(C, R, sn, cs))) return 1;
     }
+    SAG_PROF(e, 3, need ? 1 : 0);
     double subq[3] = {0.0, 0.0, 0.0};  // this substep's forward-dynamics acceleration, if a solve produced one
     if constexpr (RB::kKind == 1) {  // car: the wheel-floor friction rows are always there
       if (!need) {
@@ -2000,11 +2039,13 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
     if (!QuietOnly) {
       Phys P;
       P.fc[0] = fc[0]; P.fc[1] = fc[1]; P.fc[2] = fc[2]; P.wtau[0] = wtau[0]; P.wtau[1] = wtau[1];
-      P.mov = mov; P.err = 0; P.retry = 0;
+      P.mov = mov; P.err = 0;
       if constexpr (Coop) {
-        if (need) contact_pass<RB, Scratch, true>(C, R, sn, cs, K, fs, mov, true, h, *S, P);
+        SAG_CLK(1);
+        if (need) contact_pass<RB, true>(C, R, sn, cs, K, fs, mov, true, h, *S, Q, P);
+        SAG_CLK_RESET;
       } else {
-        warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, small, P);
+        warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, Q, P);
       }
       fc[0] = P.fc[0]; fc[1] = P.fc[1]; fc[2] = P.fc[2]; wtau[0] = P.wtau[0]; wtau[1] = P.wtau[1];
       mov = P.mov;
@@ -2047,9 +2088,11 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
       qacc_err[0] = subq[0]; qacc_err[1] = subq[1]; qacc_err[2] = subq[2];
     }
     time += h;
+    if constexpr (Coop) SAG_CLK(6);
   }
   EndOut O;
-  end_of_step<Mode, RB>(wmask, S, small, C, R, T, rng, K, mov, err != 0, qacc_err, true, obs_s, ostride, O);
+  end_of_step<Mode, RB>(wmask, S, Q, C, R, T, rng, K, mov, err != 0, qacc_err, true, obs_s, ostride, O);
+  if constexpr (Coop) SAG_CLK_RESET;
   if constexpr (Near) { if (O.bail) return 1; }
   unsigned char dn = 0;
   if (err) { dn = 1; fl |= F_PHYS_ERROR; }
@@ -2058,7 +2101,17 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
   // bookkeeping (cooperative mode: read-modify-write of global state by one lane only)
   bool writer = true;
 #if defined(__CUDA_ARCH__)
-  if constexpr (Coop) { __syncwarp(); writer = coop_lane() == 0; }
+  if constexpr (Coop) {
+    __syncwarp();
+    writer = coop_lane() == 0;
+    const int s = coop_lane();  // objects back to global memory (hazards never change)
+    if (s >= C.L.v0 && s < C.L.n) {
+      const ObjView G = global_objects(D, e);
+      const size_t i = (size_t)s * G.stride;
+      G.x[i] = S->obj[0][s]; G.y[i] = S->obj[1][s]; G.yaw[i] = S->obj[2][s];
+      G.vx[i] = S->obj[3][s]; G.vy[i] = S->obj[4][s]; G.w[i] = S->obj[5][s];
+    }
+  }
 #endif
   if (writer) {
     int ns = D.nstep[e] + 1;
@@ -2077,13 +2130,14 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& 
   reward2[0] = O.rew[0]; reward2[1] = O.rew[1];
   *cost = (unsigned char)(O.cost > 0.0);
   *done = dn;
+  if constexpr (Coop) SAG_CLK(10);
   return 0;
 }
 
 // observation at the current state (reset return value / refresh after state injection)
 template <class RB>
-SAG_HD void env_observe(unsigned wmask, Scratch* S, SmallScratch* small, const Dev& D, int e, float* obs_s, int ostride) {
-  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
+SAG_HD void env_observe(unsigned wmask, Scratch* S, const Dev& D, int e, float* obs_s, int ostride) {
+  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
   RB R;
   load_robot(D, e, C.sp, R);
@@ -2094,11 +2148,13 @@ SAG_HD void env_observe(unsigned wmask, Scratch* S, SmallScratch* small, const D
   unsigned mov = 0;  // rebuilt from the velocities: state may have been injected
   for (int s = C.L.v0; s < C.L.n; ++s) {
     if (!kind_movable(slot_kind(C.sp, C.L, s))) continue;
-    size_t i = oidx(D, s, e);
-    if (D.ovx[i] != 0.0 || D.ovy[i] != 0.0 || D.ow[i] != 0.0) mov |= 1u << s;
+    size_t i = oix(C, s);
+    if (C.O.vx[i] != 0.0 || C.O.vy[i] != 0.0 || C.O.w[i] != 0.0) mov |= 1u << s;
   }
+  SolveConsts Q;
+  solve_consts(D, C.sp, Q);
   EndOut O;
-  end_of_step<kStepFull, RB>(wmask, S, small, C, R, T, rng, K, mov, false, nullptr, false, obs_s, ostride, O);
+  end_of_step<kStepFull, RB>(wmask, S, Q, C, R, T, rng, K, mov, false, nullptr, false, obs_s, ostride, O);
   D.clear[e] = O.clear;
   D.movmask[e] = (int)mov;
 }
@@ -2114,7 +2170,7 @@ SAG_HD double slot_keepout(const Dev& D, const TaskSpec& sp, int kind) {
 
 template <class RB>
 SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_task) {
-  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e]};
+  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
   Rng rng = {D.seed, D.gid_base + (uint32_t)e, episode};
   uint32_t ctr = 0;
@@ -2145,8 +2201,8 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
           double dx = x - rxy[0], dy = y - rxy[1];
           if (sqrt(dx * dx + dy * dy) < D.robot_keepout + D.placements_margin + keepout) valid = false;
           for (int j = 0; valid && j < idx; ++j) {
-            size_t i = oidx(D, j, e);
-            double ex = x - D.ox[i], ey = y - D.oy[i];
+            size_t i = oix(C, j);
+            double ex = x - C.O.x[i], ey = y - C.O.y[i];
             double ko = slot_keepout(D, C.sp, slot_kind(C.sp, C.L, j));
             if (sqrt(ex * ex + ey * ey) < ko + D.placements_margin + keepout) valid = false;
           }
@@ -2155,7 +2211,7 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
       }
       if (!placed) { failed = true; break; }
       if (idx < 0) { rxy[0] = x; rxy[1] = y; }
-      else { size_t i = oidx(D, idx, e); D.ox[i] = x; D.oy[i] = y; }
+      else { size_t i = oix(C, idx); C.O.x[i] = x; C.O.y[i] = y; }
     }
     if (!failed) ok = true;
   }
@@ -2166,14 +2222,14 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
   double robot_rot = kTwoPi * u1;
   for (int s = 0; s < C.L.t0; ++s) {
     rng.pair(0u, ctr++, u1, u2);
-    size_t i = oidx(D, s, e);
-    D.oyaw[i] = kTwoPi * u1; D.ovx[i] = 0.0; D.ovy[i] = 0.0; D.ow[i] = 0.0;
+    size_t i = oix(C, s);
+    C.O.yaw[i] = kTwoPi * u1; C.O.vx[i] = 0.0; C.O.vy[i] = 0.0; C.O.w[i] = 0.0;
   }
-  for (int s = C.L.t0; s < C.L.n; ++s) { size_t i = oidx(D, s, e); D.oyaw[i] = 0.0; D.ovx[i] = 0.0; D.ovy[i] = 0.0; D.ow[i] = 0.0; }
-  if (C.task == T_HAUL_BOX) { size_t ib = oidx(D, C.L.box, e); D.ox[ib] = rxy[0] + kBoxSize * 3.0; D.oy[ib] = rxy[1]; }
-  if (C.sp.kind == 0 || C.sp.kind == 2) { rng.pair(0u, ctr++, u1, u2); D.oyaw[oidx(D, C.L.goal, e)] = kTwoPi * u1; }
-  if (C.sp.kind == 2 && C.sp.box_kind == K_BOX) { rng.pair(0u, ctr++, u1, u2); D.oyaw[oidx(D, C.L.box, e)] = kTwoPi * u1; }
-  if (C.sp.kind == 1) for (int i = 0; i < C.L.nbtn; ++i) { rng.pair(0u, ctr++, u1, u2); D.oyaw[oidx(D, C.L.btn0 + i, e)] = kTwoPi * u1; }
+  for (int s = C.L.t0; s < C.L.n; ++s) { size_t i = oix(C, s); C.O.yaw[i] = 0.0; C.O.vx[i] = 0.0; C.O.vy[i] = 0.0; C.O.w[i] = 0.0; }
+  if (C.task == T_HAUL_BOX) { size_t ib = oix(C, C.L.box); C.O.x[ib] = rxy[0] + kBoxSize * 3.0; C.O.y[ib] = rxy[1]; }
+  if (C.sp.kind == 0 || C.sp.kind == 2) { rng.pair(0u, ctr++, u1, u2); C.O.yaw[oix(C, C.L.goal)] = kTwoPi * u1; }
+  if (C.sp.kind == 2 && C.sp.box_kind == K_BOX) { rng.pair(0u, ctr++, u1, u2); C.O.yaw[oix(C, C.L.box)] = kTwoPi * u1; }
+  if (C.sp.kind == 1) for (int i = 0; i < C.L.nbtn; ++i) { rng.pair(0u, ctr++, u1, u2); C.O.yaw[oix(C, C.L.btn0 + i)] = kTwoPi * u1; }
   RB R;
   R.q[0] = rxy[0]; R.q[1] = rxy[1]; R.q[2] = robot_rot; R.v[0] = R.v[1] = R.v[2] = 0.0; R.ctrl[0] = R.ctrl[1] = 0.0;
   if constexpr (RB::kKind == 1) { R.wheel[0] = R.wheel[1] = 0.0; R.cq[0] = 1.0; R.cq[1] = R.cq[2] = R.cq[3] = 0.0; }
@@ -2211,15 +2267,17 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
   // clearance of the fresh layout (same definition as end_of_step's; scheduling hint only: without it the first step
   // after a reset would send the whole batch down the contact path)
   double clear = 1e30;
-  if (C.task == T_HAUL_BOX) clear = -1.0;
-  else {
-    for (int s = C.L.v0; s < C.L.n; ++s) {
-      const int kind = slot_kind(C.sp, C.L, s);
-      if (!kind_collidable(kind)) continue;
-      size_t i = oidx(D, s, e);
-      double dx = D.ox[i] - R.q[0], dy = D.oy[i] - R.q[1];
-      clear = fmin(clear, sqrt(dx * dx + dy * dy) - (RB::kReach + kind_bound(D, kind)));
-    }
+  for (int s = C.L.v0; s < C.L.n; ++s) {
+    const int kind = slot_kind(C.sp, C.L, s);
+    if (!kind_collidable(kind)) continue;
+    size_t i = oix(C, s);
+    double dx = C.O.x[i] - R.q[0], dy = C.O.y[i] - R.q[1];
+    clear = fmin(clear, sqrt(dx * dx + dy * dy) - (RB::kReach + kind_bound(D, kind)));
+  }
+  if (C.task == T_HAUL_BOX) {
+    double tdx, tdy, tlen, tdist;
+    tendon_taut(C, R, tdx, tdy, tlen, tdist);
+    clear = fmin(clear, tdist);
   }
   D.clear[e] = clear;
   D.movmask[e] = 0;

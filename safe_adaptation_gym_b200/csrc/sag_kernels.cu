@@ -60,8 +60,8 @@ struct Handle {
   cudaStream_t own_stream;
   cudaStream_t copy_stream;          // host-buffer API: bulk device-to-host copies that overlap the busy kernel
   cudaEvent_t ev_quiet, ev_copied;
-  int busy_grid;  // CTAs of k_step_busy: resident CTAs per SM x SMs
-  int busy_g;     // environments per warp in k_step_busy
+  unsigned long long launches;  // kernels launched on behalf of this handle (sag_launch_count)
+  int busy_grid;  // CTAs of k_step_coop: resident CTAs per SM x SMs
 };
 
 // coalesced write-out of the CTA's observation tile: tile[k][t] -> out[(e0 + t) * kObs + k]
@@ -91,116 +91,42 @@ __device__ __forceinline__ void write_tile4(const float* tile, float* out, int e
 }
 
 // ---- the step: two kernels --------------------------------------------------------------------
-// k_step_quiet: one thread per environment over the whole batch.  Quiet environments (nothing within reach for the
-//   whole step, nothing moving: 88-100 % of them under a random policy) take the closed-form path with no contact
-//   code at all; the others are appended to a work list and left untouched.
-// k_step_coop (default) / k_step_busy<G>: the work list.  Taking the busy environments out of the batch kernel is what
-//   keeps the quiet path free of contact code (126 registers, no divergence); see the kernels' own comments.
+// k_step_free: one thread per environment over the whole batch.  Every environment in which nothing moves takes the
+//   contact-free closed-form path: the quiet ones (nothing within reach for the whole step: 88-100 % under a random
+//   policy) without any test, the others with the exact overlap / tendon pre-test in front of every substep.  An
+//   environment with a moving body or a sticky physics error, and one whose pre-test fires (nothing has been stored at
+//   that point), is appended to the work list and left untouched.
+// k_step_coop: the work list, ONE WARP per environment (sag_core.cuh "warp-cooperative variants").  Keeping the contact
+//   code out of the batch kernel is what keeps that one at <= 128 registers and free of divergence.
 
-// per-warp write-out of up to 32 observation rows (tile column = lane)
-template <int kObs>
-__device__ __forceinline__ void write_rows(const float* tile, int tstride, float* out, int e) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll 4
-  for (int r = 0; r < 32; ++r) {
-    const int er = __shfl_sync(0xffffffffu, e, r);
-    if (er < 0) continue;
-    float* dst = out + (size_t)er * kObs;
-    const float* src = tile + r;
-    for (int k = lane; k < kObs; k += 32) dst[k] = src[k * tstride];
-  }
-}
+// The work list of a step: D.worklist[0 .. counts[0]); counts[1] = fetch counter of the cooperative kernel.  Two counter
+// sets are used alternately (the other one is cleared by this step's batch kernel for the next step).
 
-// The work list of a step: three segments of D.worklist (3 x stride ints), lengths in D.counts[0..2], D.counts[3] = fetch
-// counter of the cooperative kernel.
-//   contact  [0, c0)                  a body moves / tendon / sticky physics error: needs the contact solver for certain
-//   warm     [stride, stride + c1)    nothing moves, clearance below kHotMargin: probably touching
-//   cold     [2 stride, 2 stride + c2) something within reach only
-// Entry i of "contact, warm, cold" in this order (the order in which the busy kernel fetches them):
-__device__ __forceinline__ int worklist_at(const Dev& D, int i, int c0, int c1) {
-  return D.worklist[i < c0 ? i : (i < c0 + c1 ? D.stride + (i - c0) : 2 * D.stride + (i - c0 - c1))];
-}
 // __launch_bounds__(kBS, 4): 4 CTAs / SM (<= 128 registers) so that the whole 65,536-env batch is one wave
 template <class RB>
-__global__ void __launch_bounds__(kBS, 4) k_step_quiet(Dev D, const float* __restrict__ act, float* __restrict__ obs,
-                                                     double* __restrict__ reward, double* __restrict__ reward2,
-                                                     uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
-  constexpr int kObs = RB::kObsDim;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);  // [kObs][kTileStride]
-  int e = blockIdx.x * kBS + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x < 4) D.counts_next[threadIdx.x] = 0;
-  bool quiet = false;
-  int seg = 0;
-  if (e < D.n) {
-    RB R;
-    const int task = D.task[e];
-    load_robot(D, e, task_spec(task), R);
-    const double clear = D.clear[e];
-    const unsigned char fl = D.flags[e];
-    quiet = !(fl & F_PHYS_ERROR) && env_is_quiet(clear, R);
-    const bool contact = (fl & F_PHYS_ERROR) || task == T_HAUL_BOX || D.movmask[e] != 0;
-    seg = contact ? 0 : (clear < kHotMargin ? 1 : 2);
-  }
-  // work list append, one atomic per warp and segment
-  const unsigned busy = __ballot_sync(0xffffffffu, e < D.n && !quiet);
-  if (busy) {
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      const unsigned m = __ballot_sync(0xffffffffu, e < D.n && !quiet && seg == g);
-      if (!m) continue;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&D.counts[g], __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if ((m >> lane) & 1u) D.worklist[g * D.stride + base + __popc(m & ((1u << lane) - 1u))] = e;
-    }
-  }
-  if (!quiet) e = -1;
-  if (e >= 0) {
-    float2 a = reinterpret_cast<const float2*>(act)[e];
-    double rew[2];
-    unsigned char c, d;
-    env_step<true, RB>(0u, nullptr, nullptr, D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d);
-    reward[e] = rew[0];
-    if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
-    cost[e] = c;
-    done[e] = d;
-  }
-  // all kBS rows of the CTA in one coalesced sweep.  The columns of the non-quiet environments hold stale shared memory:
-  // their rows are rewritten by the busy kernel, which always runs after this one on the same stream.
-  __syncthreads();
-  write_tile4<kObs>(tile, obs, blockIdx.x * kBS, D.n);
-}
-
-// k_step_near (car only): the warm + cold segments of the work list, one thread per environment like the quiet kernel.
-// Runs the quiet path with the exact overlap pre-test in front of every substep (and of the final forward pass); an
-// environment whose robot does touch something is abandoned before anything is stored and appended to the contact
-// segment.  A near step of the car -- ten substeps with the two-wheel friction solve -- costs ~70 us when a whole warp
-// runs it redundantly in the cooperative kernel and there are thousands of them (its travel bound is large); the point
-// robot's near steps are cheap and few, hide under the contact steps' latency there, and a third launch would only add
-// serial latency (measured: 2.25e8 -> 1.96e8 env-steps/s), so the point robot does not use this kernel.
-template <class RB>
-constexpr bool kNearKernel = RB::kKind == 1;
-
-template <class RB>
-__global__ void __launch_bounds__(kBS, 4) k_step_near(const __grid_constant__ Dev D, const float* __restrict__ act, float* __restrict__ obs,
+__global__ void __launch_bounds__(kBS, 4) k_step_free(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                     double* __restrict__ reward, double* __restrict__ reward2,
                                                     uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   constexpr int kObs = RB::kObsDim;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);  // [kObs][kTileStride]
-  const int i = blockIdx.x * kBS + threadIdx.x;
-  const int c1 = D.counts[1], c2 = D.counts[2];
-  if (blockIdx.x * kBS >= c1 + c2) return;
+  const int e = blockIdx.x * kBS + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  int e = i < c1 + c2 ? worklist_at(D, i, 0, c1) : -1;
+  if (blockIdx.x == 0 && threadIdx.x < 4) D.counts_next[threadIdx.x] = 0;
+  bool run = false, pretest = false;
+  if (e < D.n) {
+    RB R;
+    load_robot(D, e, task_spec(D.task[e]), R);
+    const unsigned char fl = D.flags[e];
+    run = !(fl & F_PHYS_ERROR) && D.movmask[e] == 0;
+    pretest = !env_is_quiet(D.clear[e], R);
+  }
   bool bail = false;
-  if (e >= 0) {
+  if (run) {
     float2 a = reinterpret_cast<const float2*>(act)[e];
     double rew[2];
     unsigned char c, d;
-    bail = env_step<kStepNear, RB>(0u, nullptr, nullptr, D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d) != 0;
+    bail = env_step<kStepNear, RB>(0u, nullptr, D, e, a.x, a.y, tile + threadIdx.x, kTileStride, rew, &c, &d, pretest) != 0;
     if (!bail) {
       reward[e] = rew[0];
       if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
@@ -208,68 +134,26 @@ __global__ void __launch_bounds__(kBS, 4) k_step_near(const __grid_constant__ De
       done[e] = d;
     }
   }
-  const unsigned bm = __ballot_sync(0xffffffffu, bail);
-  if (bm) {
+  // work list append, one atomic per warp
+  const bool busy = e < D.n && (!run || bail);
+  const unsigned m = __ballot_sync(0xffffffffu, busy);
+  if (m) {
     int base = 0;
-    if (lane == 0) base = atomicAdd(&D.counts[0], __popc(bm));
+    if (lane == 0) base = atomicAdd(&D.counts[0], __popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (bail) D.worklist[base + __popc(bm & ((1u << lane) - 1u))] = e;
+    if (busy) D.worklist[base + __popc(m & ((1u << lane) - 1u))] = e;
   }
-  if (bail) e = -1;
-  __syncwarp();
-  write_rows<kObs>(tile + (threadIdx.x & ~31), kTileStride, obs, e);
-}
-
-// G = environments per warp (lanes 0..G-1 active).  A warp executes the union of its lanes' divergent paths and each
-// busy warp is latency-bound, so fewer environments per warp = shorter critical path, more warps = more latency hiding.
-template <int G, class RB>
-struct BusyCfg {
-  static constexpr int kObs = RB::kObsDim;
-  static constexpr int kTileStride = G + 1;
-  static constexpr size_t kTileBytes = (sizeof(float) * kObs * kTileStride + 15) / 16 * 16;
-  static constexpr size_t kSmemBytes = kTileBytes + sizeof(Scratch) + G * sizeof(SmallScratch);
-};
-
-template <int G, class RB>
-__global__ void __launch_bounds__(32) k_step_busy(Dev D, const float* __restrict__ act, float* __restrict__ obs,
-                                                   double* __restrict__ reward, double* __restrict__ reward2,
-                                                   uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);
-  Scratch* big = reinterpret_cast<Scratch*>(smem_raw + BusyCfg<G, RB>::kTileBytes);
-  SmallScratch* small = reinterpret_cast<SmallScratch*>(smem_raw + BusyCfg<G, RB>::kTileBytes + sizeof(Scratch));
-  const int lane = threadIdx.x;
-  const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + (kNearKernel<RB> ? 0 : c1 + D.counts[2]);
-  for (int chunk = blockIdx.x; chunk * G < count; chunk += gridDim.x) {
-    const int i = chunk * G + lane;
-    const int e = (lane < G && i < count) ? worklist_at(D, i, c0, c1) : -1;
-    const unsigned wmask = __ballot_sync(0xffffffffu, e >= 0);
-    if (e >= 0) {
-      float2 a = reinterpret_cast<const float2*>(act)[e];
-      double rew[2];
-      unsigned char c, d;
-      env_step<false, RB>(wmask, big, small + lane, D, e, a.x, a.y, tile + lane, BusyCfg<G, RB>::kTileStride, rew, &c, &d);
-      reward[e] = rew[0];
-      if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
-      cost[e] = c;
-      done[e] = d;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < G; ++r) {  // observation rows of this chunk, 60 floats each, all lanes help
-      const int er = __shfl_sync(0xffffffffu, e, r);
-      if (er < 0) continue;
-      float* dst = obs + (size_t)er * BusyCfg<G, RB>::kObs;
-      for (int k = lane; k < BusyCfg<G, RB>::kObs; k += 32) dst[k] = tile[k * BusyCfg<G, RB>::kTileStride + r];
-    }
-    __syncwarp();
-  }
+  // all kBS rows of the CTA in one coalesced sweep.  The columns of the work-list environments hold stale shared memory:
+  // their rows are rewritten by the cooperative kernel, which always runs after this one on the same stream.
+  __syncthreads();
+  write_tile4<kObs>(tile, obs, blockIdx.x * kBS, D.n);
 }
 
 // k_step_coop: the work list with ONE WARP per environment (sag_core.cuh "warp-cooperative variants"): the lanes run the
-// step's scalar code redundantly and split the collision phases, the overlap pre-test and the lidar pass between them.
-// A contact environment's step is a long dependent chain (~60 k instructions when run by one thread); what bounds the
-// busy phase is that chain's latency, not throughput, so the lanes are spent on shortening it.
+// step's scalar code redundantly on the warp's shared-memory working set and split the collision phases, the overlap
+// pre-test, the row set-up and the lidar pass between them.  A contact environment's step is a long dependent chain; what
+// bounds this kernel is that chain's latency, not throughput, so the lanes are spent on shortening it and the register
+// budget (<= 128) on keeping every work-list environment of the step resident at once (16 warps / SM).
 constexpr int kCoopWarps = 4;  // warps (= environments in flight) per CTA
 template <class RB>
 struct CoopCfg {
@@ -280,7 +164,7 @@ struct CoopCfg {
 };
 
 #ifndef SAG_COOP_MINBLOCKS
-#define SAG_COOP_MINBLOCKS 1
+#define SAG_COOP_MINBLOCKS 4
 #endif
 template <class RB>
 __global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_coop(const __grid_constant__ Dev D, const float* __restrict__ act,
@@ -295,19 +179,24 @@ __global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_co
   // launched with programmatic stream serialization where possible (Ops::step_busy): the grid may be resident before the
   // preceding kernel has finished; everything that kernel wrote is visible after this call (no-op otherwise)
   cudaGridDependencySynchronize();
-  const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + (kNearKernel<RB> ? 0 : c1 + D.counts[2]);
-  // dynamic fetch (a contact environment takes ~15x a near one): contact entries first, then the probably-touching ones,
-  // so that the long steps start early
-  for (;;) {
+  const int count = D.counts[0];
+  for (;;) {  // dynamic fetch: a step with several contacts takes a multiple of the common single-contact one
     int i = 0;
-    if (lane == 0) i = atomicAdd(&D.counts[3], 1);
+    if (lane == 0) i = atomicAdd(&D.counts[1], 1);
     i = __shfl_sync(0xffffffffu, i, 0);
     if (i >= count) break;
-    const int e = worklist_at(D, i, c0, c1);
+    const int e = D.worklist[i];
+#if defined(SAG_TIMING)
+    if (lane == 0) atomicAdd(&D.dbg[15], 1ull);
+    long long clk_ = clock64();
+#endif
     float2 a = reinterpret_cast<const float2*>(act)[e];
     double rew[2];
     unsigned char c, d;
-    env_step<kStepCoop, RB>(0xffffffffu, big, nullptr, D, e, a.x, a.y, tile, 1, rew, &c, &d);
+    env_step<kStepCoop, RB>(0xffffffffu, big, D, e, a.x, a.y, tile, 1, rew, &c, &d);
+#if defined(SAG_TIMING)
+    if (lane == 0) atomicAdd(&D.dbg[14], (unsigned long long)(clock64() - clk_));
+#endif
     __syncwarp();
     if (lane == 0) {
       reward[e] = rew[0];
@@ -328,7 +217,7 @@ __global__ void __launch_bounds__(kBS) k_observe(Dev D, float* __restrict__ obs)
   Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + TileCfg<RB>::kTileBytes);
   const int e0 = blockIdx.x * kBS, e = e0 + threadIdx.x;
   const unsigned wmask = __ballot_sync(0xffffffffu, e < D.n);
-  if (e < D.n) env_observe<RB>(wmask, &scratch[threadIdx.x >> 5], nullptr, D, e, tile + threadIdx.x, kTileStride);
+  if (e < D.n) env_observe<RB>(wmask, &scratch[threadIdx.x >> 5], D, e, tile + threadIdx.x, kTileStride);
   __syncthreads();
   write_tile<RB::kObsDim>(tile, obs, e0, D.n);
 }
@@ -349,8 +238,8 @@ __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __re
     for (int k = 0; k < k_steps; ++k) {
       double u1, u2;
       rng.pair(2u, base + (uint32_t)k, u1, u2);
-      env_step<false, RB>(wmask, &scratch[threadIdx.x >> 5], nullptr, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0),
-                      tile + threadIdx.x, kTileStride, rew, &c, &d);
+      env_step<kStepFull, RB>(wmask, &scratch[threadIdx.x >> 5], D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0),
+                              tile + threadIdx.x, kTileStride, rew, &c, &d);
     }
     if (reward) reward[e] = rew[0];
     if (cost) cost[e] = c;
@@ -491,9 +380,9 @@ __global__ void __launch_bounds__(128) k_fixup_host(const __grid_constant__ Dev 
                                                     double* __restrict__ reward_h, uint8_t* __restrict__ cost_h,
                                                     uint8_t* __restrict__ done_h) {
   const int lane = threadIdx.x & 31, nw = gridDim.x * 4;
-  const int c0 = D.counts[0], c1 = D.counts[1], count = c0 + c1 + D.counts[2];
+  const int count = D.counts[0];
   for (int i = blockIdx.x * 4 + (threadIdx.x >> 5); i < count; i += nw) {
-    const int e = worklist_at(D, i, c0, c1);
+    const int e = D.worklist[i];
     const float* src = obs + (size_t)e * kObs;
     float* dst = obs_h + (size_t)e * kObs;
     for (int k = lane; k < kObs; k += 32) dst[k] = src[k];
@@ -506,25 +395,14 @@ static inline int grid_for(int n) { return (n + kBS - 1) / kBS; }
 // host-side launchers, one set per robot model
 template <class RB>
 struct Ops {
-  template <int G>
-  static cudaError_t setup_busy(int* per_sm) {
-    cudaError_t ce = cudaFuncSetAttribute(k_step_busy<G, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BusyCfg<G, RB>::kSmemBytes);
-    if (ce != cudaSuccess) return ce;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_step_busy<G, RB>, 32, BusyCfg<G, RB>::kSmemBytes);
-  }
-  static cudaError_t setup_coop(int* per_sm) {
-    cudaError_t ce = cudaFuncSetAttribute(k_step_coop<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CoopCfg<RB>::kSmemBytes);
-    if (ce != cudaSuccess) return ce;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_step_coop<RB>, 32 * kCoopWarps, CoopCfg<RB>::kSmemBytes);
-  }
   static cudaError_t setup(Handle* H) {
     cudaError_t ce = cudaFuncSetAttribute(k_observe<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_rollout<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_coop<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CoopCfg<RB>::kSmemBytes);
     if (ce != cudaSuccess) return ce;
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, H->device);
-    const int G = H->busy_g;
-    ce = G == 0 ? setup_coop(&per_sm) : G == 1 ? setup_busy<1>(&per_sm) : G == 4 ? setup_busy<4>(&per_sm) : G == 32 ? setup_busy<32>(&per_sm) : setup_busy<8>(&per_sm);
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_coop<RB>, 32 * kCoopWarps, CoopCfg<RB>::kSmemBytes);
     H->busy_grid = sms * (per_sm > 0 ? per_sm : 1);
     return ce;
   }
@@ -539,54 +417,46 @@ struct Ops {
     // two counter sets used alternately: this step's is zero already (cleared by the previous step's quiet kernel, which
     // saves a memset node per step); steps of one handle must be stream-ordered
     int* t = H->D.counts; H->D.counts = H->D.counts_next; H->D.counts_next = t;
-    k_step_quiet<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kTileBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
+    k_step_free<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kTileBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
+    ++H->launches;
     return cudaGetLastError();
   }
   // rows of the busy environments -> mapped host buffers (after the bulk copy that carried the quiet rows)
   static cudaError_t fixup_host(Handle* H, const float* obs, const double* reward, const uint8_t* cost, const uint8_t* done,
                                 float* obs_h, double* reward_h, uint8_t* cost_h, uint8_t* done_h, cudaStream_t s) {
     k_fixup_host<RB::kObsDim><<<H->busy_grid, 128, 0, s>>>(H->D, obs, reward, cost, done, obs_h, reward_h, cost_h, done_h);
+    ++H->launches;
     return cudaGetLastError();
   }
   static cudaError_t step_busy(Handle* H, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done,
                                cudaStream_t s) {
-    if (kNearKernel<RB>) {
-      k_step_near<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kTileBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
-      cudaError_t ce = cudaGetLastError();
-      if (ce != cudaSuccess) return ce;
-    }
-    const int G = H->busy_g;
-    if (G == 0) {  // warp-cooperative busy path
-      const int need = (H->D.n + kCoopWarps - 1) / kCoopWarps;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(need < H->busy_grid ? need : H->busy_grid);
-      cfg.blockDim = dim3(32 * kCoopWarps);
-      cfg.dynamicSmemBytes = CoopCfg<RB>::kSmemBytes;
-      cfg.stream = s;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;  // hides this launch's latency behind the previous kernel's tail
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      return cudaLaunchKernelEx(&cfg, k_step_coop<RB>, H->D, act, obs, reward, reward2, cost, done);
-    }
-    const int chunks = (H->D.n + G - 1) / G;
-    const int grid = chunks < H->busy_grid ? chunks : H->busy_grid;
-#define SAG_LAUNCH_BUSY(GG) k_step_busy<GG, RB><<<grid, 32, BusyCfg<GG, RB>::kSmemBytes, s>>>(H->D, act, obs, reward, reward2, cost, done)
-    if (G == 1) SAG_LAUNCH_BUSY(1); else if (G == 4) SAG_LAUNCH_BUSY(4); else if (G == 32) SAG_LAUNCH_BUSY(32); else SAG_LAUNCH_BUSY(8);
-#undef SAG_LAUNCH_BUSY
-    return cudaGetLastError();
+    ++H->launches;
+    const int need = (H->D.n + kCoopWarps - 1) / kCoopWarps;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(need < H->busy_grid ? need : H->busy_grid);
+    cfg.blockDim = dim3(32 * kCoopWarps);
+    cfg.dynamicSmemBytes = CoopCfg<RB>::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;  // hides this launch's latency behind the previous kernel's tail
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_step_coop<RB>, H->D, act, obs, reward, reward2, cost, done);
   }
   static cudaError_t observe(Handle* H, float* obs, cudaStream_t s) {
     k_observe<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kSmemBytes, s>>>(H->D, obs);
+    ++H->launches;
     return cudaGetLastError();
   }
   static cudaError_t rollout(Handle* H, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, cudaStream_t s) {
     k_rollout<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kSmemBytes, s>>>(H->D, k_steps, obs, reward, cost, done);
+    ++H->launches;
     return cudaGetLastError();
   }
   static cudaError_t reset(Handle* H, const uint8_t* mask, int only_flagged, int new_task, cudaStream_t s) {
     k_reset<RB><<<grid_for(H->D.n), kBS, 0, s>>>(H->D, mask, only_flagged, new_task, H->sret, H->scost, H->sn);
+    ++H->launches;
     return cudaGetLastError();
   }
 };
@@ -624,12 +494,6 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   Dev& D = H->D;
   dev_from_config(D, *cfg);
   {
-    // busy path: 0 = warp-cooperative kernel (one warp per environment; default, 1.6x the best scalar setting), else
-    // environments per warp of the scalar busy kernel (8 was the best of 1/4/8/32); SAG_BUSY_G overrides
-    int G = 0;
-    const char* gs = getenv("SAG_BUSY_G");
-    if (gs) { int v = atoi(gs); if (v == 0 || v == 1 || v == 4 || v == 8 || v == 32) G = v; }
-    H->busy_g = G;
     cudaError_t ce = SAG_DISPATCH(H, setup(H));
     if (ce != cudaSuccess) { delete H; return fail("sag_create: kernel setup", ce); }
   }
@@ -672,6 +536,16 @@ int sag_destroy(void* handle) {
   return 0;
 }
 
+// SAG_TIMING builds: section clocks of the cooperative kernel (16 x u64, host buffer); zeroed after the read
+int sag_debug_read(void* handle, unsigned long long* out16) {
+  Handle* H = (Handle*)handle;
+  if (!H || !out16) return fail("sag_debug_read: null argument");
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out16, H->D.dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemset(H->D.dbg, 0, 16 * sizeof(unsigned long long)));
+  return 0;
+}
+unsigned long long sag_launch_count(void* handle) { return handle ? ((Handle*)handle)->launches : 0ull; }
 int sag_stride(void* handle) { return ((Handle*)handle)->D.stride; }
 int sag_obs_dim(void* handle) { return ((Handle*)handle)->D.robot == SAG_ROBOT_CAR ? SAG_OBS_CAR : SAG_OBS_POINT; }
 size_t sag_field_bytes(void* handle, int field) {

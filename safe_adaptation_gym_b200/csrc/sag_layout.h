@@ -55,6 +55,7 @@ inline void slab_bind(Dev& D, const SlabLayout& L, char* base) {
   D.rext = (double*)(base + L.off[SAG_F_ROBOT_EXT]);
   int32_t* sc = (int32_t*)(base + L.sched_off);
   D.worklist = sc; D.counts = sc + 3 * st; D.counts_next = D.counts + 8;
+  D.dbg = (unsigned long long*)(sc + 3 * st + 16);  // 16 x u64; the block is 64 ints
 }
 
 inline void dev_from_config(Dev& D, const SagConfig& c) {

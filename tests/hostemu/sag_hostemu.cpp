@@ -26,6 +26,7 @@ using namespace sag;
 namespace {
 constexpr int kBS = 128, kTileStride = kBS + 1, kObsMax = SAG_OBS_CAR;
 char g_err[512] = "";
+bool g_force_full = getenv("SAG_HOSTEMU_FULL") != nullptr;  // every environment through the full scalar path
 int fail(const char* w) { snprintf(g_err, sizeof(g_err), "%s", w); return 1; }
 struct Handle {
   Dev D;
@@ -55,11 +56,22 @@ void do_step(Handle* H, const float* act, float* obs, double* reward, double* re
   Dev& D = H->D;
   static float tile[kObsMax * kTileStride];
   static Scratch scratch;
-  static SmallScratch small;
   for (int e0 = 0; e0 < D.n; e0 += kBS) {
     for (int t = 0; t < kBS && e0 + t < D.n; ++t) {
       int e = e0 + t; double rew[2]; unsigned char c, d;
-      env_step<false, RB>(1u, &scratch, &small, D, e, act[2 * e], act[2 * e + 1], tile + t, kTileStride, rew, &c, &d);
+      // same dispatch as the CUDA kernels (sag_kernels.cu: k_step_free, then the work list): environments in which nothing
+      // moves take the contact-free path, with the exact pre-tests unless they are quiet; one whose pre-test fires has
+      // stored nothing and is stepped again by the contact path (the scalar one here, the cooperative one on the GPU)
+      bool run = false, pretest = false;
+      {
+        RB R;
+        load_robot(D, e, task_spec(D.task[e]), R);
+        run = !(D.flags[e] & F_PHYS_ERROR) && D.movmask[e] == 0;
+        pretest = !env_is_quiet(D.clear[e], R);
+      }
+      bool bail = true;
+      if (run && !g_force_full) bail = env_step<kStepNear, RB>(1u, nullptr, D, e, act[2 * e], act[2 * e + 1], tile + t, kTileStride, rew, &c, &d, pretest) != 0;
+      if (bail) env_step<kStepFull, RB>(1u, &scratch, D, e, act[2 * e], act[2 * e + 1], tile + t, kTileStride, rew, &c, &d);
       reward[e] = rew[0];
       if (reward2) { reward2[2 * e] = rew[0]; reward2[2 * e + 1] = rew[1]; }
       cost[e] = c; done[e] = d;
@@ -73,7 +85,7 @@ void do_observe(Handle* H, float* obs) {
   static float tile[kObsMax * kTileStride];
   static Scratch scratch;
   for (int e0 = 0; e0 < D.n; e0 += kBS) {
-    for (int t = 0; t < kBS && e0 + t < D.n; ++t) env_observe<RB>(1u, &scratch, nullptr, D, e0 + t, tile + t, kTileStride);
+    for (int t = 0; t < kBS && e0 + t < D.n; ++t) env_observe<RB>(1u, &scratch, D, e0 + t, tile + t, kTileStride);
     write_tile(tile, obs, e0, D.n, RB::kObsDim);
   }
 }
@@ -89,7 +101,7 @@ void do_rollout(Handle* H, int k_steps, float* obs, double* reward, uint8_t* cos
       uint32_t base = (uint32_t)D.nstep[e];
       for (int k = 0; k < k_steps; ++k) {
         double u1, u2; rng.pair(2u, base + (uint32_t)k, u1, u2);
-        env_step<false, RB>(1u, &scratch, nullptr, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + t, kTileStride, rew, &c, &d);
+        env_step<kStepFull, RB>(1u, &scratch, D, e, (float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0), tile + t, kTileStride, rew, &c, &d);
       }
       if (reward) reward[e] = rew[0];
       if (cost) cost[e] = c;
@@ -127,6 +139,7 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   return 0;
 }
 int sag_destroy(void* h) { Handle* H = (Handle*)h; if (H) { free(H->slab); delete H; } return 0; }
+unsigned long long sag_launch_count(void* h) { (void)h; return 0ull; }
 int sag_stride(void* h) { return ((Handle*)h)->D.stride; }
 int sag_obs_dim(void* h) { return obs_dim_of(((Handle*)h)->D); }
 size_t sag_field_bytes(void* h, int f) { return (f < 0 || f >= SAG_NUM_FIELDS) ? 0 : ((Handle*)h)->LY.bytes[f]; }
