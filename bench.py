@@ -349,8 +349,7 @@ def main():
         torch.cuda.synchronize()
         for _ in range(W):
             L.check(L.L.sag_step_host(h2, p(act_h), p(obs_h), p(rew_h), p(cost_h), p(done_h)))
-        L.check(L.L.sag_reset(h2, None, 0, 0, sp))
-        torch.cuda.synchronize()
+        L.check(L.L.sag_reset_host(h2, None, 0, 0, None))
         if world > 1:
             dist.barrier()
         te, ke = 0.0, 0
@@ -369,10 +368,8 @@ def main():
         for _ in range(EPISODE - t):
             step_dev(h2)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()  # episode end: reset + the first observation of the new episode to the host
-        L.check(L.L.sag_reset(h2, None, 0, 0, sp))
-        L.check(L.L.sag_observe_host(h2, p(obs_h)))
-        torch.cuda.synchronize()
+        t0 = time.perf_counter()  # episode end: env.reset() through the host API (layouts + first observation to the host)
+        L.check(L.L.sag_reset_host(h2, None, 0, 0, p(obs_h)))
         t_reset_e2e = time.perf_counter() - t0
         te_total = te + ke * t_reset_e2e / EPISODE
         t = torch.tensor([te_total], dtype=torch.float64, device=dev)

@@ -11,7 +11,10 @@
  * Conventions: extern "C", plain pointers and sizes, no C++ / torch types.  Every call returns an int
  * status (0 = ok); sag_last_error() gives the message of the last failure on the calling thread.
  * Launches are asynchronous on the caller's cudaStream_t (passed as void*).  The caller owns all I/O
- * buffers; the library owns the handle's internal SoA state.  One handle per device; not thread-safe.
+ * buffers; the library owns the handle's internal SoA state.  A handle is not thread-safe; several handles (on one or
+ * several devices) may coexist in a process: every entry point switches to the handle's device and restores the
+ * caller's.  The *_host entry points are synchronous and ordered after everything issued earlier on the device; the
+ * stream entry points are ordered by the caller's stream.
  */
 #ifndef SAG_B200_H
 #define SAG_B200_H
@@ -22,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SAG_ABI_VERSION 1
+#define SAG_ABI_VERSION 2
 #define SAG_LIDAR_BINS 16   /* safe_adaptation_gym.py:22 */
 #define SAG_OBS_POINT 60    /* 3*16 lidar + 12 sensor floats, safe_adaptation_gym.py:120-139,225-237 */
 #define SAG_OBS_CAR 72      /* + ballangvel_rear (3) + quat2mat(ballquat_rear) (9), car.xml:37-38 */
@@ -38,6 +41,8 @@ enum {
 };
 /* per-env flag bits (sag_read_field(SAG_F_FLAGS)) */
 enum { SAG_FLAG_PHYSICS_ERROR = 1, SAG_FLAG_RESAMPLE_FAILED = 2, SAG_FLAG_NEEDS_RESET = 4 };
+/* additional bit of sag_error_flags() */
+enum { SAG_ERR_BAD_TASK_ID = 8 };
 
 /* World.DEFAULT (world.py:17-34) + batching parameters.  POD, copied at sag_create. */
 typedef struct SagConfig {
@@ -80,9 +85,24 @@ int sag_obs_dim(void* handle);
 size_t sag_field_bytes(void* handle, int field);
 /* number of CUDA kernels launched on behalf of this handle so far (bench.py's gpu_launches is a difference of two reads) */
 unsigned long long sag_launch_count(void* handle);
+/* tuning hook: section clocks of the contact kernel, 16 x u64 into a HOST buffer, zeroed after the read.  All zero
+ * unless the library was built with -DSAG_TIMING (tools/late_phase.py). */
+int sag_debug_read(void* handle, unsigned long long* out16_host);
 
-/* env.set_task (safe_adaptation_gym.py:165-168): task_ids is a DEVICE int32[n_envs] array */
+/* env.set_task (safe_adaptation_gym.py:165-168): task_ids is a DEVICE int32[n_envs] array.  Statistics gathered under
+ * the previous task are folded into the per-task totals first.  An id outside [0, SAG_NUM_TASKS) is replaced by
+ * SAG_T_GO_TO_GOAL and reported through sag_error_flags (SAG_ERR_BAD_TASK_ID). */
 int sag_set_tasks(void* handle, const int32_t* task_ids_dev, void* stream);
+/* same with a HOST int32[n_envs] array (validated: out-of-range ids fail the call); synchronous */
+int sag_set_tasks_host(void* handle, const int32_t* task_ids_host);
+/* info['bound'] (safe_adaptation_gym.py:79, world.py:75-78): HOST double[n_envs] constraint bound of every environment's
+ * current Task instance; synchronous */
+int sag_bound_host(void* handle, double* bound_host);
+/* Sticky error conditions recorded by the kernels since the last call with clear != 0, readable WITHOUT synchronising
+ * (the kernels write them into mapped host memory): SAG_FLAG_RESAMPLE_FAILED -- a layout (world.py:189) or a goal
+ * (go_to_goal.py:80) could not be sampled, i.e. the reference would have raised ResamplingError out of reset / step;
+ * SAG_ERR_BAD_TASK_ID.  A condition raised by a kernel that is still running shows up in a later call. */
+int sag_error_flags(void* handle, int clear);
 
 /* env.seed (safe_adaptation_gym.py:113-118): new Philox key; per-env episode counters restart */
 int sag_seed(void* handle, uint64_t seed);
@@ -93,6 +113,14 @@ int sag_seed(void* handle, uint64_t seed);
  * flag is set (auto-reset).  new_task != 0 re-initialises task-instance state (a new Task object).
  * episode numbers are incremented per env (safe_adaptation_gym.py:97-100 `self._seed += 1`). */
 int sag_reset(void* handle, const uint8_t* mask_dev, int only_flagged, int new_task, void* stream);
+/* same, and the environments that were reset get the first observation of their new episode written into their row of
+ * obs_dev (float[n][obs_dim]; other rows untouched); was_reset_dev (uint8[n], may be NULL) tells which.  This is the
+ * auto-reset call of a vectorised wrapper: sag_step, then sag_reset_obs(only_flagged = 1) on the same buffers. */
+int sag_reset_obs(void* handle, const uint8_t* mask_dev, int only_flagged, int new_task, float* obs_dev, uint8_t* was_reset_dev,
+                  void* stream);
+/* env.reset with HOST buffers: mask_host uint8[n] or NULL, obs_host float[n][obs_dim] or NULL (= env.observation of the
+ * new episodes).  Synchronous, ordered after all earlier work of the device; fails when a layout could not be sampled. */
+int sag_reset_host(void* handle, const uint8_t* mask_host, int only_flagged, int new_task, float* obs_host);
 
 /* env.step (safe_adaptation_gym.py:56-83).  DEVICE buffers: act float[n][2]; obs float[n][obs_dim];
  * reward double[n]; reward2 double[n][2] or NULL (Unsupervised's 2-vector, unsupervised.py:66);
@@ -118,8 +146,9 @@ int sag_rollout(void* handle, int k_steps, float* obs, double* reward, uint8_t* 
 /* state injection / extraction; buffers are DEVICE pointers of sag_field_bytes(field) bytes */
 int sag_read_field(void* handle, int field, void* dst_dev, void* stream);
 int sag_write_field(void* handle, int field, const void* src_dev, void* stream);
-/* per-task episode statistics accumulated by the steps since the last call with reset != 0:
- * DEVICE double out[SAG_NUM_TASKS][3] = {sum reward, sum cost, env-steps} (the buffer NCCL all-reduces) */
+/* per-task statistics of the episodes that FINISHED (time limit or done) since the last call with reset != 0, under the
+ * task they ran with: DEVICE double out[SAG_NUM_TASKS][3] = {sum of episode returns, sum of episode costs, number of
+ * episodes} (the buffer NCCL all-reduces).  Episodes cut short by a manual reset / set_task are not counted. */
 int sag_task_stats(void* handle, double* out_dev, int reset, void* stream);
 
 /* stand-alone streaming kernels on caller-provided SoA buffers (roofline evidence)

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("SAG_B200_LIB") or os.path.join(_HERE, "csrc", "libsag
 NUM_TASKS = 14
 MAX_SLOTS = 32
 F_ROBOT, F_OBJECTS, F_TASK_F64, F_TASK_I32, F_FLAGS, F_ROBOT_EXT = range(6)
-FLAG_PHYSICS_ERROR, FLAG_RESAMPLE_FAILED, FLAG_NEEDS_RESET = 1, 2, 4
+FLAG_PHYSICS_ERROR, FLAG_RESAMPLE_FAILED, FLAG_NEEDS_RESET, ERR_BAD_TASK_ID = 1, 2, 4, 8
 
 
 class SagConfig(C.Structure):
@@ -39,7 +39,8 @@ class SagLib:
 
     SYMBOLS = [
         "sag_last_error", "sag_abi_version", "sag_default_config", "sag_create", "sag_destroy", "sag_stride",
-        "sag_obs_dim", "sag_field_bytes", "sag_launch_count", "sag_set_tasks", "sag_seed", "sag_reset", "sag_step", "sag_observe",
+        "sag_obs_dim", "sag_field_bytes", "sag_launch_count", "sag_debug_read", "sag_set_tasks", "sag_set_tasks_host", "sag_bound_host",
+        "sag_error_flags", "sag_reset_obs", "sag_reset_host", "sag_seed", "sag_reset", "sag_step", "sag_observe",
         "sag_step_host", "sag_observe_host", "sag_host_alloc", "sag_host_free", "sag_rollout", "sag_read_field",
         "sag_write_field", "sag_task_stats", "sag_lidar", "sag_cost",
     ]
@@ -59,12 +60,15 @@ class SagLib:
         L.sag_destroy.argtypes = [vp]
         L.sag_stride.argtypes = [vp]
         L.sag_obs_dim.argtypes = [vp]
+        L.sag_debug_read.argtypes = [vp, vp]
         L.sag_launch_count.restype = C.c_ulonglong
         L.sag_launch_count.argtypes = [vp]
         L.sag_field_bytes.restype = C.c_size_t
         L.sag_field_bytes.argtypes = [vp, i32]
         L.sag_set_tasks.argtypes = [vp, vp, vp]
         L.sag_seed.argtypes = [vp, C.c_uint64]
+        L.sag_error_flags.argtypes = [vp, i32]
+        L.sag_reset_obs.argtypes = [vp, u8p, i32, i32, fp, u8p, vp]
         L.sag_reset.argtypes = [vp, u8p, i32, i32, vp]
         L.sag_step.argtypes = [vp, fp, fp, dp, dp, u8p, u8p, vp]
         L.sag_observe.argtypes = [vp, fp, vp]
@@ -77,6 +81,9 @@ class SagLib:
         if host_api:
             L.sag_step_host.argtypes = [vp, fp, fp, dp, u8p, u8p]
             L.sag_observe_host.argtypes = [vp, fp]
+            L.sag_set_tasks_host.argtypes = [vp, vp]
+            L.sag_bound_host.argtypes = [vp, dp]
+            L.sag_reset_host.argtypes = [vp, u8p, i32, i32, fp]
             L.sag_host_alloc.restype = vp
             L.sag_host_alloc.argtypes = [C.c_size_t]
             L.sag_host_free.argtypes = [vp]

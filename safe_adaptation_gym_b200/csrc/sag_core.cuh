@@ -188,6 +188,8 @@ struct Dev {
   int *worklist, *counts;  // work list segments and their lengths (sag_kernels.cu)
   int* counts_next;        // the other counter set: zeroed by this step's quiet kernel for the next step
   unsigned long long* dbg; // [16] section clocks of SAG_TIMING builds
+  int* errflags;           // [4] sticky error words the host can read without a synchronisation (mapped pinned memory):
+                           // [0] a layout / goal could not be sampled (ResamplingError), [1] task id out of range
   double *time, *clear;
   unsigned *ctr, *episode;
   int* nstep;
@@ -2097,7 +2099,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
   unsigned char dn = 0;
   if (err) { dn = 1; fl |= F_PHYS_ERROR; }
   if (O.err) fl |= F_PHYS_ERROR;
-  if (O.resample_failed) fl |= F_RESAMPLE_FAILED;
+  if (O.resample_failed) { fl |= F_RESAMPLE_FAILED; D.errflags[0] = 1; }
   // bookkeeping (cooperative mode: read-modify-write of global state by one lane only)
   bool writer = true;
 #if defined(__CUDA_ARCH__)

@@ -44,6 +44,13 @@ int fail(const char* what, cudaError_t ce = cudaSuccess) {
     if (ce_ != cudaSuccess) return fail(#call, ce_); \
   } while (0)
 
+// every entry point runs on the handle's device and leaves the caller's current device as it found it
+struct DevGuard {
+  int prev, want;
+  explicit DevGuard(int d) : prev(-1), want(d) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != d) cudaSetDevice(d); }
+  ~DevGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+};
+
 struct Handle {
   Dev D;
   int device;
@@ -51,7 +58,11 @@ struct Handle {
   size_t slab_bytes;
   void* field_ptr[SAG_NUM_FIELDS];
   size_t field_bytes[SAG_NUM_FIELDS];
-  double *sret, *scost, *sn;  // per-env finished-episode statistics
+  double *sret, *scost, *sn;  // per-env finished-episode statistics (under the env's current task)
+  double* stats_acc;          // [SAG_NUM_TASKS][3]: statistics folded away when environments changed task
+  int* err_h;                 // mapped pinned int[4]: sticky error words written by the kernels (sag_error_flags)
+  int32_t* ids_d;             // staging for sag_set_tasks_host
+  uint8_t* mask_d;            // staging for sag_reset_host
   // device staging for the host-buffer API
   float* act_d;
   float* obs_d;
@@ -87,6 +98,20 @@ __device__ __forceinline__ void write_tile4(const float* tile, float* out, int e
     const int t = j / kQ, q = j - t * kQ;
     const float* src = tile + (4 * q) * kTileStride + t;
     dst[j] = make_float4(src[0], src[kTileStride], src[2 * kTileStride], src[3 * kTileStride]);
+  }
+}
+
+// per-warp write-out of up to 32 observation rows (tile column = lane; e < 0: no row)
+template <int kObs>
+__device__ __forceinline__ void write_rows(const float* tile, int tstride, float* out, int e) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const int er = __shfl_sync(0xffffffffu, e, r);
+    if (er < 0) continue;
+    float* dst = out + (size_t)er * kObs;
+    const float* src = tile + r;
+    for (int k = lane; k < kObs; k += 32) dst[k] = src[k * tstride];
   }
 }
 
@@ -249,20 +274,47 @@ __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __re
   if (obs) write_tile<RB::kObsDim>(tile, obs, e0, D.n);
 }
 
+// env.reset for the selected environments.  Statistics: an episode counts when it FINISHED (time limit or done: the
+// NEEDS_RESET flag), under the task it ran with; a manual reset of an unfinished episode is not an episode.
+// obs != nullptr: the environments that were reset get the first observation of their new episode written into their
+// row (the others' rows are left alone) and was_reset[e] = 1 / 0 tells the caller which (auto-reset, env.py).
 template <class RB>
 __global__ void __launch_bounds__(kBS) k_reset(Dev D, const uint8_t* __restrict__ mask, int only_flagged, int new_task,
-                                                double* sret, double* scost, double* sn) {
+                                                double* sret, double* scost, double* sn, float* __restrict__ obs,
+                                                uint8_t* __restrict__ was_reset) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + TileCfg<RB>::kTileBytes);
   const int e = blockIdx.x * kBS + threadIdx.x;
-  if (e >= D.n) return;
-  if (mask && !mask[e]) return;
-  if (only_flagged && !(D.flags[e] & F_NEEDS_RESET)) return;
-  if (D.nstep[e] > 0) { sret[e] += D.epret[e]; scost[e] += D.epcost[e]; sn[e] += 1.0; }
-  env_reset<RB>(D, e, D.episode[e] + 1u, new_task != 0);
+  bool doit = e < D.n;
+  if (doit && mask && !mask[e]) doit = false;
+  if (doit && only_flagged && !(D.flags[e] & F_NEEDS_RESET)) doit = false;
+  if (e < D.n && was_reset) was_reset[e] = doit ? 1 : 0;
+  if (doit) {
+    if ((D.flags[e] & F_NEEDS_RESET) && D.nstep[e] > 0) { sret[e] += D.epret[e]; scost[e] += D.epcost[e]; sn[e] += 1.0; }
+    env_reset<RB>(D, e, D.episode[e] + 1u, new_task != 0);
+    if (D.flags[e] & F_RESAMPLE_FAILED) D.errflags[0] = 1;
+  }
+  if (!obs) return;
+  const unsigned wmask = __ballot_sync(0xffffffffu, doit);
+  if (doit) env_observe<RB>(wmask, &scratch[threadIdx.x >> 5], D, e, tile + threadIdx.x, kTileStride);
+  __syncwarp();
+  write_rows<RB::kObsDim>(tile + (threadIdx.x & ~31), kTileStride, obs, doit ? e : -1);
 }
 
-__global__ void k_set_tasks(Dev D, const int32_t* __restrict__ ids) {
+// env.set_task: statistics gathered under the old task are folded into the per-task accumulator first (so that they
+// are not re-labelled), including an episode that has finished but has not been reset yet; ids are validated.
+__global__ void k_set_tasks(Dev D, const int32_t* __restrict__ ids, double* sret, double* scost, double* sn, double* acc) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < D.n) D.task[e] = ids[e];
+  if (e >= D.n) return;
+  const int old = D.task[e];
+  double r = sret[e], c = scost[e], k = sn[e];
+  if ((D.flags[e] & F_NEEDS_RESET) && D.nstep[e] > 0) { r += D.epret[e]; c += D.epcost[e]; k += 1.0; D.nstep[e] = 0; }
+  if (k != 0.0 && old >= 0 && old < SAG_NUM_TASKS) { atomicAdd(acc + 3 * old, r); atomicAdd(acc + 3 * old + 1, c); atomicAdd(acc + 3 * old + 2, k); }
+  sret[e] = 0.0; scost[e] = 0.0; sn[e] = 0.0;
+  int id = ids[e];
+  if (id < 0 || id >= SAG_NUM_TASKS) { id = SAG_T_GO_TO_GOAL; D.errflags[1] = 1; }
+  D.task[e] = id;
 }
 
 // per-task statistic reduction: out[task][3] += (sum return, sum cost, episodes) of finished episodes
@@ -397,6 +449,7 @@ template <class RB>
 struct Ops {
   static cudaError_t setup(Handle* H) {
     cudaError_t ce = cudaFuncSetAttribute(k_observe<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_reset<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_rollout<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_coop<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CoopCfg<RB>::kSmemBytes);
     if (ce != cudaSuccess) return ce;
@@ -454,8 +507,8 @@ struct Ops {
     ++H->launches;
     return cudaGetLastError();
   }
-  static cudaError_t reset(Handle* H, const uint8_t* mask, int only_flagged, int new_task, cudaStream_t s) {
-    k_reset<RB><<<grid_for(H->D.n), kBS, 0, s>>>(H->D, mask, only_flagged, new_task, H->sret, H->scost, H->sn);
+  static cudaError_t reset(Handle* H, const uint8_t* mask, int only_flagged, int new_task, float* obs, uint8_t* was_reset, cudaStream_t s) {
+    k_reset<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kSmemBytes, s>>>(H->D, mask, only_flagged, new_task, H->sret, H->scost, H->sn, obs, was_reset);
     ++H->launches;
     return cudaGetLastError();
   }
@@ -486,7 +539,8 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   if (!cfg || !handle) return fail("sag_create: null argument");
   if (cfg->n_envs <= 0) return fail("sag_create: n_envs must be positive");
   if (cfg->robot != SAG_ROBOT_POINT && cfg->robot != SAG_ROBOT_CAR) return fail("sag_create: robot must be point (0) or car (1)");
-  CK(cudaSetDevice(device));
+  DevGuard guard(device);
+  CK(cudaGetLastError());
   Handle* H = new (std::nothrow) Handle();
   if (!H) return fail("sag_create: out of host memory");
   memset(H, 0, sizeof(*H));
@@ -513,6 +567,10 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   H->cost_d = (uint8_t*)(base + LY.cost_off); H->done_d = (uint8_t*)(base + LY.done_off);
   // episode counters start at 0xFFFFFFFF so that the first reset is episode 0
   ce = cudaMemset(D.episode, 0xFF, st * sizeof(unsigned));
+  H->stats_acc = (double*)(base + LY.acc_off);
+  H->ids_d = (int32_t*)(base + LY.ids_off); H->mask_d = (uint8_t*)(base + LY.mask_off);
+  if (ce == cudaSuccess) ce = cudaHostAlloc((void**)&H->err_h, 4 * sizeof(int), cudaHostAllocMapped);
+  if (ce == cudaSuccess) { memset(H->err_h, 0, 4 * sizeof(int)); ce = cudaHostGetDevicePointer((void**)&D.errflags, H->err_h, 0); }
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&H->own_stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&H->copy_stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&H->ev_quiet, cudaEventDisableTiming);
@@ -525,8 +583,9 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
 int sag_destroy(void* handle) {
   Handle* H = (Handle*)handle;
   if (!H) return 0;
-  cudaSetDevice(H->device);
+  DevGuard guard(H->device);
   cudaDeviceSynchronize();
+  if (H->err_h) cudaFreeHost(H->err_h);
   if (H->own_stream) cudaStreamDestroy(H->own_stream);
   if (H->copy_stream) cudaStreamDestroy(H->copy_stream);
   if (H->ev_quiet) cudaEventDestroy(H->ev_quiet);
@@ -556,15 +615,51 @@ size_t sag_field_bytes(void* handle, int field) {
 int sag_set_tasks(void* handle, const int32_t* ids, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !ids) return fail("sag_set_tasks: null argument");
-  k_set_tasks<<<(H->D.n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(H->D, ids);
+  DevGuard guard(H->device);
+  k_set_tasks<<<(H->D.n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(H->D, ids, H->sret, H->scost, H->sn, H->stats_acc);
+  ++H->launches;
   CK(cudaGetLastError());
   return 0;
+}
+
+int sag_set_tasks_host(void* handle, const int32_t* ids_host) {
+  Handle* H = (Handle*)handle;
+  if (!H || !ids_host) return fail("sag_set_tasks_host: null argument");
+  for (int e = 0; e < H->D.n; ++e)
+    if (ids_host[e] < 0 || ids_host[e] >= SAG_NUM_TASKS) return fail("sag_set_tasks_host: task id out of range [0, SAG_NUM_TASKS)");
+  DevGuard guard(H->device);
+  CK(cudaDeviceSynchronize());  // the host API is ordered after everything issued through the stream API
+  CK(cudaMemcpyAsync(H->ids_d, ids_host, (size_t)H->D.n * sizeof(int32_t), cudaMemcpyHostToDevice, H->own_stream));
+  k_set_tasks<<<(H->D.n + 255) / 256, 256, 0, H->own_stream>>>(H->D, H->ids_d, H->sret, H->scost, H->sn, H->stats_acc);
+  ++H->launches;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(H->own_stream));
+  return 0;
+}
+
+int sag_bound_host(void* handle, double* bound_host) {
+  Handle* H = (Handle*)handle;
+  if (!H || !bound_host) return fail("sag_bound_host: null argument");
+  DevGuard guard(H->device);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(bound_host, H->D.bound, (size_t)H->D.n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int sag_error_flags(void* handle, int clear) {
+  Handle* H = (Handle*)handle;
+  if (!H) return 0;
+  int w = 0;
+  if (H->err_h[0]) w |= SAG_FLAG_RESAMPLE_FAILED;
+  if (H->err_h[1]) w |= SAG_ERR_BAD_TASK_ID;
+  if (clear) { H->err_h[0] = 0; H->err_h[1] = 0; }
+  return w;
 }
 
 int sag_seed(void* handle, uint64_t seed) {
   Handle* H = (Handle*)handle;
   if (!H) return fail("sag_seed: null handle");
-  CK(cudaSetDevice(H->device));
+  DevGuard guard(H->device);
   CK(cudaDeviceSynchronize());
   H->D.seed = seed;
   CK(cudaMemset(H->D.episode, 0xFF, (size_t)H->D.stride * sizeof(unsigned)));
@@ -574,7 +669,34 @@ int sag_seed(void* handle, uint64_t seed) {
 int sag_reset(void* handle, const uint8_t* mask, int only_flagged, int new_task, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H) return fail("sag_reset: null handle");
-  CK(SAG_DISPATCH(H, reset(H, mask, only_flagged, new_task, (cudaStream_t)stream)));
+  DevGuard guard(H->device);
+  CK(SAG_DISPATCH(H, reset(H, mask, only_flagged, new_task, nullptr, nullptr, (cudaStream_t)stream)));
+  return 0;
+}
+
+int sag_reset_obs(void* handle, const uint8_t* mask, int only_flagged, int new_task, float* obs, uint8_t* was_reset, void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H || !obs) return fail("sag_reset_obs: null argument");
+  DevGuard guard(H->device);
+  CK(SAG_DISPATCH(H, reset(H, mask, only_flagged, new_task, obs, was_reset, (cudaStream_t)stream)));
+  return 0;
+}
+
+int sag_reset_host(void* handle, const uint8_t* mask_h, int only_flagged, int new_task, float* obs_h) {
+  Handle* H = (Handle*)handle;
+  if (!H) return fail("sag_reset_host: null handle");
+  DevGuard guard(H->device);
+  cudaStream_t s = H->own_stream;
+  CK(cudaDeviceSynchronize());  // the host API is ordered after everything issued through the stream API
+  const uint8_t* m = nullptr;
+  if (mask_h) { CK(cudaMemcpyAsync(H->mask_d, mask_h, (size_t)H->D.n, cudaMemcpyHostToDevice, s)); m = H->mask_d; }
+  CK(SAG_DISPATCH(H, reset(H, m, only_flagged, new_task, nullptr, nullptr, s)));
+  if (obs_h) {
+    CK(SAG_DISPATCH(H, observe(H, H->obs_d, s)));
+    CK(cudaMemcpyAsync(obs_h, H->obs_d, (size_t)H->D.n * (size_t)sag_obs_dim(H) * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  if (H->err_h[0]) return fail("sag_reset_host: failed to generate a layout (ResamplingError, world.py:189); see sag_error_flags");
   return 0;
 }
 
@@ -582,6 +704,7 @@ int sag_step(void* handle, const float* act, float* obs, double* reward, double*
              void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !act || !obs || !reward || !cost || !done) return fail("sag_step: null argument");
+  DevGuard guard(H->device);
   CK(SAG_DISPATCH(H, step(H, act, obs, reward, reward2, cost, done, (cudaStream_t)stream)));
   return 0;
 }
@@ -589,6 +712,7 @@ int sag_step(void* handle, const float* act, float* obs, double* reward, double*
 int sag_observe(void* handle, float* obs, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !obs) return fail("sag_observe: null argument");
+  DevGuard guard(H->device);
   CK(SAG_DISPATCH(H, observe(H, obs, (cudaStream_t)stream)));
   return 0;
 }
@@ -596,6 +720,7 @@ int sag_observe(void* handle, float* obs, void* stream) {
 int sag_rollout(void* handle, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || k_steps <= 0) return fail("sag_rollout: bad argument");
+  DevGuard guard(H->device);
   CK(SAG_DISPATCH(H, rollout(H, k_steps, obs, reward, cost, done, (cudaStream_t)stream)));
   return 0;
 }
@@ -611,6 +736,7 @@ static void* mapped_alias(const void* p) {
 int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward_h, uint8_t* cost_h, uint8_t* done_h) {
   Handle* H = (Handle*)handle;
   if (!H || !act_h || !obs_h || !reward_h || !cost_h || !done_h) return fail("sag_step_host: null argument");
+  DevGuard guard(H->device);
   cudaStream_t s = H->own_stream;
   const size_t n = (size_t)H->D.n, od = (size_t)sag_obs_dim(H);
   CK(cudaMemcpyAsync(H->act_d, act_h, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -647,7 +773,9 @@ int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward
 int sag_observe_host(void* handle, float* obs_h) {
   Handle* H = (Handle*)handle;
   if (!H || !obs_h) return fail("sag_observe_host: null argument");
+  DevGuard guard(H->device);
   cudaStream_t s = H->own_stream;
+  CK(cudaDeviceSynchronize());  // the host API is ordered after everything issued through the stream API
   CK(SAG_DISPATCH(H, observe(H, H->obs_d, s)));
   CK(cudaMemcpyAsync(obs_h, H->obs_d, (size_t)H->D.n * (size_t)sag_obs_dim(H) * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -664,12 +792,14 @@ void sag_host_free(void* p) { if (p) cudaFreeHost(p); }
 int sag_read_field(void* handle, int field, void* dst, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !dst || field < 0 || field >= SAG_NUM_FIELDS) return fail("sag_read_field: bad argument");
+  DevGuard guard(H->device);
   CK(cudaMemcpyAsync(dst, H->field_ptr[field], H->field_bytes[field], cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 int sag_write_field(void* handle, int field, const void* src, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !src || field < 0 || field >= SAG_NUM_FIELDS) return fail("sag_write_field: bad argument");
+  DevGuard guard(H->device);
   CK(cudaMemcpyAsync(H->field_ptr[field], src, H->field_bytes[field], cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
@@ -677,11 +807,16 @@ int sag_write_field(void* handle, int field, const void* src, void* stream) {
 int sag_task_stats(void* handle, double* out, int reset, void* stream) {
   Handle* H = (Handle*)handle;
   if (!H || !out) return fail("sag_task_stats: null argument");
+  DevGuard guard(H->device);
   cudaStream_t s = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(out, 0, SAG_NUM_TASKS * 3 * sizeof(double), s));
+  CK(cudaMemcpyAsync(out, H->stats_acc, SAG_NUM_TASKS * 3 * sizeof(double), cudaMemcpyDeviceToDevice, s));
   k_task_stats<<<148, 256, 0, s>>>(H->D, H->sret, H->scost, H->sn, out);
+  ++H->launches;
   CK(cudaGetLastError());
-  if (reset) CK(cudaMemsetAsync(H->sret, 0, 3 * (size_t)H->D.stride * sizeof(double), s));
+  if (reset) {
+    CK(cudaMemsetAsync(H->sret, 0, 3 * (size_t)H->D.stride * sizeof(double), s));
+    CK(cudaMemsetAsync(H->stats_acc, 0, SAG_NUM_TASKS * 3 * sizeof(double), s));
+  }
   return 0;
 }
 

@@ -12,7 +12,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct SlabLayout {
   size_t off[SAG_NUM_FIELDS], bytes[SAG_NUM_FIELDS];
-  size_t stats_off, sched_off, act_off, obs_off, rew_off, cost_off, done_off, total;
+  size_t stats_off, sched_off, act_off, obs_off, rew_off, cost_off, done_off, acc_off, ids_off, mask_off, total;
 };
 
 inline SlabLayout slab_layout(int n, int stride, int obs_dim) {
@@ -33,6 +33,9 @@ inline SlabLayout slab_layout(int n, int stride, int obs_dim) {
   L.rew_off = total; total += align_up((size_t)n * sizeof(double), 256);
   L.cost_off = total; total += align_up((size_t)n, 256);
   L.done_off = total; total += align_up((size_t)n, 256);
+  L.acc_off = total; total += align_up(SAG_NUM_TASKS * 3 * sizeof(double), 256);
+  L.ids_off = total; total += align_up((size_t)n * sizeof(int32_t), 256);
+  L.mask_off = total; total += align_up((size_t)n, 256);
   L.total = total;
   return L;
 }

@@ -5,6 +5,12 @@ Same method names and argument meaning as the reference env, with a leading batc
     obs[N, D], reward[N], done[N], info{'cost'[N], 'bound'[N]} = env.step(actions[N, nu])
     obs[N, D] = env.reset(options={'task': task_or_list_of_tasks})
 
+Returned tensors are fresh copies by default, like the arrays the reference returns; ``copy_outputs=False`` hands out the
+internal output buffers instead (valid until the next call -- the zero-copy mode for throughput loops).
+With ``max_episode_steps > 0`` the env auto-resets like a vectorised gym wrapper: an environment whose episode ended
+(time limit, or done after a physics error) is reset inside ``step``; its row of ``obs`` is the FIRST observation of the
+new episode, ``done`` is True for it and ``info['truncated']`` marks the time-limit endings.
+
 All per-step arithmetic (dynamics, reward / goal logic, cost, pseudo-lidar) runs in the CUDA library behind
 the C ABI of ``include/sag_b200.h``; this class only owns torch tensors and passes raw pointers.  There is
 no CPU fallback: without the built library and a CUDA device construction raises.
@@ -51,6 +57,7 @@ class BatchedSafeAdaptationGym:
                  device: Union[str, torch.device, None] = None,
                  env_id_base: int = 0,
                  max_episode_steps: int = 0,
+                 copy_outputs: bool = True,
                  _test_lib=None):
         if rgb_observation:
             raise NotImplementedError('rgb_observation needs a rasteriser and is outside the B200 hot path '
@@ -98,13 +105,15 @@ class BatchedSafeAdaptationGym:
         self.stride = L.L.sag_stride(self._h)
         self.obs_dim = L.L.sag_obs_dim(self._h)
         self.max_episode_steps = int(max_episode_steps)
-        self._steps_to_expiry = None
+        self.env_id_base = int(env_id_base)
+        self.copy_outputs = bool(copy_outputs)
         n, dev = self.num_envs, self.device
         self._obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=dev)
         self._reward = torch.empty((n,), dtype=torch.float64, device=dev)
         self._reward2 = torch.empty((n, 2), dtype=torch.float64, device=dev)
         self._cost = torch.empty((n,), dtype=torch.uint8, device=dev)
         self._done = torch.empty((n,), dtype=torch.uint8, device=dev)
+        self._was_reset = torch.zeros((n,), dtype=torch.uint8, device=dev)
         self._bound = torch.full((n,), float(cfg['max_bound']), dtype=torch.float64, device=dev)
         self._task_ids = None
         self._tasks = None
@@ -136,6 +145,19 @@ class BatchedSafeAdaptationGym:
     # ------------------------------------------------------------------------------------------
     # reference API
     # ------------------------------------------------------------------------------------------
+    def _out(self, t):
+        return t.clone() if self.copy_outputs else t
+
+    def _raise_recorded_errors(self, where: str):
+        """The reference raises out of the call in which the condition occurs; the kernels record it in mapped host
+        memory instead, which is read here WITHOUT synchronising -- so an error of a step that is still in flight is
+        raised by the next call (or by check_errors(), which synchronises)."""
+        w = self._lib.L.sag_error_flags(self._h, 1)
+        if w & _abi.FLAG_RESAMPLE_FAILED:
+            raise ResamplingError('Failed to generate goal' if where == 'step' else 'Failed to generate layout')  # go_to_goal.py:80 / world.py:189
+        if w & _abi.ERR_BAD_TASK_ID:
+            raise ValueError('task id out of range')
+
     def step(self, action):
         """safe_adaptation_gym.py:56-83.  `action`: [N, 2] tensor / array in [-1, 1]."""
         act = self._as_action(action)
@@ -143,22 +165,18 @@ class BatchedSafeAdaptationGym:
         r2 = self._reward2 if self._any_unsupervised else None
         L.check(L.L.sag_step(self._h, self._p(act), self._p(self._obs), self._p(self._reward), self._p(r2),
                              self._p(self._cost), self._p(self._done), self._stream()))
-        refreshed = False
-        if self.max_episode_steps > 0:
-            L.check(L.L.sag_reset(self._h, None, 1, 0, self._stream()))
-            if self._steps_to_expiry is not None:
-                self._steps_to_expiry -= 1
-                if self._steps_to_expiry <= 0:
-                    refreshed = True
-            else:
-                refreshed = True
         reward = self._reward2 if self._any_unsupervised else self._reward
-        info = {'cost': self._cost.to(torch.float32), 'bound': self._bound}
+        info = {'cost': self._cost.to(torch.float32), 'bound': self._out(self._bound)}
         done = self._done.to(torch.bool)
-        if refreshed:  # envs that were auto-reset return the first observation of their new episode
-            L.check(L.L.sag_observe(self._h, self._p(self._obs), self._stream()))
-            self._steps_to_expiry = self.max_episode_steps
-        return self._obs, reward, done, info
+        if self.max_episode_steps > 0:
+            # auto-reset: the kernel resets the flagged environments, writes the first observation of their new episode
+            # into their rows and reports which ones it reset
+            L.check(L.L.sag_reset_obs(self._h, None, 1, 0, self._p(self._obs), self._p(self._was_reset), self._stream()))
+            was_reset = self._was_reset.to(torch.bool)
+            info['truncated'] = was_reset & ~done   # ended by the time limit, not by a physics error
+            done = done | was_reset
+        self._raise_recorded_errors('step')
+        return self._out(self._obs), self._out(reward), done, info
 
     def reset(self, *, seed: Optional[int] = None, return_info: bool = False, options: Optional[dict] = None):
         """safe_adaptation_gym.py:85-107"""
@@ -204,7 +222,7 @@ class BatchedSafeAdaptationGym:
         """safe_adaptation_gym.py:120-131: [obstacles lidar, objects lidar, goal lidar, sensors]"""
         L = self._lib
         L.check(L.L.sag_observe(self._h, self._p(self._obs), self._stream()))
-        return self._obs
+        return self._out(self._obs)
 
     @property
     def lidar_observations(self) -> torch.Tensor:
@@ -239,13 +257,11 @@ class BatchedSafeAdaptationGym:
         if mask is not None:
             m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         L.check(L.L.sag_reset(self._h, self._p(m), 0, 1 if new_task else 0, self._stream()))
-        self._steps_to_expiry = self.max_episode_steps if (mask is None and self.max_episode_steps > 0) else None
-        flags = self.get_field('flags')[:self.num_envs]
-        bad = (flags & _abi.FLAG_RESAMPLE_FAILED) != 0
         if new_task and self.base_config['random_bound']:  # world.py:75-78: drawn once per Task instance
             self._bound = self.get_field('task_f64')[14, :self.num_envs].clone()
-        if bool(bad.any()):
-            raise ResamplingError('Failed to generate layout')  # world.py:189
+        if self.device.type == 'cuda':
+            torch.cuda.current_stream(self.device).synchronize()  # reset raises like the reference does (world.py:189)
+        self._raise_recorded_errors('reset')
 
     def reset_envs(self, mask):
         """Reset only the environments where `mask` is true (vectorised-wrapper helper)."""
@@ -254,6 +270,9 @@ class BatchedSafeAdaptationGym:
 
     def check_errors(self):
         """Raise the reference's exceptions for conditions recorded on the device since the last check."""
+        if self.device.type == 'cuda':
+            torch.cuda.current_stream(self.device).synchronize()
+        self._raise_recorded_errors('step')
         flags = self.get_field('flags')[:self.num_envs]
         if bool(((flags & _abi.FLAG_RESAMPLE_FAILED) != 0).any()):
             raise ResamplingError('Failed to generate goal')  # go_to_goal.py:80
@@ -284,12 +303,16 @@ class BatchedSafeAdaptationGym:
         in-step draw counters, the task ids and the cached clearance), and the host-side step budget.  The
         finished-episode statistics of `task_stats` are not part of it."""
         return {'seed': self._seed, 'num_envs': self.num_envs, 'robot': self.robot_name,
-                'fields': {name: self.get_field(name).cpu() for name in self._FIELDS},
-                'steps_to_expiry': self._steps_to_expiry}
+                'config': dict(self.base_config), 'env_id_base': self.env_id_base, 'max_episode_steps': self.max_episode_steps,
+                'fields': {name: self.get_field(name).cpu() for name in self._FIELDS}}
 
     def load_state_dict(self, sd: dict):
         if sd['num_envs'] != self.num_envs or sd['robot'] != self.robot_name:
             raise ValueError('state_dict belongs to a different batch size / robot')
+        for key, mine in (('config', dict(self.base_config)), ('env_id_base', self.env_id_base),
+                          ('max_episode_steps', self.max_episode_steps)):
+            if key in sd and sd[key] != mine:
+                raise ValueError(f'state_dict was saved with a different {key}: {sd[key]!r} != {mine!r} (the continuation would not be bit-exact)')
         self.seed(sd['seed'])
         for name, value in sd['fields'].items():
             self.set_field(name, value)
@@ -299,7 +322,6 @@ class BatchedSafeAdaptationGym:
         self._task_ids = ids.to(self.device)
         self._any_unsupervised = bool((ids == _tasks.Unsupervised.task_id).any())
         self._observation_space = None
-        self._steps_to_expiry = sd['steps_to_expiry']
         if self.base_config['random_bound']:
             self._bound = self.get_field('task_f64')[14, :self.num_envs].clone()
 
@@ -308,7 +330,8 @@ class BatchedSafeAdaptationGym:
         L = self._lib
         L.check(L.L.sag_rollout(self._h, int(k_steps), self._p(self._obs), self._p(self._reward), self._p(self._cost),
                                 self._p(self._done), self._stream()))
-        return self._obs, self._reward, self._done.to(torch.bool), {'cost': self._cost.to(torch.float32), 'bound': self._bound}
+        return (self._out(self._obs), self._out(self._reward), self._done.to(torch.bool),
+                {'cost': self._cost.to(torch.float32), 'bound': self._out(self._bound)})
 
     def task_stats(self, reset: bool = False) -> torch.Tensor:
         """[14, 3] float64: per-task (sum of finished-episode returns, sum of costs, #episodes) on this device."""

@@ -32,7 +32,8 @@ struct Handle {
   Dev D;
   char* slab;
   SlabLayout LY;
-  double *sret, *scost, *sn;
+  double *sret, *scost, *sn, *stats_acc;
+  int err[4];
 };
 void write_tile(const float* tile, float* out, int e0, int n, int kObs) {
   int cnt = (n - e0 < kBS ? n - e0 : kBS) * kObs;
@@ -42,13 +43,23 @@ void write_tile(const float* tile, float* out, int e0, int n, int kObs) {
 int obs_dim_of(const Dev& D) { return D.robot == SAG_ROBOT_CAR ? SAG_OBS_CAR : SAG_OBS_POINT; }
 
 template <class RB>
-void do_reset(Handle* H, const uint8_t* mask, int only_flagged, int new_task) {
+void do_reset(Handle* H, const uint8_t* mask, int only_flagged, int new_task, float* obs, uint8_t* was_reset) {
   Dev& D = H->D;
+  static float tile[kObsMax * kTileStride];
+  static Scratch scratch;
   for (int e = 0; e < D.n; ++e) {
-    if (mask && !mask[e]) continue;
-    if (only_flagged && !(D.flags[e] & F_NEEDS_RESET)) continue;
-    if (D.nstep[e] > 0) { H->sret[e] += D.epret[e]; H->scost[e] += D.epcost[e]; H->sn[e] += 1.0; }
+    bool doit = true;
+    if (mask && !mask[e]) doit = false;
+    if (doit && only_flagged && !(D.flags[e] & F_NEEDS_RESET)) doit = false;
+    if (was_reset) was_reset[e] = doit ? 1 : 0;
+    if (!doit) continue;
+    if ((D.flags[e] & F_NEEDS_RESET) && D.nstep[e] > 0) { H->sret[e] += D.epret[e]; H->scost[e] += D.epcost[e]; H->sn[e] += 1.0; }
     env_reset<RB>(D, e, D.episode[e] + 1u, new_task != 0);
+    if (D.flags[e] & F_RESAMPLE_FAILED) D.errflags[0] = 1;
+    if (obs) {
+      env_observe<RB>(1u, &scratch, D, e, tile, kTileStride);
+      for (int k = 0; k < RB::kObsDim; ++k) obs[(size_t)e * RB::kObsDim + k] = tile[k * kTileStride];
+    }
   }
 }
 template <class RB>
@@ -134,24 +145,47 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   slab_bind(H->D, H->LY, H->slab);
   size_t st = H->D.stride;
   H->sret = (double*)(H->slab + H->LY.stats_off); H->scost = H->sret + st; H->sn = H->sret + 2 * st;
+  H->stats_acc = (double*)(H->slab + H->LY.acc_off);
+  H->D.errflags = H->err;
   memset(H->D.episode, 0xFF, st * sizeof(unsigned));
   *handle = H;
   return 0;
 }
 int sag_destroy(void* h) { Handle* H = (Handle*)h; if (H) { free(H->slab); delete H; } return 0; }
 unsigned long long sag_launch_count(void* h) { (void)h; return 0ull; }
+int sag_debug_read(void* h, unsigned long long* out16) { (void)h; memset(out16, 0, 16 * sizeof(unsigned long long)); return 0; }
 int sag_stride(void* h) { return ((Handle*)h)->D.stride; }
 int sag_obs_dim(void* h) { return obs_dim_of(((Handle*)h)->D); }
 size_t sag_field_bytes(void* h, int f) { return (f < 0 || f >= SAG_NUM_FIELDS) ? 0 : ((Handle*)h)->LY.bytes[f]; }
 int sag_set_tasks(void* h, const int32_t* ids, void* s) {
-  (void)s; Handle* H = (Handle*)h;
-  for (int e = 0; e < H->D.n; ++e) H->D.task[e] = ids[e];
+  (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
+  for (int e = 0; e < D.n; ++e) {  // same logic as k_set_tasks
+    const int old = D.task[e];
+    double r = H->sret[e], c = H->scost[e], k = H->sn[e];
+    if ((D.flags[e] & F_NEEDS_RESET) && D.nstep[e] > 0) { r += D.epret[e]; c += D.epcost[e]; k += 1.0; D.nstep[e] = 0; }
+    if (k != 0.0 && old >= 0 && old < SAG_NUM_TASKS) { H->stats_acc[3 * old] += r; H->stats_acc[3 * old + 1] += c; H->stats_acc[3 * old + 2] += k; }
+    H->sret[e] = H->scost[e] = H->sn[e] = 0.0;
+    int id = ids[e];
+    if (id < 0 || id >= SAG_NUM_TASKS) { id = SAG_T_GO_TO_GOAL; D.errflags[1] = 1; }
+    D.task[e] = id;
+  }
   return 0;
+}
+int sag_error_flags(void* h, int clear) {
+  Handle* H = (Handle*)h;
+  int w = (H->err[0] ? SAG_FLAG_RESAMPLE_FAILED : 0) | (H->err[1] ? SAG_ERR_BAD_TASK_ID : 0);
+  if (clear) H->err[0] = H->err[1] = 0;
+  return w;
 }
 int sag_seed(void* h, uint64_t seed) { Handle* H = (Handle*)h; H->D.seed = seed; memset(H->D.episode, 0xFF, (size_t)H->D.stride * sizeof(unsigned)); return 0; }
 int sag_reset(void* h, const uint8_t* mask, int only_flagged, int new_task, void* s) {
   (void)s; Handle* H = (Handle*)h;
-  if (H->D.robot == SAG_ROBOT_CAR) do_reset<CarRobot>(H, mask, only_flagged, new_task); else do_reset<PointRobot>(H, mask, only_flagged, new_task);
+  if (H->D.robot == SAG_ROBOT_CAR) do_reset<CarRobot>(H, mask, only_flagged, new_task, nullptr, nullptr); else do_reset<PointRobot>(H, mask, only_flagged, new_task, nullptr, nullptr);
+  return 0;
+}
+int sag_reset_obs(void* h, const uint8_t* mask, int only_flagged, int new_task, float* obs, uint8_t* was_reset, void* s) {
+  (void)s; Handle* H = (Handle*)h;
+  if (H->D.robot == SAG_ROBOT_CAR) do_reset<CarRobot>(H, mask, only_flagged, new_task, obs, was_reset); else do_reset<PointRobot>(H, mask, only_flagged, new_task, obs, was_reset);
   return 0;
 }
 int sag_step(void* h, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done, void* s) {
@@ -173,9 +207,9 @@ int sag_read_field(void* h, int f, void* dst, void* s) { (void)s; Handle* H = (H
 int sag_write_field(void* h, int f, const void* src, void* s) { (void)s; Handle* H = (Handle*)h; memcpy(H->slab + H->LY.off[f], src, H->LY.bytes[f]); return 0; }
 int sag_task_stats(void* h, double* out, int reset, void* s) {
   (void)s; Handle* H = (Handle*)h; Dev& D = H->D;
-  memset(out, 0, SAG_NUM_TASKS * 3 * sizeof(double));
+  memcpy(out, H->stats_acc, SAG_NUM_TASKS * 3 * sizeof(double));
   for (int e = 0; e < D.n; ++e) { int t = D.task[e]; out[3 * t] += H->sret[e]; out[3 * t + 1] += H->scost[e]; out[3 * t + 2] += H->sn[e]; }
-  if (reset) memset(H->sret, 0, 3 * (size_t)D.stride * sizeof(double));
+  if (reset) { memset(H->sret, 0, 3 * (size_t)D.stride * sizeof(double)); memset(H->stats_acc, 0, SAG_NUM_TASKS * 3 * sizeof(double)); }
   return 0;
 }
 int sag_lidar(const double* robot, const double* obj_xy, const uint8_t* group, int n, int nslots, float* out, void* s) {

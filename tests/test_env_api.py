@@ -5,7 +5,7 @@ import torch
 
 import oracle as O
 import safe_adaptation_gym_b200 as sag
-from common import env_state, hostemu_lib
+from common import check_autoreset_and_stats, check_stats_follow_task, env_state, hostemu_lib, make_env
 from safe_adaptation_gym_b200 import benchmark, tasks
 from safe_adaptation_gym_b200.utils import ResamplingError
 
@@ -159,3 +159,31 @@ def test_state_dict_resume_is_bit_exact():
         assert torch.equal(obs, o) and torch.equal(rew, r) and torch.equal(done, d) and torch.equal(info["cost"], c)
     with pytest.raises(ValueError):
         _make(n=n + 1).load_state_dict(sd)
+
+
+def test_autoreset_rows_truncated_mask_and_fresh_outputs():
+    check_autoreset_and_stats("hostemu")
+
+
+def test_statistics_stay_with_the_task_the_episode_ran_under():
+    check_stats_follow_task("hostemu")
+
+
+def test_state_dict_carries_config_and_rejects_a_different_one():
+    a = _make(n=3, seed=5, config={"action_noise": 0.0})
+    sd = a.state_dict()
+    assert sd["config"]["action_noise"] == 0.0 and sd["env_id_base"] == 0 and sd["max_episode_steps"] == 0
+    b = _make(n=3, seed=5)                      # default action_noise 0.01
+    with pytest.raises(ValueError):
+        b.load_state_dict(sd)
+    c = _make(n=3, seed=9, config={"action_noise": 0.0})
+    c.load_state_dict(sd)                       # same configuration: accepted
+
+
+def test_bad_task_id_is_reported_not_indexed():
+    from safe_adaptation_gym_b200 import _abi
+    env = _make(n=4, seed=5)
+    ids = torch.tensor([3, 3, 77, 3], dtype=torch.int32)
+    env._lib.check(env._lib.L.sag_set_tasks(env._h, ids.data_ptr(), None))
+    assert env._lib.L.sag_error_flags(env._h, 1) & _abi.ERR_BAD_TASK_ID
+    assert env.get_field("task_i32")[0, :4].tolist() == [3, 3, 3, 3]

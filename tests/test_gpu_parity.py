@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import oracle as O
-from common import env_state, make_env, run_parity
+from common import env_state, make_env, run_fullsize_parity, run_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def test_native_library_is_loaded():
     from safe_adaptation_gym_b200 import _abi
     L = _abi.load()
-    assert L.L.sag_abi_version() == 1
+    assert L.L.sag_abi_version() == 2
     assert L.path.endswith("csrc/libsag_b200.so")
 
 
@@ -291,3 +291,63 @@ def test_state_dict_resume_on_device():
     for a, (o, r, d) in zip(acts, ref):
         obs, rew, done, _ = other.step(a)
         assert torch.equal(obs, o) and torch.equal(rew, r) and torch.equal(done, d)
+
+
+# ---- oracle parity at the BASELINE batch sizes ---------------------------------------------
+@pytest.mark.gpu
+def test_fullsize_point_go_to_goal_oracle_parity():
+    """BASELINE config 2: 65,536 point go_to_goal environments, 300 steps, 256 environments mirrored by the oracle"""
+    s = run_fullsize_parity("point", ["go_to_goal"], n=65536, steps=300, n_sample=256)
+    assert s["contacts"] > 0 and s["max_worklist"] > 300      # the sampled envs touched things; the work list was long
+
+
+@pytest.mark.gpu
+def test_fullsize_car_go_to_goal_press_buttons_oracle_parity():
+    """BASELINE config 3: 32,768 car environments, go_to_goal + press_buttons alternating"""
+    s = run_fullsize_parity("car", ["go_to_goal", "press_buttons"], n=32768, steps=120, n_sample=96)
+    assert s["contacts"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot", ["point", "car"])
+def test_fullsize_haul_box_push_box_oracle_parity(robot):
+    """BASELINE config 4: 16,384 environments, haul_box + push_box alternating (tendon, 5-geom box)"""
+    s = run_fullsize_parity(robot, ["haul_box", "push_box"], n=16384, steps=150 if robot == "point" else 100, n_sample=96)
+    assert s["contacts"] > 0
+
+
+@pytest.mark.gpu
+def test_host_buffer_api_against_oracle():
+    """sag_step_host (pinned buffers, overlapped copy + mapped-memory fix-up) checked against the oracle, not only
+    against the device API"""
+    s = run_fullsize_parity("point", ["go_to_goal", "push_box"], n=8192, steps=250, n_sample=128, use_host_api=True)
+    assert s["max_worklist"] > 20     # the mapped-memory fix-up path carried rows
+
+
+@pytest.mark.gpu
+def test_new_abi_behaviours_on_device():
+    """auto-reset row / truncated mask, statistics keyed by the task the episode ran under, host-pointer set_task and bound,
+    two handles in one process (device guard), fresh output tensors"""
+    from common import check_autoreset_and_stats
+    check_autoreset_and_stats("cuda")
+    from safe_adaptation_gym_b200 import _abi
+    L = _abi.load()
+    a = make_env("cuda", 256, "go_to_goal", seed=3, config={"random_bound": True})
+    b = make_env("cuda", 128, "push_box", seed=4, robot="car")
+    ids = np.array([3, 10] * 128, dtype=np.int32)
+    L.check(L.L.sag_set_tasks_host(a._h, ids.ctypes.data))
+    L.check(L.L.sag_reset_host(a._h, None, 0, 1, None))
+    assert a.get_field("task_i32")[0, :256].cpu().numpy().tolist() == ids.tolist()
+    bound = np.zeros(256)
+    L.check(L.L.sag_bound_host(a._h, bound.ctypes.data_as(C.POINTER(C.c_double))))
+    np.testing.assert_array_equal(bound, a.get_field("task_f64")[14, :256].cpu().numpy())
+    assert (bound > 0).all() and (bound < 25).all() and len(np.unique(bound)) > 200
+    bad = ids.copy(); bad[7] = 99
+    assert L.L.sag_set_tasks_host(a._h, bad.ctypes.data) != 0
+    badd = torch.as_tensor(bad, device="cuda")
+    L.check(L.L.sag_set_tasks(a._h, badd.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert L.L.sag_error_flags(a._h, 1) & _abi.ERR_BAD_TASK_ID
+    assert L.L.sag_error_flags(a._h, 0) == 0
+    o1, *_ = b.step(torch.zeros((128, 2), device="cuda"))     # the other handle still works
+    assert torch.isfinite(o1).all()
