@@ -351,3 +351,22 @@ def test_new_abi_behaviours_on_device():
     assert L.L.sag_error_flags(a._h, 0) == 0
     o1, *_ = b.step(torch.zeros((128, 2), device="cuda"))     # the other handle still works
     assert torch.isfinite(o1).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot,tasks_", [("point", ["go_to_goal", "push_box", "roll_rod", "dribble_ball"]), ("car", ["go_to_goal", "push_box", "roll_rod"])])
+def test_speed_bounds_on_device(robot, tasks_):
+    """tests/test_physics_bounds.py on the CUDA path: 4096 random-action environments, no body faster than an elastic
+    collision with the robot allows, nothing non-finite"""
+    n = 4096
+    env = make_env("cuda", n, [tasks_[e % len(tasks_)] for e in range(n)], seed=31, robot=robot)
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    term = 1.5 if robot == "point" else 1.0
+    for t in range(300):
+        obs, rew, done, info = env.step(torch.rand((n, 2), device="cuda", generator=g) * 2 - 1)
+        if t % 20 == 19:
+            r, o = env.get_field("robot")[:, :n], env.get_field("objects")[:, :, :n]
+            assert torch.isfinite(r).all() and torch.isfinite(o).all() and torch.isfinite(obs).all()
+            assert float(torch.hypot(r[3], r[4]).max()) <= 1.1 * term
+            assert float(torch.hypot(o[3], o[4]).max()) <= 2.5 * term
+    assert not bool(done.any())
