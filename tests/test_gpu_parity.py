@@ -370,3 +370,37 @@ def test_speed_bounds_on_device(robot, tasks_):
             assert float(torch.hypot(r[3], r[4]).max()) <= 1.1 * term
             assert float(torch.hypot(o[3], o[4]).max()) <= 2.5 * term
     assert not bool(done.any())
+
+
+@pytest.mark.gpu
+def test_integration_md_ctypes_stub_runs_as_written():
+    """the reference-side binding shown in INTEGRATION.md (numpy in / out, host pointers only) is executed verbatim and
+    must return what the torch-side env returns"""
+    import os
+    import re
+    from safe_adaptation_gym_b200 import _abi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = [b for b in re.findall(r"```python\n(.*?)```", md, re.S) if "class B200Bridge" in b][0]
+    ns = {}
+    exec(code, ns)
+    n = 64
+    names = ["go_to_goal", "push_box"] * (n // 2)
+    br = ns["B200Bridge"](_abi.LIB_PATH, n, names, seed=12, config={"random_bound": 1})
+    env = make_env("cuda", n, names, seed=12, config={"random_bound": True})
+    np.testing.assert_array_equal(br.obs, env.observation.cpu().numpy())
+    np.testing.assert_array_equal(br.bound, env.get_field("task_f64")[14, :n].cpu().numpy())
+    rs = np.random.RandomState(0)
+    for t in range(30):
+        a = rs.uniform(-1, 1, (n, 2)).astype(np.float32)
+        obs, rew, done, info = br.step(a)
+        o2, r2, d2, i2 = env.step(torch.from_numpy(a))
+        np.testing.assert_array_equal(obs, o2.cpu().numpy())
+        np.testing.assert_array_equal(rew, r2.cpu().numpy())
+        np.testing.assert_array_equal(info["cost"], i2["cost"].cpu().numpy().astype(np.float64))
+        np.testing.assert_array_equal(info["bound"], i2["bound"].cpu().numpy())
+    obs = br.reset()
+    env.reset()
+    np.testing.assert_array_equal(obs, env.observation.cpu().numpy())
+    with pytest.raises(KeyError):
+        br.set_task("fly_to_goal")
