@@ -85,9 +85,9 @@ int sag_obs_dim(void* handle);
 size_t sag_field_bytes(void* handle, int field);
 /* number of CUDA kernels launched on behalf of this handle so far (bench.py's gpu_launches is a difference of two reads) */
 unsigned long long sag_launch_count(void* handle);
-/* tuning hook: section clocks of the contact kernel, 16 x u64 into a HOST buffer, zeroed after the read.  All zero
+/* tuning hook: section clocks of the contact kernel, 18 x u64 into a HOST buffer, zeroed after the read.  All zero
  * unless the library was built with -DSAG_TIMING (tools/late_phase.py). */
-int sag_debug_read(void* handle, unsigned long long* out16_host);
+int sag_debug_read(void* handle, unsigned long long* out18_host);
 
 /* env.set_task (safe_adaptation_gym.py:165-168): task_ids is a DEVICE int32[n_envs] array.  Statistics gathered under
  * the previous task are folded into the per-task totals first.  An id outside [0, SAG_NUM_TASKS) is replaced by

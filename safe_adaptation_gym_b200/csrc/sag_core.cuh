@@ -37,10 +37,13 @@ extern long* sag_prof_ptr;  // tests/hostemu instrumentation: per-env work count
 #define SAG_CLK_DECL long long clk_ = clock64()
 #define SAG_CLK_RESET do { clk_ = clock64(); } while (0)
 #define SAG_CLK(i) do { long long now_ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&D.dbg[i], (unsigned long long)(now_ - clk_)); clk_ = now_; } while (0)
+// same, and the interval is also added to this environment's own section sum g (0 detect, 1 setup, 2 pgs) in the warp's Scratch
+#define SAG_CLKG(i, g, Sref) do { long long now_ = clock64(); if ((threadIdx.x & 31) == 0) { atomicAdd(&D.dbg[i], (unsigned long long)(now_ - clk_)); (Sref).tsum[g] += (unsigned long long)(now_ - clk_); } clk_ = now_; } while (0)
 #else
 #define SAG_CLK_DECL do { } while (0)
 #define SAG_CLK_RESET do { } while (0)
 #define SAG_CLK(i) do { } while (0)
+#define SAG_CLKG(i, g, Sref) do { } while (0)
 #endif
 
 namespace sag {
@@ -659,6 +662,13 @@ struct Scratch {
   int bslot[kMaxBodies];
   SolveConsts Q;                 // cooperative kernel: this environment's constants (scalar paths keep them in registers)
   double obj[6][kMaxObj];        // cooperative kernel: the environment's object arrays for the duration of a step (ObjView)
+  static constexpr int kItems = 96;
+  double sc[2][kMaxObj];         // cooperative kernel: sin / cos of the objects' yaw, valid where scvalid has the slot's bit
+  unsigned scvalid, pad_;
+  int items[kItems];             // cooperative kernel: flattened part pairs of the object-pair narrow phase
+#if defined(SAG_TIMING)
+  unsigned long long tsum[4];    // this environment's section clocks (tuning builds)
+#endif
 };
 
 // env_step / end_of_step modes: full scalar path (one thread = one environment, contact solver included), quiet-only
@@ -795,10 +805,26 @@ SAG_HD void car_free_solve(const CarRobot& R, double sn, double cs, const PtCons
 // computed by the same arithmetic as in the scalar path, so results are bit-identical (tests/test_gpu_parity.py runs
 // the oracle against this path).
 // ------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+// Phase alignment of the cooperative kernel's warps (SAG_COOP_ALIGN builds): every warp of the CTA arrives at a barrier at
+// the top of each substep and before the end-of-step pass, so that the 16 environments of an SM walk through the same
+// code at the same time and share its instruction-cache lines instead of evicting each other's.  A warp without an
+// environment executes the same number of barriers (coop_idle_step).
+__device__ __forceinline__ void coop_align() {
+#if defined(SAG_COOP_ALIGN) && defined(__CUDA_ARCH__)
+  asm volatile("bar.sync 0;" ::: "memory");
+#endif
+}
+template <class RB>
+__device__ __forceinline__ void coop_idle_step() {
+#pragma unroll 1
+  for (int k = 0; k <= RB::kNsub; ++k) coop_align();
+}
+
+#endif
 #if defined(__CUDA_ARCH__)
 constexpr unsigned kFullWarp = 0xffffffffu;
 __device__ __forceinline__ int coop_lane() { return threadIdx.x & 31; }
-
 // ordered append: lane order = canonical order; n in {0, 1, 2} hits per lane
 __device__ __forceinline__ bool coop_append(Con* con, int cap, int& ncon, bool& overflow, int n, const Hit* hits, int ba, int bb) {
   const int lane = coop_lane();
@@ -825,12 +851,18 @@ __device__ __forceinline__ bool coop_append(Con* con, int cap, int& ncon, bool& 
 //     pm[j] = {i < j} held by lane j, so that walking j upwards and the bits of pm[j] upwards is the canonical pair order.
 //   narrow phase: ONE copy of the collide() code; each trip hands up to 32 geom pairs to the lanes -- phase 1: (robot geom,
 //     object part) items of all near objects in slot order (only the push box has more than one part and it is the last
-//     slot); phase 2: the part pairs of one near object pair.  Hits are appended in lane order (= canonical order).
+//     slot); phase 2: the part pairs of ALL near object pairs, flattened into the warp's item list in canonical order (a
+//     multi-contact cluster -- the environments that set the kernel's duration -- is then one trip, not one per pair).
+//     Hits are appended in lane order (= canonical order).  sin / cos of an object's yaw are cached per slot until the
+//     object is integrated again (Scratch::sc, scvalid).
 template <class RB>
-__device__ __noinline__ void detect_coop(const Ctx& C, const RB& R, double sn, double cs, unsigned mov, Con* con, int cap,
+__device__ __noinline__ void detect_coop(const Ctx& C, const RB& R, double sn, double cs, unsigned mov, Scratch& S,
                                          int& ncon_out, bool& overflow_out, unsigned& touch_out, unsigned& active_out) {
   const Dev& D = C.D;
   const int lane = coop_lane();
+  constexpr int cap = Scratch::kCon;
+  Con* con = S.con;
+  SAG_CLK_DECL;
   int ncon = 0;
   bool overflow = false;
   unsigned touch = 0, active = mov;
@@ -855,20 +887,21 @@ __device__ __noinline__ void detect_coop(const Ctx& C, const RB& R, double sn, d
   const unsigned near_single = near1m & ~boxbit;
   const int n_single = __popc(near_single) * RB::kNGeom;
   const int total1 = n_single + ((near1m & boxbit) ? RB::kNGeom * 5 : 0);
+  SAG_CLK(2);
   // ---- narrow phase trips
-  int base1 = 0, phase = total1 > 0 ? 0 : 1;
+  int base = 0, total = total1, phase = total1 > 0 ? 0 : 1;
+  bool pairs_built = false, sequential = false;
   unsigned pm = 0, jm = 0, pmj = 0;
   int pj = -1;
-  bool pairs_built = false;
   for (;;) {
     // -- next trip: per-lane item (geom A of body ia / part pa, geom B of slot sb / part pb); ia < 0: robot geom pa
     bool have = false;
     int ia = -1, pa = 0, sb = 0, pb = 0;
     if (phase == 0) {
-      if (base1 >= total1) { phase = 1; continue; }
-      const int t = base1 + lane;
-      base1 += 32;
-      if (t < total1) {
+      if (base >= total) { phase = 1; continue; }
+      const int t = base + lane;
+      base += 32;
+      if (t < total) {
         have = true;
         if (t < n_single) { const int rank = t / RB::kNGeom; pa = t - rank * RB::kNGeom; sb = (int)__fns(near_single, 0, rank + 1); pb = 0; }
         else { const int u = t - n_single; pa = u / 5; pb = u - pa * 5; sb = C.L.box; }
@@ -894,23 +927,49 @@ __device__ __noinline__ void detect_coop(const Ctx& C, const RB& R, double sn, d
           if (lane == a) pm |= below;
         }
         jm = __ballot_sync(kFullWarp, pm != 0);
+        if (!jm) { SAG_CLK(12); break; }
+        // flatten the part pairs of all near pairs into S.items, canonical order: j ascending (lane order), i ascending,
+        // part of i outer, part of j inner.  Only the push box has parts, and as the last slot it can only be a j.
+        const int npl = ((boxbit >> lane) & 1u) ? 5 : 1;
+        const int cnt = __popc(pm) * npl;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFullWarp, incl, d); if (lane >= d) incl += v; }
+        total = __shfl_sync(kFullWarp, incl, 31);
+        base = 0;
+        if (total <= Scratch::kItems) {
+          int off = incl - cnt;
+          for (unsigned m = pm; m; m &= m - 1) {
+            const int i = __ffs((int)m) - 1;
+            for (int b = 0; b < npl; ++b) S.items[off++] = i | (lane << 8) | (b << 16);
+          }
+          __syncwarp();
+        } else sequential = true;  // more near part pairs than the list holds (a heap of bodies): one pair per trip
+        SAG_CLK(12);
       }
-      if (!pmj) {
-        if (!jm) break;
-        pj = __ffs((int)jm) - 1;
-        jm &= jm - 1;
-        pmj = __shfl_sync(kFullWarp, pm, pj);
+      if (!sequential) {
+        if (base >= total) break;
+        const int t = base + lane;
+        base += 32;
+        if (t < total) { const int it = S.items[t]; have = true; ia = it & 0xff; sb = (it >> 8) & 0xff; pa = 0; pb = it >> 16; }
+      } else {
+        if (!pmj) {
+          if (!jm) break;
+          pj = __ffs((int)jm) - 1;
+          jm &= jm - 1;
+          pmj = __shfl_sync(kFullWarp, pm, pj);
+        }
+        const int pi = __ffs((int)pmj) - 1;
+        pmj &= pmj - 1;
+        const int npj = kind_nparts(slot_kind(C.sp, C.L, pj)), items = kind_nparts(slot_kind(C.sp, C.L, pi)) * npj;
+        if (lane < items) { have = true; ia = pi; pa = lane / npj; sb = pj; pb = lane - pa * npj; }
       }
-      const int pi = __ffs((int)pmj) - 1;
-      pmj &= pmj - 1;
-      const int ki = slot_kind(C.sp, C.L, pi), kj = slot_kind(C.sp, C.L, pj);
-      const int npj = kind_nparts(kj), items = kind_nparts(ki) * npj;  // part of i outer, part of j inner
-      if (lane < items) { have = true; ia = pi; pa = lane / npj; sb = pj; pb = lane - pa * npj; }
     }
     // -- narrow phase of this trip
     Hit hits[2];
     int n = 0;
     bool mvb = false, mva = false;
+    unsigned newsc = 0;  // slots whose sin / cos this lane has just computed and cached
     if (have) {
       Geom ga, gb;
       const int kb = slot_kind(C.sp, C.L, sb);
@@ -918,7 +977,10 @@ __device__ __noinline__ void detect_coop(const Ctx& C, const RB& R, double sn, d
       {
         const size_t i = oix(C, sb);
         double oc = 1.0, os = 0.0;
-        if (mvb) sag_sincos(C.O.yaw[i], &os, &oc);
+        if (mvb) {
+          if ((S.scvalid >> sb) & 1u) { os = S.sc[0][sb]; oc = S.sc[1][sb]; }
+          else { sag_sincos(C.O.yaw[i], &os, &oc); S.sc[0][sb] = os; S.sc[1][sb] = oc; newsc |= 1u << sb; }
+        }
         obj_geom(D, kb, pb, C.O.x[i], C.O.y[i], oc, os, gb);
       }
       if (ia < 0) R.geom(pa, sn, cs, ga);
@@ -927,15 +989,23 @@ __device__ __noinline__ void detect_coop(const Ctx& C, const RB& R, double sn, d
         mva = kind_movable(ka);
         const size_t i = oix(C, ia);
         double oc = 1.0, os = 0.0;
-        if (mva) sag_sincos(C.O.yaw[i], &os, &oc);
+        if (mva) {
+          if ((S.scvalid >> ia) & 1u) { os = S.sc[0][ia]; oc = S.sc[1][ia]; }
+          else { sag_sincos(C.O.yaw[i], &os, &oc); S.sc[0][ia] = os; S.sc[1][ia] = oc; newsc |= 1u << ia; }
+        }
         obj_geom(D, ka, pa, C.O.x[i], C.O.y[i], oc, os, ga);
       }
       n = collide(ga, gb, hits);
     }
     const bool stored = coop_append(con, cap, ncon, overflow, n, hits, ia < 0 ? 0 : (mva ? 1 + ia : -1), mvb ? 1 + sb : -1);
+    newsc = __reduce_or_sync(kFullWarp, newsc);
+    if (newsc) { __syncwarp(); S.scvalid |= newsc; __syncwarp(); }  // every lane stores the same word
     if (phase == 0) {
       touch |= __reduce_or_sync(kFullWarp, stored ? 1u << sb : 0u);
       active |= __reduce_or_sync(kFullWarp, (n && mvb) ? 1u << sb : 0u);
+      SAG_CLK(11);
+    } else {
+      SAG_CLK(13);
     }
   }
   __syncwarp();
@@ -1014,7 +1084,10 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   SAG_CLK_DECL;
   if constexpr (Coop) {
 #if defined(__CUDA_ARCH__)
-    detect_coop<RB>(C, R, sn, cs, mov, con, kCapCon, ncon, overflow, touch, active);
+    detect_coop<RB>(C, R, sn, cs, mov, S, ncon, overflow, touch, active);
+#if defined(SAG_TIMING)
+    { long long now_ = clock64(); if ((threadIdx.x & 31) == 0) S.tsum[0] += (unsigned long long)(now_ - clk_); }
+#endif
 #endif
   } else {
   Hit hits[2];
@@ -1097,7 +1170,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   }
   P.touch = touch;
   P.mov = mov;
-  if constexpr (Coop) SAG_CLK(2);
+  if constexpr (Coop) SAG_CLK_RESET;
   SAG_PROF(e, 2, ncon);
   P.fc[0] = P.fc[1] = P.fc[2] = 0.0;
   P.wtau[0] = P.wtau[1] = 0.0;
@@ -1178,6 +1251,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
     }
   }
   if (overflow) { ncon = 0; tendon = false; }  // car: the wheel rows are still solved, nothing else
+  if constexpr (Coop) SAG_CLKG(8, 1, S);
   // one row pair per active contact, in contact order.  Cooperative mode: contact i is set up by lane i (ncon <= 16),
   // the row index is the rank of the contact among the active ones.
   int i_begin = 0, i_end = ncon, my_row = 0;
@@ -1257,10 +1331,51 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
   SAG_PROF(e, 9, nrow); SAG_PROF(e, 10, nb); SAG_PROF(e, 11, any_row ? 1 : 0);
   SAG_PROF_MAX(e, 12, ncon); SAG_PROF_MAX(e, 13, nb); SAG_PROF_MAX(e, 14, nrow);
   { int oo = 0; for (int i = 0; i < ncon; ++i) if (con[i].ba != 0) oo = 1; SAG_PROF_MAX(e, 15, oo); (void)oo; }
-  if constexpr (Coop) SAG_CLK(3);
+  if constexpr (Coop) SAG_CLKG(3, 1, S);
   // Projected Gauss-Seidel; stops after kSweeps sweeps or when a sweep changes the forces by < kPgsTol (relative, L1).
-  // Strictly sequential visits; in the cooperative kernel all lanes run them redundantly on the warp's shared-memory
-  // working set (broadcast reads, identical stores): the visit chain is latency-bound and has no parallelism to hand out.
+  // The row visits are strictly sequential; in the cooperative kernel all lanes run them redundantly on the warp's
+  // shared-memory working set (broadcast reads, identical stores).  Every visit first stages ALL the constants it needs in
+  // registers (one batch of loads, one wait) -- the compiler cannot hoist shared-memory loads over the visit's own stores.
+  // The floor-friction visits of different bodies touch disjoint state, so the cooperative kernel runs them one body per
+  // lane; their contributions to the running sums are then added in body order, as the sequential sweep does.
+  auto floor_visit = [&](int b, double& tdf, double& tf) {
+    SAG_PROF(e, 5, 1);
+    const bool isb = S.bslot[b] == C.L.box;
+    const double Al = isb ? Q.bim : Q.vim, At = isb ? Q.bii : Q.vii;
+    const double inv_lin = isb ? Q.b_inv_lin : Q.v_inv_lin, inv_tor = isb ? Q.b_inv_tor : Q.v_inv_tor;
+    const double flin = isb ? Q.bflin : Q.vflin, ftor = isb ? Q.bftor : Q.vftor, bfl = isb ? Q.bbfl : Q.vbfl;
+    const double vx = S.bv[b][0], vy = S.bv[b][1], w = S.bv[b][2];
+    double* acs = acc[1 + b];
+    double* flb = ffl[b];
+    const double fl0 = flb[0], fl1 = flb[1], fl2 = flb[2];
+    double ac[3] = {acs[0], acs[1], acs[2]};  // registers for the visit, stored back at the end
+    double f0, f1, d0, d1;
+    if (isb && rod) {  // one row across the axis (rolling, body x) and one along it (sliding, body y), clamped separately
+      const double inv_x = 1.0 / (Q.rix + rr * Q.rix), inv_y = 1.0 / (Q.riy + rr * Q.riy);
+      double au = ac[0] * rc + ac[1] * rs, aw = -ac[0] * rs + ac[1] * rc;
+      double vu = vx * rc + vy * rs, vw = -vx * rs + vy * rc;
+      f0 = fl0 - (au + bfl * vu + rr * Q.rix * fl0) * inv_x;
+      f1 = fl1 - (aw + bfl * vw + rr * Q.riy * fl1) * inv_y;
+      f0 = clampd(f0, -Q.bfx, Q.bfx); f1 = clampd(f1, -Q.bfy, Q.bfy);
+      d0 = f0 - fl0; d1 = f1 - fl1;
+      double du = d0 * Q.rix, dw = d1 * Q.riy;
+      ac[0] += du * rc - dw * rs; ac[1] += du * rs + dw * rc;
+    } else {
+      f0 = fl0 - (ac[0] + bfl * vx + rr * Al * fl0) * inv_lin;
+      f1 = fl1 - (ac[1] + bfl * vy + rr * Al * fl1) * inv_lin;
+      double nf = sqrt(f0 * f0 + f1 * f1);
+      if (nf > flin) { double sc = flin / nf; f0 *= sc; f1 *= sc; }
+      d0 = f0 - fl0; d1 = f1 - fl1;
+      ac[0] += d0 * Al; ac[1] += d1 * Al;
+    }
+    double f2 = fl2 - (ac[2] + bfl * w + rr * At * fl2) * inv_tor;
+    f2 = clampd(f2, -ftor, ftor);
+    double d2 = f2 - fl2;
+    ac[2] += d2 * At;
+    flb[0] = f0; flb[1] = f1; flb[2] = f2;
+    acs[0] = ac[0]; acs[1] = ac[1]; acs[2] = ac[2];
+    tdf = fabs(d0) + fabs(d1) + fabs(d2); tf = fabs(f0) + fabs(f1) + fabs(f2);
+  };
 #pragma unroll 1
   for (int it = 0; it < kSweeps; ++it) {
     double sdf = 0.0, sf = 0.0;
@@ -1269,9 +1384,16 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
     for (int i = 0; i < nrow; ++i) {
       Row& r = rows[i];
       if (kCarRobot && r.type == 2) { wheel_row_update(r, acc[0], acc[r.bb], sdf, sf); continue; }
-      // one visit of a contact row pair (normal, tangent) or of the tendon row (one row): the two bodies' accelerations
-      // stay in registers for the whole visit
+      // one visit of a contact row pair (normal, tangent) or of the tendon row (one row)
       const int ba = r.ba, bb = r.bb, nk = (i == tendon_row) ? 1 : 2;
+      const double bound = r.bound;
+      double ja[2][3], jb[2][3], wa[2][3], wb[2][3], aref[2], Rk[2], inv[2], f[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { ja[k][d] = r.ja[k][d]; jb[k][d] = r.jb[k][d]; wa[k][d] = r.wa[k][d]; wb[k][d] = r.wb[k][d]; }
+        aref[k] = r.aref[k]; Rk[k] = r.R[k]; inv[k] = r.inv[k]; f[k] = r.f[k];
+      }
       double aa[3] = {0.0, 0.0, 0.0}, ab[3] = {0.0, 0.0, 0.0};
       if (ba >= 0) { aa[0] = acc[ba][0]; aa[1] = acc[ba][1]; aa[2] = acc[ba][2]; }
       if (bb >= 0) { ab[0] = acc[bb][0]; ab[1] = acc[bb][1]; ab[2] = acc[bb][2]; }
@@ -1281,68 +1403,52 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
         if (k >= nk) break;
         SAG_PROF(e, 4, 1);
         double a = 0.0;
-        if (ba >= 0) a += dot3(r.ja[k], aa);
-        if (bb >= 0) a += dot3(r.jb[k], ab);
-        const double fo = r.f[k];
-        double fn = fo - (a - r.aref[k] + r.R[k] * fo) * r.inv[k];
+        if (ba >= 0) a += dot3(ja[k], aa);
+        if (bb >= 0) a += dot3(jb[k], ab);
+        const double fo = f[k];
+        double fn = fo - (a - aref[k] + Rk[k] * fo) * inv[k];
         if (k == 0) { if (fn < 0.0) fn = 0.0; }
-        else { double lim = r.bound * r.f[0]; fn = clampd(fn, -lim, lim); }
+        else { double lim = bound * f[0]; fn = clampd(fn, -lim, lim); }
         double df = fn - fo;
-        r.f[k] = fn;
+        f[k] = fn;
         sdf += fabs(df); sf += fabs(fn);
         if (df != 0.0) {
           changed = true;
-          if (ba >= 0) { aa[0] += r.wa[k][0] * df; aa[1] += r.wa[k][1] * df; aa[2] += r.wa[k][2] * df; }
-          if (bb >= 0) { ab[0] += r.wb[k][0] * df; ab[1] += r.wb[k][1] * df; ab[2] += r.wb[k][2] * df; }
+          if (ba >= 0) { aa[0] += wa[k][0] * df; aa[1] += wa[k][1] * df; aa[2] += wa[k][2] * df; }
+          if (bb >= 0) { ab[0] += wb[k][0] * df; ab[1] += wb[k][1] * df; ab[2] += wb[k][2] * df; }
         }
       }
+      r.f[0] = f[0];
+      if (nk == 2) r.f[1] = f[1];
       if (changed) {
         if (ba >= 0) { acc[ba][0] = aa[0]; acc[ba][1] = aa[1]; acc[ba][2] = aa[2]; }
         if (bb >= 0) { acc[bb][0] = ab[0]; acc[bb][1] = ab[1]; acc[bb][2] = ab[2]; }
       }
     }
     // floor-friction rows of every body in the table
+    bool floors_done = false;
+#if defined(__CUDA_ARCH__)
+    if constexpr (Coop) {
+      floors_done = true;
+      __syncwarp();
+      const int b = coop_lane();
+      double tdf = 0.0, tf = 0.0;
+      if (b < nb) floor_visit(b, tdf, tf);
+      __syncwarp();
+      for (int k = 0; k < nb; ++k) { sdf += __shfl_sync(kFullWarp, tdf, k); sf += __shfl_sync(kFullWarp, tf, k); }
+    }
+#endif
+    if (!floors_done) {
 #pragma unroll 1
-    for (int b = 0; b < nb; ++b) {
-      SAG_PROF(e, 5, 1);
-      const bool isb = S.bslot[b] == C.L.box;
-      const double Al = isb ? Q.bim : Q.vim, At = isb ? Q.bii : Q.vii;
-      const double inv_lin = isb ? Q.b_inv_lin : Q.v_inv_lin, inv_tor = isb ? Q.b_inv_tor : Q.v_inv_tor;
-      const double flin = isb ? Q.bflin : Q.vflin, ftor = isb ? Q.bftor : Q.vftor, bfl = isb ? Q.bbfl : Q.vbfl;
-      const double vx = S.bv[b][0], vy = S.bv[b][1], w = S.bv[b][2];
-      double* acs = acc[1 + b];
-      double* flb = ffl[b];
-      double ac[3] = {acs[0], acs[1], acs[2]};  // registers for the visit, stored back at the end
-      double f0, f1, d0, d1;
-      if (isb && rod) {  // one row across the axis (rolling, body x) and one along it (sliding, body y), clamped separately
-        const double inv_x = 1.0 / (Q.rix + rr * Q.rix), inv_y = 1.0 / (Q.riy + rr * Q.riy);
-        double au = ac[0] * rc + ac[1] * rs, aw = -ac[0] * rs + ac[1] * rc;
-        double vu = vx * rc + vy * rs, vw = -vx * rs + vy * rc;
-        f0 = flb[0] - (au + bfl * vu + rr * Q.rix * flb[0]) * inv_x;
-        f1 = flb[1] - (aw + bfl * vw + rr * Q.riy * flb[1]) * inv_y;
-        f0 = clampd(f0, -Q.bfx, Q.bfx); f1 = clampd(f1, -Q.bfy, Q.bfy);
-        d0 = f0 - flb[0]; d1 = f1 - flb[1];
-        double du = d0 * Q.rix, dw = d1 * Q.riy;
-        ac[0] += du * rc - dw * rs; ac[1] += du * rs + dw * rc;
-      } else {
-        f0 = flb[0] - (ac[0] + bfl * vx + rr * Al * flb[0]) * inv_lin;
-        f1 = flb[1] - (ac[1] + bfl * vy + rr * Al * flb[1]) * inv_lin;
-        double nf = sqrt(f0 * f0 + f1 * f1);
-        if (nf > flin) { double sc = flin / nf; f0 *= sc; f1 *= sc; }
-        d0 = f0 - flb[0]; d1 = f1 - flb[1];
-        ac[0] += d0 * Al; ac[1] += d1 * Al;
+      for (int b = 0; b < nb; ++b) {
+        double tdf, tf;
+        floor_visit(b, tdf, tf);
+        sdf += tdf; sf += tf;
       }
-      double f2 = flb[2] - (ac[2] + bfl * w + rr * At * flb[2]) * inv_tor;
-      f2 = clampd(f2, -ftor, ftor);
-      double d2 = f2 - flb[2];
-      ac[2] += d2 * At;
-      flb[0] = f0; flb[1] = f1; flb[2] = f2;
-      acs[0] = ac[0]; acs[1] = ac[1]; acs[2] = ac[2];
-      sdf += fabs(d0) + fabs(d1) + fabs(d2); sf += fabs(f0) + fabs(f1) + fabs(f2);
     }
     if (sdf <= kPgsTol * sf) break;
   }
-  if constexpr (Coop) SAG_CLK(4);
+  if constexpr (Coop) SAG_CLKG(4, 2, S);
   P.qacc[0] = acc[0][0]; P.qacc[1] = acc[0][1]; P.qacc[2] = acc[0][2];
   for (int i = 0; i < nrow; ++i) {
     const Row& r = rows[i];
@@ -1377,6 +1483,7 @@ SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double c
     const unsigned handled = __reduce_or_sync(kFullWarp, b < nb ? 1u << sb : 0u);
     const unsigned nowmov = __reduce_or_sync(kFullWarp, moving ? 1u << sb : 0u);
     P.mov = (P.mov & ~handled) | nowmov;
+    S.scvalid &= ~handled;  // their yaw has changed (every lane stores the same word)
     if (__any_sync(kFullWarp, bad)) P.err = 1;
     __syncwarp();
     SAG_CLK(5);
@@ -1953,6 +2060,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
     }
     C.O.x = S->obj[0]; C.O.y = S->obj[1]; C.O.yaw = S->obj[2]; C.O.vx = S->obj[3]; C.O.vy = S->obj[4]; C.O.w = S->obj[5];
     C.O.stride = 1;
+    S->scvalid = 0u;
     __syncwarp();
   }
 #endif
@@ -2008,6 +2116,9 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
   if constexpr (Coop) SAG_CLK(0);
 #pragma unroll 1
   for (int k = 0; k < RB::kNsub; ++k) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (Coop) coop_align();
+#endif
     double sn, cs, fs[3], fc[3] = {0.0, 0.0, 0.0}, wtau[2] = {0.0, 0.0}, rhs[3], a[3], p, q;
     sag_sincos(R.q[2], &sn, &cs);
     R.pq(sn, cs, p, q);
@@ -2092,6 +2203,9 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
     time += h;
     if constexpr (Coop) SAG_CLK(6);
   }
+#if defined(__CUDA_ARCH__)
+  if constexpr (Coop) coop_align();
+#endif
   EndOut O;
   end_of_step<Mode, RB>(wmask, S, Q, C, R, T, rng, K, mov, err != 0, qacc_err, true, obs_s, ostride, O);
   if constexpr (Coop) SAG_CLK_RESET;

@@ -127,9 +127,11 @@ __device__ __forceinline__ void write_rows(const float* tile, int tstride, float
 // The work list of a step: D.worklist[0 .. counts[0]); counts[1] = fetch counter of the cooperative kernel.  Two counter
 // sets are used alternately (the other one is cleared by this step's batch kernel for the next step).
 
-// __launch_bounds__(kBS, 4): 4 CTAs / SM (<= 128 registers) so that the whole 65,536-env batch is one wave
+// __launch_bounds__(kBS, 4): 4 CTAs / SM (<= 128 registers) so that the whole 65,536-env point batch is one wave.  The car's
+// contact-free step carries the two wheel-row pairs of its friction solve through ten substeps x ten sweeps: it needs
+// the registers more than the occupancy (32,768 envs are 7 warps / SM), so it gets 2 CTAs / SM and no spills.
 template <class RB>
-__global__ void __launch_bounds__(kBS, 4) k_step_free(Dev D, const float* __restrict__ act, float* __restrict__ obs,
+__global__ void __launch_bounds__(kBS, RB::kKind == 1 ? 2 : 4) k_step_free(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                     double* __restrict__ reward, double* __restrict__ reward2,
                                                     uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
   constexpr int kObs = RB::kObsDim;
@@ -179,7 +181,11 @@ __global__ void __launch_bounds__(kBS, 4) k_step_free(Dev D, const float* __rest
 // pre-test, the row set-up and the lidar pass between them.  A contact environment's step is a long dependent chain; what
 // bounds this kernel is that chain's latency, not throughput, so the lanes are spent on shortening it and the register
 // budget (<= 128) on keeping every work-list environment of the step resident at once (16 warps / SM).
-constexpr int kCoopWarps = 4;  // warps (= environments in flight) per CTA
+#if defined(SAG_COOP_ALIGN)
+constexpr int kCoopWarps = 16;  // one CTA per SM: all of an SM's environments are phase-aligned (sag_core.cuh: coop_align)
+#else
+constexpr int kCoopWarps = 4;   // warps (= environments in flight) per CTA
+#endif
 template <class RB>
 struct CoopCfg {
   static constexpr int kObs = RB::kObsDim;
@@ -189,7 +195,11 @@ struct CoopCfg {
 };
 
 #ifndef SAG_COOP_MINBLOCKS
+#if defined(SAG_COOP_ALIGN)
+#define SAG_COOP_MINBLOCKS 1
+#else
 #define SAG_COOP_MINBLOCKS 4
+#endif
 #endif
 template <class RB>
 __global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_coop(const __grid_constant__ Dev D, const float* __restrict__ act,
@@ -205,14 +215,24 @@ __global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_co
   // preceding kernel has finished; everything that kernel wrote is visible after this call (no-op otherwise)
   cudaGridDependencySynchronize();
   const int count = D.counts[0];
+#if defined(SAG_COOP_ALIGN)
+  // static assignment, entries strided over the CTAs; every warp of the CTA runs the same number of rounds
+  const int per_round = gridDim.x * kCoopWarps;
+  for (int base = 0; base < count; base += per_round) {
+    const int i = base + warp * gridDim.x + blockIdx.x;
+    if (i >= count) { coop_idle_step<RB>(); continue; }
+    const int e = D.worklist[i];
+#else
   for (;;) {  // dynamic fetch: a step with several contacts takes a multiple of the common single-contact one
     int i = 0;
     if (lane == 0) i = atomicAdd(&D.counts[1], 1);
     i = __shfl_sync(0xffffffffu, i, 0);
     if (i >= count) break;
     const int e = D.worklist[i];
+#endif
 #if defined(SAG_TIMING)
-    if (lane == 0) atomicAdd(&D.dbg[15], 1ull);
+    if (lane == 0) { atomicAdd(&D.dbg[15], 1ull); big->tsum[0] = big->tsum[1] = big->tsum[2] = 0ull; }
+    __syncwarp();
     long long clk_ = clock64();
 #endif
     float2 a = reinterpret_cast<const float2*>(act)[e];
@@ -220,7 +240,14 @@ __global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_co
     unsigned char c, d;
     env_step<kStepCoop, RB>(0xffffffffu, big, D, e, a.x, a.y, tile, 1, rew, &c, &d);
 #if defined(SAG_TIMING)
-    if (lane == 0) atomicAdd(&D.dbg[14], (unsigned long long)(clock64() - clk_));
+    if (lane == 0) {
+      const unsigned long long tot = (unsigned long long)(clock64() - clk_);
+      atomicAdd(&D.dbg[14], tot);
+      // slowest environment of the interval: total cycles in the high bits so that one atomicMax keeps its section sums
+      const unsigned long long key = (tot << 40) | ((big->tsum[2] >> 10) << 20) | (big->tsum[0] >> 10);
+      atomicMax(&D.dbg[16], key);
+      atomicMax(&D.dbg[17], (tot << 40) | (big->tsum[1] >> 10));
+    }
 #endif
     __syncwarp();
     if (lane == 0) {
@@ -600,8 +627,8 @@ int sag_debug_read(void* handle, unsigned long long* out16) {
   Handle* H = (Handle*)handle;
   if (!H || !out16) return fail("sag_debug_read: null argument");
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out16, H->D.dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  CK(cudaMemset(H->D.dbg, 0, 16 * sizeof(unsigned long long)));
+  CK(cudaMemcpy(out16, H->D.dbg, 18 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemset(H->D.dbg, 0, 18 * sizeof(unsigned long long)));
   return 0;
 }
 unsigned long long sag_launch_count(void* handle) { return handle ? ((Handle*)handle)->launches : 0ull; }

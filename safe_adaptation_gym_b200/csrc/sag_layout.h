@@ -27,7 +27,7 @@ inline SlabLayout slab_layout(int n, int stride, int obs_dim) {
   size_t total = 0;
   for (int f = 0; f < SAG_NUM_FIELDS; ++f) { L.off[f] = total; total += align_up(L.bytes[f], 256); }
   L.stats_off = total; total += align_up(3 * st * sizeof(double), 256);
-  L.sched_off = total; total += align_up((3 * st + 64) * sizeof(int32_t), 256);
+  L.sched_off = total; total += align_up((3 * st + 96) * sizeof(int32_t), 256);
   L.act_off = total; total += align_up((size_t)n * 2 * sizeof(float), 256);
   L.obs_off = total; total += align_up((size_t)n * obs_dim * sizeof(float), 256);
   L.rew_off = total; total += align_up((size_t)n * sizeof(double), 256);
@@ -58,7 +58,7 @@ inline void slab_bind(Dev& D, const SlabLayout& L, char* base) {
   D.rext = (double*)(base + L.off[SAG_F_ROBOT_EXT]);
   int32_t* sc = (int32_t*)(base + L.sched_off);
   D.worklist = sc; D.counts = sc + 3 * st; D.counts_next = D.counts + 8;
-  D.dbg = (unsigned long long*)(sc + 3 * st + 16);  // 16 x u64; the block is 64 ints
+  D.dbg = (unsigned long long*)(sc + 3 * st + 16);  // 18 x u64 (36 ints) after the two counter sets (16 ints); the block is 96 ints
 }
 
 inline void dev_from_config(Dev& D, const SagConfig& c) {

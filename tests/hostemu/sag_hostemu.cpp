@@ -153,7 +153,7 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
 }
 int sag_destroy(void* h) { Handle* H = (Handle*)h; if (H) { free(H->slab); delete H; } return 0; }
 unsigned long long sag_launch_count(void* h) { (void)h; return 0ull; }
-int sag_debug_read(void* h, unsigned long long* out16) { (void)h; memset(out16, 0, 16 * sizeof(unsigned long long)); return 0; }
+int sag_debug_read(void* h, unsigned long long* out16) { (void)h; memset(out16, 0, 18 * sizeof(unsigned long long)); return 0; }
 int sag_stride(void* h) { return ((Handle*)h)->D.stride; }
 int sag_obs_dim(void* h) { return obs_dim_of(((Handle*)h)->D); }
 size_t sag_field_bytes(void* h, int f) { return (f < 0 || f >= SAG_NUM_FIELDS) ? 0 : ((Handle*)h)->LY.bytes[f]; }

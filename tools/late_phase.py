@@ -43,11 +43,12 @@ for ph in phases:
     ts.sort()
     out.append(f"{ph}: med {ts[5]:.0f} min {ts[0]:.0f} max {ts[-1]:.0f}")
     if os.environ.get("SAG_TIMING_READ"):
-        buf = (C.c_ulonglong * 16)()
+        buf = (C.c_ulonglong * 18)()
         L.L.sag_debug_read.argtypes = [C.c_void_p, C.c_void_p]
         L.check(L.L.sag_debug_read(h, buf))
         v = list(buf)
         ne = max(1, v[15])
-        names = ["prologue", "substep-pre", "detect", "setup", "pgs", "post", "robot-int", "eos-passA", "-", "eos-rest", "epilogue", "", "", "", "env_step total", "env-steps"]
-        out.append("\n   cycles/env-step: " + ", ".join(f"{names[i]} {v[i] / ne:.0f}" for i in range(16) if v[i] and i != 15) + f" | env-steps {v[15]}\n")
+        names = ["prologue", "substep-pre", "det-broad1", "setup-rows", "pgs", "post", "robot-int", "eos-passA", "setup-table", "eos-rest", "epilogue", "det-narrow1", "det-broad2", "det-narrow2", "env_step total", "env-steps"]
+        out.append("\n   cycles/env-step: " + ", ".join(f"{names[i]} {v[i] / ne:.0f}" for i in range(16) if v[i] and i != 15) + f" | env-steps {v[15]}\n"
+                   + f"   slowest env-step of the interval: total {v[16] >> 40} cycles, pgs {((v[16] >> 20) & 0xfffff) << 10}, detect {(v[16] & 0xfffff) << 10}, setup {(v[17] & 0xffffffffff) << 10}\n")
 print(os.environ.get("SAG_B200_LIB", "default").split("/")[-1], cfgname, "step us @phase |", " | ".join(out))

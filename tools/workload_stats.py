@@ -55,7 +55,7 @@ def main():
             for e in np.nonzero(cen)[0]:
                 key = (int(prof[e, 12]), int(prof[e, 14]), int(prof[e, 13]), int(prof[e, 15]))
                 hist[key] = hist.get(key, 0) + 1
-        if (t + 1) % 50 == 0:
+        if (t + 1) % int(os.environ.get('EVERY','50')) == 0:
             p = acc
             ps = max(p[0], 1)
             print(f"{t+1:4d}  {100*accn[1]/accn[0]:6.2f}  {100*accn[2]/accn[0]:6.2f}   {p[0]/max(accn[2],1):5.2f} {p[3]/max(accn[2],1):5.2f}  {p[2]/ps:5.2f} {p[9]/ps:5.2f} {p[10]/ps:5.2f} "
