@@ -193,6 +193,10 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    # every rank on its GPU's NUMA node with cores of its own, BEFORE any pinned allocation (pages are first-touched there)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from probe_d2h import bind_rank_to_gpu_node
+    binding = bind_rank_to_gpu_node(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     dev = torch.device("cuda", local_rank)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -340,10 +344,16 @@ def main():
         h2 = env2._h
         od = env.obs_dim
         act_h = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-        obs_h = torch.empty((n, od), dtype=torch.float32).pin_memory()
-        rew_h = torch.empty((n,), dtype=torch.float64).pin_memory()
-        cost_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
-        done_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
+
+        class _Raw:  # the four output buffers: one pinned block from the library, laid out for a single D2H copy per step
+            def __init__(self, ptr):
+                self.ptr = ptr
+
+            def data_ptr(self):
+                return self.ptr
+        ptrs = [C.c_void_p() for _ in range(4)]
+        L.check(L.L.sag_host_alloc_outputs(h2, *[C.byref(x) for x in ptrs]))
+        obs_h, rew_h, cost_h, done_h = (_Raw(x.value) for x in ptrs)
         cpu_gen = torch.Generator(); cpu_gen.manual_seed(99 + rank)
         act_h.uniform_(-1, 1, generator=cpu_gen)
         torch.cuda.synchronize()
@@ -376,9 +386,33 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         te_total = float(t[0])
-        e2e = {"value": world * n * ke / te_total, "unit": UNIT, "h2d_bytes_per_step": n * 2 * 4,
-               "d2h_bytes_per_step": n * (od * 4 + 8 + 1 + 1), "steps": ke, "reset_ms": 1e3 * t_reset_e2e,
-               "api": "sag_step_host (C ABI, pinned host buffers), same strata as `value`"}
+        d2h = n * (od * 4 + 8 + 1 + 1)
+        # host ceiling: all ranks pull one step's outputs to pinned memory at the same time, back to back (tools/probe_d2h.py)
+        src = torch.empty(d2h, dtype=torch.uint8, device=dev)
+        dst = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+        dst.fill_(0)
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(40):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        ceiling_gbs = world * d2h * 40 / float(tc[0]) / 1e9
+        e2e_value = world * n * ke / te_total
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 2 * 4,
+               "d2h_bytes_per_step": d2h, "steps": ke, "reset_ms": 1e3 * t_reset_e2e,
+               "d2h_gbs": e2e_value / n * d2h / 1e9, "host_ceiling_gbs": ceiling_gbs,
+               "host_ceiling_frac": (e2e_value / n * d2h / 1e9) / ceiling_gbs,
+               "host_ceiling_note": "ceiling = all ranks copying one step's outputs device -> pinned host back to back, nothing else",
+               "binding": binding,
+               "api": "sag_step_host (C ABI; one pinned output block, a single D2H copy per step), same strata as `value`"}
+        L.L.sag_host_free(C.c_void_p(ptrs[0].value))
         env2.close()
 
     # ---- per-task statistics: the only collective on this path (NCCL all-reduce of a [14,3] fp64 buffer)

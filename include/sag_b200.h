@@ -137,6 +137,9 @@ int sag_observe(void* handle, float* obs, void* stream);
 int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward_h, uint8_t* cost_h, uint8_t* done_h);
 int sag_observe_host(void* handle, float* obs_h);
 void* sag_host_alloc(size_t bytes);
+/* the four output buffers of sag_step_host as ONE pinned block laid out like the library's device staging area, so that
+ * a step needs a single device-to-host copy; free with sag_host_free(*obs_h) */
+int sag_host_alloc_outputs(void* handle, float** obs_h, double** reward_h, uint8_t** cost_h, uint8_t** done_h);
 void sag_host_free(void* p);
 
 /* K steps per launch with on-device Philox U(-1,1) actions (stream 2); benchmark helper.  Writes the last

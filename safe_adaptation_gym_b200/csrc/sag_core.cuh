@@ -32,6 +32,11 @@ extern long* sag_prof_ptr;  // tests/hostemu instrumentation: per-env work count
 #define SAG_PROF_MAX(e, i, n) do { } while (0)
 #endif
 
+// Phase alignment of the cooperative kernel's warps is on by default (coop_align below; -DSAG_COOP_NOALIGN for A/B runs)
+#if !defined(SAG_COOP_NOALIGN) && !defined(SAG_COOP_ALIGN)
+#define SAG_COOP_ALIGN 1
+#endif
+
 // SAG_TIMING (tuning builds only): the cooperative kernel accumulates clock64() intervals per section into D.dbg[16]
 #if defined(SAG_TIMING) && defined(__CUDA_ARCH__)
 #define SAG_CLK_DECL long long clk_ = clock64()
@@ -806,7 +811,7 @@ SAG_HD void car_free_solve(const CarRobot& R, double sn, double cs, const PtCons
 // the oracle against this path).
 // ------------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
-// Phase alignment of the cooperative kernel's warps (SAG_COOP_ALIGN builds): every warp of the CTA arrives at a barrier at
+// Phase alignment of the cooperative kernel's warps: every warp of the CTA arrives at a barrier at
 // the top of each substep and before the end-of-step pass, so that the 16 environments of an SM walk through the same
 // code at the same time and share its instruction-cache lines instead of evicting each other's.  A warp without an
 // environment executes the same number of barriers (coop_idle_step).
@@ -1604,6 +1609,15 @@ SAG_HD int slot_group(const Ctx& C, int s, int kind, int gbtn, int bstate, int a
   return 1;
 }
 
+// sqrt(d2) < thr, evaluated exactly: the root is only taken when d2 is within 1e-6 (relative) of thr^2 -- outside that
+// band the comparison of the squares decides, far beyond the rounding error of either side
+SAG_HD bool sqrt_less(double d2, double thr) {
+  const double lo = thr * 0.999999, hi = thr * 1.000001;
+  if (d2 < lo * lo) return true;
+  if (d2 > hi * hi) return false;
+  return sqrt(d2) < thr;
+}
+
 // ------------------------------------------------------------------------------------------------
 // goal resampling (go_to_goal.py:59-80): the rectangle grows x1.01 after every failed draw
 // ------------------------------------------------------------------------------------------------
@@ -1616,7 +1630,7 @@ SAG_HD int resample_goal(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t
     double xmin = rect[0] + kGoalKeepout, ymin = rect[1] + kGoalKeepout, xmax = rect[2] - kGoalKeepout, ymax = rect[3] - kGoalKeepout;
     double x = xmin + (xmax - xmin) * u1, y = ymin + (ymax - ymin) * u2;
     bool valid = true;
-    { double dx = x - rx, dy = y - ry; if (sqrt(dx * dx + dy * dy) < D.robot_keepout + kGoalKeepout) valid = false; }
+    { double dx = x - rx, dy = y - ry; if (sqrt_less(dx * dx + dy * dy, D.robot_keepout + kGoalKeepout)) valid = false; }
     for (int s = 0; valid && s < C.L.n; ++s) {
       if (s == C.L.goal) continue;
       int kind = slot_kind(C.sp, C.L, s);
@@ -1624,7 +1638,7 @@ SAG_HD int resample_goal(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t
                 : kind == K_PILLAR ? D.k_pillar : kind == K_BUTTON ? kButtonsKeepout : C.sp.box_keepout;
       size_t i = oix(C, s);
       double dx = x - C.O.x[i], dy = y - C.O.y[i];
-      if (sqrt(dx * dx + dy * dy) < ko + kGoalKeepout) valid = false;
+      if (sqrt_less(dx * dx + dy * dy, ko + kGoalKeepout)) valid = false;
     }
     if (valid) { gx = x; gy = y; return 0; }
 #pragma unroll
@@ -2295,6 +2309,11 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
   double rxy[2] = {0.0, 0.0};
   bool ok = false;
   const double ext = C.sp.extent;
+  // the placed bodies' positions and keepout + margin, thread-private (the rejection loop below reads them ~10^3 times)
+  double px[kMaxObj], py[kMaxObj], pk[kMaxObj];
+  for (int j = 0; j < kMaxObj; ++j) { px[j] = 0.0; py[j] = 0.0; pk[j] = 0.0; }
+  for (int j = 0; j < C.L.n; ++j) pk[j] = slot_keepout(D, C.sp, slot_kind(C.sp, C.L, j)) + D.placements_margin;
+  const double rk = D.robot_keepout + D.placements_margin;
   for (int attempt = 0; attempt < 10000 && !ok && draws_left >= 0; ++attempt) {
     bool failed = false;
     for (int idx = -1; idx < C.L.n && !failed; ++idx) {
@@ -2315,22 +2334,21 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
         bool valid = true;
         if (idx >= 0) {
           double dx = x - rxy[0], dy = y - rxy[1];
-          if (sqrt(dx * dx + dy * dy) < D.robot_keepout + D.placements_margin + keepout) valid = false;
+          if (sqrt_less(dx * dx + dy * dy, rk + keepout)) valid = false;
           for (int j = 0; valid && j < idx; ++j) {
-            size_t i = oix(C, j);
-            double ex = x - C.O.x[i], ey = y - C.O.y[i];
-            double ko = slot_keepout(D, C.sp, slot_kind(C.sp, C.L, j));
-            if (sqrt(ex * ex + ey * ey) < ko + D.placements_margin + keepout) valid = false;
+            double ex = x - px[j], ey = y - py[j];
+            if (sqrt_less(ex * ex + ey * ey, pk[j] + keepout)) valid = false;
           }
         }
         if (valid) { placed = true; break; }
       }
       if (!placed) { failed = true; break; }
       if (idx < 0) { rxy[0] = x; rxy[1] = y; }
-      else { size_t i = oix(C, idx); C.O.x[i] = x; C.O.y[i] = y; }
+      else { px[idx] = x; py[idx] = y; }
     }
     if (!failed) ok = true;
   }
+  for (int j = 0; j < C.L.n; ++j) { size_t i = oix(C, j); C.O.x[i] = px[j]; C.O.y[i] = py[j]; }
   if (!ok) fl |= F_RESAMPLE_FAILED;
   // yaw draws in the reference's order
   double u1, u2;

@@ -181,11 +181,10 @@ __global__ void __launch_bounds__(kBS, RB::kKind == 1 ? 2 : 4) k_step_free(Dev D
 // pre-test, the row set-up and the lidar pass between them.  A contact environment's step is a long dependent chain; what
 // bounds this kernel is that chain's latency, not throughput, so the lanes are spent on shortening it and the register
 // budget (<= 128) on keeping every work-list environment of the step resident at once (16 warps / SM).
-#if defined(SAG_COOP_ALIGN)
-constexpr int kCoopWarps = 16;  // one CTA per SM: all of an SM's environments are phase-aligned (sag_core.cuh: coop_align)
-#else
-constexpr int kCoopWarps = 4;   // warps (= environments in flight) per CTA
+#ifndef SAG_COOP_WARPS
+#define SAG_COOP_WARPS 16
 #endif
+constexpr int kCoopWarps = SAG_COOP_WARPS;  // warps (= environments in flight) per CTA; 16 = one CTA per SM at 128 registers
 template <class RB>
 struct CoopCfg {
   static constexpr int kObs = RB::kObsDim;
@@ -195,11 +194,7 @@ struct CoopCfg {
 };
 
 #ifndef SAG_COOP_MINBLOCKS
-#if defined(SAG_COOP_ALIGN)
-#define SAG_COOP_MINBLOCKS 1
-#else
-#define SAG_COOP_MINBLOCKS 4
-#endif
+#define SAG_COOP_MINBLOCKS (16 / SAG_COOP_WARPS)
 #endif
 template <class RB>
 __global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_coop(const __grid_constant__ Dev D, const float* __restrict__ act,
@@ -215,21 +210,14 @@ __global__ void __launch_bounds__(32 * kCoopWarps, SAG_COOP_MINBLOCKS) k_step_co
   // preceding kernel has finished; everything that kernel wrote is visible after this call (no-op otherwise)
   cudaGridDependencySynchronize();
   const int count = D.counts[0];
-#if defined(SAG_COOP_ALIGN)
-  // static assignment, entries strided over the CTAs; every warp of the CTA runs the same number of rounds
+  // Static assignment, entries strided over the CTAs so that a short list spreads over all SMs (one environment per SM
+  // up to 148 entries: no two chains share a scheduler or an instruction cache before they have to); every warp of the
+  // CTA runs the same number of rounds, which the phase alignment (sag_core.cuh: coop_align) relies on.
   const int per_round = gridDim.x * kCoopWarps;
   for (int base = 0; base < count; base += per_round) {
-    const int i = base + warp * gridDim.x + blockIdx.x;
+    const int i = base + (warp * gridDim.x + blockIdx.x);
     if (i >= count) { coop_idle_step<RB>(); continue; }
     const int e = D.worklist[i];
-#else
-  for (;;) {  // dynamic fetch: a step with several contacts takes a multiple of the common single-contact one
-    int i = 0;
-    if (lane == 0) i = atomicAdd(&D.counts[1], 1);
-    i = __shfl_sync(0xffffffffu, i, 0);
-    if (i >= count) break;
-    const int e = D.worklist[i];
-#endif
 #if defined(SAG_TIMING)
     if (lane == 0) { atomicAdd(&D.dbg[15], 1ull); big->tsum[0] = big->tsum[1] = big->tsum[2] = 0ull; }
     __syncwarp();
@@ -777,10 +765,17 @@ int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward
     CK(SAG_DISPATCH(H, step_quiet(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s)));
     CK(cudaEventRecord(H->ev_quiet, s));
     CK(cudaStreamWaitEvent(c, H->ev_quiet, 0));
-    CK(cudaMemcpyAsync(obs_h, H->obs_d, n * od * sizeof(float), cudaMemcpyDeviceToHost, c));
-    CK(cudaMemcpyAsync(reward_h, H->rew_d, n * sizeof(double), cudaMemcpyDeviceToHost, c));
-    CK(cudaMemcpyAsync(cost_h, H->cost_d, n, cudaMemcpyDeviceToHost, c));
-    CK(cudaMemcpyAsync(done_h, H->done_d, n, cudaMemcpyDeviceToHost, c));
+    const bool packed = (char*)reward_h - (char*)obs_h == (char*)H->rew_d - (char*)H->obs_d &&
+                        (char*)cost_h - (char*)obs_h == (char*)H->cost_d - (char*)H->obs_d &&
+                        (char*)done_h - (char*)obs_h == (char*)H->done_d - (char*)H->obs_d;
+    if (packed) {  // buffers from sag_host_alloc_outputs: one copy for all four outputs
+      CK(cudaMemcpyAsync(obs_h, H->obs_d, (size_t)((char*)H->done_d - (char*)H->obs_d) + n, cudaMemcpyDeviceToHost, c));
+    } else {
+      CK(cudaMemcpyAsync(obs_h, H->obs_d, n * od * sizeof(float), cudaMemcpyDeviceToHost, c));
+      CK(cudaMemcpyAsync(reward_h, H->rew_d, n * sizeof(double), cudaMemcpyDeviceToHost, c));
+      CK(cudaMemcpyAsync(cost_h, H->cost_d, n, cudaMemcpyDeviceToHost, c));
+      CK(cudaMemcpyAsync(done_h, H->done_d, n, cudaMemcpyDeviceToHost, c));
+    }
     CK(cudaEventRecord(H->ev_copied, c));
     CK(SAG_DISPATCH(H, step_busy(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s)));
     CK(cudaStreamWaitEvent(s, H->ev_copied, 0));
@@ -806,6 +801,23 @@ int sag_observe_host(void* handle, float* obs_h) {
   CK(SAG_DISPATCH(H, observe(H, H->obs_d, s)));
   CK(cudaMemcpyAsync(obs_h, H->obs_d, (size_t)H->D.n * (size_t)sag_obs_dim(H) * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// One pinned block laid out like the handle's device staging area (obs, reward, cost, done at the same relative offsets):
+// sag_step_host then moves all four outputs with ONE device-to-host copy.  Free with sag_host_free(*obs_h).
+int sag_host_alloc_outputs(void* handle, float** obs_h, double** reward_h, uint8_t** cost_h, uint8_t** done_h) {
+  Handle* H = (Handle*)handle;
+  if (!H || !obs_h || !reward_h || !cost_h || !done_h) return fail("sag_host_alloc_outputs: null argument");
+  DevGuard guard(H->device);
+  const size_t span = (size_t)((char*)H->done_d - (char*)H->obs_d) + (size_t)H->D.n;
+  char* p = nullptr;
+  CK(cudaHostAlloc((void**)&p, span, cudaHostAllocDefault));
+  memset(p, 0, span);
+  *obs_h = (float*)p;
+  *reward_h = (double*)(p + ((char*)H->rew_d - (char*)H->obs_d));
+  *cost_h = (uint8_t*)(p + ((char*)H->cost_d - (char*)H->obs_d));
+  *done_h = (uint8_t*)(p + ((char*)H->done_d - (char*)H->obs_d));
   return 0;
 }
 
