@@ -388,19 +388,12 @@ def main():
         te_total = float(t[0])
         d2h = n * (od * 4 + 8 + 1 + 1)
         # host ceiling: all ranks pull one step's outputs to pinned memory at the same time, back to back (tools/probe_d2h.py)
-        src = torch.empty(d2h, dtype=torch.uint8, device=dev)
-        dst = torch.empty(d2h, dtype=torch.uint8).pin_memory()
-        dst.fill_(0)
-        for _ in range(3):
-            dst.copy_(src, non_blocking=True)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(40):
-            dst.copy_(src, non_blocking=True)
-        torch.cuda.synchronize()
-        tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        secs = C.c_double()
+        L.check(L.L.sag_probe_d2h(h2, d2h, 40, C.byref(secs)))
+        tc = torch.tensor([secs.value], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
         ceiling_gbs = world * d2h * 40 / float(tc[0]) / 1e9

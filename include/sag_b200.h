@@ -137,6 +137,9 @@ int sag_observe(void* handle, float* obs, void* stream);
 int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward_h, uint8_t* cost_h, uint8_t* done_h);
 int sag_observe_host(void* handle, float* obs_h);
 void* sag_host_alloc(size_t bytes);
+/* measurement helper: `reps` back-to-back device -> pinned-host copies of `bytes` bytes with the allocation and copy calls of
+ * sag_step_host; *seconds = elapsed time (CUDA events).  The host ceiling bench.py reports e2e against. */
+int sag_probe_d2h(void* handle, size_t bytes, int reps, double* seconds);
 /* the four output buffers of sag_step_host as ONE pinned block laid out like the library's device staging area, so that
  * a step needs a single device-to-host copy; free with sag_host_free(*obs_h) */
 int sag_host_alloc_outputs(void* handle, float** obs_h, double** reward_h, uint8_t** cost_h, uint8_t** done_h);

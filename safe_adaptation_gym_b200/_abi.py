@@ -41,7 +41,7 @@ class SagLib:
         "sag_last_error", "sag_abi_version", "sag_default_config", "sag_create", "sag_destroy", "sag_stride",
         "sag_obs_dim", "sag_field_bytes", "sag_launch_count", "sag_debug_read", "sag_set_tasks", "sag_set_tasks_host", "sag_bound_host",
         "sag_error_flags", "sag_reset_obs", "sag_reset_host", "sag_seed", "sag_reset", "sag_step", "sag_observe",
-        "sag_step_host", "sag_observe_host", "sag_host_alloc", "sag_host_alloc_outputs", "sag_host_free", "sag_rollout", "sag_read_field",
+        "sag_step_host", "sag_observe_host", "sag_host_alloc", "sag_host_alloc_outputs", "sag_probe_d2h", "sag_host_free", "sag_rollout", "sag_read_field",
         "sag_write_field", "sag_task_stats", "sag_lidar", "sag_cost",
     ]
 
@@ -87,6 +87,7 @@ class SagLib:
             L.sag_host_alloc.restype = vp
             L.sag_host_alloc.argtypes = [C.c_size_t]
             L.sag_host_free.argtypes = [vp]
+            L.sag_probe_d2h.argtypes = [vp, C.c_size_t, i32, C.POINTER(C.c_double)]
             L.sag_host_alloc_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
 
     def check(self, rc):

@@ -861,7 +861,7 @@ __device__ __forceinline__ bool coop_append(Con* con, int cap, int& ncon, bool& 
 //     Hits are appended in lane order (= canonical order).  sin / cos of an object's yaw are cached per slot until the
 //     object is integrated again (Scratch::sc, scvalid).
 template <class RB>
-__device__ __noinline__ void detect_coop(const Ctx& C, const RB& R, double sn, double cs, unsigned mov, Scratch& S,
+__device__ __forceinline__ void detect_coop(const Ctx& C, const RB& R, double sn, double cs, unsigned mov, Scratch& S,
                                          int& ncon_out, bool& overflow_out, unsigned& touch_out, unsigned& active_out) {
   const Dev& D = C.D;
   const int lane = coop_lane();
@@ -1072,8 +1072,18 @@ SAG_HD void solve_consts(const Dev& D, const TaskSpec& sp, SolveConsts& Q) {
 }
 
 template <class RB, bool Coop>
+SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, const PtConst& K, const double* fs,
+                              unsigned mov, bool integrate, double h, Scratch& S, const SolveConsts& Q, Phys& P);
+// scalar paths: one out-of-line copy; the cooperative kernel inlines the body at its single call site (env_step), so
+// that the environment's registers need not travel through local memory
+template <class RB, bool Coop>
 SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double cs, const PtConst& K, const double* fs,
                                   unsigned mov, bool integrate, double h, Scratch& S, const SolveConsts& Q, Phys& P) {
+  contact_pass_body<RB, Coop>(C, R, sn, cs, K, fs, mov, integrate, h, S, Q, P);
+}
+template <class RB, bool Coop>
+SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, const PtConst& K, const double* fs,
+                              unsigned mov, bool integrate, double h, Scratch& S, const SolveConsts& Q, Phys& P) {
   constexpr int kCapCon = Scratch::kCon, kCapBodies = Scratch::kBodies;
   const Dev& D = C.D;
   const int e = C.e;
@@ -1860,7 +1870,8 @@ __device__ __forceinline__ void pass_a_coop(const Ctx& C, const RB& R, double cs
 
 template <int Mode, class RB>
 SAG_HD void end_of_step(unsigned wmask, Scratch* S, const SolveConsts& Q, const Ctx& C, const RB& R, TaskState& T, const Rng& rng, const PtConst& K,
-                        unsigned mov, bool phys_err, const double* qacc_err, bool with_reward, float* obs_s, int ostride, EndOut& O) {
+                        unsigned mov, bool phys_err, const double* qacc_err, bool with_reward, float* obs_s, int ostride, EndOut& O,
+                        const Phys* Pfwd = nullptr) {
   constexpr bool QuietOnly = Mode == kStepQuiet || Mode == kStepNear, Coop = Mode == kStepCoop, Near = Mode == kStepNear;
   const Dev& D = C.D;
   const int e = C.e;
@@ -1938,6 +1949,9 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, const SolveConsts& Q, const 
   // A PhysicsError in physics.step returns the observation at once (safe_adaptation_gym.py:73-75): no forward(), the
   // accelerometer shows the last substep's acceleration, no reward / cost evaluation.
   const bool skip_forward = phys_err && qacc_err != nullptr;
+  if (Pfwd) {  // cooperative kernel: the forward pass has been evaluated as the last trip of env_step's pass loop
+    P = *Pfwd;
+  } else {
   if (!QuietOnly && !skip_forward) {  // (a quiet step ends with positive clearance: no contact is possible)
     const bool near_ = !(clear > 0.0 && mov == 0);
     if constexpr (Coop) {
@@ -1960,6 +1974,7 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, const SolveConsts& Q, const 
     SAG_CLK_RESET;
   } else if (!QuietOnly) {
     warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, Q, P);
+  }
   }
   qacc[0] = P.qacc[0]; qacc[1] = P.qacc[1]; qacc[2] = P.qacc[2];
   touch = P.touch;
@@ -2128,24 +2143,32 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
   SAG_PROF(e, 7, quiet ? 0 : 1);
   double qacc_err[3] = {0.0, 0.0, 0.0};
   if constexpr (Coop) SAG_CLK(0);
+  // Cooperative kernel: the final forward() (safe_adaptation_gym.py:76) runs as one more trip of this loop -- without
+  // integration -- so that the contact pass has a single call site and is inlined there.  Its `need` is the one
+  // end_of_step would compute: clear > 0 (nothing within reach, tendon slack) implies no overlap and a slack tendon.
+  Phys Pfwd;
+  Pfwd.qacc[0] = Pfwd.qacc[1] = Pfwd.qacc[2] = 0.0; Pfwd.touch = 0; Pfwd.err = 0; Pfwd.mov = mov;
+  constexpr int kTrips = Coop ? RB::kNsub + 1 : RB::kNsub;
 #pragma unroll 1
-  for (int k = 0; k < RB::kNsub; ++k) {
+  for (int k = 0; k < kTrips; ++k) {
 #if defined(__CUDA_ARCH__)
     if constexpr (Coop) coop_align();
 #endif
+    const bool fwd = Coop && k == RB::kNsub;
+    if (fwd && err) { Pfwd.qacc[0] = qacc_err[0]; Pfwd.qacc[1] = qacc_err[1]; Pfwd.qacc[2] = qacc_err[2]; break; }  // :73-75, no forward()
     double sn, cs, fs[3], fc[3] = {0.0, 0.0, 0.0}, wtau[2] = {0.0, 0.0}, rhs[3], a[3], p, q;
     sag_sincos(R.q[2], &sn, &cs);
     R.pq(sn, cs, p, q);
     R.smooth(sn, cs, fs);
     bool need = false;
     bool taut = false;
-    if (tendon_task && (Near ? pretest : (Mode != kStepQuiet && !quiet))) {
+    if (tendon_task && (fwd || (Near ? pretest : (Mode != kStepQuiet && !quiet)))) {
       double tdx, tdy, tlen, tdist;
       taut = tendon_taut(C, R, tdx, tdy, tlen, tdist);
     }
     if constexpr (Coop) {
 #if defined(__CUDA_ARCH__)
-      need = !quiet && (mov != 0 || taut || robot_overlaps_any_coop(C, R, sn, cs));
+      need = (fwd || !quiet) && (mov != 0 || taut || robot_overlaps_any_coop(C, R, sn, cs));
 #endif
     } else if (!QuietOnly) {
       need = !quiet && (mov != 0 || taut || robot_overlaps_any(C, R, sn, cs));
@@ -2169,8 +2192,17 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
       P.mov = mov; P.err = 0;
       if constexpr (Coop) {
         SAG_CLK(1);
-        if (need) contact_pass<RB, true>(C, R, sn, cs, K, fs, mov, true, h, *S, Q, P);
+        if (need) contact_pass_body<RB, true>(C, R, sn, cs, K, fs, mov, !fwd, h, *S, Q, P);
         SAG_CLK_RESET;
+        if (fwd) {  // forward(): acceleration + contacts at the final state, nothing is integrated
+          if (need) { Pfwd = P; }
+          else {
+            if (RB::kKind == 1) { Pfwd.qacc[0] = subq[0]; Pfwd.qacc[1] = subq[1]; Pfwd.qacc[2] = subq[2]; }
+            else pt_solve(p, q, K.ia0, K.is0, fs, Pfwd.qacc);
+            Pfwd.touch = 0; Pfwd.err = 0;
+          }
+          break;
+        }
       } else {
         warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, Q, P);
       }
@@ -2217,11 +2249,8 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
     time += h;
     if constexpr (Coop) SAG_CLK(6);
   }
-#if defined(__CUDA_ARCH__)
-  if constexpr (Coop) coop_align();
-#endif
   EndOut O;
-  end_of_step<Mode, RB>(wmask, S, Q, C, R, T, rng, K, mov, err != 0, qacc_err, true, obs_s, ostride, O);
+  end_of_step<Mode, RB>(wmask, S, Q, C, R, T, rng, K, mov, err != 0, qacc_err, true, obs_s, ostride, O, Coop ? &Pfwd : nullptr);
   if constexpr (Coop) SAG_CLK_RESET;
   if constexpr (Near) { if (O.bail) return 1; }
   unsigned char dn = 0;

@@ -821,6 +821,33 @@ int sag_host_alloc_outputs(void* handle, float** obs_h, double** reward_h, uint8
   return 0;
 }
 
+// Measurement helper (tools/probe_d2h.py, bench.py): `reps` back-to-back device -> pinned-host copies of `bytes` bytes on the
+// handle's device, with the same allocation and copy calls sag_step_host uses; returns the elapsed seconds.
+int sag_probe_d2h(void* handle, size_t bytes, int reps, double* seconds) {
+  Handle* H = (Handle*)handle;
+  if (!H || !seconds || bytes == 0 || reps <= 0) return fail("sag_probe_d2h: bad argument");
+  DevGuard guard(H->device);
+  if (bytes > H->slab_bytes) bytes = H->slab_bytes;
+  void* p = nullptr;
+  CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+  memset(p, 0, bytes);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  cudaStream_t s = H->copy_stream;
+  CK(cudaDeviceSynchronize());
+  for (int i = 0; i < 3; ++i) CK(cudaMemcpyAsync(p, H->slab, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(e0, s));
+  for (int i = 0; i < reps; ++i) CK(cudaMemcpyAsync(p, H->slab, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(e1, s));
+  CK(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  *seconds = 1e-3 * (double)ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFreeHost(p);
+  return 0;
+}
+
 void* sag_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { fail("sag_host_alloc: cudaHostAlloc failed"); return nullptr; }

@@ -77,20 +77,22 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = int(args.mb * 2**20)
-    src = torch.empty(n, dtype=torch.uint8, device="cuda")
-    dst = torch.empty(n, dtype=torch.uint8).pin_memory()
-    dst.fill_(0)  # first touch
-    for _ in range(5):
-        dst.copy_(src, non_blocking=True)
+    # the copies are issued by the library itself (cudaHostAlloc + cudaMemcpyAsync, exactly what sag_step_host does)
+    import ctypes as C
+    from safe_adaptation_gym_b200 import _abi
+    L = _abi.load()
+    cfg = L.default_config()
+    cfg.n_envs = 65536
+    h = C.c_void_p()
+    L.check(L.L.sag_create(C.byref(cfg), local_rank, C.byref(h)))
+    secs = C.c_double()
+    L.check(L.L.sag_probe_d2h(h, n, 5, C.byref(secs)))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.reps):
-        dst.copy_(src, non_blocking=True)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    L.check(L.L.sag_probe_d2h(h, n, args.reps, C.byref(secs)))
+    dt = secs.value
+    L.L.sag_destroy(h)
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

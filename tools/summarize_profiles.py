@@ -33,6 +33,12 @@ def raw(rep):
             if k in d:
                 rec[k] = d[k] + " " + units[hdr.index(k)]
         for k, v in d.items():
+            if "issue_stalled" in k and k.endswith("per_issue_active.ratio"):
+                try:
+                    if float(v) > 0.3:
+                        rec["stall_per_issue_" + k.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")] = round(float(v), 2)
+                except ValueError:
+                    pass
             if "issue_stalled" in k and k.endswith("per_warp_active.pct"):
                 try:
                     if float(v) > 5:
