@@ -287,7 +287,10 @@ SAG_HD int hit_circle_box(const Geom& Cc, const Geom& B, bool circle_is_a, Hit* 
   return 1;
 }
 
-SAG_HD_NOINLINE int hit_box_box(const Geom& A, const Geom& B, Hit* o) {
+SAG_HD int hit_box_box_body(const Geom& A, const Geom& B, Hit* o);
+// out of line for the scalar paths (several call sites); the cooperative kernel's single narrow-phase site inlines the body
+SAG_HD_NOINLINE int hit_box_box(const Geom& A, const Geom& B, Hit* o) { return hit_box_box_body(A, B, o); }
+SAG_HD int hit_box_box_body(const Geom& A, const Geom& B, Hit* o) {
   double dx = B.cx - A.cx, dy = B.cy - A.cy;
   double best = -1e300, bsign = 1.0, bux = 0.0, buy = 0.0;
   int bi = -1;
@@ -349,6 +352,12 @@ SAG_HD int collide(const Geom& A, const Geom& B, Hit* o) {
   if (!A.is_box) return hit_circle_box(A, B, true, o);
   if (!B.is_box) return hit_circle_box(B, A, false, o);
   return hit_box_box(A, B, o);
+}
+SAG_HD int collide_inl(const Geom& A, const Geom& B, Hit* o) {
+  if (!A.is_box && !B.is_box) return hit_circle_circle(A, B, o);
+  if (!A.is_box) return hit_circle_box(A, B, true, o);
+  if (!B.is_box) return hit_circle_box(B, A, false, o);
+  return hit_box_box_body(A, B, o);
 }
 
 // Overlap predicates: the first stage of the hit_* routines above with the same arithmetic, so "no overlap" here
@@ -820,10 +829,13 @@ __device__ __forceinline__ void coop_align() {
   asm volatile("bar.sync 0;" ::: "memory");
 #endif
 }
+#ifndef SAG_ALIGN_EVERY
+#define SAG_ALIGN_EVERY 1   // a barrier in front of every SAG_ALIGN_EVERY-th trip of the pass loop
+#endif
 template <class RB>
 __device__ __forceinline__ void coop_idle_step() {
 #pragma unroll 1
-  for (int k = 0; k <= RB::kNsub; ++k) coop_align();
+  for (int k = 0; k <= RB::kNsub; ++k) if (k % SAG_ALIGN_EVERY == 0) coop_align();
 }
 
 #endif
@@ -1000,7 +1012,7 @@ __device__ __forceinline__ void detect_coop(const Ctx& C, const RB& R, double sn
         }
         obj_geom(D, ka, pa, C.O.x[i], C.O.y[i], oc, os, ga);
       }
-      n = collide(ga, gb, hits);
+      n = collide_inl(ga, gb, hits);
     }
     const bool stored = coop_append(con, cap, ncon, overflow, n, hits, ia < 0 ? 0 : (mva ? 1 + ia : -1), mvb ? 1 + sb : -1);
     newsc = __reduce_or_sync(kFullWarp, newsc);
@@ -2152,7 +2164,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
 #pragma unroll 1
   for (int k = 0; k < kTrips; ++k) {
 #if defined(__CUDA_ARCH__)
-    if constexpr (Coop) coop_align();
+    if constexpr (Coop) { if (k % SAG_ALIGN_EVERY == 0) coop_align(); }
 #endif
     const bool fwd = Coop && k == RB::kNsub;
     if (fwd && err) { Pfwd.qacc[0] = qacc_err[0]; Pfwd.qacc[1] = qacc_err[1]; Pfwd.qacc[2] = qacc_err[2]; break; }  // :73-75, no forward()
