@@ -32,6 +32,12 @@ struct TileCfg {
 };
 
 thread_local char g_err[512] = "";
+// pinned output blocks handed out by sag_host_alloc_outputs (single-copy layout); process-wide, cleared by sag_host_free
+void* g_packed_blocks[64];
+bool is_packed_block(const void* p) {
+  for (int k = 0; k < 64; ++k) if (g_packed_blocks[k] == p && p) return true;
+  return false;
+}
 
 int fail(const char* what, cudaError_t ce = cudaSuccess) {
   if (ce != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(ce));
@@ -71,6 +77,7 @@ struct Handle {
   cudaStream_t own_stream;
   cudaStream_t copy_stream;          // host-buffer API: bulk device-to-host copies that overlap the busy kernel
   cudaEvent_t ev_quiet, ev_copied;
+  cudaEvent_t ev_chunk[8];
   unsigned long long launches;  // kernels launched on behalf of this handle (sag_launch_count)
   int busy_grid;  // CTAs of k_step_coop: resident CTAs per SM x SMs
 };
@@ -133,13 +140,15 @@ __device__ __forceinline__ void write_rows(const float* tile, int tstride, float
 template <class RB>
 __global__ void __launch_bounds__(kBS, RB::kKind == 1 ? 2 : 4) k_step_free(Dev D, const float* __restrict__ act, float* __restrict__ obs,
                                                     double* __restrict__ reward, double* __restrict__ reward2,
-                                                    uint8_t* __restrict__ cost, uint8_t* __restrict__ done) {
+                                                    uint8_t* __restrict__ cost, uint8_t* __restrict__ done, int e_first) {
+  // environments [e_first, e_first + gridDim.x * kBS) of the batch (the host-buffer step launches the batch in chunks
+  // so that the device-to-host copy of a chunk's observations runs under the next chunk's kernel); e_first % kBS == 0
   constexpr int kObs = RB::kObsDim;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);  // [kObs][kTileStride]
-  const int e = blockIdx.x * kBS + threadIdx.x;
+  const int e = e_first + blockIdx.x * kBS + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x < 4) D.counts_next[threadIdx.x] = 0;
+  if (e_first == 0 && blockIdx.x == 0 && threadIdx.x < 4) D.counts_next[threadIdx.x] = 0;
   bool run = false, pretest = false;
   if (e < D.n) {
     RB R;
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(kBS, RB::kKind == 1 ? 2 : 4) k_step_free(Dev D
   // all kBS rows of the CTA in one coalesced sweep.  The columns of the work-list environments hold stale shared memory:
   // their rows are rewritten by the cooperative kernel, which always runs after this one on the same stream.
   __syncthreads();
-  write_tile4<kObs>(tile, obs, blockIdx.x * kBS, D.n);
+  write_tile4<kObs>(tile, obs, e_first + blockIdx.x * kBS, D.n);
 }
 
 // k_step_coop: the work list with ONE WARP per environment (sag_core.cuh "warp-cooperative variants"): the lanes run the
@@ -485,7 +494,15 @@ struct Ops {
     // two counter sets used alternately: this step's is zero already (cleared by the previous step's quiet kernel, which
     // saves a memset node per step); steps of one handle must be stream-ordered
     int* t = H->D.counts; H->D.counts = H->D.counts_next; H->D.counts_next = t;
-    k_step_free<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kTileBytes, s>>>(H->D, act, obs, reward, reward2, cost, done);
+    k_step_free<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kTileBytes, s>>>(H->D, act, obs, reward, reward2, cost, done, 0);
+    ++H->launches;
+    return cudaGetLastError();
+  }
+  // one chunk [e0, e1) of the batch kernel (e0 a multiple of kBS); the first chunk swaps the work-list counter sets
+  static cudaError_t step_free_range(Handle* H, int e0, int e1, const float* act, float* obs, double* reward, double* reward2,
+                                     uint8_t* cost, uint8_t* done, cudaStream_t s) {
+    if (e0 == 0) { int* t = H->D.counts; H->D.counts = H->D.counts_next; H->D.counts_next = t; }
+    k_step_free<RB><<<grid_for(e1 - e0), kBS, TileCfg<RB>::kTileBytes, s>>>(H->D, act, obs, reward, reward2, cost, done, e0);
     ++H->launches;
     return cudaGetLastError();
   }
@@ -590,6 +607,7 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&H->copy_stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&H->ev_quiet, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&H->ev_copied, cudaEventDisableTiming);
+  for (int k = 0; k < 8 && ce == cudaSuccess; ++k) ce = cudaEventCreateWithFlags(&H->ev_chunk[k], cudaEventDisableTiming);
   if (ce != cudaSuccess) { cudaFree(H->slab); delete H; return fail("sag_create: init", ce); }
   *handle = H;
   return 0;
@@ -605,6 +623,7 @@ int sag_destroy(void* handle) {
   if (H->copy_stream) cudaStreamDestroy(H->copy_stream);
   if (H->ev_quiet) cudaEventDestroy(H->ev_quiet);
   if (H->ev_copied) cudaEventDestroy(H->ev_copied);
+  for (int k = 0; k < 8; ++k) if (H->ev_chunk[k]) cudaEventDestroy(H->ev_chunk[k]);
   cudaFree(H->slab);
   delete H;
   return 0;
@@ -761,17 +780,29 @@ int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward
   if (obs_m && rew_m && cost_m && done_m) {
     // Pinned output buffers: the bulk device-to-host copy starts as soon as the quiet kernel is done and runs under the
     // busy kernel; the rows the busy kernel produced (5-30 % of them) follow as direct writes into the mapped buffers.
+    // The copy of the observation rows (16 MB: the long pole of the step at PCIe speed) starts when the batch kernel is
+    // done and runs under the contact kernel.  (Launching the batch kernel in chunks so that copies could start earlier
+    // was measured and lost: the kernel's duration is the latency of one thread's step, not throughput, so every chunk
+    // costs as much as the whole batch -- e2e 1.51e8 -> 1.27e8.  SAG_HOST_CHUNKS re-enables it for experiments.)
     cudaStream_t c = H->copy_stream;
-    CK(SAG_DISPATCH(H, step_quiet(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s)));
-    CK(cudaEventRecord(H->ev_quiet, s));
-    CK(cudaStreamWaitEvent(c, H->ev_quiet, 0));
-    const bool packed = (char*)reward_h - (char*)obs_h == (char*)H->rew_d - (char*)H->obs_d &&
-                        (char*)cost_h - (char*)obs_h == (char*)H->cost_d - (char*)H->obs_d &&
-                        (char*)done_h - (char*)obs_h == (char*)H->done_d - (char*)H->obs_d;
-    if (packed) {  // buffers from sag_host_alloc_outputs: one copy for all four outputs
-      CK(cudaMemcpyAsync(obs_h, H->obs_d, (size_t)((char*)H->done_d - (char*)H->obs_d) + n, cudaMemcpyDeviceToHost, c));
+    static const int env_chunks = getenv("SAG_HOST_CHUNKS") ? atoi(getenv("SAG_HOST_CHUNKS")) : 1;
+    const int nch = (env_chunks >= 1 && env_chunks <= 8 && n >= 8 * 4096) ? env_chunks : 1;
+    const int per = (((int)n + nch - 1) / nch + kBS - 1) / kBS * kBS;
+    for (int k = 0; k < nch; ++k) {
+      const int e0 = k * per, e1 = e0 + per < (int)n ? e0 + per : (int)n;
+      if (e0 >= e1) break;
+      CK(SAG_DISPATCH(H, step_free_range(H, e0, e1, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s)));
+      CK(cudaEventRecord(H->ev_chunk[k], s));
+      CK(cudaStreamWaitEvent(c, H->ev_chunk[k], 0));
+      CK(cudaMemcpyAsync(obs_h + (size_t)e0 * od, H->obs_d + (size_t)e0 * od, (size_t)(e1 - e0) * od * sizeof(float), cudaMemcpyDeviceToHost, c));
+    }
+    bool packed = is_packed_block(obs_h);  // a block from sag_host_alloc_outputs, used as handed out
+    packed = packed && (char*)reward_h - (char*)obs_h == (char*)H->rew_d - (char*)H->obs_d &&
+             (char*)cost_h - (char*)obs_h == (char*)H->cost_d - (char*)H->obs_d &&
+             (char*)done_h - (char*)obs_h == (char*)H->done_d - (char*)H->obs_d;
+    if (packed) {  // buffers from sag_host_alloc_outputs: reward, cost and done in one copy
+      CK(cudaMemcpyAsync(reward_h, H->rew_d, (size_t)((char*)H->done_d - (char*)H->rew_d) + n, cudaMemcpyDeviceToHost, c));
     } else {
-      CK(cudaMemcpyAsync(obs_h, H->obs_d, n * od * sizeof(float), cudaMemcpyDeviceToHost, c));
       CK(cudaMemcpyAsync(reward_h, H->rew_d, n * sizeof(double), cudaMemcpyDeviceToHost, c));
       CK(cudaMemcpyAsync(cost_h, H->cost_d, n, cudaMemcpyDeviceToHost, c));
       CK(cudaMemcpyAsync(done_h, H->done_d, n, cudaMemcpyDeviceToHost, c));
@@ -814,6 +845,7 @@ int sag_host_alloc_outputs(void* handle, float** obs_h, double** reward_h, uint8
   char* p = nullptr;
   CK(cudaHostAlloc((void**)&p, span, cudaHostAllocDefault));
   memset(p, 0, span);
+  for (int k = 0; k < 64; ++k) if (!g_packed_blocks[k]) { g_packed_blocks[k] = p; break; }
   *obs_h = (float*)p;
   *reward_h = (double*)(p + ((char*)H->rew_d - (char*)H->obs_d));
   *cost_h = (uint8_t*)(p + ((char*)H->cost_d - (char*)H->obs_d));
@@ -853,7 +885,11 @@ void* sag_host_alloc(size_t bytes) {
   if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { fail("sag_host_alloc: cudaHostAlloc failed"); return nullptr; }
   return p;
 }
-void sag_host_free(void* p) { if (p) cudaFreeHost(p); }
+void sag_host_free(void* p) {
+  if (!p) return;
+  for (int k = 0; k < 64; ++k) if (g_packed_blocks[k] == p) g_packed_blocks[k] = nullptr;
+  cudaFreeHost(p);
+}
 
 int sag_read_field(void* handle, int field, void* dst, void* stream) {
   Handle* H = (Handle*)handle;
