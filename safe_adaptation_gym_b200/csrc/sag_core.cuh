@@ -1557,6 +1557,48 @@ SAG_HD bool robot_overlaps_any(const Ctx& C, const RB& R, double sn, double cs) 
   return false;
 }
 
+// The same pre-test restricted to candidate slots.  `cand` must contain every collidable slot whose centre can come within
+// reach + bound of the robot during the step (near_candidates below); the others fail the broad test above anyway.
+template <class RB>
+SAG_HD bool robot_overlaps_masked(const Ctx& C, const RB& R, double sn, double cs, unsigned cand) {
+  const Dev& D = C.D;
+  for (unsigned m = cand; m; m &= m - 1) {
+    const int s = ctz32(m);
+    const int kind = slot_kind(C.sp, C.L, s);
+    size_t i = oix(C, s);
+    double x = C.O.x[i], y = C.O.y[i];
+    double dx = x - R.q[0], dy = y - R.q[1], reach = RB::kReach + kind_bound(D, kind);
+    if (dx * dx + dy * dy > reach * reach) continue;
+    double oc = 1.0, os = 0.0;
+    if (kind_movable(kind)) sag_sincos(C.O.yaw[i], &os, &oc);
+    for (int pt = 0; pt < kind_nparts(kind); ++pt) {
+      Geom go;
+      obj_geom(D, kind, pt, x, y, oc, os, go);
+      for (int rg = 0; rg < RB::kNGeom; ++rg) {
+        Geom grg;
+        R.geom(rg, sn, cs, grg);
+        if (overlap(grg, go)) return true;
+      }
+    }
+  }
+  return false;
+}
+// collidable slots within reach + bound + travel of the robot at the start of a contact-free step: nothing moves but the
+// robot, and it moves by less than `travel` (RB::travel_bound, conservative) before the step ends
+template <class RB>
+SAG_HD unsigned near_candidates(const Ctx& C, const RB& R, double travel) {
+  const Dev& D = C.D;
+  unsigned cand = 0;
+  for (int s = C.L.v0; s < C.L.n; ++s) {
+    const int kind = slot_kind(C.sp, C.L, s);
+    if (!kind_collidable(kind)) continue;
+    size_t i = oix(C, s);
+    double dx = C.O.x[i] - R.q[0], dy = C.O.y[i] - R.q[1], reach = RB::kReach + kind_bound(D, kind) + travel;
+    if (!(dx * dx + dy * dy > reach * reach)) cand |= 1u << s;
+  }
+  return cand;
+}
+
 // Contact path of a warp of the scalar (one thread = one environment) kernels: the lanes that need it take turns on the
 // warp's Scratch.  `wmask` = lanes of this warp that own an environment (all of them call this together).  On the host
 // there is a single lane.
@@ -1883,7 +1925,7 @@ __device__ __forceinline__ void pass_a_coop(const Ctx& C, const RB& R, double cs
 template <int Mode, class RB>
 SAG_HD void end_of_step(unsigned wmask, Scratch* S, const SolveConsts& Q, const Ctx& C, const RB& R, TaskState& T, const Rng& rng, const PtConst& K,
                         unsigned mov, bool phys_err, const double* qacc_err, bool with_reward, float* obs_s, int ostride, EndOut& O,
-                        const Phys* Pfwd = nullptr) {
+                        const Phys* Pfwd = nullptr, unsigned cand = 0xffffffffu) {
   constexpr bool QuietOnly = Mode == kStepQuiet || Mode == kStepNear, Coop = Mode == kStepCoop, Near = Mode == kStepNear;
   const Dev& D = C.D;
   const int e = C.e;
@@ -1956,7 +1998,7 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, const SolveConsts& Q, const 
   P.err = 0; P.touch = 0;
   bool need = false;
   if constexpr (Near) {  // forward() at the final state would list a contact: not a contact-free step after all
-    if (!(clear > 0.0) && (taut || robot_overlaps_any(C, R, sn, cs))) { O.bail = 1; return; }
+    if (!(clear > 0.0) && (taut || robot_overlaps_masked(C, R, sn, cs, cand))) { O.bail = 1; return; }
   }
   // A PhysicsError in physics.step returns the observation at once (safe_adaptation_gym.py:73-75): no forward(), the
   // accelerometer shows the last substep's acceleration, no reward / cost evaluation.
@@ -2121,6 +2163,8 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
   if constexpr (Coop) solve_consts(D, C.sp, S->Q);
   const SolveConsts& Q = Coop ? S->Q : Qloc;
   const bool tendon_task = C.task == T_HAUL_BOX;
+  unsigned cand = 0;  // contact-free modes with pre-tests: the slots the robot can reach during this step
+  if constexpr (Near) { if (pretest) cand = near_candidates(C, R, R.travel_bound()); }
   // action noise + clip (:58-67)
   double act0 = (double)a0, act1 = (double)a1;
   if (D.action_noise != 0.0) {
@@ -2186,7 +2230,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
       need = !quiet && (mov != 0 || taut || robot_overlaps_any(C, R, sn, cs));
     }
     if constexpr (Near) {
-      if (pretest && (taut || robot_overlaps_any(C, R, sn, cs))) return 1;
+      if (pretest && (taut || robot_overlaps_masked(C, R, sn, cs, cand))) return 1;
     }
     SAG_PROF(e, 3, need ? 1 : 0);
     double subq[3] = {0.0, 0.0, 0.0};  // this substep's forward-dynamics acceleration, if a solve produced one
@@ -2262,7 +2306,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
     if constexpr (Coop) SAG_CLK(6);
   }
   EndOut O;
-  end_of_step<Mode, RB>(wmask, S, Q, C, R, T, rng, K, mov, err != 0, qacc_err, true, obs_s, ostride, O, Coop ? &Pfwd : nullptr);
+  end_of_step<Mode, RB>(wmask, S, Q, C, R, T, rng, K, mov, err != 0, qacc_err, true, obs_s, ostride, O, Coop ? &Pfwd : nullptr, cand);
   if constexpr (Coop) SAG_CLK_RESET;
   if constexpr (Near) { if (O.bail) return 1; }
   unsigned char dn = 0;
