@@ -2502,4 +2502,247 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
   D.movmask[e] = 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative reset (device only): ONE WARP resets one environment.  The rejection samplers (world.py:191-217,
+// go_to_goal.py:59-80) draw candidate k from Philox counter ctr + k, so a round of candidates is a set of independent
+// draws: a round evaluates 8 candidates, the validity checks of one candidate split over 4 lanes (lane = 4 * candidate +
+// group; under the reference's keepouts the first valid draw is among the first eight 94 % of the time), and a ballot
+// picks the FIRST valid one -- the very draw the sequential sampler would have stopped at; the counter advances by exactly
+// the draws it would have used (per-object limit of 1000 draws and the layout's draw budget included).  Same arithmetic
+// per candidate, so layouts are bit-identical to env_reset / the oracle (tests/test_gpu_parity.py).  px / py / pk: 32
+// doubles each of the warp's shared memory (positions placed so far, keepout + margin per slot).
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+constexpr int kResetCand = 8;  // candidates per round; lane = 4 * candidate + check group
+// index of the first candidate (< window) none of whose four lanes raised `bad`, or -1
+__device__ __forceinline__ int coop_first_valid(bool bad, int window) {
+  const unsigned mb = __ballot_sync(kFullWarp, bad);
+  const unsigned t = mb | (mb >> 1) | (mb >> 2) | (mb >> 3);   // bit 4c: some lane of candidate c said bad
+  const unsigned wmask = window >= kResetCand ? 0x11111111u : (((1u << (4 * window)) - 1u) & 0x11111111u);
+  const unsigned okm = ~t & wmask;
+  return okm ? ((__ffs((int)okm) - 1) >> 2) : -1;
+}
+__device__ __forceinline__ int resample_goal_coop(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& ctr, double rx, double ry,
+                                                  double& gx, double& gy) {
+  const Dev& D = C.D;
+  const int lane = coop_lane();
+  const int cand = lane >> 2, grp = lane & 3;  // 8 candidates per round, the checks of one candidate split over 4 lanes
+  double base[4] = {-1.5, -1.5, 1.5, 1.5};  // the rectangle after the failed draws so far (x1.01 per failure, go_to_goal.py:76-79)
+  int used = 0;
+  const int kMaxDraws = 500000;
+  while (used < kMaxDraws) {
+    const int window = min(kResetCand, kMaxDraws - used);
+    double rect[4] = {base[0], base[1], base[2], base[3]};
+    for (int t = 0; t < cand; ++t) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rect[k] = rect[k] * 1.01;
+    }
+    double u1, u2;
+    rng.pair(stream, ctr + (uint32_t)cand, u1, u2);
+    double xmin = rect[0] + kGoalKeepout, ymin = rect[1] + kGoalKeepout, xmax = rect[2] - kGoalKeepout, ymax = rect[3] - kGoalKeepout;
+    double x = xmin + (xmax - xmin) * u1, y = ymin + (ymax - ymin) * u2;
+    bool bad = false;
+    if (grp == 0) { double dx = x - rx, dy = y - ry; if (sqrt_less(dx * dx + dy * dy, D.robot_keepout + kGoalKeepout)) bad = true; }
+    for (int s = grp; s < C.L.n; s += 4) {
+      if (s == C.L.goal) continue;
+      int kind = slot_kind(C.sp, C.L, s);
+      double ko = kind == K_HAZARD ? D.k_hazard : kind == K_VASE ? D.k_vase : kind == K_GREMLIN ? D.k_gremlin
+                : kind == K_PILLAR ? D.k_pillar : kind == K_BUTTON ? kButtonsKeepout : C.sp.box_keepout;
+      size_t i = oix(C, s);
+      double dx = x - C.O.x[i], dy = y - C.O.y[i];
+      if (sqrt_less(dx * dx + dy * dy, ko + kGoalKeepout)) bad = true;
+    }
+    const int first = coop_first_valid(bad, window);
+    if (first >= 0) {
+      gx = __shfl_sync(kFullWarp, x, first * 4); gy = __shfl_sync(kFullWarp, y, first * 4);
+      ctr += (uint32_t)(first + 1);
+      return 0;
+    }
+    ctr += (uint32_t)window; used += window;
+    for (int t = 0; t < window; ++t) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) base[k] = base[k] * 1.01;
+    }
+  }
+  return 1;
+}
+
+// task.reset() with the cooperative goal sampler (otherwise task_reset above, run redundantly by every lane)
+template <class RB>
+__device__ __forceinline__ int task_reset_coop(const Ctx& C, const Rng& rng, uint32_t stream, uint32_t& ctr, const RB& R, TaskState& T) {
+  if (C.sp.kind == 1) {
+    if (C.task == T_COLLECT) T.amask = (1 << C.L.nbtn) - 1;
+    else sample_goal_button(C, rng, stream, ctr, R, T);
+    return 0;
+  }
+  double gx = 0.0, gy = 0.0;
+  if (resample_goal_coop(C, rng, stream, ctr, R.q[0], R.q[1], gx, gy)) return 1;
+  size_t ig = oix(C, C.L.goal);
+  __syncwarp();
+  if (coop_lane() == 0) { C.O.x[ig] = gx; C.O.y[ig] = gy; }
+  __syncwarp();
+  T.last0 = dist2d(R.q[0], R.q[1], gx, gy);
+  if (C.task == T_CATCH_GOAL) { T.cgox = gx; T.cgoy = gy; }
+  if (C.sp.kind == 2) {
+    size_t ib = oix(C, C.L.box);
+    double bx = C.O.x[ib], by = C.O.y[ib];
+    T.last1 = dist2d(gx, gy, bx, by);
+    T.last0 = dist2d(R.q[0], R.q[1], bx, by);
+  }
+  return 0;
+}
+
+template <class RB>
+__device__ __noinline__ void env_reset_coop(const Dev& D, int e, uint32_t episode, bool new_task, double* px, double* py, double* pk) {
+  const int lane = coop_lane();
+  const int cand = lane >> 2, grp = lane & 3;  // 8 placement candidates per round, each checked by 4 lanes
+  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e], global_objects(D, e)};
+  C.L = make_slots(C.sp);
+  const ObjView G = C.O;
+  Rng rng = {D.seed, D.gid_base + (uint32_t)e, episode};
+  uint32_t ctr = 0;
+  long draws_left = D.max_layout_draws > 0 ? D.max_layout_draws : (1L << 22);
+  unsigned char fl = 0;
+  double rxy[2] = {0.0, 0.0};
+  bool ok = false;
+  const double ext = C.sp.extent;
+  px[lane] = 0.0; py[lane] = 0.0;
+  pk[lane] = lane < C.L.n ? slot_keepout(D, C.sp, slot_kind(C.sp, C.L, lane)) + D.placements_margin : 0.0;
+  __syncwarp();
+  const double rk = D.robot_keepout + D.placements_margin;
+  for (int attempt = 0; attempt < 10000 && !ok && draws_left >= 0; ++attempt) {
+    bool failed = false;
+    for (int idx = -1; idx < C.L.n && !failed; ++idx) {
+      int kind = idx < 0 ? K_NONE : slot_kind(C.sp, C.L, idx);
+      double keepout = idx < 0 ? D.robot_keepout : slot_keepout(D, C.sp, kind);
+      double half = ext;
+      if (kind == K_GOAL) half = 1.5;
+      else if (kind == K_BUTTON) half = C.sp.button_rect;
+      else if ((kind == K_BOX || kind == K_ROD || kind == K_BALL) && C.sp.box_rect > 0.0) half = C.sp.box_rect;
+      const double xmin = -half + keepout, xmax = half - keepout;
+      bool placed = false;
+      double x = 0.0, y = 0.0;
+      int used = 0;  // draws spent on this object (limit 1000, world.py:209)
+      while (used < 1000) {
+        if (draws_left <= 0) { draws_left = -1; failed = true; break; }  // the layout's draw budget is spent
+        int window = 1000 - used;
+        if (window > kResetCand) window = kResetCand;
+        if ((long)window > draws_left) window = (int)draws_left;
+        double u1, u2;
+        rng.pair(0u, ctr + (uint32_t)cand, u1, u2);
+        const double cx = xmin + (xmax - xmin) * u1, cy = xmin + (xmax - xmin) * u2;
+        bool bad = false;
+        if (idx >= 0) {
+          if (grp == 0) { double dx = cx - rxy[0], dy = cy - rxy[1]; if (sqrt_less(dx * dx + dy * dy, rk + keepout)) bad = true; }
+          for (int j = grp; j < idx; j += 4) {
+            double ex = cx - px[j], ey = cy - py[j];
+            if (sqrt_less(ex * ex + ey * ey, pk[j] + keepout)) bad = true;
+          }
+        }
+        const int first = coop_first_valid(bad, window);
+        if (first >= 0) {
+          x = __shfl_sync(kFullWarp, cx, first * 4); y = __shfl_sync(kFullWarp, cy, first * 4);
+          ctr += (uint32_t)(first + 1); draws_left -= first + 1; used += first + 1;
+          placed = true;
+          break;
+        }
+        ctr += (uint32_t)window; draws_left -= window; used += window;
+      }
+      if (!placed) { failed = true; break; }
+      if (idx < 0) { rxy[0] = x; rxy[1] = y; }
+      else {
+        __syncwarp();
+        if (lane == 0) { px[idx] = x; py[idx] = y; }
+        __syncwarp();
+      }
+    }
+    if (!failed) ok = true;
+  }
+  if (!ok) fl |= F_RESAMPLE_FAILED;
+  if (C.task == T_HAUL_BOX) {  // haul_box.py:17-18: the box is put next to the robot whatever was sampled for it
+    __syncwarp();
+    if (lane == 0) { px[C.L.box] = rxy[0] + kBoxSize * 3.0; py[C.L.box] = rxy[1]; }
+  }
+  __syncwarp();
+  // yaw draws in the reference's order (world.py:115-136): robot, obstacle slots [0, t0), then goal / box / buttons.  Draw d
+  // of that list is counter ctr + d; the lane of a slot evaluates the slot's own draw.
+  const int n_extra = (C.sp.kind == 0 ? 1 : C.sp.kind == 2 ? (C.sp.box_kind == K_BOX ? 2 : 1) : C.L.nbtn);
+  const int n_yaw = 1 + C.L.t0 + n_extra;
+  double robot_rot, yaw_l = 0.0;
+  {
+    double u1, u2;
+    rng.pair(0u, ctr, u1, u2);
+    robot_rot = kTwoPi * u1;
+    int d = -1;  // this lane's slot: which draw?
+    if (lane < C.L.t0) d = 1 + lane;
+    else if (lane < C.L.n) {
+      if (C.sp.kind == 1) d = 1 + C.L.t0 + (lane - C.L.btn0);
+      else if (lane == C.L.goal) d = 1 + C.L.t0;
+      else if (lane == C.L.box && C.sp.box_kind == K_BOX) d = 2 + C.L.t0;
+    }
+    if (d >= 0) { rng.pair(0u, ctr + (uint32_t)d, u1, u2); yaw_l = kTwoPi * u1; }
+  }
+  ctr += (uint32_t)n_yaw;
+  if (lane < C.L.n) {
+    const size_t i = (size_t)lane * G.stride;
+    G.x[i] = px[lane]; G.y[i] = py[lane]; G.yaw[i] = yaw_l; G.vx[i] = 0.0; G.vy[i] = 0.0; G.w[i] = 0.0;
+  }
+  // from here on the object positions are read from the warp's shared memory (task_reset, clearance)
+  C.O.x = px; C.O.y = py; C.O.stride = 1;
+  RB R;
+  R.q[0] = rxy[0]; R.q[1] = rxy[1]; R.q[2] = robot_rot; R.v[0] = R.v[1] = R.v[2] = 0.0; R.ctrl[0] = R.ctrl[1] = 0.0;
+  if constexpr (RB::kKind == 1) { R.wheel[0] = R.wheel[1] = 0.0; R.cq[0] = 1.0; R.cq[1] = R.cq[2] = R.cq[3] = 0.0; }
+  R.damp_xy = C.sp.damp_xy; R.gear_x = C.sp.gear_x;
+  TaskState T;
+  load_task_state(D, e, T);
+  double sc0 = D.cscale0[e], sc1 = D.cscale1[e];
+  if (new_task) {  // World.__init__ (world.py:72-78): per-Task-instance draws, Philox stream 3 (see env_reset)
+    double u[2];
+    rng.pair(3u, 0u, u[0], u[1]);
+    double sc[2];
+    for (int k = 0; k < 2; ++k) {
+      double tn, tc;
+      sag_sincos(kPi * (u[k] - 0.5), &tn, &tc);
+      sc[k] = (tn / tc) * D.ctrl_range_scale + 1.0;
+    }
+    sc0 = sc[0]; sc1 = sc[1];
+    rng.pair(3u, 1u, u[0], u[1]);
+    if (lane == 0) { D.cscale0[e] = sc0; D.cscale1[e] = sc1; D.bound[e] = D.random_bound ? 0.0 + (D.max_bound - 0.0) * u[0] : D.max_bound; }
+  }
+  if (D.ctrl_range_scale != 0.0) { R.ctrl[0] = clampd(0.0, -1.0 * sc0, 1.0 * sc0); R.ctrl[1] = clampd(0.0, -1.0 * sc1, 1.0 * sc1); }
+  if (new_task) {
+    T.cgcur = 1.0; T.cgnext = 0.2; T.cgtimer = 0; T.bstate = 1; T.btimer = kButtonDelay; T.gbtn = 0;
+    T.amask = C.task == T_COLLECT ? (1 << C.L.nbtn) - 1 : 0; T.cgox = T.cgoy = 0.0; T.last0 = T.last1 = 0.0;
+  }
+  if (ok && task_reset_coop(C, rng, 0u, ctr, R, T)) fl |= F_RESAMPLE_FAILED;
+  T.ctr = 0;
+  __syncwarp();
+  // clearance of the fresh layout, one slot per lane (a min: the order of the operands does not matter)
+  double cl = 1e30;
+  if (lane >= C.L.v0 && lane < C.L.n) {
+    const int kind = slot_kind(C.sp, C.L, lane);
+    if (kind_collidable(kind)) {
+      double dx = px[lane] - R.q[0], dy = py[lane] - R.q[1];
+      cl = sqrt(dx * dx + dy * dy) - (RB::kReach + kind_bound(D, kind));
+    }
+  }
+  double clear = fmin(1e30, coop_min(cl));
+  if (C.task == T_HAUL_BOX) {
+    double tdx, tdy, tlen, tdist;
+    tendon_taut(C, R, tdx, tdy, tlen, tdist);
+    clear = fmin(clear, tdist);
+  }
+  if (lane == 0) {
+    if (C.L.goal >= 0) { const size_t ig = (size_t)C.L.goal * G.stride; G.x[ig] = px[C.L.goal]; G.y[ig] = py[C.L.goal]; }
+    store_robot(D, e, R);
+    store_task_state(D, e, T);
+    D.episode[e] = episode; D.nstep[e] = 0; D.time[e] = 0.0; D.epret[e] = 0.0; D.epcost[e] = 0.0; D.flags[e] = fl;
+    D.clear[e] = clear;
+    D.movmask[e] = 0;
+  }
+  __syncwarp();
+}
+#endif  // __CUDA_ARCH__
+
 }  // namespace sag

@@ -298,32 +298,64 @@ __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __re
   if (obs) write_tile<RB::kObsDim>(tile, obs, e0, D.n);
 }
 
-// env.reset for the selected environments.  Statistics: an episode counts when it FINISHED (time limit or done: the
-// NEEDS_RESET flag), under the task it ran with; a manual reset of an unfinished episode is not an episode.
+// env.reset for the selected environments, ONE WARP per environment that is reset (sag_core.cuh: env_reset_coop -- 32
+// placement candidates per round, the first valid one wins, exactly the sequence of world.py:191-217).  A CTA of four
+// warps looks after 32 consecutive environments: every warp finds the selected ones with one coalesced read + ballot and
+// takes every fourth of them, so that a sparse reset (auto-reset of the few environments that expired in this step) costs
+// one layout's latency and a whole-batch reset is one wave of warps.
+// Statistics: an episode counts when it FINISHED (time limit or done: the NEEDS_RESET flag), under the task it ran with;
+// a manual reset of an unfinished episode is not an episode.
 // obs != nullptr: the environments that were reset get the first observation of their new episode written into their
 // row (the others' rows are left alone) and was_reset[e] = 1 / 0 tells the caller which (auto-reset, env.py).
+constexpr int kResetWarps = 4;
 template <class RB>
-__global__ void __launch_bounds__(kBS) k_reset(Dev D, const uint8_t* __restrict__ mask, int only_flagged, int new_task,
-                                                double* sret, double* scost, double* sn, float* __restrict__ obs,
-                                                uint8_t* __restrict__ was_reset) {
+struct ResetCfg {
+  static constexpr size_t kRowBytes = (sizeof(float) * RB::kObsDim + 15) / 16 * 16;
+  static constexpr size_t kPlaceBytes = 3 * 32 * sizeof(double);
+  static constexpr size_t kPerWarp = kPlaceBytes + kRowBytes + (sizeof(Scratch) + 15) / 16 * 16;
+  static constexpr size_t kSmemBytes = kPerWarp * kResetWarps;
+};
+template <class RB, bool WithObs>
+__global__ void __launch_bounds__(32 * kResetWarps) k_reset(Dev D, const uint8_t* __restrict__ mask, int only_flagged, int new_task,
+                                                            double* sret, double* scost, double* sn, float* __restrict__ obs,
+                                                            uint8_t* __restrict__ was_reset, int gpc) {
+  // gpc: environments per CTA (4 .. 32): small batches get one warp per environment, large ones eight per warp
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);
-  Scratch* scratch = reinterpret_cast<Scratch*>(smem_raw + TileCfg<RB>::kTileBytes);
-  const int e = blockIdx.x * kBS + threadIdx.x;
-  bool doit = e < D.n;
-  if (doit && mask && !mask[e]) doit = false;
-  if (doit && only_flagged && !(D.flags[e] & F_NEEDS_RESET)) doit = false;
-  if (e < D.n && was_reset) was_reset[e] = doit ? 1 : 0;
-  if (doit) {
-    if ((D.flags[e] & F_NEEDS_RESET) && D.nstep[e] > 0) { sret[e] += D.epret[e]; scost[e] += D.epcost[e]; sn[e] += 1.0; }
-    env_reset<RB>(D, e, D.episode[e] + 1u, new_task != 0);
-    if (D.flags[e] & F_RESAMPLE_FAILED) D.errflags[0] = 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* mine = smem_raw + (size_t)warp * (WithObs ? ResetCfg<RB>::kPerWarp : ResetCfg<RB>::kPlaceBytes);
+  double* px = reinterpret_cast<double*>(mine);
+  double* py = px + 32;
+  double* pk = py + 32;
+  float* row = reinterpret_cast<float*>(mine + ResetCfg<RB>::kPlaceBytes);
+  Scratch* scratch = reinterpret_cast<Scratch*>(mine + ResetCfg<RB>::kPlaceBytes + ResetCfg<RB>::kRowBytes);
+  const int e_l = blockIdx.x * gpc + lane;  // this lane looks at environment e_l of the CTA's gpc
+  bool doit = lane < gpc && e_l < D.n;
+  unsigned char fl_l = 0;
+  if (doit) fl_l = D.flags[e_l];
+  if (doit && mask && !mask[e_l]) doit = false;
+  if (doit && only_flagged && !(fl_l & F_NEEDS_RESET)) doit = false;
+  if (warp == 0 && lane < gpc && e_l < D.n && was_reset) was_reset[e_l] = doit ? 1 : 0;
+  unsigned todo = __ballot_sync(0xffffffffu, doit);
+  int rank = 0;
+  for (; todo; todo &= todo - 1, ++rank) {
+    if ((rank & (kResetWarps - 1)) != warp) continue;
+    const int e = blockIdx.x * gpc + (__ffs((int)todo) - 1);
+    const unsigned char fl = D.flags[e];
+    const unsigned episode = D.episode[e] + 1u;
+    if (lane == 0 && (fl & F_NEEDS_RESET) && D.nstep[e] > 0) { sret[e] += D.epret[e]; scost[e] += D.epcost[e]; sn[e] += 1.0; }
+    __syncwarp();
+#if defined(__CUDA_ARCH__)
+    env_reset_coop<RB>(D, e, episode, new_task != 0, px, py, pk);
+#endif
+    if (lane == 0 && (D.flags[e] & F_RESAMPLE_FAILED)) D.errflags[0] = 1;
+    if constexpr (WithObs) {
+      if (lane == 0) env_observe<RB>(1u, scratch, D, e, row, 1);
+      __syncwarp();
+      float* dst = obs + (size_t)e * RB::kObsDim;
+      for (int k = lane; k < RB::kObsDim; k += 32) dst[k] = row[k];
+      __syncwarp();
+    }
   }
-  if (!obs) return;
-  const unsigned wmask = __ballot_sync(0xffffffffu, doit);
-  if (doit) env_observe<RB>(wmask, &scratch[threadIdx.x >> 5], D, e, tile + threadIdx.x, kTileStride);
-  __syncwarp();
-  write_rows<RB::kObsDim>(tile + (threadIdx.x & ~31), kTileStride, obs, doit ? e : -1);
 }
 
 // env.set_task: statistics gathered under the old task are folded into the per-task accumulator first (so that they
@@ -473,7 +505,7 @@ template <class RB>
 struct Ops {
   static cudaError_t setup(Handle* H) {
     cudaError_t ce = cudaFuncSetAttribute(k_observe<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_reset<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_reset<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ResetCfg<RB>::kSmemBytes);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_rollout<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_coop<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CoopCfg<RB>::kSmemBytes);
     if (ce != cudaSuccess) return ce;
@@ -540,9 +572,18 @@ struct Ops {
     return cudaGetLastError();
   }
   static cudaError_t reset(Handle* H, const uint8_t* mask, int only_flagged, int new_task, float* obs, uint8_t* was_reset, cudaStream_t s) {
-    k_reset<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kSmemBytes, s>>>(H->D, mask, only_flagged, new_task, H->sret, H->scost, H->sn, obs, was_reset);
+    // environments per CTA of four warps: one per warp while that still fills the GPU, eight per warp for large batches
+    const int gpc = H->D.n <= 8192 ? kResetWarps : (H->D.n <= 16384 ? 2 * kResetWarps : (H->D.n <= 32768 ? 4 * kResetWarps : 32));
+    const int grid = (H->D.n + gpc - 1) / gpc;
     ++H->launches;
-    return cudaGetLastError();
+    if (obs && (mask || only_flagged)) {  // selective reset: the first observation of the new episodes is written by the same kernel
+      k_reset<RB, true><<<grid, 32 * kResetWarps, ResetCfg<RB>::kSmemBytes, s>>>(H->D, mask, only_flagged, new_task, H->sret, H->scost, H->sn, obs, was_reset, gpc);
+      return cudaGetLastError();
+    }
+    k_reset<RB, false><<<grid, 32 * kResetWarps, ResetCfg<RB>::kPlaceBytes * kResetWarps, s>>>(H->D, mask, only_flagged, new_task, H->sret, H->scost, H->sn, nullptr, was_reset, gpc);
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess && obs) ce = observe(H, obs, s);  // whole-batch reset: one thread per environment is the faster observation pass
+    return ce;
   }
 };
 
