@@ -25,11 +25,12 @@
 extern "C" {
 #endif
 
-#define SAG_ABI_VERSION 2
+#define SAG_ABI_VERSION 3
 #define SAG_LIDAR_BINS 16   /* safe_adaptation_gym.py:22 */
 #define SAG_OBS_POINT 60    /* 3*16 lidar + 12 sensor floats, safe_adaptation_gym.py:120-139,225-237 */
 #define SAG_OBS_CAR 72      /* + ballangvel_rear (3) + quat2mat(ballquat_rear) (9), car.xml:37-38 */
 #define SAG_MAX_SLOTS 32
+#define SAG_MAX_GREMLINS 4
 
 enum { SAG_ROBOT_POINT = 0, SAG_ROBOT_CAR = 1 };
 /* task ids: alphabetical registry order of the reference, benchmark/__init__.py:16-20 */
@@ -57,6 +58,9 @@ typedef struct SagConfig {
   double hazards_size, vases_size, pillars_size, gremlins_size;
   double hazards_keepout, gremlins_keepout, vases_keepout, pillars_keepout;
   double gremlins_travel, robot_ctrl_range_scale, action_noise, max_bound;
+  int32_t num_gremlins;       /* Task.obstacles[2] (task.py:70) of a user-defined task: gremlins per environment, 0 .. SAG_MAX_GREMLINS.
+                                 Every task of the reference's registry has 0; world.py:157-165, primitive_objects.py:57-86 */
+  int32_t reserved_;
 } SagConfig;
 
 /* state fields for injection / extraction (parity tests, checkpointing).  All arrays are SoA,
@@ -70,6 +74,8 @@ enum {
                          moving_mask (derived; rebuilt by sag_observe after an injection) */
   SAG_F_FLAGS = 4,    /* uint8 [stride] */
   SAG_F_ROBOT_EXT = 5,/* double [6][stride]: car only -- wheel rates (2), castor ball-joint quaternion w,x,y,z (4) */
+  SAG_F_GREMLINS = 6, /* double [2 + 3 * SAG_MAX_GREMLINS][stride]: mocap position of the last kinematics pass (x, y), then the weld
+                         anchor (spawn x, y, yaw) of each gremlin */
   SAG_NUM_FIELDS
 };
 

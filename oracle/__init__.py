@@ -29,7 +29,8 @@ class Config(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "placements_margin", "robot_keepout", "hazards_size", "vases_size", "pillars_size", "gremlins_size",
         "hazards_keepout", "gremlins_keepout", "vases_keepout", "pillars_keepout", "gremlins_travel",
-        "robot_ctrl_range_scale", "action_noise", "max_bound")] + [("random_bound", C.c_int), ("max_layout_draws", C.c_int)]
+        "robot_ctrl_range_scale", "action_noise", "max_bound")] + [("random_bound", C.c_int), ("max_layout_draws", C.c_int),
+                                                                  ("num_gremlins", C.c_int)]
 
 
 class Obj(C.Structure):
@@ -100,6 +101,11 @@ def lib():
     L.orc_phys_time.restype = C.c_double
     L.orc_phys_time.argtypes = [C.c_void_p]
     L.orc_phys_clear.argtypes = [C.c_void_p]
+    L.orc_phys_set_mocap_pos.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    L.orc_env_get_gremlin_state.argtypes = [C.c_void_p, dp]
+    L.orc_env_set_gremlin_state.argtypes = [C.c_void_p, dp]
+    L.orc_env_num_gremlins.argtypes = [C.c_void_p]
+    L.orc_env_slot_types.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.orc_phys_add_obj.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
     L.orc_lidar.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, dp, dp, dp]
     L.orc_lidar_literal.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, dp, dp, dp]
@@ -287,6 +293,32 @@ class OracleEnv:
     @property
     def time(self):
         return self.L.orc_phys_time(self.h)
+
+    def set_mocap_pos(self, x, y):
+        """data.mocap_pos of the gremlins' mocap bodies (mujoco_bridge.py:232-233; world.py:157-165 writes one value to all)"""
+        self.L.orc_phys_set_mocap_pos(self.h, float(x), float(y))
+
+    @property
+    def num_gremlins(self):
+        return self.L.orc_env_num_gremlins(self.h)
+
+    @property
+    def gremlin_state(self):
+        """[mocap_pos (2), mocap position seen by the last kinematics pass (2), spawn x, y, yaw per gremlin]"""
+        o = np.zeros(4 + 3 * 4)
+        self.L.orc_env_get_gremlin_state(self.h, _dp(o))
+        return o[:4 + 3 * self.num_gremlins]
+
+    @gremlin_state.setter
+    def gremlin_state(self, v):
+        o = np.zeros(4 + 3 * 4)
+        o[:len(v)] = v
+        self.L.orc_env_set_gremlin_state(self.h, _dp(o))
+
+    def slot_types(self):
+        t = (C.c_int * 32)()
+        self.L.orc_env_slot_types(self.h, t)
+        return list(t)[:self.nobj]
 
     def clear_world(self):
         self.L.orc_phys_clear(self.h)

@@ -59,6 +59,8 @@
 /* MuJoCo default soft-constraint parameters [EXT]: solref (0.02, 1), solimp (0.9,0.95,0.001,0.5,2) */
 #define SOL_TC 0.02
 #define SOL_DR 1.0
+#define WELD_SOL_TC 0.02   /* primitive_objects.py:80-82: <weld solref=".02 1.5"/> */
+#define WELD_SOL_DR 1.5
 #define IMP_D0 0.9
 #define IMP_DMAX 0.95
 #define IMP_WIDTH 0.001
@@ -146,6 +148,12 @@ struct orc_env {
   orc_contact con[ORC_MAX_CON];
   int error;
   int tendon_slot; /* haul_box.py:21-30; -1 = none */
+  /* gremlins (primitive_objects.py:57-86): weld between the free body and its mocap body.  The mocap bodies sit at the
+   * world origin in the XML (the geom carries the offset), so the weld's relative pose at compile time is the
+   * gremlin's spawn pose and the weld target is spawn pose + mocap_pos [EXT].  mocap_pos: what set_mocap_pos wrote;
+   * mocap_kin: what the last kinematics pass saw (stale for the first substep of physics.step) */
+  double mocap_pos[2], mocap_kin[2];
+  double gspawn[ORC_MAX_OBJ][3];
   int touched[ORC_MAX_OBJ]; /* movable body had an active constraint row in the last forward pass */
   int overflow;             /* contact / body limit exceeded in the last forward pass: constraint solve skipped */
   /* world / task (world.py, tasks/ *.py) */
@@ -591,7 +599,9 @@ typedef struct {
   int ba, bb;
   double ja[2][3], jb[2][3]; /* row 0 normal, row 1 tangent */
   double aref[2], diag[2], R[2], f[2], inv[2];
-  int type;     /* 0 contact (normal, tangent), 2 wheel-floor friction (longitudinal, lateral; disc bound) */
+  int type;     /* 0 contact (normal, tangent) / tendon limit, 1 equality (weld: bilateral, no projection),
+                   2 wheel-floor friction (longitudinal, lateral; disc bound) */
+  int nk;       /* scalar rows in this entry: 2, or 1 (tendon, weld yaw) */
   double bound; /* type 2: mu * N */
 } crow;
 
@@ -604,9 +614,10 @@ static void apply(solve_ctx* S, int body, const double* j, double df) {
   S->acc[body][0] += t[0] * df; S->acc[body][1] += t[1] * df; S->acc[body][2] += t[2] * df;
 }
 
-static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
+static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot, int stale_mocap) {
   solve_ctx S;
   crow rows[ORC_MAX_CON + 3];
+  const int row_cap = ORC_MAX_CON + 3;
   int nrow = 0;
   int touched[ORC_MAX_OBJ];
   double ffl[ORC_MAX_OBJ][3];
@@ -643,7 +654,7 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
       double bx = i == 0 ? -0.1 : 0.1, by = 0.1;              /* wheel bodies, car.xml:21,25 */
       double rx = bx * cs - by * sn, ry = bx * sn + by * cs;  /* lever arm in the world frame */
       crow* r = &rows[nrow++];
-      r->type = 2; r->bound = FRICTION_MU * cm.nwheel;
+      r->type = 2; r->nk = 2; r->bound = FRICTION_MU * cm.nwheel;
       r->ba = 0; r->bb = WHEEL_BODY(i);
       r->ja[0][0] = -sn; r->ja[0][1] = cs; r->ja[0][2] = rx * cs - ry * -sn;  /* rolling direction = body y */
       r->jb[0][0] = CAR_WHEEL_R; r->jb[0][1] = 0.0; r->jb[0][2] = 0.0;
@@ -664,8 +675,9 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
     const orc_contact* c = &e->con[i];
     if (!(c->dist < 0.0)) continue;
     if (c->ba < 0 && c->bb < 0) continue;
+    if (nrow >= row_cap) { e->error = 1; e->overflow = 1; break; }  /* only reachable with weld rows in the table */
     crow* r = &rows[nrow++];
-    r->type = 0; r->bound = FRICTION_MU;
+    r->type = 0; r->nk = 2; r->bound = FRICTION_MU;
     r->ba = c->ba; r->bb = c->bb;
     /* a ball / rod geom has priority 1 (dribble_ball.py:38, roll_rod.py:40): the contact takes its friction and
      * solref instead of the max / default mix [EXT] */
@@ -706,8 +718,10 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
     double len = sqrt(dx * dx + dy * dy + dz * dz);
     double dist = TENDON_MAX - len;
     if (dist < 0.0) {
+      if (nrow >= row_cap) { e->error = 1; e->overflow = 1; }
+      else {
       crow* r = &rows[nrow]; tendon_row = nrow++;
-      r->type = 0; r->bound = 0.0;
+      r->type = 0; r->nk = 1; r->bound = 0.0;
       r->ba = 0; r->bb = 1 + e->tendon_slot;
       /* d(dist)/dq : robot +d/len, box -d/len */
       r->ja[0][0] = dx / len; r->ja[0][1] = dy / len; r->ja[0][2] = 0.0;
@@ -721,7 +735,41 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
       r->aref[0] = -bdamp * (dot3(r->ja[0], va) + dot3(r->jb[0], vb)) - d * kbase * dist;
       r->f[0] = 0.0;
       touched[e->tendon_slot] = 1;
+      }
     }
+  }
+  /* gremlin welds (primitive_objects.py:79-82, world.py:157-165): a soft equality between the gremlin and its mocap
+   * body, target = spawn pose + mocap position [EXT], solref (0.02, 1.5), default solimp; planar reduction: one
+   * bilateral row pair (x, y) and one bilateral row (yaw) per gremlin, impedance per row from its own residual.  The
+   * first substep of physics.step still sees the mocap position of the previous kinematics pass. */
+  {
+    const double* mp = stale_mocap ? e->mocap_kin : e->mocap_pos;
+    const double wb_ = 2.0 / (IMP_DMAX * WELD_SOL_TC);
+    const double wk_ = 1.0 / (IMP_DMAX * IMP_DMAX * WELD_SOL_TC * WELD_SOL_TC * WELD_SOL_DR * WELD_SOL_DR);
+    for (int s = 0; s < e->nobj; ++s) {
+      if (e->obj[s].type != ORC_GREMLIN) continue;
+      if (nrow + 2 > row_cap) { e->error = 1; e->overflow = 1; break; }
+      const orc_obj* o = &e->obj[s];
+      double res[3] = {o->x - (e->gspawn[s][0] + mp[0]), o->y - (e->gspawn[s][1] + mp[1]), o->yaw - e->gspawn[s][2]};
+      double vb[3]; body_vel(e, 1 + s, vb);
+      for (int part = 0; part < 2; ++part) {
+        crow* r = &rows[nrow++];
+        r->type = 1; r->nk = part == 0 ? 2 : 1; r->bound = 0.0;
+        r->ba = -1; r->bb = 1 + s;
+        for (int k = 0; k < 2; ++k) for (int d = 0; d < 3; ++d) { r->ja[k][d] = 0.0; r->jb[k][d] = 0.0; }
+        if (part == 0) { r->jb[0][0] = 1.0; r->jb[1][1] = 1.0; } else r->jb[0][2] = 1.0;
+        for (int k = 0; k < r->nk; ++k) {
+          double t[3], resid = part == 0 ? res[k] : res[2];
+          minv_mul(&S, r->bb, r->jb[k], t);
+          double diag = dot3(r->jb[k], t), d = impedance(resid);
+          r->diag[k] = diag; r->R[k] = (1.0 - d) / d * diag;
+          r->aref[k] = -wb_ * dot3(r->jb[k], vb) - d * wk_ * resid;
+          r->f[k] = 0.0;
+        }
+      }
+      touched[s] = 1;
+    }
+    if (!stale_mocap) { e->mocap_kin[0] = e->mocap_pos[0]; e->mocap_kin[1] = e->mocap_pos[1]; }
   }
   /* floor-friction rows for awake / touched movable bodies (plane contact reduced to the plane) */
   int nfl = 0, flslot[ORC_MAX_OBJ];
@@ -739,14 +787,14 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
    * denominator is taken once per row.  Terminates after PGS_SWEEPS sweeps or when one sweep changes the forces by
    * less than PGS_TOL relative (L1) -- MuJoCo's own solvers stop at `tolerance` = 1e-8 [EXT]. */
   for (int i = 0; i < nrow; ++i) {
-    int nk = (i == tendon_row) ? 1 : 2;
-    for (int k = 0; k < nk; ++k) rows[i].inv[k] = 1.0 / (rows[i].diag[k] + rows[i].R[k]);
+    for (int k = 0; k < rows[i].nk; ++k) rows[i].inv[k] = 1.0 / (rows[i].diag[k] + rows[i].R[k]);
   }
+  (void)tendon_row;
   for (int it = 0; it < PGS_SWEEPS; ++it) {
     double sdf = 0.0, sf = 0.0;
     for (int i = 0; i < nrow; ++i) {
       crow* r = &rows[i];
-      int nk = (i == tendon_row) ? 1 : 2;
+      int nk = r->nk;
       if (r->type == 2) { /* wheel: both slip rows, then project the pair onto the friction disc */
         double fo[2] = {r->f[0], r->f[1]};
         for (int k = 0; k < 2; ++k) {
@@ -774,7 +822,8 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
         if (r->ba >= 0) a += dot3(r->ja[k], S.acc[r->ba]);
         if (r->bb >= 0) a += dot3(r->jb[k], S.acc[r->bb]);
         double fn = r->f[k] - (a - r->aref[k] + r->R[k] * r->f[k]) * r->inv[k];
-        if (k == 0) { if (fn < 0.0) fn = 0.0; }
+        if (r->type == 1) { /* equality: bilateral, unbounded */ }
+        else if (k == 0) { if (fn < 0.0) fn = 0.0; }
         else { double lim = r->bound * r->f[0]; fn = clampd(fn, -lim, lim); }
         double df = fn - r->f[k];
         r->f[k] = fn;
@@ -829,7 +878,7 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
   fcon_robot[0] = fcon_robot[1] = fcon_robot[2] = 0.0;
   for (int i = 0; i < nrow; ++i) {
     crow* r = &rows[i];
-    int nk = (i == tendon_row) ? 1 : 2;
+    int nk = r->nk;
     for (int k = 0; k < nk; ++k) {
       if (r->ba == 0) for (int d = 0; d < 3; ++d) fcon_robot[d] += r->ja[k][d] * r->f[k];
       if (r->bb == 0) for (int d = 0; d < 3; ++d) fcon_robot[d] += r->jb[k][d] * r->f[k];
@@ -845,7 +894,7 @@ static void forward_dynamics(orc_env* e, double* fsmooth, double* fcon_robot) {
 
 void orc_phys_forward(orc_env* e) {
   double fs[3], fc[3];
-  forward_dynamics(e, fs, fc);
+  forward_dynamics(e, fs, fc, 0);
 }
 
 static int bad(double x) { return !(fabs(x) <= 1e10); } /* NaN or > mjMAXVAL [EXT] */
@@ -896,7 +945,7 @@ static void car_integrate_extra(orc_env* e) {
 void orc_phys_step(orc_env* e, int nstep) {
   for (int it = 0; it < nstep; ++it) {
     double fs[3], fc[3], rhs[3], a[3];
-    forward_dynamics(e, fs, fc);
+    forward_dynamics(e, fs, fc, it == 0);  /* mj_step2 first: the mocap edit is not seen yet (App. B.1) */
     pt_mat Mh; pt_matrix(e, e->h, &Mh);
     for (int k = 0; k < 3; ++k) rhs[k] = fs[k] + fc[k];
     pt_solve(&Mh, rhs, a);
@@ -1049,17 +1098,21 @@ static const task_spec TASKS[ORC_NUM_TASKS] = {
     /* unsupervised        */ {{5, 6, 0, 1}, 2.0, 0, 0, 0, 0, 0, 0},           /* unsupervised.py:80 */
 };
 
-int orc_task_nobj(int task) {
+static int task_nobj_g(int task, int ng) {
   const task_spec* t = &TASKS[task];
-  int n = t->obstacles[0] + t->obstacles[1] + t->obstacles[2] + t->obstacles[3];
+  int n = t->obstacles[0] + t->obstacles[1] + ng + t->obstacles[3];
   if (t->kind == 0) n += 1; else if (t->kind == 1) n += t->nbuttons; else n += 2;
   return n;
 }
-void orc_task_slot_types(int task, int* types) {
+int orc_task_nobj(int task) { return task_nobj_g(task, TASKS[task].obstacles[2]); }
+static void task_slot_types_g(int task, int ng, int* types);
+void orc_task_slot_types(int task, int* types) { task_slot_types_g(task, TASKS[task].obstacles[2], types); }
+/* ng: Task.obstacles[2] -- 0 in every shipped task (task.py:70 and the overrides), set through orc_config.num_gremlins */
+static void task_slot_types_g(int task, int ng, int* types) {
   const task_spec* t = &TASKS[task];
   static const int kinds[4] = {ORC_HAZARD, ORC_VASE, ORC_GREMLIN, ORC_PILLAR};
   int n = 0;
-  for (int k = 0; k < 4; ++k) for (int i = 0; i < t->obstacles[k]; ++i) types[n++] = kinds[k];
+  for (int k = 0; k < 4; ++k) for (int i = 0; i < (k == 2 ? ng : t->obstacles[k]); ++i) types[n++] = kinds[k];
   if (t->kind == 0) types[n++] = ORC_GOAL;
   else if (t->kind == 1) for (int i = 0; i < t->nbuttons; ++i) types[n++] = ORC_BUTTON;
   else { types[n++] = ORC_GOAL; types[n++] = t->box_type; }
@@ -1071,15 +1124,15 @@ void orc_default_config(orc_config* c) { /* world.py:17-34 */
   c->hazards_size = 0.2; c->vases_size = 0.1; c->pillars_size = 0.2; c->gremlins_size = 0.1;
   c->hazards_keepout = 0.18; c->gremlins_keepout = 0.4; c->vases_keepout = 0.15; c->pillars_keepout = 0.3;
   c->gremlins_travel = 0.35; c->robot_ctrl_range_scale = 0.0; c->action_noise = 0.01; c->max_bound = 25.0;
-  c->random_bound = 0; c->max_layout_draws = 0;
+  c->random_bound = 0; c->max_layout_draws = 0; c->num_gremlins = 0;
 }
 
 static void setup_slots(orc_env* e) {
   /* world.py:53-102 (_setup_placements, keepouts) + task.setup_placements */
   const task_spec* t = &TASKS[e->task];
   int types[ORC_MAX_OBJ];
-  orc_task_slot_types(e->task, types);
-  e->nobj = orc_task_nobj(e->task);
+  task_slot_types_g(e->task, e->cfg.num_gremlins, types);
+  e->nobj = task_nobj_g(e->task, e->cfg.num_gremlins);
   e->goal_slot = e->box_slot = e->first_button = -1;
   e->nbuttons = t->nbuttons;
   e->tendon_slot = -1;
@@ -1287,6 +1340,9 @@ int orc_env_reset(orc_env* e, uint32_t episode) {
   e->v[0] = e->v[1] = e->v[2] = 0.0; e->ctrl[0] = e->ctrl[1] = 0.0;
   e->wheel_w[0] = e->wheel_w[1] = 0.0; e->cq[0] = 1.0; e->cq[1] = e->cq[2] = e->cq[3] = 0.0;
   e->time = 0.0; e->error = 0;
+  /* gremlins: weld anchor = spawn pose; the mocap bodies start at the world origin (primitive_objects.py:24-31,71-77) */
+  e->mocap_pos[0] = e->mocap_pos[1] = e->mocap_kin[0] = e->mocap_kin[1] = 0.0;
+  for (int s = 0; s < e->nobj; ++s) { e->gspawn[s][0] = e->obj[s].x; e->gspawn[s][1] = e->obj[s].y; e->gspawn[s][2] = e->obj[s].yaw; }
   orc_phys_forward(e);
   /* World.reset -> task.reset, world.py:167-170 */
   if (task_reset(e, 0)) return 1;
@@ -1411,6 +1467,10 @@ static int compute_reward(orc_env* e, double* reward) {
 
 /* CatchGoal.set_mocaps, catch_goal.py:20-31 */
 static void set_mocaps(orc_env* e) {
+  if (e->cfg.num_gremlins > 0) { /* World.set_mocaps, world.py:157-165: every gremlin's mocap gets the same target */
+    double phase = e->time;
+    orc_phys_set_mocap_pos(e, sag_sin(phase) * e->cfg.gremlins_travel, sag_cos(phase) * e->cfg.gremlins_travel);
+  }
   if (e->task != ORC_T_CATCH_GOAL) return;
   e->cg_timer = e->cg_timer - 1 > 0 ? e->cg_timer - 1 : 0;
   if (e->cg_timer == 0) {
@@ -1486,7 +1546,21 @@ void orc_env_set_dyn_params(orc_env* e, double damp_xy, double gear_x) { e->damp
 void orc_env_get_ctrlrange(const orc_env* e, double* lo, double* hi) { for (int k = 0; k < 2; ++k) { lo[k] = e->ctrl_lo[k]; hi[k] = e->ctrl_hi[k]; } }
 void orc_env_set_ctrlrange(orc_env* e, const double* lo, const double* hi) { for (int k = 0; k < 2; ++k) { e->ctrl_lo[k] = lo[k]; e->ctrl_hi[k] = hi[k]; } }
 
+void orc_phys_set_mocap_pos(orc_env* e, double x, double y) { e->mocap_pos[0] = x; e->mocap_pos[1] = y; }
+int orc_env_num_gremlins(const orc_env* e) { return e->cfg.num_gremlins; }
+void orc_env_slot_types(const orc_env* e, int* types) { task_slot_types_g(e->task, e->cfg.num_gremlins, types); }
+void orc_env_get_gremlin_state(const orc_env* e, double* o) {
+  o[0] = e->mocap_pos[0]; o[1] = e->mocap_pos[1]; o[2] = e->mocap_kin[0]; o[3] = e->mocap_kin[1];
+  int g = 0;
+  for (int s = 0; s < e->nobj; ++s) if (e->obj[s].type == ORC_GREMLIN) { for (int k = 0; k < 3; ++k) o[4 + 3 * g + k] = e->gspawn[s][k]; ++g; }
+}
+void orc_env_set_gremlin_state(orc_env* e, const double* o) {
+  e->mocap_pos[0] = o[0]; e->mocap_pos[1] = o[1]; e->mocap_kin[0] = o[2]; e->mocap_kin[1] = o[3];
+  int g = 0;
+  for (int s = 0; s < e->nobj; ++s) if (e->obj[s].type == ORC_GREMLIN) { for (int k = 0; k < 3; ++k) e->gspawn[s][k] = o[4 + 3 * g + k]; ++g; }
+}
 void orc_phys_clear(orc_env* e) {
+  e->mocap_pos[0] = e->mocap_pos[1] = e->mocap_kin[0] = e->mocap_kin[1] = 0.0;
   e->nobj = 0; e->goal_slot = e->box_slot = e->first_button = -1; e->nbuttons = 0; e->tendon_slot = -1;
   e->time = 0.0; e->error = 0; e->ncon = 0;
   e->v[0] = e->v[1] = e->v[2] = 0.0; e->ctrl[0] = e->ctrl[1] = 0.0;
@@ -1498,6 +1572,7 @@ int orc_phys_add_obj(orc_env* e, int type, double x, double y, double yaw, doubl
   orc_obj* o = &e->obj[s];
   memset(o, 0, sizeof(*o));
   o->type = type; o->x = x; o->y = y; o->yaw = yaw; o->keepout = keepout; o->group = group;
+  e->gspawn[s][0] = x; e->gspawn[s][1] = y; e->gspawn[s][2] = yaw;
   e->has_rect[s] = 0;
   if (type == ORC_GOAL) e->goal_slot = s;
   if (type == ORC_BOX || type == ORC_ROD || type == ORC_BALL) { e->box_slot = s; if (e->task == ORC_T_HAUL_BOX) e->tendon_slot = s; }

@@ -33,6 +33,7 @@ extern "C" {
 #define ORC_MAX_CON 16      /* contacts per forward pass; more -> PhysicsError (MuJoCo: nconmax) */
 #define ORC_MAX_BODIES 8    /* movable bodies with constraint rows per forward pass; more -> PhysicsError */
 #define ORC_MAX_PARTS 5
+#define ORC_MAX_GREMLINS 4   /* each one adds two weld rows to the solver's row table */
 #define ORC_NUM_LIDAR_BINS 16   /* safe_adaptation_gym.py:22 */
 #define ORC_OBS_MAX 72          /* car: 48 + 24 */
 
@@ -62,6 +63,7 @@ typedef struct {
   double robot_ctrl_range_scale, action_noise, max_bound;
   int random_bound;
   int max_layout_draws; /* draw budget per reset; 0 = default (1<<22). Documented cap. */
+  int num_gremlins;     /* Task.obstacles[2] of a user-defined task (task.py:70); 0 in every shipped task */
 } orc_config;
 
 typedef struct {
@@ -131,6 +133,13 @@ void orc_phys_sensors(const orc_env* e, double* out);      /* _sensors order, :2
 int orc_phys_error(const orc_env* e);
 double orc_phys_time(const orc_env* e);
 /* injected-world building for the golden harness (MujocoBridge.rebuild stand-in) */
+/* gremlin mocap bodies (primitive_objects.py:57-86): data.mocap_pos of every '<gremlin>mocap' body (world.py:157-165
+ * writes the same value to all of them), mujoco_bridge.py:232-233; and the weld anchor = the gremlin's spawn pose */
+void orc_phys_set_mocap_pos(orc_env* e, double x, double y);
+void orc_env_get_gremlin_state(const orc_env* e, double* out /* mocap_pos[2], mocap_kin[2], then x0,y0,yaw0 per gremlin slot */);
+void orc_env_set_gremlin_state(orc_env* e, const double* in);
+int orc_env_num_gremlins(const orc_env* e);
+void orc_env_slot_types(const orc_env* e, int* types);
 void orc_phys_clear(orc_env* e);
 int orc_phys_add_obj(orc_env* e, int type, double x, double y, double yaw, double keepout, int group);
 

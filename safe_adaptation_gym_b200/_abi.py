@@ -13,7 +13,8 @@ LIB_PATH = os.environ.get("SAG_B200_LIB") or os.path.join(_HERE, "csrc", "libsag
 
 NUM_TASKS = 14
 MAX_SLOTS = 32
-F_ROBOT, F_OBJECTS, F_TASK_F64, F_TASK_I32, F_FLAGS, F_ROBOT_EXT = range(6)
+MAX_GREMLINS = 4
+F_ROBOT, F_OBJECTS, F_TASK_F64, F_TASK_I32, F_FLAGS, F_ROBOT_EXT, F_GREMLINS = range(7)
 FLAG_PHYSICS_ERROR, FLAG_RESAMPLE_FAILED, FLAG_NEEDS_RESET, ERR_BAD_TASK_ID = 1, 2, 4, 8
 
 
@@ -27,6 +28,7 @@ class SagConfig(C.Structure):
         ("pillars_keepout", C.c_double),
         ("gremlins_travel", C.c_double), ("robot_ctrl_range_scale", C.c_double), ("action_noise", C.c_double),
         ("max_bound", C.c_double),
+        ("num_gremlins", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

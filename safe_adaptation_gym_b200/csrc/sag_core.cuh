@@ -95,6 +95,8 @@ constexpr double kPgsTol = 1e-8;
 constexpr double kSleepV = 1e-8;
 constexpr int kMaxObj = 32;
 constexpr int kMaxCon = 16;
+constexpr int kMaxGremlins = 4;           // each one adds two weld rows to the solver's row table
+constexpr double kWeldSolTc = 0.02, kWeldSolDr = 1.5;  // primitive_objects.py:80-82: <weld solref=".02 1.5"/>
 constexpr double kHotMargin = 0.05;     // scheduling only: clearance below which an env is planned as "hot"
 constexpr double kRobotReach = 0.16;    // >= |hinge -> far arrow corner| = hypot(0.15, 0.05)
 
@@ -140,6 +142,10 @@ SAG_HD TaskSpec task_spec(int t) {
   return s;
 }
 
+// task descriptor of an environment of this handle: the task's table entry + the handle's gremlin count
+struct Dev;
+SAG_HD TaskSpec spec_for(const Dev& D, int t);
+
 // slot layout = placement order without the robot (world.py:83-90): hazards, vases, gremlins, pillars, task objects
 struct Slots {
   int h0, v0, g0, p0, t0, n;  // first slot of each kind, total
@@ -178,11 +184,15 @@ struct Dev {
   unsigned long long seed;
   unsigned gid_base;
   int max_layout_draws, max_episode_steps;
+  int num_gremlins;        // Task.obstacles[2] of a user-defined task (task.py:70); 0 in every shipped task
+  double gremlins_travel;  // world.py:28
   // robot
   double *rx, *ry, *ryaw, *rvx, *rvy, *rw;
   double *ctrl0, *ctrl1;
   double *cscale0, *cscale1, *bound;  // per Task instance: ctrl-range scale per actuator, constraint bound (world.py:72-78)
   double* rext;  // car extras [6][stride]: wheel rates (2), castor ball-joint quaternion (4)
+  // gremlins [2 + 3 * kMaxGremlins][stride]: mocap position seen by the last kinematics pass (2), spawn x, y, yaw per gremlin
+  double* grem;
   // objects [slot][env]
   double *ox, *oy, *oyaw, *ovx, *ovy, *ow;
   // task / bookkeeping
@@ -205,6 +215,7 @@ struct Dev {
   unsigned char* flags;
 };
 
+SAG_HD TaskSpec spec_for(const Dev& D, int t) { TaskSpec s = task_spec(t); s.ng = D.num_gremlins; return s; }
 SAG_HD size_t oidx(const Dev& D, int slot, int e) { return (size_t)slot * D.stride + e; }
 
 // View of ONE environment's object arrays: field[slot * stride].  Global memory: pointers offset by the environment
@@ -547,6 +558,7 @@ constexpr CarModel kCar = car_model();
 
 struct PointRobot {
   static constexpr int kKind = 0, kNGeom = 2, kNsub = kPtNsub, kObsDim = 60;
+  static constexpr bool kGremlins = false;  // the gremlin code paths exist only in the *G instantiations (below)
   static constexpr double kH = kPtH, kReach = kRobotReach;
   double q[3], v[3];
   double ctrl[2];
@@ -580,6 +592,7 @@ struct PointRobot {
 
 struct CarRobot {
   static constexpr int kKind = 1, kNGeom = kCarNGeom, kNsub = kCarNsub, kObsDim = 72;
+  static constexpr bool kGremlins = false;
   static constexpr double kH = kCarH, kReach = 0.22;  // >= farthest footprint corner (wheel: hypot(0.155, 0.15))
   double q[3], v[3];
   double ctrl[2];
@@ -630,6 +643,11 @@ struct CarRobot {
   }
 };
 
+// Environments with gremlins (Task.obstacles[2] > 0: no task of the reference's registry) run the same code instantiated
+// with kGremlins = true; the default instantiations carry none of the weld / mocap code.
+struct PointRobotG : PointRobot { static constexpr bool kGremlins = true; };
+struct CarRobotG : CarRobot { static constexpr bool kGremlins = true; };
+
 SAG_HD bool bad_val(double x) { return !(fabs(x) <= 1e10); }
 
 SAG_HD double impedance(double r) {
@@ -647,7 +665,8 @@ SAG_HD double impedance(double r) {
 struct Con { int ba, bb; double nx, ny, px, py, dist; };  // ba/bb: -1 static, 0 robot, 1 + slot movable object
 struct Row {  // one contact (normal k=0, tangent k=1), the tendon limit (k=0 only) or one car wheel (longitudinal, lateral)
   int ba, bb;                 // indices into Scratch::acc (-1 static, 0 robot, 1 + compact body id, NB + 1 + wheel)
-  int type, pad_;             // 0 contact / tendon, 2 wheel-floor friction pair (disc bound)
+  int type, nk;               // type 0 contact / tendon, 1 equality (weld: bilateral), 2 wheel-floor friction pair (disc bound);
+                              // nk scalar rows in this entry: 2, or 1 (tendon, weld yaw)
   double bound;               // type 2: mu * N
   double ja[2][3], jb[2][3];  // Jacobian rows w.r.t. body a / b
   double wa[2][3], wb[2][3];  // M^-1 J^T, precomputed
@@ -662,6 +681,7 @@ struct SolveConsts {
   double v_inv_lin, v_inv_tor, b_inv_lin, b_inv_tor;  // 1 / (A + R) of the floor-friction rows
   double vflin, vftor, vbfl, bflin, bftor, bbfl;      // floor-friction bounds, damping rate of the floor rows
   double rix, riy, bfx, bfy;                          // rod: 1 / mx, 1 / my, per-axis bounds
+  double gim, gii, g_inv_lin, g_inv_tor, gflin, gftor, gbfl;  // gremlins (their size is a config value of its own)
 };
 
 // Working set of the contact solver of ONE environment, kept in shared memory (local memory would put every access
@@ -730,7 +750,7 @@ SAG_HD void wheel_row_setup(const CarRobot& R, int i, double sn, double cs, doub
   const double bdamp = 2.0 / (kImpDmax * kSolTc), rr0 = (1.0 - kImpD0) / kImpD0;
   double bx = i == 0 ? -0.1 : 0.1, by = 0.1;
   double rx = bx * cs - by * sn, ry = bx * sn + by * cs;
-  r.type = 2; r.pad_ = 0; r.bound = kMu * kCar.nwheel;
+  r.type = 2; r.nk = 2; r.bound = kMu * kCar.nwheel;
   r.ba = 0; r.bb = wheel_body;
   r.ja[0][0] = -sn; r.ja[0][1] = cs; r.ja[0][2] = rx * cs - ry * -sn;
   r.jb[0][0] = kCarWheelR; r.jb[0][1] = 0.0; r.jb[0][2] = 0.0;
@@ -1081,21 +1101,27 @@ SAG_HD void solve_consts(const Dev& D, const TaskSpec& sp, SolveConsts& Q) {
   Q.rix = Q.riy = 0.0;
   if (bkind == K_ROD) { Q.rix = 1.0 / BP.mx; Q.riy = 1.0 / BP.my; }
   Q.bfx = BP.fx; Q.bfy = BP.fy;
+  if (D.num_gremlins > 0) {
+    const BodyPar GP = kind_body(D, K_GREMLIN);
+    Q.gim = 1.0 / GP.m; Q.gii = 1.0 / GP.iz;
+    Q.g_inv_lin = 1.0 / (Q.gim + rr * Q.gim); Q.g_inv_tor = 1.0 / (Q.gii + rr * Q.gii);
+    Q.gflin = GP.flin; Q.gftor = GP.ftor; Q.gbfl = GP.bfl;
+  }
 }
 
 template <class RB, bool Coop>
 SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, const PtConst& K, const double* fs,
-                              unsigned mov, bool integrate, double h, Scratch& S, const SolveConsts& Q, Phys& P);
+                              unsigned mov, bool integrate, double h, Scratch& S, const SolveConsts& Q, Phys& P, const double* mocap);
 // scalar paths: one out-of-line copy; the cooperative kernel inlines the body at its single call site (env_step), so
 // that the environment's registers need not travel through local memory
 template <class RB, bool Coop>
 SAG_HD_NOINLINE void contact_pass(const Ctx& C, const RB& R, double sn, double cs, const PtConst& K, const double* fs,
-                                  unsigned mov, bool integrate, double h, Scratch& S, const SolveConsts& Q, Phys& P) {
-  contact_pass_body<RB, Coop>(C, R, sn, cs, K, fs, mov, integrate, h, S, Q, P);
+                                  unsigned mov, bool integrate, double h, Scratch& S, const SolveConsts& Q, Phys& P, const double* mocap) {
+  contact_pass_body<RB, Coop>(C, R, sn, cs, K, fs, mov, integrate, h, S, Q, P, mocap);
 }
 template <class RB, bool Coop>
 SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, const PtConst& K, const double* fs,
-                              unsigned mov, bool integrate, double h, Scratch& S, const SolveConsts& Q, Phys& P) {
+                              unsigned mov, bool integrate, double h, Scratch& S, const SolveConsts& Q, Phys& P, const double* mocap) {
   constexpr int kCapCon = Scratch::kCon, kCapBodies = Scratch::kBodies;
   const Dev& D = C.D;
   const int e = C.e;
@@ -1212,12 +1238,19 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
   }
   const bool any_row = (touched & 0x80000000u) != 0;
   touched &= 0x7fffffffu;
+  int nactive = 0;  // contact rows (counted only where weld rows share the row table)
+  if constexpr (RB::kGremlins) for (int i = 0; i < ncon; ++i) { const Con& c = con[i]; if (c.dist < 0.0 && !(c.ba < 0 && c.bb < 0)) ++nactive; }
   double tdx = 0.0, tdy = 0.0, tlen = 0.0, tdist = 0.0;
   bool tendon = false;
   if (C.task == T_HAUL_BOX) {  // tendon length limit, haul_box.py:21-30
     tendon = tendon_taut(C, R, tdx, tdy, tlen, tdist);
     if (tendon) touched |= 1u << C.L.box;
   }
+  // gremlins: welded to their mocap bodies (primitive_objects.py:79-82), so always in the body table
+  const int ng = RB::kGremlins ? C.sp.ng : 0;
+  if (ng > 0) touched |= ((1u << ng) - 1u) << C.L.g0;
+  // the row table holds kMaxCon + 3 entries; with weld rows in it the active contacts may not fit: a PhysicsError
+  if ((RB::kKind == 1 ? 2 : 0) + nactive + (tendon ? 1 : 0) + 2 * ng > kMaxCon + 3) overflow = true;
   double racc[3];
   pt_solve(p, q, K.ia0, K.is0, fs, racc);
   P.qacc[0] = racc[0]; P.qacc[1] = racc[1]; P.qacc[2] = racc[2];
@@ -1229,7 +1262,7 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
   if (overflow) P.err = 1;
   if (!kCarRobot) {
     if (overflow) return;
-    if (!any_row && !tendon && mov == 0) return;  // nothing to solve, nothing to move
+    if (!any_row && !tendon && mov == 0 && ng == 0) return;  // nothing to solve, nothing to move
   }
   // ---- body table: compact ids in slot order, velocities read once
   nb = 0;
@@ -1253,7 +1286,8 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
     if (body == 0) { pt_solve(p, q, K.ia0, K.is0, j, o); return; }
     const bool isb = body - 1 == C.L.box;
     if (isb && rod) { o[0] = rma * j[0] + rmb * j[1]; o[1] = rmb * j[0] + rmc * j[1]; o[2] = j[2] * Q.bii; return; }
-    double im = isb ? Q.bim : Q.vim, ii = isb ? Q.bii : Q.vii;
+    const bool isg = RB::kGremlins && body - 1 >= C.L.g0 && body - 1 < C.L.p0;
+    double im = isb ? Q.bim : (isg ? Q.gim : Q.vim), ii = isb ? Q.bii : (isg ? Q.gii : Q.vii);
     o[0] = j[0] * im; o[1] = j[1] * im; o[2] = j[2] * ii;
   };
   auto bvel = [&](int body, double* v) {
@@ -1278,6 +1312,8 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
     }
   }
   if (overflow) { ncon = 0; tendon = false; }  // car: the wheel rows are still solved, nothing else
+  const int nweld = overflow ? 0 : ng;
+  (void)nweld;
   if constexpr (Coop) SAG_CLKG(8, 1, S);
   // one row pair per active contact, in contact order.  Cooperative mode: contact i is set up by lane i (ncon <= 16),
   // the row index is the rank of the contact among the active ones.
@@ -1300,7 +1336,7 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
     if (!(c.dist < 0.0)) continue;
     if (c.ba < 0 && c.bb < 0) continue;
     Row& r = Coop ? rows[my_row] : rows[nrow++];
-    r.type = 0; r.pad_ = 0; r.bound = kMu;  // contact rows: friction coefficient of the pair
+    r.type = 0; r.nk = 2; r.bound = kMu;  // contact rows: friction coefficient of the pair
     double cb = bdamp, ck = kbase;
     if (bkind > K_BOX && (c.ba - 1 == C.L.box || c.bb - 1 == C.L.box)) {  // priority-1 geom: its friction / solref
       r.bound = kPrioMu;
@@ -1335,7 +1371,7 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
 #endif
   if (tendon) {
     Row& r = rows[nrow]; tendon_row = nrow++;
-    r.type = 0; r.pad_ = 0; r.bound = 0.0;
+    r.type = 0; r.nk = 1; r.bound = 0.0;
     const int bbox = 1 + C.L.box;
     r.ba = 0; r.bb = 1 + cid(C.L.box);
     r.ja[0][0] = tdx / tlen; r.ja[0][1] = tdy / tlen; r.ja[0][2] = 0.0;
@@ -1349,6 +1385,36 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
     r.inv[0] = 1.0 / (diag + r.R[0]);
     r.aref[0] = -bdamp * (dot3(r.ja[0], va) + dot3(r.jb[0], vb)) - d * kbase * tdist;
     r.f[0] = 0.0;
+  }
+  // gremlin welds (primitive_objects.py:79-82, world.py:157-165): soft equality between the gremlin and its mocap body,
+  // target = spawn pose + mocap position [EXT], solref (0.02, 1.5), default solimp.  Planar reduction: one bilateral
+  // row pair (x, y) and one bilateral row (yaw) per gremlin, the impedance of a row from its own residual.
+  if constexpr (RB::kGremlins)
+  for (int g = 0; g < nweld; ++g) {
+    const int s = C.L.g0 + g;
+    const size_t i = oix(C, s);
+    const double wbd = 2.0 / (kImpDmax * kWeldSolTc);
+    const double wkk = 1.0 / (kImpDmax * kImpDmax * kWeldSolTc * kWeldSolTc * kWeldSolDr * kWeldSolDr);
+    const double* sp0 = D.grem + (size_t)(2 + 3 * g) * D.stride + e;
+    const double res[3] = {C.O.x[i] - (sp0[0] + mocap[0]), C.O.y[i] - (sp0[D.stride] + mocap[1]), C.O.yaw[i] - sp0[2 * (size_t)D.stride]};
+    const double vb[3] = {C.O.vx[i], C.O.vy[i], C.O.w[i]};
+    const int body = 1 + cid(s);
+    for (int part = 0; part < 2; ++part) {
+      Row& r = rows[nrow++];
+      r.type = 1; r.nk = part == 0 ? 2 : 1; r.bound = 0.0;
+      r.ba = -1; r.bb = body;
+      for (int k = 0; k < 2; ++k) for (int d = 0; d < 3; ++d) { r.ja[k][d] = 0.0; r.jb[k][d] = 0.0; r.wa[k][d] = 0.0; r.wb[k][d] = 0.0; }
+      if (part == 0) { r.jb[0][0] = 1.0; r.jb[1][1] = 1.0; } else r.jb[0][2] = 1.0;
+      for (int k = 0; k < 2; ++k) { r.aref[k] = 0.0; r.R[k] = 0.0; r.inv[k] = 0.0; r.f[k] = 0.0; }
+      for (int k = 0; k < r.nk; ++k) {
+        const double resid = part == 0 ? res[k] : res[2];
+        minv(1 + s, r.jb[k], r.wb[k]);
+        const double diag = dot3(r.jb[k], r.wb[k]), d = impedance(resid);
+        r.R[k] = (1.0 - d) / d * diag;
+        r.inv[k] = 1.0 / (diag + r.R[k]);
+        r.aref[k] = -wbd * dot3(r.jb[k], vb) - d * wkk * resid;
+      }
+    }
   }
   // body accelerations: acc[0] = robot, acc[1 + compact id] = movable object
   double (*ffl)[3] = S.ffl;
@@ -1368,9 +1434,11 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
   auto floor_visit = [&](int b, double& tdf, double& tf) {
     SAG_PROF(e, 5, 1);
     const bool isb = S.bslot[b] == C.L.box;
-    const double Al = isb ? Q.bim : Q.vim, At = isb ? Q.bii : Q.vii;
-    const double inv_lin = isb ? Q.b_inv_lin : Q.v_inv_lin, inv_tor = isb ? Q.b_inv_tor : Q.v_inv_tor;
-    const double flin = isb ? Q.bflin : Q.vflin, ftor = isb ? Q.bftor : Q.vftor, bfl = isb ? Q.bbfl : Q.vbfl;
+    const bool isg = RB::kGremlins && S.bslot[b] >= C.L.g0 && S.bslot[b] < C.L.p0;
+    const double Al = isb ? Q.bim : (isg ? Q.gim : Q.vim), At = isb ? Q.bii : (isg ? Q.gii : Q.vii);
+    const double inv_lin = isb ? Q.b_inv_lin : (isg ? Q.g_inv_lin : Q.v_inv_lin), inv_tor = isb ? Q.b_inv_tor : (isg ? Q.g_inv_tor : Q.v_inv_tor);
+    const double flin = isb ? Q.bflin : (isg ? Q.gflin : Q.vflin), ftor = isb ? Q.bftor : (isg ? Q.gftor : Q.vftor);
+    const double bfl = isb ? Q.bbfl : (isg ? Q.gbfl : Q.vbfl);
     const double vx = S.bv[b][0], vy = S.bv[b][1], w = S.bv[b][2];
     double* acs = acc[1 + b];
     double* flb = ffl[b];
@@ -1412,7 +1480,8 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
       Row& r = rows[i];
       if (kCarRobot && r.type == 2) { wheel_row_update(r, acc[0], acc[r.bb], sdf, sf); continue; }
       // one visit of a contact row pair (normal, tangent) or of the tendon row (one row)
-      const int ba = r.ba, bb = r.bb, nk = (i == tendon_row) ? 1 : 2;
+      const int ba = r.ba, bb = r.bb, nk = r.nk;
+      const bool bilateral = RB::kGremlins && r.type == 1;
       const double bound = r.bound;
       double ja[2][3], jb[2][3], wa[2][3], wb[2][3], aref[2], Rk[2], inv[2], f[2];
 #pragma unroll
@@ -1434,7 +1503,8 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
         if (bb >= 0) a += dot3(jb[k], ab);
         const double fo = f[k];
         double fn = fo - (a - aref[k] + Rk[k] * fo) * inv[k];
-        if (k == 0) { if (fn < 0.0) fn = 0.0; }
+        if (bilateral) { }  // equality row: no projection
+        else if (k == 0) { if (fn < 0.0) fn = 0.0; }
         else { double lim = bound * f[0]; fn = clampd(fn, -lim, lim); }
         double df = fn - fo;
         f[k] = fn;
@@ -1479,7 +1549,7 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
   P.qacc[0] = acc[0][0]; P.qacc[1] = acc[0][1]; P.qacc[2] = acc[0][2];
   for (int i = 0; i < nrow; ++i) {
     const Row& r = rows[i];
-    int nk = (i == tendon_row) ? 1 : 2;
+    int nk = r.nk;
     for (int k = 0; k < nk; ++k) {
       if (r.ba == 0) for (int d = 0; d < 3; ++d) P.fc[d] += r.ja[k][d] * r.f[k];
       if (r.bb == 0) for (int d = 0; d < 3; ++d) P.fc[d] += r.jb[k][d] * r.f[k];
@@ -1604,19 +1674,20 @@ SAG_HD unsigned near_candidates(const Ctx& C, const RB& R, double travel) {
 // there is a single lane.
 template <class RB>
 SAG_HD void warp_contact_pass(unsigned wmask, bool need, const Ctx& C, const RB& R, double sn, double cs, const PtConst& K,
-                              const double* fs, unsigned mov, bool integrate, double h, Scratch* S, const SolveConsts& Q, Phys& P) {
+                              const double* fs, unsigned mov, bool integrate, double h, Scratch* S, const SolveConsts& Q, Phys& P,
+                              const double* mocap) {
 #if defined(__CUDA_ARCH__)
   unsigned todo = __ballot_sync(wmask, need);
   const int lane = threadIdx.x & 31;
   while (todo) {
     const int turn = __ffs((int)todo) - 1;
     todo &= todo - 1;
-    if (lane == turn) contact_pass<RB, false>(C, R, sn, cs, K, fs, mov, integrate, h, *S, Q, P);
+    if (lane == turn) contact_pass<RB, false>(C, R, sn, cs, K, fs, mov, integrate, h, *S, Q, P, mocap);
     __syncwarp(wmask);
   }
 #else
   (void)wmask;
-  if (need) contact_pass<RB, false>(C, R, sn, cs, K, fs, mov, integrate, h, *S, Q, P);
+  if (need) contact_pass<RB, false>(C, R, sn, cs, K, fs, mov, integrate, h, *S, Q, P, mocap);
 #endif
 }
 
@@ -1925,7 +1996,7 @@ __device__ __forceinline__ void pass_a_coop(const Ctx& C, const RB& R, double cs
 template <int Mode, class RB>
 SAG_HD void end_of_step(unsigned wmask, Scratch* S, const SolveConsts& Q, const Ctx& C, const RB& R, TaskState& T, const Rng& rng, const PtConst& K,
                         unsigned mov, bool phys_err, const double* qacc_err, bool with_reward, float* obs_s, int ostride, EndOut& O,
-                        const Phys* Pfwd = nullptr, unsigned cand = 0xffffffffu) {
+                        const Phys* Pfwd = nullptr, unsigned cand = 0xffffffffu, const double* mocap = nullptr) {
   constexpr bool QuietOnly = Mode == kStepQuiet || Mode == kStepNear, Coop = Mode == kStepCoop, Near = Mode == kStepNear;
   const Dev& D = C.D;
   const int e = C.e;
@@ -2007,13 +2078,14 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, const SolveConsts& Q, const 
     P = *Pfwd;
   } else {
   if (!QuietOnly && !skip_forward) {  // (a quiet step ends with positive clearance: no contact is possible)
-    const bool near_ = !(clear > 0.0 && mov == 0);
+    const bool always = RB::kGremlins && C.sp.ng > 0;  // a welded gremlin is a constraint row in every pass
+    const bool near_ = !(clear > 0.0 && mov == 0) || always;
     if constexpr (Coop) {
 #if defined(__CUDA_ARCH__)
-      need = near_ && (mov != 0 || taut || robot_overlaps_any_coop(C, R, sn, cs));
+      need = near_ && (always || mov != 0 || taut || robot_overlaps_any_coop(C, R, sn, cs));
 #endif
     } else {
-      need = near_ && (mov != 0 || taut || robot_overlaps_any(C, R, sn, cs));
+      need = near_ && (always || mov != 0 || taut || robot_overlaps_any(C, R, sn, cs));
     }
   }
   if (skip_forward) {
@@ -2024,16 +2096,16 @@ SAG_HD void end_of_step(unsigned wmask, Scratch* S, const SolveConsts& Q, const 
   }
   if constexpr (Coop) {
     SAG_CLK(7);
-    if (need) contact_pass<RB, true>(C, R, sn, cs, K, fs, mov, false, 0.0, *S, Q, P);
+    if (need) contact_pass<RB, true>(C, R, sn, cs, K, fs, mov, false, 0.0, *S, Q, P, mocap);
     SAG_CLK_RESET;
   } else if (!QuietOnly) {
-    warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, Q, P);
+    warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, false, 0.0, S, Q, P, mocap);
   }
   }
   qacc[0] = P.qacc[0]; qacc[1] = P.qacc[1]; qacc[2] = P.qacc[2];
   touch = P.touch;
   O.err = P.err;
-  if (mov != 0) clear = -1.0;
+  if (mov != 0 || (RB::kGremlins && C.sp.ng > 0)) clear = -1.0;
   O.clear = clear;
   O.mov = mov;
   O.touch = touch;
@@ -2131,7 +2203,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
                      unsigned char* cost, unsigned char* done, bool pretest = true) {
   constexpr bool QuietOnly = Mode == kStepQuiet || Mode == kStepNear, Coop = Mode == kStepCoop, Near = Mode == kStepNear;
   SAG_CLK_DECL;
-  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e], global_objects(D, e)};
+  Ctx C = {D, e, spec_for(D, D.task[e]), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
 #if defined(__CUDA_ARCH__)
   if constexpr (Coop) {  // stage the object arrays in the warp's working set, one slot per lane; written back at the end
@@ -2190,11 +2262,19 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
     R.ctrl[1] = clampd(act1, -1.0, 1.0);
   }
   set_mocaps(C, rng, T, time);  // :71
+  // World.set_mocaps (world.py:157-165): every gremlin's mocap body goes to travel * (sin t, cos t).  The first substep of
+  // physics.step still sees the position of the previous kinematics pass; from the second on, the new one.
+  const bool gremlins = RB::kGremlins && C.sp.ng > 0;
+  double moc_old[2] = {0.0, 0.0}, moc_new[2] = {0.0, 0.0};
+  if (gremlins) {
+    moc_old[0] = D.grem[e]; moc_old[1] = D.grem[(size_t)D.stride + e];
+    moc_new[0] = sag_sin(time) * D.gremlins_travel; moc_new[1] = sag_cos(time) * D.gremlins_travel;
+  }
   // physics.step(nstep) (:72).  "Quiet" envs (nothing within reach for the whole step, nothing moving) skip
   // contact detection; the bound on the hinge point's travel is conservative.
   unsigned char fl = D.flags[e];
   int err = (fl & F_PHYS_ERROR) ? 1 : 0;  // a physics error is sticky until the env is reset
-  const bool quiet = QuietOnly ? true : env_is_quiet(D.clear[e], R);
+  const bool quiet = QuietOnly ? true : env_is_quiet(D.clear[e], R);  // (gremlin environments keep clear = -1)
   (void)Coop;
   SAG_PROF(e, 7, quiet ? 0 : 1);
   double qacc_err[3] = {0.0, 0.0, 0.0};
@@ -2224,10 +2304,10 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
     }
     if constexpr (Coop) {
 #if defined(__CUDA_ARCH__)
-      need = (fwd || !quiet) && (mov != 0 || taut || robot_overlaps_any_coop(C, R, sn, cs));
+      need = (fwd || !quiet) && (gremlins || mov != 0 || taut || robot_overlaps_any_coop(C, R, sn, cs));
 #endif
     } else if (!QuietOnly) {
-      need = !quiet && (mov != 0 || taut || robot_overlaps_any(C, R, sn, cs));
+      need = !quiet && (gremlins || mov != 0 || taut || robot_overlaps_any(C, R, sn, cs));
     }
     if constexpr (Near) {
       if (pretest && (taut || robot_overlaps_masked(C, R, sn, cs, cand))) return 1;
@@ -2248,7 +2328,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
       P.mov = mov; P.err = 0;
       if constexpr (Coop) {
         SAG_CLK(1);
-        if (need) contact_pass_body<RB, true>(C, R, sn, cs, K, fs, mov, !fwd, h, *S, Q, P);
+        if (need) contact_pass_body<RB, true>(C, R, sn, cs, K, fs, mov, !fwd, h, *S, Q, P, k == 0 ? moc_old : moc_new);
         SAG_CLK_RESET;
         if (fwd) {  // forward(): acceleration + contacts at the final state, nothing is integrated
           if (need) { Pfwd = P; }
@@ -2260,7 +2340,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
           break;
         }
       } else {
-        warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, Q, P);
+        warp_contact_pass(wmask, need, C, R, sn, cs, K, fs, mov, true, h, S, Q, P, k == 0 ? moc_old : moc_new);
       }
       fc[0] = P.fc[0]; fc[1] = P.fc[1]; fc[2] = P.fc[2]; wtau[0] = P.wtau[0]; wtau[1] = P.wtau[1];
       mov = P.mov;
@@ -2306,7 +2386,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
     if constexpr (Coop) SAG_CLK(6);
   }
   EndOut O;
-  end_of_step<Mode, RB>(wmask, S, Q, C, R, T, rng, K, mov, err != 0, qacc_err, true, obs_s, ostride, O, Coop ? &Pfwd : nullptr, cand);
+  end_of_step<Mode, RB>(wmask, S, Q, C, R, T, rng, K, mov, err != 0, qacc_err, true, obs_s, ostride, O, Coop ? &Pfwd : nullptr, cand, moc_new);
   if constexpr (Coop) SAG_CLK_RESET;
   if constexpr (Near) { if (O.bail) return 1; }
   unsigned char dn = 0;
@@ -2339,6 +2419,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
     D.time[e] = time;
     D.clear[e] = O.clear;
     D.movmask[e] = (int)O.mov;
+    if (gremlins) { D.grem[e] = moc_new[0]; D.grem[(size_t)D.stride + e] = moc_new[1]; }
     store_robot(D, e, R);
     store_task_state(D, e, T);
   }
@@ -2352,7 +2433,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
 // observation at the current state (reset return value / refresh after state injection)
 template <class RB>
 SAG_HD void env_observe(unsigned wmask, Scratch* S, const Dev& D, int e, float* obs_s, int ostride) {
-  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e], global_objects(D, e)};
+  Ctx C = {D, e, spec_for(D, D.task[e]), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
   RB R;
   load_robot(D, e, C.sp, R);
@@ -2369,7 +2450,9 @@ SAG_HD void env_observe(unsigned wmask, Scratch* S, const Dev& D, int e, float* 
   SolveConsts Q;
   solve_consts(D, C.sp, Q);
   EndOut O;
-  end_of_step<kStepFull, RB>(wmask, S, Q, C, R, T, rng, K, mov, false, nullptr, false, obs_s, ostride, O);
+  double moc[2] = {0.0, 0.0};
+  if (RB::kGremlins && C.sp.ng > 0) { moc[0] = D.grem[e]; moc[1] = D.grem[(size_t)D.stride + e]; }
+  end_of_step<kStepFull, RB>(wmask, S, Q, C, R, T, rng, K, mov, false, nullptr, false, obs_s, ostride, O, nullptr, 0xffffffffu, moc);
   D.clear[e] = O.clear;
   D.movmask[e] = (int)mov;
 }
@@ -2385,7 +2468,7 @@ SAG_HD double slot_keepout(const Dev& D, const TaskSpec& sp, int kind) {
 
 template <class RB>
 SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_task) {
-  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e], global_objects(D, e)};
+  Ctx C = {D, e, spec_for(D, D.task[e]), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
   Rng rng = {D.seed, D.gid_base + (uint32_t)e, episode};
   uint32_t ctr = 0;
@@ -2498,6 +2581,15 @@ SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_t
     tendon_taut(C, R, tdx, tdy, tlen, tdist);
     clear = fmin(clear, tdist);
   }
+  if (RB::kGremlins && C.sp.ng > 0) {  // gremlins: weld anchor = spawn pose, mocap bodies at the world origin; never a quiet environment
+    clear = -1.0;
+    D.grem[e] = 0.0; D.grem[(size_t)D.stride + e] = 0.0;
+    for (int g = 0; g < C.sp.ng; ++g) {
+      const size_t i = oix(C, C.L.g0 + g);
+      double* sp0 = D.grem + (size_t)(2 + 3 * g) * D.stride + e;
+      sp0[0] = C.O.x[i]; sp0[D.stride] = C.O.y[i]; sp0[2 * (size_t)D.stride] = C.O.yaw[i];
+    }
+  }
   D.clear[e] = clear;
   D.movmask[e] = 0;
 }
@@ -2597,7 +2689,7 @@ template <class RB>
 __device__ __noinline__ void env_reset_coop(const Dev& D, int e, uint32_t episode, bool new_task, double* px, double* py, double* pk) {
   const int lane = coop_lane();
   const int cand = lane >> 2, grp = lane & 3;  // 8 placement candidates per round, each checked by 4 lanes
-  Ctx C = {D, e, task_spec(D.task[e]), Slots(), D.task[e], global_objects(D, e)};
+  Ctx C = {D, e, spec_for(D, D.task[e]), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
   const ObjView G = C.O;
   Rng rng = {D.seed, D.gid_base + (uint32_t)e, episode};
@@ -2732,6 +2824,14 @@ __device__ __noinline__ void env_reset_coop(const Dev& D, int e, uint32_t episod
     double tdx, tdy, tlen, tdist;
     tendon_taut(C, R, tdx, tdy, tlen, tdist);
     clear = fmin(clear, tdist);
+  }
+  if (RB::kGremlins && C.sp.ng > 0) {
+    clear = -1.0;
+    if (lane == 0) { D.grem[e] = 0.0; D.grem[(size_t)D.stride + e] = 0.0; }
+    if (lane >= C.L.g0 && lane < C.L.p0) {
+      double* sp0 = D.grem + (size_t)(2 + 3 * (lane - C.L.g0)) * D.stride + e;
+      sp0[0] = px[lane]; sp0[D.stride] = py[lane]; sp0[2 * (size_t)D.stride] = yaw_l;
+    }
   }
   if (lane == 0) {
     if (C.L.goal >= 0) { const size_t ig = (size_t)C.L.goal * G.stride; G.x[ig] = px[C.L.goal]; G.y[ig] = py[C.L.goal]; }

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kBS, RB::kKind == 1 ? 2 : 4) k_step_free(Dev D
     RB R;
     load_robot(D, e, task_spec(D.task[e]), R);
     const unsigned char fl = D.flags[e];
-    run = !(fl & F_PHYS_ERROR) && D.movmask[e] == 0;
+    run = !(fl & F_PHYS_ERROR) && D.movmask[e] == 0 && D.num_gremlins == 0;  // (a welded gremlin is a constraint row in every pass)
     pretest = !env_is_quiet(D.clear[e], R);
   }
   bool bail = false;
@@ -587,7 +587,10 @@ struct Ops {
   }
 };
 
-#define SAG_DISPATCH(H, call) ((H)->D.robot == SAG_ROBOT_CAR ? Ops<CarRobot>::call : Ops<PointRobot>::call)
+// one set of kernels per robot model; environments with gremlins (SagConfig.num_gremlins > 0) use the *G instantiations
+#define SAG_DISPATCH(H, call)                                                                                     \
+  ((H)->D.robot == SAG_ROBOT_CAR ? ((H)->D.num_gremlins > 0 ? Ops<CarRobotG>::call : Ops<CarRobot>::call)          \
+                                 : ((H)->D.num_gremlins > 0 ? Ops<PointRobotG>::call : Ops<PointRobot>::call))
 
 }  // namespace
 
@@ -612,6 +615,7 @@ int sag_create(const SagConfig* cfg, int device, void** handle) {
   if (!cfg || !handle) return fail("sag_create: null argument");
   if (cfg->n_envs <= 0) return fail("sag_create: n_envs must be positive");
   if (cfg->robot != SAG_ROBOT_POINT && cfg->robot != SAG_ROBOT_CAR) return fail("sag_create: robot must be point (0) or car (1)");
+  if (cfg->num_gremlins < 0 || cfg->num_gremlins > SAG_MAX_GREMLINS) return fail("sag_create: num_gremlins must be in [0, SAG_MAX_GREMLINS]");
   DevGuard guard(device);
   CK(cudaGetLastError());
   Handle* H = new (std::nothrow) Handle();

@@ -24,6 +24,7 @@ inline SlabLayout slab_layout(int n, int stride, int obs_dim) {
   L.bytes[SAG_F_TASK_I32] = 10 * st * sizeof(int32_t);
   L.bytes[SAG_F_FLAGS] = st;
   L.bytes[SAG_F_ROBOT_EXT] = 6 * st * sizeof(double);
+  L.bytes[SAG_F_GREMLINS] = (2 + 3 * (size_t)SAG_MAX_GREMLINS) * st * sizeof(double);
   size_t total = 0;
   for (int f = 0; f < SAG_NUM_FIELDS; ++f) { L.off[f] = total; total += align_up(L.bytes[f], 256); }
   L.stats_off = total; total += align_up(3 * st * sizeof(double), 256);
@@ -56,6 +57,7 @@ inline void slab_bind(Dev& D, const SlabLayout& L, char* base) {
   D.nstep = ii + 6 * st; D.ctr = (unsigned*)(ii + 7 * st); D.episode = (unsigned*)(ii + 8 * st); D.movmask = ii + 9 * st;
   D.flags = (unsigned char*)(base + L.off[SAG_F_FLAGS]);
   D.rext = (double*)(base + L.off[SAG_F_ROBOT_EXT]);
+  D.grem = (double*)(base + L.off[SAG_F_GREMLINS]);
   int32_t* sc = (int32_t*)(base + L.sched_off);
   D.worklist = sc; D.counts = sc + 3 * st; D.counts_next = D.counts + 8;
   D.dbg = (unsigned long long*)(sc + 3 * st + 16);  // 18 x u64 (36 ints) after the two counter sets (16 ints); the block is 96 ints
@@ -75,6 +77,7 @@ inline void dev_from_config(Dev& D, const SagConfig& c) {
   D.max_bound = c.max_bound; D.ctrl_range_scale = c.robot_ctrl_range_scale; D.random_bound = c.random_bound;
   D.seed = c.seed; D.gid_base = c.env_id_base;
   D.max_layout_draws = c.max_layout_draws; D.max_episode_steps = c.max_episode_steps;
+  D.num_gremlins = c.num_gremlins; D.gremlins_travel = c.gremlins_travel;
 }
 
 }  // namespace sag

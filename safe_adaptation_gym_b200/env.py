@@ -33,7 +33,9 @@ WORLD_DEFAULT = {
     'pillars_keepout': 0.3, 'gremlins_travel': 0.35, 'obstacles_size_noise_scale': 0.0,
     'robot_ctrl_range_scale': 0.0, 'action_noise': 0.01, 'max_bound': 25, 'random_bound': False,
 }
-_EXTRA_KEYS = {'max_layout_draws'}
+# max_layout_draws: draw budget of a layout; num_gremlins: Task.obstacles[2] of a user-defined task (task.py:70; every
+# task of the reference's registry has 0 gremlins) -- gremlins per environment, world.py:157-165
+_EXTRA_KEYS = {'max_layout_draws', 'num_gremlins'}
 _ROBOT_TO_CONTROL_FREQUENCY = {'doggo': 12, 'point': 5, 'car': 10}  # safe_adaptation_gym.py:15-19
 
 
@@ -94,6 +96,7 @@ class BatchedSafeAdaptationGym:
         c.max_episode_steps = int(max_episode_steps)
         c.max_layout_draws = int(cfg.get('max_layout_draws', 0))
         c.random_bound = 1 if cfg['random_bound'] else 0
+        c.num_gremlins = int(cfg.get('num_gremlins', 0))
         for k in ('placements_margin', 'robot_keepout', 'hazards_size', 'vases_size', 'pillars_size', 'gremlins_size',
                   'hazards_keepout', 'gremlins_keepout', 'vases_keepout', 'pillars_keepout', 'gremlins_travel',
                   'robot_ctrl_range_scale', 'action_noise', 'max_bound'):
@@ -279,7 +282,8 @@ class BatchedSafeAdaptationGym:
 
     _FIELDS = {'robot': (_abi.F_ROBOT, torch.float64, (6,)), 'objects': (_abi.F_OBJECTS, torch.float64, (6, _abi.MAX_SLOTS)),
                'task_f64': (_abi.F_TASK_F64, torch.float64, (15,)), 'task_i32': (_abi.F_TASK_I32, torch.int32, (10,)),
-               'flags': (_abi.F_FLAGS, torch.uint8, ()), 'robot_ext': (_abi.F_ROBOT_EXT, torch.float64, (6,))}
+               'flags': (_abi.F_FLAGS, torch.uint8, ()), 'robot_ext': (_abi.F_ROBOT_EXT, torch.float64, (6,)),
+               'gremlins': (_abi.F_GREMLINS, torch.float64, (2 + 3 * _abi.MAX_GREMLINS,))}
 
     def get_field(self, name: str) -> torch.Tensor:
         """Copy of an internal SoA state field, shape (*lead, stride) (see include/sag_b200.h SAG_F_*)."""

@@ -153,6 +153,11 @@ def run_parity(backend, task_names, n, steps, seed, config=None, policy="drive",
             ro, oo = oracle_state(orc)
             np.testing.assert_array_equal(r1, ro, err_msg=f"robot state step {t}")
             np.testing.assert_array_equal(o1, oo, err_msg=f"object state step {t}")
+            ng = int(cfg.get("num_gremlins", 0))
+            if ng:  # mocap position of the last kinematics pass + weld anchors
+                g = env.get_field("gremlins").cpu().numpy()[:, :n].T
+                for e in range(n):
+                    np.testing.assert_array_equal(g[e, :2 + 3 * ng], orc[e].gremlin_state[2:], err_msg=f"gremlin state env {e} step {t}")
     stats["moved_objects"] = float(np.abs(oo[:, :, :2] - o0[:, :, :2]).max())
     env.close()
     return stats

@@ -249,6 +249,19 @@ class FakeBridge:
         self.user_groups = _NamedView(robot=np.array([0.0]))
         for name, (body_strs, weld) in config["bodies"].items():
             body = ET.fromstring(body_strs[0])
+            if name.startswith("gremlins"):
+                # primitive_objects.py:57-86: free body + mocap body + weld.  The mocap BODY has no pos (world origin), its
+                # geom carries the offset and does not collide; the weld's solref is what the oracle's weld rows use
+                mocap = ET.fromstring(body_strs[1])
+                w = ET.fromstring(weld)
+                assert mocap.get("mocap") == "true" and mocap.get("pos") is None and mocap.get("name") == name + "mocap"
+                mg = mocap.find("geom")
+                assert mg.get("contype") == "0" and mg.get("conaffinity") == "0" and mg.get("pos") == body.get("pos")
+                assert (w.get("body1"), w.get("body2")) == (name, name + "mocap")
+                assert [float(t) for t in w.get("solref").split()] == [0.02, 1.5]
+                assert float(body.find("geom").get("density")) == 0.001
+            else:
+                assert not weld
             if name == "circle":  # unsupervised.py:25-46: visual only, never in the layout
                 continue
             pos = [float(t) for t in body.get("pos").split()]
@@ -342,8 +355,9 @@ class FakeBridge:
     def set_body_pos(self, name, pos):
         self.env.set_obj(self._slot(name), x=float(pos[0]), y=float(pos[1]))
 
-    def set_mocap_pos(self, name, pos):
-        raise NotImplementedError
+    def set_mocap_pos(self, name, pos):  # mujoco_bridge.py:232-233; world.py:157-165 writes one value to every gremlin's mocap
+        assert name.endswith("mocap") and name[:-5] in self.names and float(pos[2]) == 0.0
+        self.env.set_mocap_pos(float(pos[0]), float(pos[1]))
 
     def set_control(self, action):
         self.env.set_control(action)
@@ -383,6 +397,14 @@ def make_env(task_key, config=None, seed=0, robot="point"):
     import safe_adaptation_gym.safe_adaptation_gym as sag
     from safe_adaptation_gym.benchmark import TASKS
 
+    config = dict(config or {})
+    gremlins = int(config.pop("num_gremlins", 0))  # not a World key: Task.obstacles[2] of a user-defined task (task.py:70)
+    task_cls = TASKS[task_key]
+    if gremlins:
+        base_obstacles = list(task_cls().obstacles)
+        task_cls = type(task_cls.__name__ + "WithGremlins", (task_cls,),
+                        {"obstacles": property(lambda self: [base_obstacles[0], base_obstacles[1], gremlins, base_obstacles[3]])})
+
     sag.Robot = FakeRobot
     sag.MujocoBridge = FakeBridge
     FakeBridge.TASK = task_key
@@ -391,7 +413,7 @@ def make_env(task_key, config=None, seed=0, robot="point"):
         env = sag.SafeAdaptationGym("xmls/%s.xml" % robot, config=config, render_lidars_and_collision=False)
         del EVENTS[:]
         env.seed(seed)
-        env.set_task(TASKS[task_key]())
+        env.set_task(task_cls())
     finally:
         pass
     return env
@@ -551,9 +573,25 @@ def sampler_goldens():
     return out
 
 
+def gremlin_episodes():
+    """World.set_mocaps (world.py:157-165) + primitive_objects.get_gremlin run by the reference for a user-defined task
+    with Task.obstacles[2] = 2 (no task of the registry has gremlins)."""
+    episodes = []
+    for task_key, seed, steps, mode, robot in [("go_to_goal", 31, 300, "drive", "point"), ("press_buttons", 32, 250, "drive", "point"),
+                                               ("push_box", 33, 250, "drive", "point"), ("go_to_goal", 34, 200, "drive", "car")]:
+        ep = record_episode(task_key, seed, steps, mode, config={"action_noise": 0.01, "num_gremlins": 2}, robot=robot)
+        print("gremlins", robot, task_key, "return", sum(r[-1] for s in ep["segments"] for r in s["reward"]),
+              "cost", sum(sum(s["cost"]) for s in ep["segments"]), "replay", len(ep["replay"]))
+        episodes.append(ep)
+    np.savez_compressed(os.path.join(HERE, "episodes_gremlins.npz"), data=np.frombuffer(json.dumps(episodes).encode(), dtype=np.uint8))
+
+
 def main():
     install_stubs()
     os.makedirs(HERE, exist_ok=True)
+    if "gremlins" in sys.argv[1:]:  # only the gremlin episodes (the other fixtures are left as they are)
+        gremlin_episodes()
+        return
     with open(os.path.join(HERE, "lidar_kat.json"), "w") as f:
         json.dump(lidar_kats(), f)
     with open(os.path.join(HERE, "layouts.json"), "w") as f:
@@ -577,6 +615,7 @@ def main():
               "cost", sum(sum(s["cost"]) for s in ep["segments"]), "replay", len(ep["replay"]))
         episodes.append(ep)
     np.savez_compressed(os.path.join(HERE, "episodes.npz"), data=np.frombuffer(json.dumps(episodes).encode(), dtype=np.uint8))
+    gremlin_episodes()
 
 
 if __name__ == "__main__":

@@ -50,7 +50,7 @@ def test_abi_library_exports_every_declared_symbol():
     L = ctypes.CDLL(lib)
     for sym in declared:
         assert hasattr(L, sym), sym
-    assert L.sag_abi_version() == 2
+    assert L.sag_abi_version() == 3
     cfg = _abi.SagConfig()
     L.sag_default_config(ctypes.byref(cfg))
     assert (cfg.robot_keepout, cfg.hazards_size, cfg.vases_keepout, cfg.action_noise, cfg.max_bound) == (0.4, 0.2, 0.15, 0.01, 25.0)

@@ -12,8 +12,11 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def _episodes():
-    raw = np.load(os.path.join(G, "episodes.npz"))["data"]
-    return json.loads(raw.tobytes().decode())
+    out = []
+    for name in ("episodes.npz", "episodes_gremlins.npz"):  # the second: a user-defined task with Task.obstacles[2] = 2
+        raw = np.load(os.path.join(G, name))["data"]
+        out += json.loads(raw.tobytes().decode())
+    return out
 
 
 EPISODES = _episodes()
@@ -62,7 +65,7 @@ def test_layout_sampler_matches_reference_world():
     assert n >= 60
 
 
-@pytest.mark.parametrize("ep", EPISODES, ids=[f"{e.get('robot', 'point')}-{e['task']}-{e['seed']}" for e in EPISODES])
+@pytest.mark.parametrize("ep", EPISODES, ids=[f"{e.get('robot', 'point')}-{e['task']}-{e['seed']}" + ("-gremlins" if e["config"].get("num_gremlins") else "") for e in EPISODES])
 def test_episode_matches_reference_step_loop(ep):
     """safe_adaptation_gym.py:56-107 + world.py + tasks/*.py executed by the reference over oracle physics,
     vs the oracle's own restatement of that logic, on the same recorded random stream."""
@@ -96,7 +99,8 @@ def test_geometry_constants_match_reference_xml():
     """sizes / heights the reference's primitive_objects.py emitted into the XML vs the oracle's constants"""
     want = {"hazards": ("cylinder", [0.2, 0.01], 0.02), "vases": ("box", [0.1, 0.1, 0.1], 0.1 - 4e-5),
             "pillars": ("cylinder", [0.2, 0.5], 0.5), "goal": ("cylinder", [0.3, 0.15], 0.16),
-            "buttons": ("sphere", [0.1, 0.1, 0.1], 0.1), "box": ("box", [0.2, 0.2, 0.2], 0.2)}
+            "buttons": ("sphere", [0.1, 0.1, 0.1], 0.1), "box": ("box", [0.2, 0.2, 0.2], 0.2),
+            "gremlins": ("box", [0.1, 0.1, 0.1], 0.1)}  # primitive_objects.py:63-72
     # the 'box' body of roll_rod.py:27-34 (cylinder radius 0.08, half length 0.3) and dribble_ball.py:24-30 (sphere 0.14)
     box_by_task = {"roll_rod": ("cylinder", [0.08, 0.3], 0.08), "dribble_ball": ("sphere", [0.14], 0.14)}
     seen = set()

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def test_native_library_is_loaded():
     from safe_adaptation_gym_b200 import _abi
     L = _abi.load()
-    assert L.L.sag_abi_version() == 2
+    assert L.L.sag_abi_version() == 3
     assert L.path.endswith("csrc/libsag_b200.so")
 
 
@@ -404,3 +404,34 @@ def test_integration_md_ctypes_stub_runs_as_written():
     np.testing.assert_array_equal(obs, env.observation.cpu().numpy())
     with pytest.raises(KeyError):
         br.set_task("fly_to_goal")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot,tasks_", [("point", ["go_to_goal", "press_buttons", "push_box", "haul_box"]),
+                                          ("car", ["go_to_goal", "press_buttons", "push_box"])])
+def test_gremlins_welded_to_orbiting_mocaps(robot, tasks_):
+    """world.py:157-165 + primitive_objects.py:57-86 (user-defined task with Task.obstacles[2] > 0): weld rows in the
+    cooperative contact kernel, mocap staleness in the first substep, contact cost, weld anchors -- bit-exact vs the oracle"""
+    for ng in (1, 3):
+        s = run_parity("cuda", tasks_ * 4, n=4 * len(tasks_), steps=250, seed=61 + ng, config={"num_gremlins": ng, "action_noise": 0.01},
+                       robot=robot)
+        assert s["moved_objects"] > 0.3 and s["contacts"] > 0, s
+
+
+@pytest.mark.gpu
+def test_gremlin_environment_reset_and_checkpoint():
+    """masked reset + state_dict round trip carry the gremlin field (weld anchors, mocap position)"""
+    cfg = {"num_gremlins": 2, "action_noise": 0.0}
+    a = make_env("cuda", 64, "go_to_goal", seed=9, config=cfg)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    for _ in range(30):
+        a.step(torch.rand((64, 2), device="cuda", generator=g) * 2 - 1)
+    sd = a.state_dict()
+    b = make_env("cuda", 64, "go_to_goal", seed=10, config=cfg)
+    b.load_state_dict(sd)
+    for _ in range(30):
+        act = torch.rand((64, 2), device="cuda", generator=g) * 2 - 1
+        oa, ra, _, _ = a.step(act)
+        ob, rb, _, _ = b.step(act)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb)
+    assert "gremlins" in sd["fields"] and float(sd["fields"]["gremlins"][:2, :64].abs().max()) > 0.1

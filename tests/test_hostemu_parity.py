@@ -76,3 +76,11 @@ def test_chain_behind_the_task_body(task):
     from common import run_chain_case
     moved, nmoved, maxcon = run_chain_case("hostemu", "point", task=task, steps=60)
     assert moved > 0.05 and nmoved >= 2 and maxcon >= 2, (moved, nmoved, maxcon)
+
+
+@pytest.mark.parametrize("robot,task", [("point", "go_to_goal"), ("point", "push_box"), ("car", "press_buttons")])
+def test_gremlins_welded_to_orbiting_mocaps(robot, task):
+    """world.py:157-165 + primitive_objects.py:57-86 for a user-defined task with Task.obstacles[2] = 2 (no registry task has
+    gremlins): weld rows, mocap staleness in the first substep, contact cost; plus the weld anchors / mocap state"""
+    s = run_parity("hostemu", task, n=4, steps=200, seed=61, config={"num_gremlins": 2, "action_noise": 0.01}, robot=robot)
+    assert s["moved_objects"] > 0.3, s   # the gremlins orbit their spawn position at radius gremlins_travel = 0.35
