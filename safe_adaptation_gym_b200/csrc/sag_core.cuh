@@ -144,7 +144,7 @@ SAG_HD TaskSpec task_spec(int t) {
 
 // task descriptor of an environment of this handle: the task's table entry + the handle's gremlin count
 struct Dev;
-SAG_HD TaskSpec spec_for(const Dev& D, int t);
+SAG_HD TaskSpec spec_for(const Dev& D, int t, bool gremlins);
 
 // slot layout = placement order without the robot (world.py:83-90): hazards, vases, gremlins, pillars, task objects
 struct Slots {
@@ -215,7 +215,8 @@ struct Dev {
   unsigned char* flags;
 };
 
-SAG_HD TaskSpec spec_for(const Dev& D, int t) { TaskSpec s = task_spec(t); s.ng = D.num_gremlins; return s; }
+// gremlins = RB::kGremlins: in the default instantiations the count is the compile-time constant 0 of the task table
+SAG_HD TaskSpec spec_for(const Dev& D, int t, bool gremlins) { TaskSpec s = task_spec(t); if (gremlins) s.ng = D.num_gremlins; return s; }
 SAG_HD size_t oidx(const Dev& D, int slot, int e) { return (size_t)slot * D.stride + e; }
 
 // View of ONE environment's object arrays: field[slot * stride].  Global memory: pointers offset by the environment
@@ -1090,7 +1091,7 @@ SAG_HD bool tendon_taut(const Ctx& C, const RB& R, double& tdx, double& tdy, dou
   return tdist < 0.0;
 }
 
-SAG_HD void solve_consts(const Dev& D, const TaskSpec& sp, SolveConsts& Q) {
+SAG_HD void solve_consts(const Dev& D, const TaskSpec& sp, SolveConsts& Q, bool gremlins) {
   const int bkind = sp.box_kind;
   const BodyPar VP = kind_body(D, K_VASE), BP = kind_body(D, bkind ? bkind : K_BOX);
   const double rr = (1.0 - kImpD0) / kImpD0;
@@ -1101,7 +1102,7 @@ SAG_HD void solve_consts(const Dev& D, const TaskSpec& sp, SolveConsts& Q) {
   Q.rix = Q.riy = 0.0;
   if (bkind == K_ROD) { Q.rix = 1.0 / BP.mx; Q.riy = 1.0 / BP.my; }
   Q.bfx = BP.fx; Q.bfy = BP.fy;
-  if (D.num_gremlins > 0) {
+  if (gremlins) {
     const BodyPar GP = kind_body(D, K_GREMLIN);
     Q.gim = 1.0 / GP.m; Q.gii = 1.0 / GP.iz;
     Q.g_inv_lin = 1.0 / (Q.gim + rr * Q.gim); Q.g_inv_tor = 1.0 / (Q.gii + rr * Q.gii);
@@ -1480,7 +1481,7 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
       Row& r = rows[i];
       if (kCarRobot && r.type == 2) { wheel_row_update(r, acc[0], acc[r.bb], sdf, sf); continue; }
       // one visit of a contact row pair (normal, tangent) or of the tendon row (one row)
-      const int ba = r.ba, bb = r.bb, nk = r.nk;
+      const int ba = r.ba, bb = r.bb, nk = RB::kGremlins ? r.nk : ((i == tendon_row) ? 1 : 2);
       const bool bilateral = RB::kGremlins && r.type == 1;
       const double bound = r.bound;
       double ja[2][3], jb[2][3], wa[2][3], wb[2][3], aref[2], Rk[2], inv[2], f[2];
@@ -1549,7 +1550,7 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
   P.qacc[0] = acc[0][0]; P.qacc[1] = acc[0][1]; P.qacc[2] = acc[0][2];
   for (int i = 0; i < nrow; ++i) {
     const Row& r = rows[i];
-    int nk = r.nk;
+    int nk = RB::kGremlins ? r.nk : ((i == tendon_row) ? 1 : 2);
     for (int k = 0; k < nk; ++k) {
       if (r.ba == 0) for (int d = 0; d < 3; ++d) P.fc[d] += r.ja[k][d] * r.f[k];
       if (r.bb == 0) for (int d = 0; d < 3; ++d) P.fc[d] += r.jb[k][d] * r.f[k];
@@ -2203,7 +2204,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
                      unsigned char* cost, unsigned char* done, bool pretest = true) {
   constexpr bool QuietOnly = Mode == kStepQuiet || Mode == kStepNear, Coop = Mode == kStepCoop, Near = Mode == kStepNear;
   SAG_CLK_DECL;
-  Ctx C = {D, e, spec_for(D, D.task[e]), Slots(), D.task[e], global_objects(D, e)};
+  Ctx C = {D, e, spec_for(D, D.task[e], RB::kGremlins), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
 #if defined(__CUDA_ARCH__)
   if constexpr (Coop) {  // stage the object arrays in the warp's working set, one slot per lane; written back at the end
@@ -2231,8 +2232,8 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
   // constants of the contact solver: the cooperative kernel keeps them in the warp's shared-memory working set (every
   // lane writes the same values), the scalar path in registers / local memory; the contact-free modes need none
   SolveConsts Qloc;
-  if constexpr (Mode == kStepFull) solve_consts(D, C.sp, Qloc);
-  if constexpr (Coop) solve_consts(D, C.sp, S->Q);
+  if constexpr (Mode == kStepFull) solve_consts(D, C.sp, Qloc, RB::kGremlins);
+  if constexpr (Coop) solve_consts(D, C.sp, S->Q, RB::kGremlins);
   const SolveConsts& Q = Coop ? S->Q : Qloc;
   const bool tendon_task = C.task == T_HAUL_BOX;
   unsigned cand = 0;  // contact-free modes with pre-tests: the slots the robot can reach during this step
@@ -2433,7 +2434,7 @@ SAG_HD int env_step(unsigned wmask, Scratch* S, const Dev& D, int e, float a0, f
 // observation at the current state (reset return value / refresh after state injection)
 template <class RB>
 SAG_HD void env_observe(unsigned wmask, Scratch* S, const Dev& D, int e, float* obs_s, int ostride) {
-  Ctx C = {D, e, spec_for(D, D.task[e]), Slots(), D.task[e], global_objects(D, e)};
+  Ctx C = {D, e, spec_for(D, D.task[e], RB::kGremlins), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
   RB R;
   load_robot(D, e, C.sp, R);
@@ -2448,7 +2449,7 @@ SAG_HD void env_observe(unsigned wmask, Scratch* S, const Dev& D, int e, float* 
     if (C.O.vx[i] != 0.0 || C.O.vy[i] != 0.0 || C.O.w[i] != 0.0) mov |= 1u << s;
   }
   SolveConsts Q;
-  solve_consts(D, C.sp, Q);
+  solve_consts(D, C.sp, Q, RB::kGremlins);
   EndOut O;
   double moc[2] = {0.0, 0.0};
   if (RB::kGremlins && C.sp.ng > 0) { moc[0] = D.grem[e]; moc[1] = D.grem[(size_t)D.stride + e]; }
@@ -2468,7 +2469,7 @@ SAG_HD double slot_keepout(const Dev& D, const TaskSpec& sp, int kind) {
 
 template <class RB>
 SAG_HD_NOINLINE void env_reset(const Dev& D, int e, uint32_t episode, bool new_task) {
-  Ctx C = {D, e, spec_for(D, D.task[e]), Slots(), D.task[e], global_objects(D, e)};
+  Ctx C = {D, e, spec_for(D, D.task[e], RB::kGremlins), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
   Rng rng = {D.seed, D.gid_base + (uint32_t)e, episode};
   uint32_t ctr = 0;
@@ -2689,7 +2690,7 @@ template <class RB>
 __device__ __noinline__ void env_reset_coop(const Dev& D, int e, uint32_t episode, bool new_task, double* px, double* py, double* pk) {
   const int lane = coop_lane();
   const int cand = lane >> 2, grp = lane & 3;  // 8 placement candidates per round, each checked by 4 lanes
-  Ctx C = {D, e, spec_for(D, D.task[e]), Slots(), D.task[e], global_objects(D, e)};
+  Ctx C = {D, e, spec_for(D, D.task[e], RB::kGremlins), Slots(), D.task[e], global_objects(D, e)};
   C.L = make_slots(C.sp);
   const ObjView G = C.O;
   Rng rng = {D.seed, D.gid_base + (uint32_t)e, episode};
