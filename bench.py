@@ -393,16 +393,19 @@ def main():
             dist.barrier()
         secs = C.c_double()
         L.check(L.L.sag_probe_d2h(h2, d2h, 40, C.byref(secs)))
-        tc = torch.tensor([secs.value], dtype=torch.float64, device=dev)
+        # sum over ranks of each rank's own copy rate while all ranks copy (ranks behind different PCIe switches get
+        # different shares, so total bytes / slowest rank's time would understate the aggregate)
+        tc = torch.tensor([d2h * 40 / secs.value / 1e9], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-        ceiling_gbs = world * d2h * 40 / float(tc[0]) / 1e9
+            dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+        ceiling_gbs = float(tc[0])
         e2e_value = world * n * ke / te_total
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 2 * 4,
                "d2h_bytes_per_step": d2h, "steps": ke, "reset_ms": 1e3 * t_reset_e2e,
                "d2h_gbs": e2e_value / n * d2h / 1e9, "host_ceiling_gbs": ceiling_gbs,
                "host_ceiling_frac": (e2e_value / n * d2h / 1e9) / ceiling_gbs,
-               "host_ceiling_note": "ceiling = all ranks copying one step's outputs device -> pinned host back to back, nothing else",
+               "host_ceiling_note": ("ceiling = sum of the ranks' copy rates while ALL ranks copy one step's outputs device -> pinned host back to "
+                                     "back; with several ranks the e2e steps are not in lockstep, so their copies contend less than the probe's"),
                "binding": binding,
                "api": "sag_step_host (C ABI; one pinned output block, a single D2H copy per step), same strata as `value`"}
         L.L.sag_host_free(C.c_void_p(ptrs[0].value))
