@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import oracle as O
-from common import env_state, make_env, run_fullsize_parity, run_parity
+from common import env_state, make_env, make_oracles, oracle_state, run_fullsize_parity, run_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -435,3 +435,40 @@ def test_gremlin_environment_reset_and_checkpoint():
         ob, rb, _, _ = b.step(act)
         assert torch.equal(oa, ob) and torch.equal(ra, rb)
     assert "gremlins" in sd["fields"] and float(sd["fields"]["gremlins"][:2, :64].abs().max()) > 0.1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot,task", [("point", "roll_rod"), ("point", "go_to_goal"), ("car", "press_buttons"), ("point", "haul_box"),
+                                        ("car", "push_box_scarce")])
+def test_warp_cooperative_reset_layouts_bit_exact(robot, task):
+    """the reset kernel (one warp per environment, 8 candidates x 4 check lanes per round) against the oracle's sequential
+    sampler over 512 environments and three consecutive episodes: roll_rod restarts whole layouts 0.7 times per reset, a
+    crowded go_to_goal goal burns all 1000 draws now and then -- positions, yaws, goal resample and draw counters must agree"""
+    n = 512
+    cfg = {"action_noise": 0.0}
+    env = make_env("cuda", n, task, seed=1234, config=cfg, robot=robot)
+    orc = make_oracles(n, task, seed=1234, config=cfg, robot=robot)
+    for episode in range(3):
+        if episode:
+            env.reset()
+            for o in orc:
+                assert o.reset(episode) == 0
+        r1, o1 = env_state(env)
+        ro, oo = oracle_state(orc)
+        np.testing.assert_array_equal(r1, ro, err_msg=f"robot, episode {episode}")
+        np.testing.assert_array_equal(o1, oo, err_msg=f"objects, episode {episode}")
+        ts = env.get_field("task_f64").cpu().numpy()[:, :n]
+        want = np.array([o.task_state[:2] for o in orc]).T
+        np.testing.assert_array_equal(ts[:2], want, err_msg="last distances after task.reset")
+    # a masked reset touches the selected environments only
+    before_r, before_o = env_state(env)
+    mask = torch.zeros(n, dtype=torch.bool, device="cuda"); mask[::7] = True
+    env.reset_envs(mask)
+    r2, o2 = env_state(env)
+    keep = ~mask.cpu().numpy()
+    np.testing.assert_array_equal(r2[keep], before_r[keep]); np.testing.assert_array_equal(o2[keep], before_o[keep])
+    for e in np.nonzero(~keep)[0]:
+        assert orc[e].reset(3) == 0
+    ro, oo = oracle_state(orc)
+    np.testing.assert_array_equal(r2[~keep], ro[~keep]); np.testing.assert_array_equal(o2[~keep], oo[~keep])
+    env.close()
