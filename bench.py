@@ -287,6 +287,9 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
+    # the clocks of the timed region are in; stop polling nvidia-smi before the end-to-end leg (its queries take driver
+    # locks that now and then stall a synchronous host call for milliseconds)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     launches_total = launches_now(h) - l0
     ms = [(ph, a.elapsed_time(b)) for ph, a, b in timed]
     reset_ms = sum(a.elapsed_time(b) for a, b in reset_evs) / len(reset_evs)
@@ -424,7 +427,6 @@ def main():
     stats = stats.cpu().numpy()
 
     if rank == 0:
-        clocks = sampler.stop(t_wall0, t_wall1)
         peak, peak_src = peaks()
         avg_s = total_ms * 1e-3 / K
         achieved = cfg["b_alg"] * n / avg_s / 1e9
