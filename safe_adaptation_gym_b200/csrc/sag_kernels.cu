@@ -509,6 +509,21 @@ struct Ops {
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_rollout<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<RB>::kSmemBytes);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_coop<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CoopCfg<RB>::kSmemBytes);
     if (ce != cudaSuccess) return ce;
+    // Local memory: the observation / auto-reset / rollout kernels carry the scalar contact path (stack frames of ~1.6 KB
+    // per thread, above the default 1 KB limit), so the driver would re-size its local-memory pool whenever one of them
+    // follows a run of step kernels -- a device-wide stall of tens to hundreds of milliseconds on the first env.reset()
+    // after an episode (measured).  Raising the stack limit once to the largest frame keeps the pool at that size.
+    {
+      size_t need = 0;
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, k_observe<RB>) == cudaSuccess && fa.localSizeBytes > need) need = fa.localSizeBytes;
+      if (cudaFuncGetAttributes(&fa, k_reset<RB, true>) == cudaSuccess && fa.localSizeBytes > need) need = fa.localSizeBytes;
+      if (cudaFuncGetAttributes(&fa, k_rollout<RB>) == cudaSuccess && fa.localSizeBytes > need) need = fa.localSizeBytes;
+      need = (need + 255) / 256 * 256;
+      size_t cur = 0;
+      if (cudaDeviceGetLimit(&cur, cudaLimitStackSize) == cudaSuccess && cur < need) cudaDeviceSetLimit(cudaLimitStackSize, need);
+      cudaGetLastError();
+    }
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, H->device);
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_coop<RB>, 32 * kCoopWarps, CoopCfg<RB>::kSmemBytes);
