@@ -1,3 +1,6 @@
+#!/bin/bash
+# Everything behind profiles/r02_final_*: run on the GPU box as `gpurun -- 'bash tools/final_run.sh'`, then
+# `python tools/summarize_profiles.py f` here turns the .ncu-rep files into the small tracked summaries.
 mkdir -p gpurun_out
 python bench.py --steps 20 --warmup 5 > gpurun_out/f_bench20.json 2> gpurun_out/f_bench20.err
 python bench.py --steps 200 --warmup 10 --stagger > gpurun_out/f_bench200.json 2> gpurun_out/f_bench200.err

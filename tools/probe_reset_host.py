@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Wall-clock of env.reset() through the host API (sag_reset_host / sag_observe_host) after 30 steps, for three
+BASELINE configs -- the probe that exposed the local-memory re-size stall."""
 import ctypes as C, os, sys, time, torch
 sys.path.insert(0, os.getcwd())
 import bench
