@@ -212,7 +212,7 @@ def main():
     task_objs = [TASKS[t]() for t in cfg["tasks"]]
 
     def make_env():
-        env = BatchedSafeAdaptationGym("xmls/%s.xml" % cfg["robot"], num_envs=n, device=dev, env_id_base=rank * n, max_episode_steps=0)
+        env = BatchedSafeAdaptationGym("xmls/%s.xml" % cfg["robot"], num_envs=n, device=dev, env_id_base=rank * n, max_episode_steps=EPISODE)  # step 1000 flags the episode as finished: its return / cost enter the per-task statistics at the reset
         env.seed(666)
         env.set_task([task_objs[(rank * n + e) % len(task_objs)] for e in range(n)])
         return env
