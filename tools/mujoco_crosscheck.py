@@ -42,6 +42,10 @@ TOLERANCE = {
     ("car", "free"): {"pos": 5e-2, "yaw": 1e-1, "vel": 1e-1},        # reduced planar differential drive vs 3-D free body
     ("car", "static"): {"pos": 1e-1, "yaw": 3e-1, "vel": 3e-1},
     ("car", "movable"): {"pos": 2e-1, "yaw": 5e-1, "vel": 5e-1, "disp": 0.5},
+    # a user-defined task with one gremlin (Task.obstacles[2] = 1): the gremlin's position while it follows its mocap target
+    # (weld as three planar rows vs MuJoCo's 6-row weld; `gpos` = max position error of the gremlin, robot compared as in "free")
+    ("point", "gremlin"): {"pos": 2e-3, "yaw": 2e-2, "vel": 1e-2, "gpos": 3e-2},
+    ("car", "gremlin"): {"pos": 5e-2, "yaw": 1e-1, "vel": 1e-1, "gpos": 3e-2},
 }
 
 
@@ -62,7 +66,7 @@ def wrap(a):
 class RefEnv:
     """The reference environment behind the accessors this script needs."""
 
-    def __init__(self, robot, task, seed, selftest, reference_path):
+    def __init__(self, robot, task, seed, selftest, reference_path, gremlins=0):
         self.selftest = selftest
         self.robot_name = robot
         if selftest:
@@ -70,7 +74,10 @@ class RefEnv:
             import make_golden as G
             if "dm_control" not in sys.modules:
                 G.install_stubs()
-            self.env = G.make_env(task, config={"action_noise": 0.0}, seed=seed, robot=robot)
+            cfg = {"action_noise": 0.0}
+            if gremlins:
+                cfg["num_gremlins"] = gremlins
+            self.env = G.make_env(task, config=cfg, seed=seed, robot=robot)
             np.random.RandomState = G._RealRS   # make_env installs a recording RandomState for the golden generator
         else:
             if reference_path:
@@ -78,6 +85,12 @@ class RefEnv:
             import safe_adaptation_gym  # the unmodified reference
             self.env = safe_adaptation_gym.make(robot, task, seed=seed, config={"action_noise": 0.0},
                                                 render_lidar_and_collision=False)
+            if gremlins:  # a user-defined task: the registry task with Task.obstacles[2] = gremlins (task.py:70)
+                from safe_adaptation_gym.benchmark import TASKS
+                base = TASKS[task]
+                counts = list(base().obstacles)
+                cls = type(base.__name__ + "WithGremlins", (base,), {"obstacles": property(lambda self: [counts[0], counts[1], gremlins, counts[3]])})
+                self.env.set_task(cls())
             self.env.reset()
         self.bridge = self.env.mujoco_bridge
         self.names = [n for n in self.env._world._layout.keys() if n != "robot"]   # placement order (world.py:83-90)
@@ -110,9 +123,9 @@ class RefEnv:
         return sum(1 for g1, g2 in c if ("robot" in str(g1)) != ("robot" in str(g2)) and "floor" not in str(g1) + str(g2))
 
 
-def mirror_oracle(ref, robot, task):
+def mirror_oracle(ref, robot, task, gremlins=0):
     import oracle as O
-    o = O.OracleEnv(robot, task, config={"action_noise": 0.0}, seed=0, env_gid=0)
+    o = O.OracleEnv(robot, task, config={"action_noise": 0.0, "num_gremlins": gremlins}, seed=0, env_gid=0)
     assert o.reset(0) == 0
     r = ref.robot()
     st = o.robot_state
@@ -124,6 +137,12 @@ def mirror_oracle(ref, robot, task):
         b = ref.body(name)
         o.set_obj(s, x=float(b[0]), y=float(b[1]), yaw=float(b[2]), vx=0.0, vy=0.0, w=0.0)
     ts = o.task_state    # distances the task remembers (go_to_goal.py:50-57) follow from the injected poses
+    if gremlins:  # weld anchors = the poses just injected; mocap bodies at the world origin (fresh physics)
+        anchors = []
+        for s, name in enumerate(ref.names):
+            if name.startswith("gremlins"):
+                anchors += list(ref.body(name))
+        o.gremlin_state = [0.0, 0.0, 0.0, 0.0] + anchors
     o.forward()
     return o, ts
 
@@ -133,7 +152,7 @@ def policy(tier, o, rng, t):
     s = o.robot_state
     objs = o.objects()
     kinds = objs[:, 0].astype(int)
-    if tier == "free":
+    if tier in ("free", "gremlin"):
         return rng.uniform(-1, 1, 2)
     want = O.PILLAR if tier == "static" else O.VASE
     cand = objs[kinds == want][:, 2:4]
@@ -149,8 +168,10 @@ def policy(tier, o, rng, t):
 
 def run_tier(robot, tier, steps, seed, selftest, reference_path):
     import oracle as O
-    ref = RefEnv(robot, "go_to_goal", seed, selftest, reference_path)
-    o, _ = mirror_oracle(ref, robot, "go_to_goal")
+    ng = 1 if tier == "gremlin" else 0
+    ref = RefEnv(robot, "go_to_goal", seed, selftest, reference_path, gremlins=ng)
+    o, _ = mirror_oracle(ref, robot, "go_to_goal", gremlins=ng)
+    gslots = [s for s, name in enumerate(ref.names) if name.startswith("gremlins")]
     rng = np.random.RandomState(100 + seed)
     objs0 = o.objects()
     err = {"pos": 0.0, "yaw": 0.0, "vel": 0.0}
@@ -162,7 +183,7 @@ def run_tier(robot, tier, steps, seed, selftest, reference_path):
         touching = len([c for c in o.contacts() if c.ba == 0 or c.bb == 0]) > 0 or ref.ncontacts() > 0
         if touching and first_contact is None:
             first_contact = t
-        if tier == "free" and first_contact is not None:
+        if tier in ("free", "gremlin") and first_contact is not None:
             break
         if tier != "free" and first_contact is not None and t > first_contact + 100:
             break
@@ -170,6 +191,9 @@ def run_tier(robot, tier, steps, seed, selftest, reference_path):
         err["pos"] = max(err["pos"], float(np.hypot(r[0] - s[0], r[1] - s[1])))
         err["yaw"] = max(err["yaw"], float(abs(wrap(r[2] - s[2]))))
         err["vel"] = max(err["vel"], float(np.hypot(r[3] - s[3], r[4] - s[4])))
+        for gs in gslots:
+            b, oo = ref.body(ref.names[gs]), o.objects()[gs]
+            err["gpos"] = max(err.get("gpos", 0.0), float(np.hypot(b[0] - oo[2], b[1] - oo[3])))
         compared += 1
     out = dict(err, steps_compared=compared, first_contact=first_contact)
     if tier == "movable":
@@ -204,7 +228,7 @@ def main():
             return 3
     rows, ok = [], True
     for robot in ("point", "car"):
-        for tier in ("free", "static", "movable"):
+        for tier in ("free", "static", "movable", "gremlin"):
             worst = {}
             for seed in range(args.seeds):
                 r = run_tier(robot, tier, args.steps, seed, args.selftest, args.reference)
