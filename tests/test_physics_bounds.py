@@ -67,6 +67,6 @@ def test_mujoco_crosscheck_harness_selftest():
     tool = os.path.join(root, "tools", "mujoco_crosscheck.py")
     r = subprocess.run([sys.executable, tool, "--selftest", "--steps", "120", "--seeds", "1"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.count(" OK") == 6
+    assert r.stdout.count(" OK") == 8   # {point, car} x {free, static, movable, gremlin}
     r = subprocess.run([sys.executable, tool], capture_output=True, text=True, timeout=120)
     assert r.returncode == 3 and "NOT RUN" in r.stdout
