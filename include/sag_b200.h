@@ -154,8 +154,9 @@ int sag_probe_d2h(void* handle, size_t bytes, int reps, double* seconds);
 int sag_host_alloc_outputs(void* handle, float** obs_h, double** reward_h, uint8_t** cost_h, uint8_t** done_h);
 void sag_host_free(void* p);
 
-/* K steps per launch with on-device Philox U(-1,1) actions (stream 2); benchmark helper.  Writes the last
- * step's obs/reward/cost/done (any may be NULL). */
+/* K steps with on-device Philox U(-1,1) actions (stream 2, counter = the environment's step count), enqueued in one call:
+ * K x (action kernel + the two step kernels); benchmark helper.  Writes the last step's obs/reward/cost/done (any may be
+ * NULL). */
 int sag_rollout(void* handle, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* stream);
 
 /* state injection / extraction; buffers are DEVICE pointers of sag_field_bytes(field) bytes */

@@ -298,6 +298,16 @@ __global__ void __launch_bounds__(kBS) k_rollout(Dev D, int k_steps, float* __re
   if (obs) write_tile<RB::kObsDim>(tile, obs, e0, D.n);
 }
 
+// synthetic actions of sag_rollout: U(-1, 1) from Philox stream 2, counter = the environment's step count
+__global__ void __launch_bounds__(256) k_rollout_actions(Dev D, float* __restrict__ act) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= D.n) return;
+  Rng rng = {D.seed, D.gid_base + (uint32_t)e, D.episode[e]};
+  double u1, u2;
+  rng.pair(2u, (uint32_t)D.nstep[e], u1, u2);
+  reinterpret_cast<float2*>(act)[e] = make_float2((float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0));
+}
+
 // env.reset for the selected environments, ONE WARP per environment that is reset (sag_core.cuh: env_reset_coop -- 32
 // placement candidates per round, the first valid one wins, exactly the sequence of world.py:191-217).  A CTA of four
 // warps looks after 32 consecutive environments: every warp finds the selected ones with one coalesced read + ballot and
@@ -582,8 +592,25 @@ struct Ops {
     return cudaGetLastError();
   }
   static cudaError_t rollout(Handle* H, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, cudaStream_t s) {
-    k_rollout<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kSmemBytes, s>>>(H->D, k_steps, obs, reward, cost, done);
-    ++H->launches;
+    // K x (action kernel + the two step kernels): the same path as sag_step, so a rollout runs at the step's speed (the
+    // single-launch scalar form k_rollout, one thread per environment with the contact solver inline, is 3x slower at
+    // BASELINE batch sizes; SAG_ROLLOUT_FUSED=1 selects it for comparison).  Outputs of the last step are returned.
+    static const bool fused = getenv("SAG_ROLLOUT_FUSED") != nullptr;
+    if (fused) {
+      k_rollout<RB><<<grid_for(H->D.n), kBS, TileCfg<RB>::kSmemBytes, s>>>(H->D, k_steps, obs, reward, cost, done);
+      ++H->launches;
+      return cudaGetLastError();
+    }
+    float* o = obs ? obs : H->obs_d;
+    double* r = reward ? reward : H->rew_d;
+    uint8_t* c = cost ? cost : H->cost_d;
+    uint8_t* d = done ? done : H->done_d;
+    for (int k = 0; k < k_steps; ++k) {
+      k_rollout_actions<<<(H->D.n + 255) / 256, 256, 0, s>>>(H->D, H->act_d);
+      ++H->launches;
+      cudaError_t ce = step(H, H->act_d, o, r, nullptr, c, d, s);
+      if (ce != cudaSuccess) return ce;
+    }
     return cudaGetLastError();
   }
   static cudaError_t reset(Handle* H, const uint8_t* mask, int only_flagged, int new_task, float* obs, uint8_t* was_reset, cudaStream_t s) {
