@@ -472,3 +472,30 @@ def test_warp_cooperative_reset_layouts_bit_exact(robot, task):
     ro, oo = oracle_state(orc)
     np.testing.assert_array_equal(r2[~keep], ro[~keep]); np.testing.assert_array_equal(o2[~keep], oo[~keep])
     env.close()
+
+
+@pytest.mark.gpu
+def test_two_handles_on_two_devices_in_one_process():
+    """every entry point runs on its handle's device and leaves the caller's current device alone (DevGuard): two
+    environments on cuda:0 and cuda:1 stepped alternately from one process give what each gives alone"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg = {"action_noise": 0.0}
+    n = 256
+    a0 = make_env("cuda", n, "go_to_goal", seed=5, config=cfg, device="cuda:0")
+    a1 = make_env("cuda", n, "push_box", seed=6, config=cfg, device="cuda:1")
+    b0 = make_env("cuda", n, "go_to_goal", seed=5, config=cfg, device="cuda:0")
+    assert torch.cuda.current_device() == 0
+    g = torch.Generator(); g.manual_seed(3)
+    for _ in range(40):
+        act = torch.rand((n, 2), generator=g) * 2 - 1
+        o0, r0, _, _ = a0.step(act.to("cuda:0"))
+        o1, r1, _, _ = a1.step(act.to("cuda:1"))
+        ob, rb, _, _ = b0.step(act.to("cuda:0"))
+        assert o1.device.index == 1 and torch.isfinite(o1).all()
+        assert torch.equal(o0, ob) and torch.equal(r0, rb)
+        assert torch.cuda.current_device() == 0
+    a1.reset(); a0.reset()
+    assert torch.cuda.current_device() == 0
+    for e in (a0, a1, b0):
+        e.close()
