@@ -202,7 +202,7 @@ struct Dev {
   double *cgcur, *cgnext, *cgox, *cgoy;
   int* cgtimer;
   int* movmask;  // bit s: movable object s has a non-zero velocity (derived state, rebuilt by env_observe)
-  // work list of the environments that are not quiet in the current step (k_step_quiet -> k_step_busy)
+  // work list of the environments with a contact or a moving body in the current step (k_step_free -> k_step_coop)
   int *worklist, *counts;  // work list segments and their lengths (sag_kernels.cu)
   int* counts_next;        // the other counter set: zeroed by this step's quiet kernel for the next step
   unsigned long long* dbg; // [16] section clocks of SAG_TIMING builds

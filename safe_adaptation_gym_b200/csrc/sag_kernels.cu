@@ -1,12 +1,14 @@
 // sag_kernels.cu -- CUDA kernels (sm_100a) + the C ABI declared in include/sag_b200.h.
 //
-// The step is two kernels: k_step_quiet, one thread per environment over the whole batch (closed-form
-// path, appends the environments that are not quiet to a work list), and k_step_coop, the work list with ONE WARP per
-// environment, the lanes splitting the collision phases / overlap test / lidar pass and the contact solver's working
-// set in shared memory (k_step_busy<G>, its scalar predecessor, stays selectable).  State is SoA / environment-minor so
-// that every global access of a quiet warp is one contiguous 256-byte (fp64) segment; observation tiles (lidar bins
-// are accumulated in them) live in shared memory and are written out row by row.  No tensor cores: nothing here is
-// a dense contraction.  The per-environment logic is in sag_core.cuh; every kernel is templated on the robot model.
+// The step is two kernels: k_step_free, one thread per environment over the whole batch (every environment
+// in which nothing moves: closed-form path, with an exact overlap pre-test where something is within reach; it appends
+// the others to a work list), and k_step_coop, the work list with ONE WARP per environment, the lanes splitting the
+// collision phases / row set-up / floor rows / lidar pass and the contact solver's working set in shared memory
+// (the scalar one-thread-per-environment contact path lives on in the observe kernels).  Resets run one warp per environment
+// too (k_reset).  State is SoA / environment-minor so that every global access of a batch warp is one contiguous 256-byte
+// (fp64) segment; observation tiles (lidar bins are accumulated in them) live in shared memory and are written out row by
+// row.  No tensor cores: nothing here is a dense contraction.  The per-environment logic is in sag_core.cuh; every kernel
+// is templated on the robot model.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>

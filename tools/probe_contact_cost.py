@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Probe: how long is a step when exactly K environments are in contact and all others are quiet?
 Puts the robot of K environments (env ids 0, 32, 64, ...) next to their first vase, driving into it, and times
-sag_step with CUDA events.  PROBE_K=0,256,2048 selects the K values; SAG_BUSY_G selects the busy kernel."""
+sag_step with CUDA events.  PROBE_K=0,256,2048 selects the K values."""
 import ctypes as C
 import sys, os
 import torch
