@@ -310,11 +310,12 @@ __global__ void __launch_bounds__(256) k_rollout_actions(Dev D, float* __restric
   reinterpret_cast<float2*>(act)[e] = make_float2((float)(2.0 * u1 - 1.0), (float)(2.0 * u2 - 1.0));
 }
 
-// env.reset for the selected environments, ONE WARP per environment that is reset (sag_core.cuh: env_reset_coop -- 32
-// placement candidates per round, the first valid one wins, exactly the sequence of world.py:191-217).  A CTA of four
-// warps looks after 32 consecutive environments: every warp finds the selected ones with one coalesced read + ballot and
-// takes every fourth of them, so that a sparse reset (auto-reset of the few environments that expired in this step) costs
-// one layout's latency and a whole-batch reset is one wave of warps.
+// env.reset for the selected environments, ONE WARP per environment that is reset (sag_core.cuh: env_reset_coop -- 8
+// placement candidates x 4 check lanes per round, the first valid draw wins: exactly the sequence of world.py:191-217).
+// A CTA of four warps looks after `gpc` consecutive environments (4 for small batches: one per warp; 32 for large ones):
+// every warp finds the selected ones with one coalesced read + ballot and takes every fourth of them, so that a sparse
+// reset (auto-reset of the few environments that expired in this step) costs one layout's latency and a whole-batch reset
+// keeps every SM full of warps.
 // Statistics: an episode counts when it FINISHED (time limit or done: the NEEDS_RESET flag), under the task it ran with;
 // a manual reset of an unfinished episode is not an episode.
 // obs != nullptr: the environments that were reset get the first observation of their new episode written into their

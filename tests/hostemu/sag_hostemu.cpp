@@ -123,6 +123,13 @@ void do_rollout(Handle* H, int k_steps, float* obs, double* reward, uint8_t* cos
 }
 }  // namespace
 
+// one instantiation per robot model; environments with gremlins use the *G variants (as SAG_DISPATCH in sag_kernels.cu)
+#define HOSTEMU_DISPATCH(H, fn, args)                                                                  \
+  do {                                                                                                 \
+    if ((H)->D.robot == SAG_ROBOT_CAR) { if ((H)->D.num_gremlins > 0) fn<CarRobotG> args; else fn<CarRobot> args; } \
+    else { if ((H)->D.num_gremlins > 0) fn<PointRobotG> args; else fn<PointRobot> args; }              \
+  } while (0)
+
 extern "C" {
 const char* sag_last_error(void) { return g_err; }
 int sag_abi_version(void) { return SAG_ABI_VERSION; }
@@ -180,32 +187,27 @@ int sag_error_flags(void* h, int clear) {
 int sag_seed(void* h, uint64_t seed) { Handle* H = (Handle*)h; H->D.seed = seed; memset(H->D.episode, 0xFF, (size_t)H->D.stride * sizeof(unsigned)); return 0; }
 int sag_reset(void* h, const uint8_t* mask, int only_flagged, int new_task, void* s) {
   (void)s; Handle* H = (Handle*)h;
-  if (H->D.robot == SAG_ROBOT_CAR) { if (H->D.num_gremlins > 0) do_reset<CarRobotG>(H, mask, only_flagged, new_task, nullptr, nullptr); else do_reset<CarRobot>(H, mask, only_flagged, new_task, nullptr, nullptr); }
-  else { if (H->D.num_gremlins > 0) do_reset<PointRobotG>(H, mask, only_flagged, new_task, nullptr, nullptr); else do_reset<PointRobot>(H, mask, only_flagged, new_task, nullptr, nullptr); }
+  HOSTEMU_DISPATCH(H, do_reset, (H, mask, only_flagged, new_task, nullptr, nullptr));
   return 0;
 }
 int sag_reset_obs(void* h, const uint8_t* mask, int only_flagged, int new_task, float* obs, uint8_t* was_reset, void* s) {
   (void)s; Handle* H = (Handle*)h;
-  if (H->D.robot == SAG_ROBOT_CAR) { if (H->D.num_gremlins > 0) do_reset<CarRobotG>(H, mask, only_flagged, new_task, obs, was_reset); else do_reset<CarRobot>(H, mask, only_flagged, new_task, obs, was_reset); }
-  else { if (H->D.num_gremlins > 0) do_reset<PointRobotG>(H, mask, only_flagged, new_task, obs, was_reset); else do_reset<PointRobot>(H, mask, only_flagged, new_task, obs, was_reset); }
+  HOSTEMU_DISPATCH(H, do_reset, (H, mask, only_flagged, new_task, obs, was_reset));
   return 0;
 }
 int sag_step(void* h, const float* act, float* obs, double* reward, double* reward2, uint8_t* cost, uint8_t* done, void* s) {
   (void)s; Handle* H = (Handle*)h;
-  if (H->D.robot == SAG_ROBOT_CAR) { if (H->D.num_gremlins > 0) do_step<CarRobotG>(H, act, obs, reward, reward2, cost, done); else do_step<CarRobot>(H, act, obs, reward, reward2, cost, done); }
-  else { if (H->D.num_gremlins > 0) do_step<PointRobotG>(H, act, obs, reward, reward2, cost, done); else do_step<PointRobot>(H, act, obs, reward, reward2, cost, done); }
+  HOSTEMU_DISPATCH(H, do_step, (H, act, obs, reward, reward2, cost, done));
   return 0;
 }
 int sag_observe(void* h, float* obs, void* s) {
   (void)s; Handle* H = (Handle*)h;
-  if (H->D.robot == SAG_ROBOT_CAR) { if (H->D.num_gremlins > 0) do_observe<CarRobotG>(H, obs); else do_observe<CarRobot>(H, obs); }
-  else { if (H->D.num_gremlins > 0) do_observe<PointRobotG>(H, obs); else do_observe<PointRobot>(H, obs); }
+  HOSTEMU_DISPATCH(H, do_observe, (H, obs));
   return 0;
 }
 int sag_rollout(void* h, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* s) {
   (void)s; Handle* H = (Handle*)h;
-  if (H->D.robot == SAG_ROBOT_CAR) { if (H->D.num_gremlins > 0) do_rollout<CarRobotG>(H, k_steps, obs, reward, cost, done); else do_rollout<CarRobot>(H, k_steps, obs, reward, cost, done); }
-  else { if (H->D.num_gremlins > 0) do_rollout<PointRobotG>(H, k_steps, obs, reward, cost, done); else do_rollout<PointRobot>(H, k_steps, obs, reward, cost, done); }
+  HOSTEMU_DISPATCH(H, do_rollout, (H, k_steps, obs, reward, cost, done));
   return 0;
 }
 int sag_read_field(void* h, int f, void* dst, void* s) { (void)s; Handle* H = (Handle*)h; memcpy(dst, H->slab + H->LY.off[f], H->LY.bytes[f]); return 0; }
