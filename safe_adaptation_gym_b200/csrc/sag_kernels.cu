@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 
@@ -863,7 +864,19 @@ int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward
   DevGuard guard(H->device);
   cudaStream_t s = H->own_stream;
   const size_t n = (size_t)H->D.n, od = (size_t)sag_obs_dim(H);
+#if defined(SAG_E2E_TIMING)  // tuning builds: where does an end-to-end step spend its time?  (events on the handle's two streams)
+  static cudaEvent_t te[6];
+  static double tacc[6];
+  static int tcnt = 0;
+  if (!te[0]) for (int i = 0; i < 6; ++i) cudaEventCreate(&te[i]);
+  struct timespec w0, w1;
+  clock_gettime(CLOCK_MONOTONIC, &w0);
+  cudaEventRecord(te[0], s);
+#endif
   CK(cudaMemcpyAsync(H->act_d, act_h, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+#if defined(SAG_E2E_TIMING)
+  cudaEventRecord(te[1], s);
+#endif
   float* obs_m = (float*)mapped_alias(obs_h);
   double* rew_m = (double*)mapped_alias(reward_h);
   uint8_t *cost_m = (uint8_t*)mapped_alias(cost_h), *done_m = (uint8_t*)mapped_alias(done_h);
@@ -877,6 +890,11 @@ int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward
     // was measured and lost: the kernel's duration is the latency of one thread's step, not throughput, so every chunk
     // costs as much as the whole batch -- e2e 1.51e8 -> 1.27e8.  SAG_HOST_CHUNKS re-enables it for experiments.)
     cudaStream_t c = H->copy_stream;
+    // (Reading the actions straight from the pinned host buffer in the kernels instead of copying them first: no difference,
+    // 1.556e8 either way.  A split copy -- head of the observation rows under the contact kernel, tail + reward / cost / done after it so that
+    // the fix-up runs under the tail, split point adapted from the previous step's timings -- was measured and lost by 1-5 %:
+    // the contact kernel's duration varies by +-20 us from step to step, and a copy engine that waits costs more than the
+    // 27 us fix-up it hides.)
     static const int env_chunks = getenv("SAG_HOST_CHUNKS") ? atoi(getenv("SAG_HOST_CHUNKS")) : 1;
     const int nch = (env_chunks >= 1 && env_chunks <= 8 && n >= 8 * 4096) ? env_chunks : 1;
     const int per = (((int)n + nch - 1) / nch + kBS - 1) / kBS * kBS;
@@ -900,10 +918,33 @@ int sag_step_host(void* handle, const float* act_h, float* obs_h, double* reward
       CK(cudaMemcpyAsync(done_h, H->done_d, n, cudaMemcpyDeviceToHost, c));
     }
     CK(cudaEventRecord(H->ev_copied, c));
+#if defined(SAG_E2E_TIMING)
+    cudaEventRecord(te[3], c);   // bulk copy done
+    cudaEventRecord(te[2], s);   // batch kernel done (the copy stream waited for the same point)
+#endif
     CK(SAG_DISPATCH(H, step_busy(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s)));
+#if defined(SAG_E2E_TIMING)
+    cudaEventRecord(te[4], s);   // contact kernel done
+#endif
     CK(cudaStreamWaitEvent(s, H->ev_copied, 0));
     CK(SAG_DISPATCH(H, fixup_host(H, H->obs_d, H->rew_d, H->cost_d, H->done_d, obs_m, rew_m, cost_m, done_m, s)));
+#if defined(SAG_E2E_TIMING)
+    cudaEventRecord(te[5], s);
+#endif
     CK(cudaStreamSynchronize(s));
+#if defined(SAG_E2E_TIMING)
+    clock_gettime(CLOCK_MONOTONIC, &w1);
+    {
+      float ms;
+      for (int i = 1; i < 6; ++i) { cudaEventElapsedTime(&ms, te[0], te[i]); tacc[i] += ms; }
+      tacc[0] += 1e3 * (double)(w1.tv_sec - w0.tv_sec) + 1e-6 * (double)(w1.tv_nsec - w0.tv_nsec);
+      if (++tcnt % 40 == 0) {
+        fprintf(stderr, "sag_step_host (avg of 40, ms since the first enqueue): h2d done %.3f, batch kernel done %.3f, bulk copy done %.3f, contact kernel done %.3f, fix-up done %.3f | wall %.3f\n",
+                tacc[1] / 40, tacc[2] / 40, tacc[3] / 40, tacc[4] / 40, tacc[5] / 40, tacc[0] / 40);
+        for (int i = 0; i < 6; ++i) tacc[i] = 0.0;
+      }
+    }
+#endif
     return 0;
   }
   CK(SAG_DISPATCH(H, step(H, H->act_d, H->obs_d, H->rew_d, nullptr, H->cost_d, H->done_d, s)));

@@ -298,7 +298,27 @@ def run_fullsize_parity(robot, task_cycle, n, steps, n_sample, seed=666, action_
     g = torch.Generator(device="cuda"); g.manual_seed(seed + 1)
     L = env._lib
     od = env.obs_dim
-    if use_host_api:
+    if use_host_api == "packed":
+        # the output block of sag_host_alloc_outputs (one pinned block laid out like the device staging area): sag_step_host
+        # then moves all four outputs with a single device-to-host copy per step
+        import ctypes as C
+        ptrs = [C.c_void_p() for _ in range(4)]
+        L.check(L.L.sag_host_alloc_outputs(env._h, *[C.byref(x) for x in ptrs]))
+
+        class _View:
+            def __init__(self, ptr, ctype, shape):
+                self.ptr = ptr
+                self.arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=shape)
+
+            def data_ptr(self):
+                return self.ptr
+
+            def __getitem__(self, i):
+                return torch.from_numpy(self.arr[i].copy())
+        act_h = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+        obs_h = _View(ptrs[0].value, C.c_float, (n, od)); rew_h = _View(ptrs[1].value, C.c_double, (n,))
+        cost_h = _View(ptrs[2].value, C.c_uint8, (n,)); done_h = _View(ptrs[3].value, C.c_uint8, (n,))
+    elif use_host_api:
         act_h = torch.empty((n, 2), dtype=torch.float32).pin_memory()
         obs_h = torch.empty((n, od), dtype=torch.float32).pin_memory()
         rew_h = torch.empty((n,), dtype=torch.float64).pin_memory()
@@ -332,6 +352,8 @@ def run_fullsize_parity(robot, task_cycle, n, steps, n_sample, seed=666, action_
             np.testing.assert_array_equal(o1[ids], oo, err_msg=f"object state step {t}")
             mm = env.get_field("task_i32")[9, :n]
             stats["max_worklist"] = max(stats["max_worklist"], int((mm != 0).sum()))
+    if use_host_api == "packed":
+        L.L.sag_host_free(ptrs[0])
     env.close()
     return stats
 

@@ -325,6 +325,15 @@ def test_host_buffer_api_against_oracle():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("robot,n", [("point", 16384), ("car", 8192)])
+def test_host_buffer_api_packed_block_against_oracle(robot, n):
+    """sag_step_host with the output block of sag_host_alloc_outputs (all four outputs in ONE device-to-host copy per step,
+    actions read from the pinned host buffer by the kernels) against the oracle"""
+    s = run_fullsize_parity(robot, ["go_to_goal", "push_box"], n=n, steps=200, n_sample=128, use_host_api="packed")
+    assert s["max_worklist"] > 20
+
+
+@pytest.mark.gpu
 def test_new_abi_behaviours_on_device():
     """auto-reset row / truncated mask, statistics keyed by the task the episode ran under, host-pointer set_task and bound,
     two handles in one process (device guard), fresh output tensors"""
