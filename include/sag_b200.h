@@ -154,6 +154,14 @@ int sag_probe_d2h(void* handle, size_t bytes, int reps, double* seconds);
 int sag_host_alloc_outputs(void* handle, float** obs_h, double** reward_h, uint8_t** cost_h, uint8_t** done_h);
 void sag_host_free(void* p);
 
+/* The outputs of a step as fresh arrays in one launch (device pointers): obs rows, reward (reward_cols = 1, or 2 for the
+ * Unsupervised task's pair), cost as float32 -- the reference returns float(cost > 0.), world.py:155 --, done as bool bytes,
+ * and (bound_out != NULL) info['bound'].  What the reference's step() returns are new numpy arrays
+ * (safe_adaptation_gym.py:80-83); the Python mirror hands out copies through this call. */
+int sag_export_outputs(void* handle, const float* obs, const double* reward, int reward_cols, const uint8_t* cost, const uint8_t* done,
+                       const double* bound, float* obs_out, double* reward_out, float* cost_out, uint8_t* done_out, double* bound_out,
+                       void* stream);
+
 /* K steps with on-device Philox U(-1,1) actions (stream 2, counter = the environment's step count), enqueued in one call:
  * K x (action kernel + the two step kernels); benchmark helper.  Writes the last step's obs/reward/cost/done (any may be
  * NULL). */

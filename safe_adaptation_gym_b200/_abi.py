@@ -44,7 +44,7 @@ class SagLib:
         "sag_obs_dim", "sag_field_bytes", "sag_launch_count", "sag_debug_read", "sag_set_tasks", "sag_set_tasks_host", "sag_bound_host",
         "sag_error_flags", "sag_reset_obs", "sag_reset_host", "sag_seed", "sag_reset", "sag_step", "sag_observe",
         "sag_step_host", "sag_observe_host", "sag_host_alloc", "sag_host_alloc_outputs", "sag_probe_d2h", "sag_host_free", "sag_rollout", "sag_read_field",
-        "sag_write_field", "sag_task_stats", "sag_lidar", "sag_cost",
+        "sag_write_field", "sag_task_stats", "sag_lidar", "sag_cost", "sag_export_outputs",
     ]
 
     def __init__(self, path, host_api=True):
@@ -75,6 +75,7 @@ class SagLib:
         L.sag_step.argtypes = [vp, fp, fp, dp, dp, u8p, u8p, vp]
         L.sag_observe.argtypes = [vp, fp, vp]
         L.sag_rollout.argtypes = [vp, i32, fp, dp, u8p, u8p, vp]
+        L.sag_export_outputs.argtypes = [vp, fp, dp, i32, u8p, u8p, dp, fp, dp, fp, u8p, dp, vp]
         L.sag_read_field.argtypes = [vp, i32, vp, vp]
         L.sag_write_field.argtypes = [vp, i32, vp, vp]
         L.sag_task_stats.argtypes = [vp, dp, i32, vp]

@@ -512,6 +512,27 @@ __global__ void __launch_bounds__(128) k_fixup_host(const __grid_constant__ Dev 
   }
 }
 
+// env.step's return values as FRESH arrays in one launch (the host mirror hands out copies by default, like the reference's
+// numpy arrays): obs rows as float4, reward (1 or 2 columns), cost as float32 (world.py:155 returns a float), done as bool
+// bytes, bound.  Five separate framework copies / casts cost ~6 us of stream time each.
+__global__ void __launch_bounds__(256) k_export_outputs(int n, int obs_quads, int reward_cols, const float4* __restrict__ obs,
+                                                        const double* __restrict__ reward, const uint8_t* __restrict__ cost,
+                                                        const uint8_t* __restrict__ done, const double* __restrict__ bound,
+                                                        float4* __restrict__ obs_out, double* __restrict__ reward_out,
+                                                        float* __restrict__ cost_out, uint8_t* __restrict__ done_out,
+                                                        double* __restrict__ bound_out) {
+  const size_t total = (size_t)n * obs_quads;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    obs_out[i] = obs[i];
+    if (i < (size_t)n) {
+      for (int k = 0; k < reward_cols; ++k) reward_out[i * reward_cols + k] = reward[i * reward_cols + k];
+      cost_out[i] = (float)cost[i];
+      done_out[i] = done[i] ? 1 : 0;
+      if (bound_out) bound_out[i] = bound[i];
+    }
+  }
+}
+
 static inline int grid_for(int n) { return (n + kBS - 1) / kBS; }
 
 // host-side launchers, one set per robot model
@@ -831,6 +852,25 @@ int sag_step(void* handle, const float* act, float* obs, double* reward, double*
   if (!H || !act || !obs || !reward || !cost || !done) return fail("sag_step: null argument");
   DevGuard guard(H->device);
   CK(SAG_DISPATCH(H, step(H, act, obs, reward, reward2, cost, done, (cudaStream_t)stream)));
+  return 0;
+}
+
+int sag_export_outputs(void* handle, const float* obs, const double* reward, int reward_cols, const uint8_t* cost, const uint8_t* done,
+                       const double* bound, float* obs_out, double* reward_out, float* cost_out, uint8_t* done_out, double* bound_out,
+                       void* stream) {
+  Handle* H = (Handle*)handle;
+  if (!H || !obs || !reward || !cost || !done || !obs_out || !reward_out || !cost_out || !done_out || (reward_cols != 1 && reward_cols != 2) ||
+      (bound_out && !bound))
+    return fail("sag_export_outputs: bad argument");
+  DevGuard guard(H->device);
+  const int quads = sag_obs_dim(H) / 4;
+  const size_t total = (size_t)H->D.n * quads;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  k_export_outputs<<<grid, 256, 0, (cudaStream_t)stream>>>(H->D.n, quads, reward_cols, (const float4*)obs, reward, cost, done, bound,
+                                                          (float4*)obs_out, reward_out, cost_out, done_out, bound_out);
+  ++H->launches;
+  CK(cudaGetLastError());
   return 0;
 }
 

@@ -169,17 +169,32 @@ class BatchedSafeAdaptationGym:
         L.check(L.L.sag_step(self._h, self._p(act), self._p(self._obs), self._p(self._reward), self._p(r2),
                              self._p(self._cost), self._p(self._done), self._stream()))
         reward = self._reward2 if self._any_unsupervised else self._reward
-        info = {'cost': self._cost.to(torch.float32), 'bound': self._out(self._bound)}
-        done = self._done.to(torch.bool)
+        was_reset = None
         if self.max_episode_steps > 0:
             # auto-reset: the kernel resets the flagged environments, writes the first observation of their new episode
             # into their rows and reports which ones it reset
             L.check(L.L.sag_reset_obs(self._h, None, 1, 0, self._p(self._obs), self._p(self._was_reset), self._stream()))
             was_reset = self._was_reset.to(torch.bool)
+        if self.copy_outputs:
+            # fresh arrays, as the reference returns them (safe_adaptation_gym.py:80-83) -- one launch for all of them
+            n, dev = self.num_envs, self.device
+            obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=dev)
+            rew = torch.empty_like(reward)
+            cost = torch.empty((n,), dtype=torch.float32, device=dev)
+            done = torch.empty((n,), dtype=torch.bool, device=dev)
+            bound = torch.empty((n,), dtype=torch.float64, device=dev)
+            L.check(L.L.sag_export_outputs(self._h, self._p(self._obs), self._p(reward), 2 if self._any_unsupervised else 1,
+                                           self._p(self._cost), self._p(self._done), self._p(self._bound), self._p(obs), self._p(rew),
+                                           self._p(cost), self._p(done), self._p(bound), self._stream()))
+        else:  # views of the internal buffers, valid until the next call
+            obs, rew, bound = self._obs, reward, self._bound
+            cost, done = self._cost.to(torch.float32), self._done.view(torch.bool)
+        info = {'cost': cost, 'bound': bound}
+        if was_reset is not None:
             info['truncated'] = was_reset & ~done   # ended by the time limit, not by a physics error
             done = done | was_reset
         self._raise_recorded_errors('step')
-        return self._out(self._obs), self._out(reward), done, info
+        return obs, rew, done, info
 
     def reset(self, *, seed: Optional[int] = None, return_info: bool = False, options: Optional[dict] = None):
         """safe_adaptation_gym.py:85-107"""

@@ -205,6 +205,16 @@ int sag_observe(void* h, float* obs, void* s) {
   HOSTEMU_DISPATCH(H, do_observe, (H, obs));
   return 0;
 }
+int sag_export_outputs(void* h, const float* obs, const double* reward, int reward_cols, const uint8_t* cost, const uint8_t* done,
+                       const double* bound, float* obs_out, double* reward_out, float* cost_out, uint8_t* done_out, double* bound_out,
+                       void* s) {
+  (void)s; Handle* H = (Handle*)h;
+  const int n = H->D.n, od = obs_dim_of(H->D);
+  memcpy(obs_out, obs, (size_t)n * od * sizeof(float));
+  memcpy(reward_out, reward, (size_t)n * reward_cols * sizeof(double));
+  for (int e = 0; e < n; ++e) { cost_out[e] = (float)cost[e]; done_out[e] = done[e] ? 1 : 0; if (bound_out) bound_out[e] = bound[e]; }
+  return 0;
+}
 int sag_rollout(void* h, int k_steps, float* obs, double* reward, uint8_t* cost, uint8_t* done, void* s) {
   (void)s; Handle* H = (Handle*)h;
   HOSTEMU_DISPATCH(H, do_rollout, (H, k_steps, obs, reward, cost, done));
