@@ -1479,7 +1479,20 @@ SAG_HD void contact_pass_body(const Ctx& C, const RB& R, double sn, double cs, c
 #pragma unroll 1
     for (int i = 0; i < nrow; ++i) {
       Row& r = rows[i];
-      if (kCarRobot && r.type == 2) { wheel_row_update(r, acc[0], acc[r.bb], sdf, sf); continue; }
+      if (kCarRobot && r.type == 2) {
+        // the wheel visit on a register copy of the row: one batch of loads instead of a reload after every store to r.f
+        Row Lr;
+        Lr.bound = r.bound;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) { Lr.ja[k][d] = r.ja[k][d]; Lr.jb[k][d] = r.jb[k][d]; Lr.wa[k][d] = r.wa[k][d]; Lr.wb[k][d] = r.wb[k][d]; }
+          Lr.aref[k] = r.aref[k]; Lr.R[k] = r.R[k]; Lr.inv[k] = r.inv[k]; Lr.f[k] = r.f[k];
+        }
+        wheel_row_update(Lr, acc[0], acc[r.bb], sdf, sf);
+        r.f[0] = Lr.f[0]; r.f[1] = Lr.f[1];
+        continue;
+      }
       // one visit of a contact row pair (normal, tangent) or of the tendon row (one row)
       const int ba = r.ba, bb = r.bb, nk = RB::kGremlins ? r.nk : ((i == tendon_row) ? 1 : 2);
       const bool bilateral = RB::kGremlins && r.type == 1;
