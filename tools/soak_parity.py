@@ -20,6 +20,8 @@ if __name__ == "__main__":
     cfg = {"action_noise": 0.01}
     if os.environ.get("SOAK_KNOBS"):   # adaptation knobs on: Cauchy-scaled ctrl ranges (incl. inverted ones), random bound
         cfg.update({"robot_ctrl_range_scale": 0.5, "random_bound": True})
+    if os.environ.get("SOAK_GREMLINS"):   # a user-defined task with gremlins on top of every registry task (world.py:157-165)
+        cfg["num_gremlins"] = int(os.environ["SOAK_GREMLINS"])
     for robot in ("point", "car"):
         for i, task in enumerate(TASKS):
             t0 = time.time()
